@@ -1,0 +1,103 @@
+"""ctypes binding of include/protograd_b200.h — the only way the host side reaches the GPU.
+
+There is no CPU fallback: if the shared library is missing the import fails loudly, and every
+compute call on a box without a B200 raises `PGError`.
+"""
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libprotograd_b200.so")
+
+PG_F32, PG_F64, PG_BF16 = 0, 1, 2
+ACT_NONE, ACT_RELU = 0, 1
+ADD, SUB = 0, 1
+X_PLUS_C, X_MINUS_C, C_MINUS_X, X_TIMES_C, X_OVER_C, C_OVER_X = range(6)
+SCALAR_F64, SCALAR2_F64, MATH_FAST = 1, 2, 4
+
+
+class PGError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or python protograd.jl_b200/build.py). There is no CPU fallback.")
+
+lib = ctypes.CDLL(LIB_PATH)
+lib.pg_last_error.restype = c_char_p
+
+_P, _I, _L, _D, _Z = c_void_p, c_int, c_int64, c_double, c_size_t
+_SIGS = {
+    "pg_version": [],
+    "pg_device_count": [POINTER(c_int)],
+    "pg_init": [_I, POINTER(_P)],
+    "pg_destroy": [_P],
+    "pg_set_stream": [_P, _P],
+    "pg_get_stream": [_P, POINTER(_P)],
+    "pg_sync": [_P],
+    "pg_launch_count": [_P, POINTER(c_int64)],
+    "pg_reserve_workspace": [_P, _Z],
+    "pg_malloc": [_P, _Z, POINTER(_P)],
+    "pg_free": [_P, _P],
+    "pg_memset0": [_P, _P, _Z],
+    "pg_copy_d2d": [_P, _P, _P, _Z],
+    "pg_upload": [_P, _P, _P, _Z],
+    "pg_download": [_P, _P, _P, _Z],
+    "pg_download_async": [_P, _P, _P, _Z],
+    "pg_host_alloc": [_Z, POINTER(_P)],
+    "pg_host_free": [_P],
+    "pg_graph_begin": [_P],
+    "pg_graph_end": [_P, POINTER(_P)],
+    "pg_graph_launch": [_P, _P],
+    "pg_graph_destroy": [_P, _P],
+    "pg_vec_binary": [_P, _I, _I, _P, _P, _P, _L],
+    "pg_vec_scalar": [_P, _I, _I, _P, _P, _D, _I, _L],
+    "pg_vec_axpy": [_P, _I, _P, _P, _D, _P, _I, _I, _L],
+    "pg_vec_fill": [_P, _I, _P, _D, _L],
+    "pg_vec_dot": [_P, _I, _P, _P, _L, POINTER(c_double)],
+    "pg_vec_cast_bf16": [_P, _P, _P, _L],
+    "pg_opt_gd": [_P, _I, _P, _P, _L, _D, _I, _P],
+    "pg_opt_heavyball": [_P, _I, _P, _P, _P, _L, _D, _D, _I, _P],
+    "pg_opt_nesterov": [_P, _I, _P, _P, _P, _L, _D, _D, _I, _P],
+    "pg_opt_adam": [_P, _I, _P, _P, _P, _P, _P, _P, _L, _D, _D, _D, _D, _L, _I, _P],
+    "pg_linear_fwd": [_P, _I, _P, _P, _P, _P, _L, _L, _L, _I],
+    "pg_linear_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L],
+    "pg_tc_linear_fwd": [_P, _P, _P, _P, _P, _I, _L, _L, _L, _I],
+    "pg_tc_linear_bwd": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _L, _L],
+    "pg_tc_gemm": [_P, _I, _P, _P, _P, _I, _L, _L, _L],
+    "pg_conv2d_fwd": [_P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I],
+    "pg_conv2d_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I],
+    "pg_maxpool2d_fwd": [_P, _I, _P, _P, _L, _I, _I, _I],
+    "pg_maxpool2d_bwd": [_P, _I, _P, _P, _P, _L, _I, _I, _I],
+    "pg_meanpool2d_fwd": [_P, _I, _P, _P, _L, _I, _I, _I],
+    "pg_meanpool2d_bwd": [_P, _I, _P, _P, _L, _I, _I, _I],
+    "pg_relu_fwd": [_P, _I, _P, _P, _L],
+    "pg_relu_bwd": [_P, _I, _P, _P, _P, _L],
+    "pg_softmax_ce_fwd_bwd": [_P, _I, _P, _P, _P, _P, _P, _L, _I, _D],
+    "pg_softmax_ce_idx_fwd_bwd": [_P, _I, _P, POINTER(c_int32), _P, _P, _P, _L, _I, _D],
+    "pg_softmax_fwd": [_P, _I, _P, _P, _L, _I],
+    "pg_softmax_bwd": [_P, _I, _P, _P, _P, _L, _I],
+    "pg_cross_entropy_fwd_bwd": [_P, _I, _P, _P, _P, _P, _L, _I, _D],
+    "pg_mse_fwd_bwd": [_P, _I, _P, _P, _P, _P, _L, _D],
+    "pg_class_error": [_P, _I, _P, _P, _L, _I, POINTER(c_double)],
+    "pg_loss_read": [_P, _I, _P, POINTER(c_double)],
+}
+
+EXPORTS = tuple(_SIGS) + ("pg_last_error",)
+
+for _name, _args in _SIGS.items():
+    _f = getattr(lib, _name)  # AttributeError here == header/library drift, which must be loud
+    _f.argtypes = _args
+    _f.restype = c_int
+
+
+def check(rc):
+    if rc != 0:
+        raise PGError(f"protograd_b200 error {rc}: {lib.pg_last_error().decode(errors='replace')}")
+
+
+def call(name, *args):
+    check(getattr(lib, name)(*args))

@@ -1,0 +1,201 @@
+// capi.cu — lifecycle, memory, stream/graph plumbing of the C ABI (include/protograd_b200.h).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void pg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int pg_ws_ensure(pg_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return PG_OK;
+  if (ctx->capturing) {
+    pg_set_error("workspace of %zu bytes needed during graph capture (have %zu): call pg_reserve_workspace first", bytes, ctx->ws_bytes);
+    return PG_ERR_NOMEM;
+  }
+  PG_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->ws) PG_CHECK_CUDA(cudaFree(ctx->ws));
+  ctx->ws = nullptr;
+  ctx->ws_bytes = 0;
+  size_t want = bytes + (bytes >> 2);
+  PG_CHECK_CUDA(cudaMalloc(&ctx->ws, want));
+  ctx->ws_bytes = want;
+  return PG_OK;
+}
+
+extern "C" {
+
+const char* pg_last_error(void) { return g_err; }
+int pg_version(void) { return 100; }
+
+int pg_device_count(int* n) {
+  PG_REQUIRE(n != nullptr, "null out pointer");
+  *n = 0;
+  PG_CHECK_CUDA(cudaGetDeviceCount(n));
+  return PG_OK;
+}
+
+int pg_init(int device, pg_ctx** out) {
+  PG_REQUIRE(out != nullptr, "null out pointer");
+  *out = nullptr;
+  int n = 0;
+  PG_CHECK_CUDA(cudaGetDeviceCount(&n));
+  if (n <= 0) {
+    pg_set_error("no CUDA device: this library has no CPU fallback");
+    return PG_ERR_CUDA;
+  }
+  PG_REQUIRE(device >= 0 && device < n, "device index out of range");
+  PG_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PG_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    pg_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return PG_ERR_UNSUPPORTED;
+  }
+  pg_ctx* c = new pg_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  PG_CHECK_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  PG_CHECK_CUDA(cudaMalloc((void**)&c->counters, 64 * sizeof(unsigned int)));
+  PG_CHECK_CUDA(cudaMemset(c->counters, 0, 64 * sizeof(unsigned int)));
+  PG_CHECK_CUDA(cudaMalloc((void**)&c->result_slot, 16 * sizeof(double)));
+  PG_CHECK_CUDA(cudaMallocHost((void**)&c->result_host, 16 * sizeof(double)));
+  *out = c;
+  int rc = pg_ws_ensure(c, (size_t)32 << 20);
+  if (rc != PG_OK) return rc;
+  return PG_OK;
+}
+
+int pg_destroy(pg_ctx* ctx) {
+  if (!ctx) return PG_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->counters) cudaFree(ctx->counters);
+  if (ctx->result_slot) cudaFree(ctx->result_slot);
+  if (ctx->result_host) cudaFreeHost(ctx->result_host);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return PG_OK;
+}
+
+int pg_set_stream(pg_ctx* ctx, void* s) {
+  PG_CHECK_CTX(ctx);
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return PG_OK;
+}
+int pg_get_stream(pg_ctx* ctx, void** s) {
+  PG_CHECK_CTX(ctx);
+  *s = (void*)ctx->stream;
+  return PG_OK;
+}
+int pg_sync(pg_ctx* ctx) {
+  PG_CHECK_CTX(ctx);
+  PG_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PG_OK;
+}
+int pg_launch_count(pg_ctx* ctx, int64_t* n) {
+  PG_CHECK_CTX(ctx);
+  *n = ctx->launches;
+  return PG_OK;
+}
+int pg_reserve_workspace(pg_ctx* ctx, size_t bytes) {
+  PG_CHECK_CTX(ctx);
+  return pg_ws_ensure(ctx, bytes);
+}
+
+int pg_malloc(pg_ctx* ctx, size_t bytes, void** dptr) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(dptr != nullptr, "null out pointer");
+  PG_CHECK_CUDA(cudaSetDevice(ctx->device));
+  PG_CHECK_CUDA(cudaMalloc(dptr, bytes ? bytes : 16));
+  return PG_OK;
+}
+int pg_free(pg_ctx* ctx, void* dptr) {
+  PG_CHECK_CTX(ctx);
+  if (dptr) PG_CHECK_CUDA(cudaFree(dptr));
+  return PG_OK;
+}
+int pg_memset0(pg_ctx* ctx, void* dptr, size_t bytes) {
+  PG_CHECK_CTX(ctx);
+  PG_CHECK_CUDA(cudaMemsetAsync(dptr, 0, bytes, ctx->stream));
+  return PG_OK;
+}
+int pg_copy_d2d(pg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  PG_CHECK_CTX(ctx);
+  PG_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return PG_OK;
+}
+int pg_upload(pg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  PG_CHECK_CTX(ctx);
+  PG_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return PG_OK;
+}
+int pg_download_async(pg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  PG_CHECK_CTX(ctx);
+  PG_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return PG_OK;
+}
+int pg_download(pg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  int rc = pg_download_async(ctx, dst, src, bytes);
+  if (rc != PG_OK) return rc;
+  PG_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PG_OK;
+}
+int pg_host_alloc(size_t bytes, void** p) {
+  PG_REQUIRE(p != nullptr, "null out pointer");
+  PG_CHECK_CUDA(cudaMallocHost(p, bytes ? bytes : 16));
+  return PG_OK;
+}
+int pg_host_free(void* p) {
+  if (p) PG_CHECK_CUDA(cudaFreeHost(p));
+  return PG_OK;
+}
+
+int pg_graph_begin(pg_ctx* ctx) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(!ctx->capturing, "already capturing");
+  PG_CHECK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  ctx->capturing = true;
+  return PG_OK;
+}
+int pg_graph_end(pg_ctx* ctx, void** graph_exec) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(ctx->capturing, "not capturing");
+  ctx->capturing = false;
+  cudaGraph_t g = nullptr;
+  PG_CHECK_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+  cudaGraphExec_t ge = nullptr;
+  PG_CHECK_CUDA(cudaGraphInstantiate(&ge, g, 0));
+  PG_CHECK_CUDA(cudaGraphDestroy(g));
+  *graph_exec = (void*)ge;
+  return PG_OK;
+}
+int pg_graph_launch(pg_ctx* ctx, void* graph_exec) {
+  PG_CHECK_CTX(ctx);
+  PG_CHECK_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, ctx->stream));
+  return PG_OK;
+}
+int pg_graph_destroy(pg_ctx* ctx, void* graph_exec) {
+  PG_CHECK_CTX(ctx);
+  if (graph_exec) PG_CHECK_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  return PG_OK;
+}
+
+int pg_loss_read(pg_ctx* ctx, int dtype, const void* loss_dev, double* result) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(result != nullptr && loss_dev != nullptr, "null pointer");
+  size_t sz = dtype == PG_F64 ? 8 : 4;
+  PG_CHECK_CUDA(cudaMemcpyAsync(ctx->result_host, loss_dev, sz, cudaMemcpyDeviceToHost, ctx->stream));
+  PG_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  *result = dtype == PG_F64 ? *(double*)ctx->result_host : (double)*(float*)ctx->result_host;
+  return PG_OK;
+}
+
+}  // extern "C"

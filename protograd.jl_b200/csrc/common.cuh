@@ -1,0 +1,95 @@
+// common.cuh — context, error convention, small device helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/protograd_b200.h"
+
+struct pg_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  // scratch: split-K partials, block partials for reductions
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // small persistent scratch: [0..63] counters (zeroed), [64..] result slots
+  unsigned int* counters = nullptr;
+  double* result_slot = nullptr;     // device
+  double* result_host = nullptr;     // pinned
+  bool capturing = false;
+  // driver entry point for TMA descriptor encoding (resolved lazily, no libcuda link dependency)
+  void* encode_tiled = nullptr;
+};
+
+void pg_set_error(const char* fmt, ...);
+
+#define PG_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      pg_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PG_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define PG_REQUIRE(cond, msg)                                     \
+  do {                                                            \
+    if (!(cond)) {                                                \
+      pg_set_error("%s: %s (%s:%d)", __func__, msg, __FILE__, __LINE__); \
+      return PG_ERR_ARG;                                          \
+    }                                                             \
+  } while (0)
+
+#define PG_CHECK_CTX(ctx) PG_REQUIRE((ctx) != nullptr, "null context")
+
+// call after every kernel launch
+#define PG_LAUNCHED(ctx)                         \
+  do {                                           \
+    (ctx)->launches++;                           \
+    PG_CHECK_CUDA(cudaGetLastError());           \
+  } while (0)
+
+int pg_ws_ensure(pg_ctx* ctx, size_t bytes);  // grow scratch (fails during graph capture)
+
+// column sums out[n] = sum_m X[m][n]; in_dtype f32/f64 (out same type) or bf16 (out f32)
+int pg_colsum_launch(pg_ctx* ctx, int in_dtype, const void* X, void* out, int64_t M, int64_t N);
+
+static inline int64_t pg_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ------------------------------------------------------------------------
+template <typename T> struct Eps;
+template <> struct Eps<float> { static __device__ __forceinline__ float v() { return 1.1920929e-07f; } };
+template <> struct Eps<double> { static __device__ __forceinline__ double v() { return 2.220446049250313e-16; } };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum (blockDim.x multiple of 32, <= 1024); result valid in thread 0.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 */) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? smem[threadIdx.x] : T(0);
+  if (w == 0) v = warp_sum(v);
+  __syncthreads();
+  return v;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v) { return (float)v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }

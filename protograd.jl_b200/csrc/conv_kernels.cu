@@ -1,0 +1,390 @@
+// conv_kernels.cu — Conv (src/layers.jl:59 -> NNlib.conv: TRUE convolution, kernel flipped in both
+// spatial dims, stride 1, no padding), its gradients (NNlib ∇conv_filter / ∇conv_data), max/mean
+// pooling with window == stride (layers.jl:93,99; NNlib ∇maxpool routes to the FIRST max, kW
+// fastest) and relu (layers.jl:81; relu'(0) = 0).  NCHW row-major == Julia [W,H,C,N].
+// The MNIST-size layers (Cin 1/6, Cout 6/16, 5x5) are activation-bandwidth-bound, so these are
+// direct CUDA-core kernels with coalesced W-fastest indexing, weights staged in shared memory.
+#include "common.cuh"
+
+namespace {
+
+constexpr int COT = 8;  // output channels per thread in the forward kernel
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b, T* __restrict__ y,
+                int64_t N, int Cin, int H, int W, int Cout, int kH, int kW, int relu, int w_in_smem) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* ws = reinterpret_cast<T*>(smem_raw);
+  const int Ho = H - kH + 1, Wo = W - kW + 1;
+  const int co0 = blockIdx.y * COT;
+  const int nco = (Cout - co0) < COT ? (Cout - co0) : COT;
+  const int wsz = Cin * kH * kW;
+  if (w_in_smem) {
+    for (int i = threadIdx.x; i < nco * wsz; i += blockDim.x) ws[i] = w[(int64_t)co0 * wsz + i];
+    __syncthreads();
+  }
+  const T* wt = w_in_smem ? ws : (w + (int64_t)co0 * wsz);
+  const int64_t total = N * Ho * Wo;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % Wo);
+    const int i = (int)((idx / Wo) % Ho);
+    const int64_t n = idx / ((int64_t)Wo * Ho);
+    T acc[COT];
+#pragma unroll
+    for (int c = 0; c < COT; ++c) acc[c] = T(0);
+    for (int ci = 0; ci < Cin; ++ci) {
+      const T* xp = x + ((n * Cin + ci) * H + i) * W + j;
+      for (int a = 0; a < kH; ++a) {
+        for (int bb = 0; bb < kW; ++bb) {
+          const T xv = xp[(kH - 1 - a) * W + (kW - 1 - bb)];
+          const int wo = (ci * kH + a) * kW + bb;
+#pragma unroll
+          for (int c = 0; c < COT; ++c)
+            if (c < nco) acc[c] += xv * wt[c * wsz + wo];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < COT; ++c) {
+      if (c < nco) {
+        T v = acc[c] + (b ? b[co0 + c] : T(0));
+        if (relu) v = v < T(0) ? T(0) : v;
+        y[((n * Cout + co0 + c) * Ho + i) * Wo + j] = v;
+      }
+    }
+  }
+}
+
+// dx[n,ci,u,v] = sum_{co,a,b} dy[n,co,u-(kH-1-a), v-(kW-1-b)] * w[co,ci,a,b]
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_dgrad_kernel(const T* __restrict__ dy, const T* __restrict__ w, T* __restrict__ dx, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW) {
+  const int Ho = H - kH + 1, Wo = W - kW + 1;
+  const int64_t total = N * Cin * H * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % W);
+    const int u = (int)((idx / W) % H);
+    const int ci = (int)((idx / ((int64_t)W * H)) % Cin);
+    const int64_t n = idx / ((int64_t)W * H * Cin);
+    T acc = T(0);
+    for (int co = 0; co < Cout; ++co) {
+      const T* dyp = dy + (n * Cout + co) * Ho * Wo;
+      const T* wp = w + ((int64_t)co * Cin + ci) * kH * kW;
+      for (int a = 0; a < kH; ++a) {
+        const int i = u - (kH - 1 - a);
+        if (i < 0 || i >= Ho) continue;
+        for (int bb = 0; bb < kW; ++bb) {
+          const int j = v - (kW - 1 - bb);
+          if (j < 0 || j >= Wo) continue;
+          acc += dyp[i * Wo + j] * wp[a * kW + bb];
+        }
+      }
+    }
+    dx[idx] = acc;
+  }
+}
+
+// dw[co,ci,a,b] = sum_{n,i,j} x[n,ci,i+KS-1-a, j+KS-1-b] * dy[n,co,i,j];  db[co] = sum dy.
+// grid (Cout*Cin, S): block reduces its slice of (n,i,j) into partials[s][co][ci][KS*KS].
+template <typename T, int KS>
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dw_part, T* __restrict__ db_part,
+                  int64_t N, int Cin, int H, int W, int Cout, int64_t pos_per_split) {
+  constexpr int KK = KS * KS;
+  __shared__ T sm[8][KK + 1];
+  const int co = blockIdx.x / Cin, ci = blockIdx.x % Cin;
+  const int Ho = H - KS + 1, Wo = W - KS + 1;
+  const int64_t total = N * Ho * Wo;
+  const int64_t pb = (int64_t)blockIdx.y * pos_per_split;
+  const int64_t pe = pb + pos_per_split < total ? pb + pos_per_split : total;
+  T acc[KK];
+#pragma unroll
+  for (int k = 0; k < KK; ++k) acc[k] = T(0);
+  T dsum = T(0);
+  for (int64_t idx = pb + threadIdx.x; idx < pe; idx += blockDim.x) {
+    const int j = (int)(idx % Wo);
+    const int i = (int)((idx / Wo) % Ho);
+    const int64_t n = idx / ((int64_t)Wo * Ho);
+    const T g = dy[((n * Cout + co) * Ho + i) * Wo + j];
+    dsum += g;
+    const T* xp = x + ((n * Cin + ci) * H + i) * W + j;
+#pragma unroll
+    for (int a = 0; a < KS; ++a)
+#pragma unroll
+      for (int bb = 0; bb < KS; ++bb) acc[a * KS + bb] += xp[(KS - 1 - a) * W + (KS - 1 - bb)] * g;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < KK; ++k) {
+    T v = warp_sum(acc[k]);
+    if (lane == 0) sm[wid][k] = v;
+  }
+  {
+    T v = warp_sum(dsum);
+    if (lane == 0) sm[wid][KK] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= KK) {
+    T s = T(0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += sm[q][threadIdx.x];
+    if (threadIdx.x < KK) dw_part[((int64_t)blockIdx.y * Cout * Cin + blockIdx.x) * KK + threadIdx.x] = s;
+    else if (ci == 0 && db_part) db_part[(int64_t)blockIdx.y * Cout + co] = s;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_splits_kernel(const T* __restrict__ part, T* __restrict__ out, int64_t n, int splits) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T s = T(0);
+  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * n + i];
+  out[i] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t NC, int H, int W, int k) {
+  const int Ho = (H - k) / k + 1, Wo = (W - k) / k + 1;
+  const int64_t total = NC * Ho * Wo;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % Wo), i = (int)((idx / Wo) % Ho);
+    const int64_t nc = idx / ((int64_t)Wo * Ho);
+    const T* xp = x + (nc * H + (int64_t)i * k) * W + (int64_t)j * k;
+    T m = xp[0];
+    for (int a = 0; a < k; ++a)
+      for (int b = 0; b < k; ++b) { T v = xp[a * W + b]; m = v > m ? v : m; }
+    y[idx] = m;
+  }
+}
+
+// dx must be zero-filled beforehand (border rows/cols outside any window stay zero)
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int64_t NC, int H, int W, int k) {
+  const int Ho = (H - k) / k + 1, Wo = (W - k) / k + 1;
+  const int64_t total = NC * Ho * Wo;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % Wo), i = (int)((idx / Wo) % Ho);
+    const int64_t nc = idx / ((int64_t)Wo * Ho);
+    const int64_t base = (nc * H + (int64_t)i * k) * W + (int64_t)j * k;
+    const T* xp = x + base;
+    T m = xp[0];
+    int am = 0;
+    for (int a = 0; a < k; ++a)
+      for (int b = 0; b < k; ++b) { T v = xp[a * W + b]; if (v > m) { m = v; am = a * W + b; } }  // strict >: first max wins
+    dx[base + am] = dy[idx];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) meanpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t NC, int H, int W, int k) {
+  const int Ho = (H - k) / k + 1, Wo = (W - k) / k + 1;
+  const int64_t total = NC * Ho * Wo;
+  const T inv = T(1) / T(k * k);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % Wo), i = (int)((idx / Wo) % Ho);
+    const int64_t nc = idx / ((int64_t)Wo * Ho);
+    const T* xp = x + (nc * H + (int64_t)i * k) * W + (int64_t)j * k;
+    T s = T(0);
+    for (int a = 0; a < k; ++a)
+      for (int b = 0; b < k; ++b) s += xp[a * W + b];
+    y[idx] = s * inv;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) meanpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int64_t NC, int H, int W, int k) {
+  const int Ho = (H - k) / k + 1, Wo = (W - k) / k + 1;
+  const int64_t total = NC * H * W;
+  const T inv = T(1) / T(k * k);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % W), u = (int)((idx / W) % H);
+    const int64_t nc = idx / ((int64_t)W * H);
+    const int i = u / k, j = v / k;
+    dx[idx] = (i < Ho && j < Wo) ? dy[(nc * Ho + i) * Wo + j] * inv : T(0);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) relu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    T v = x[i];
+    y[i] = v < T(0) ? T(0) : v;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = y[i] > T(0) ? dy[i] : T(0);
+}
+
+inline unsigned grid_for(pg_ctx* ctx, int64_t total) {
+  int64_t blocks = pg_cdiv(total, 256);
+  int64_t cap = (int64_t)ctx->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+template <typename T>
+int conv_fwd_t(pg_ctx* ctx, const T* x, const T* w, const T* b, T* y, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW, int act) {
+  const int Ho = H - kH + 1, Wo = W - kW + 1;
+  int64_t total = N * Ho * Wo;
+  if (total <= 0) return PG_OK;
+  size_t wbytes = (size_t)COT * Cin * kH * kW * sizeof(T);
+  int in_smem = wbytes <= 48 * 1024;
+  dim3 grid(grid_for(ctx, total), (unsigned)pg_cdiv(Cout, COT));
+  conv_fwd_kernel<T><<<grid, 256, in_smem ? wbytes : 0, ctx->stream>>>(x, w, b, y, N, Cin, H, W, Cout, kH, kW, act == PG_ACT_RELU, in_smem);
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+template <typename T, int KS>
+int conv_wgrad_t(pg_ctx* ctx, const T* x, const T* dy, T* dw, T* db, int64_t N, int Cin, int H, int W, int Cout) {
+  const int Ho = H - KS + 1, Wo = W - KS + 1;
+  const int64_t total = N * Ho * Wo;
+  const int64_t pairs = (int64_t)Cout * Cin;
+  int64_t want = pg_cdiv(4 * (int64_t)ctx->num_sms, pairs);
+  int64_t maxs = pg_cdiv(total, 1024);
+  int S = (int)(want < maxs ? want : maxs);
+  if (S < 1) S = 1;
+  if (S > 4096) S = 4096;
+  int64_t pps = pg_cdiv(total, S);
+  S = (int)pg_cdiv(total, pps);
+  if (total <= 0) { S = 1; pps = 1; }
+  const int64_t nw = pairs * KS * KS;
+  size_t need = (size_t)S * (nw + Cout) * sizeof(T);
+  int rc = pg_ws_ensure(ctx, need);
+  if (rc != PG_OK) return rc;
+  T* dw_part = (T*)ctx->ws;
+  T* db_part = dw_part + (size_t)S * nw;
+  dim3 grid((unsigned)pairs, (unsigned)S);
+  conv_wgrad_kernel<T, KS><<<grid, 256, 0, ctx->stream>>>(x, dy, dw_part, db ? db_part : nullptr, N, Cin, H, W, Cout, pps);
+  PG_LAUNCHED(ctx);
+  if (dw) {
+    reduce_splits_kernel<T><<<(unsigned)pg_cdiv(nw, 256), 256, 0, ctx->stream>>>(dw_part, dw, nw, S);
+    PG_LAUNCHED(ctx);
+  }
+  if (db) {
+    reduce_splits_kernel<T><<<(unsigned)pg_cdiv(Cout, 256), 256, 0, ctx->stream>>>(db_part, db, Cout, S);
+    PG_LAUNCHED(ctx);
+  }
+  return PG_OK;
+}
+
+template <typename T>
+int conv_bwd_t(pg_ctx* ctx, const T* x, const T* w, const T* dy, T* dw, T* db, T* dx, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW) {
+  int rc = PG_OK;
+  if (dw || db) {
+    PG_REQUIRE(kH == kW, "conv weight gradient supports square filters only");
+    switch (kH) {
+      case 1: rc = conv_wgrad_t<T, 1>(ctx, x, dy, dw, db, N, Cin, H, W, Cout); break;
+      case 2: rc = conv_wgrad_t<T, 2>(ctx, x, dy, dw, db, N, Cin, H, W, Cout); break;
+      case 3: rc = conv_wgrad_t<T, 3>(ctx, x, dy, dw, db, N, Cin, H, W, Cout); break;
+      case 4: rc = conv_wgrad_t<T, 4>(ctx, x, dy, dw, db, N, Cin, H, W, Cout); break;
+      case 5: rc = conv_wgrad_t<T, 5>(ctx, x, dy, dw, db, N, Cin, H, W, Cout); break;
+      case 7: rc = conv_wgrad_t<T, 7>(ctx, x, dy, dw, db, N, Cin, H, W, Cout); break;
+      default:
+        pg_set_error("pg_conv2d_bwd: filter size %d unsupported (1,2,3,4,5,7)", kH);
+        return PG_ERR_UNSUPPORTED;
+    }
+    if (rc != PG_OK) return rc;
+  }
+  if (dx) {
+    int64_t total = N * Cin * H * W;
+    if (total > 0) {
+      conv_dgrad_kernel<T><<<grid_for(ctx, total), 256, 0, ctx->stream>>>(dy, w, dx, N, Cin, H, W, Cout, kH, kW);
+      PG_LAUNCHED(ctx);
+    }
+  }
+  return PG_OK;
+}
+
+}  // namespace
+
+#define PG_FLOAT_DTYPE(dtype) PG_REQUIRE((dtype) == PG_F32 || (dtype) == PG_F64, "dtype must be PG_F32 or PG_F64")
+#define DISPATCH_T(call_f32, call_f64) \
+  if (dtype == PG_F32) { call_f32; } else { call_f64; }
+
+extern "C" {
+
+int pg_conv2d_fwd(pg_ctx* ctx, int dtype, const void* x, const void* w, const void* b, void* y, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW, int act) {
+  PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
+  PG_REQUIRE(x && w && y, "null pointer");
+  PG_REQUIRE(kH >= 1 && kW >= 1 && H >= kH && W >= kW && Cin >= 1 && Cout >= 1, "bad conv geometry");
+  if (dtype == PG_F32) return conv_fwd_t<float>(ctx, (const float*)x, (const float*)w, (const float*)b, (float*)y, N, Cin, H, W, Cout, kH, kW, act);
+  return conv_fwd_t<double>(ctx, (const double*)x, (const double*)w, (const double*)b, (double*)y, N, Cin, H, W, Cout, kH, kW, act);
+}
+
+int pg_conv2d_bwd(pg_ctx* ctx, int dtype, const void* x, const void* w, const void* dy, void* dw, void* db, void* dx, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW) {
+  PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
+  PG_REQUIRE(dy != nullptr, "null dy");
+  PG_REQUIRE(kH >= 1 && kW >= 1 && H >= kH && W >= kW && Cin >= 1 && Cout >= 1, "bad conv geometry");
+  if (dtype == PG_F32) return conv_bwd_t<float>(ctx, (const float*)x, (const float*)w, (const float*)dy, (float*)dw, (float*)db, (float*)dx, N, Cin, H, W, Cout, kH, kW);
+  return conv_bwd_t<double>(ctx, (const double*)x, (const double*)w, (const double*)dy, (double*)dw, (double*)db, (double*)dx, N, Cin, H, W, Cout, kH, kW);
+}
+
+int pg_maxpool2d_fwd(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t NC, int H, int W, int k) {
+  PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
+  PG_REQUIRE(x && y && k >= 1 && H >= k && W >= k, "bad pool geometry");
+  int64_t total = NC * ((H - k) / k + 1) * ((W - k) / k + 1);
+  if (total <= 0) return PG_OK;
+  DISPATCH_T((maxpool_fwd_kernel<float><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const float*)x, (float*)y, NC, H, W, k)),
+             (maxpool_fwd_kernel<double><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const double*)x, (double*)y, NC, H, W, k)));
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+int pg_maxpool2d_bwd(pg_ctx* ctx, int dtype, const void* x, const void* dy, void* dx, int64_t NC, int H, int W, int k) {
+  PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
+  PG_REQUIRE(x && dy && dx && k >= 1 && H >= k && W >= k, "bad pool geometry");
+  int64_t total = NC * ((H - k) / k + 1) * ((W - k) / k + 1);
+  if (total <= 0) return PG_OK;
+  PG_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)NC * H * W * (dtype == PG_F64 ? 8 : 4), ctx->stream));
+  DISPATCH_T((maxpool_bwd_kernel<float><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const float*)x, (const float*)dy, (float*)dx, NC, H, W, k)),
+             (maxpool_bwd_kernel<double><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const double*)x, (const double*)dy, (double*)dx, NC, H, W, k)));
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+int pg_meanpool2d_fwd(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t NC, int H, int W, int k) {
+  PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
+  PG_REQUIRE(x && y && k >= 1 && H >= k && W >= k, "bad pool geometry");
+  int64_t total = NC * ((H - k) / k + 1) * ((W - k) / k + 1);
+  if (total <= 0) return PG_OK;
+  DISPATCH_T((meanpool_fwd_kernel<float><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const float*)x, (float*)y, NC, H, W, k)),
+             (meanpool_fwd_kernel<double><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const double*)x, (double*)y, NC, H, W, k)));
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+int pg_meanpool2d_bwd(pg_ctx* ctx, int dtype, const void* dy, void* dx, int64_t NC, int H, int W, int k) {
+  PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
+  PG_REQUIRE(dy && dx && k >= 1 && H >= k && W >= k, "bad pool geometry");
+  int64_t total = NC * H * W;
+  if (total <= 0) return PG_OK;
+  DISPATCH_T((meanpool_bwd_kernel<float><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const float*)dy, (float*)dx, NC, H, W, k)),
+             (meanpool_bwd_kernel<double><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const double*)dy, (double*)dx, NC, H, W, k)));
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+int pg_relu_fwd(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t n) {
+  PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
+  if (n <= 0) return PG_OK;
+  DISPATCH_T((relu_fwd_kernel<float><<<grid_for(ctx, n), 256, 0, ctx->stream>>>((const float*)x, (float*)y, n)),
+             (relu_fwd_kernel<double><<<grid_for(ctx, n), 256, 0, ctx->stream>>>((const double*)x, (double*)y, n)));
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+int pg_relu_bwd(pg_ctx* ctx, int dtype, const void* y, const void* dy, void* dx, int64_t n) {
+  PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
+  if (n <= 0) return PG_OK;
+  DISPATCH_T((relu_bwd_kernel<float><<<grid_for(ctx, n), 256, 0, ctx->stream>>>((const float*)y, (const float*)dy, (float*)dx, n)),
+             (relu_bwd_kernel<double><<<grid_for(ctx, n), 256, 0, ctx->stream>>>((const double*)y, (const double*)dy, (double*)dx, n)));
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+}  // extern "C"

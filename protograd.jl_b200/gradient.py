@@ -1,0 +1,92 @@
+"""eval_with_pullback — the AD-backend seam of src/gradient.jl:1-2 and
+ext/ProtoGradZygoteExt.jl:6-13, with a `:B200` backend instead of `:Zygote`.
+
+    out, pb = eval_with_pullback(f, m)        # forward runs now, on the GPU
+    grad = pb()                               # zero-argument pullback; typeof(grad) == typeof(m)
+
+`out` is a `Loss` (a Number-like handle: float(out) is the only host sync, as the reference's loop
+only reads it on log steps, examples/01_mnist_mlp.jl:49-51).  `grad` is arena-backed like `m`, so
+`step!(state, grad)` is one fused kernel.  The gradient container is allocated once per model and
+REUSED by later pullbacks of the same model (the reference allocates a fresh one each call).
+"""
+import ctypes
+import weakref
+
+import numpy as np
+
+from . import trace as T
+from .capi import call
+from .device import Context, DeviceArray, dtype_code
+from .model import Model
+
+_BACKENDS = ("B200",)
+_grad_cache = weakref.WeakKeyDictionary()
+
+
+class Loss:
+    """Device-resident scalar; float() synchronises and reads it (pg_loss_read)."""
+
+    def __init__(self, buf):
+        self._buf = buf
+        self._val = None
+
+    def __float__(self):
+        if self._val is None:
+            r = ctypes.c_double()
+            call("pg_loss_read", self._buf.ctx.h, dtype_code(self._buf.dtype), self._buf.ptr, ctypes.byref(r))
+            self._val = r.value
+        return self._val
+
+    item = __float__
+
+    @property
+    def dtype(self):
+        return self._buf.dtype
+
+    def __repr__(self):
+        return f"Loss({float(self)!r})"
+
+    def __format__(self, spec):
+        return format(float(self), spec)
+
+    def _cmp(self, o):
+        return float(self), float(o)
+
+    def __lt__(self, o): a, b = self._cmp(o); return a < b
+    def __le__(self, o): a, b = self._cmp(o); return a <= b
+    def __gt__(self, o): a, b = self._cmp(o); return a > b
+    def __ge__(self, o): a, b = self._cmp(o); return a >= b
+    def __sub__(self, o): return float(self) - float(o)
+    def __rsub__(self, o): return float(o) - float(self)
+    def __add__(self, o): return float(self) + float(o)
+    __radd__ = __add__
+
+
+def eval_with_pullback(f, m, backend="B200", math="fp32"):
+    """src/gradient.jl:1-2.  `math`: "fp32" (FP32/FP64 SIMT, rel 1e-5) or "bf16" (tcgen05 tensor cores)."""
+    if backend not in _BACKENDS:
+        raise ValueError(f"unknown AD backend {backend}")          # gradient.jl:1
+    if not isinstance(m, Model):
+        raise TypeError("the B200 backend differentiates with respect to a Model")
+    ctx, base, total, leaves = m.arena()
+    tr = T.Trace(ctx or Context.get(), leaves, math)
+    prev = T.set_current(tr)
+    try:
+        out = f(m)
+    finally:
+        T.set_current(prev)
+    if not isinstance(out, T.Tensor) or out.shape != ():
+        raise TypeError("the objective must return a scalar loss (cross_entropy / mse)")
+    plan = T.Plan.get(tr, out)
+    plan.forward(tr)
+    loss = Loss(plan.vals[out.id])
+
+    def pullback():
+        g = _grad_cache.get(m)
+        if g is None:
+            g = _grad_cache[m] = m.zero()
+        gleaves = g.allparams()
+        plan.backward(gleaves)
+        return g
+
+    return loss, pullback

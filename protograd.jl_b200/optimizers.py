@@ -1,0 +1,144 @@
+"""Optimizers — host mirror of src/optimizers/*.jl: `init(optimizer, variable)` / `step(state, grad)`
+(`step!` in Julia).  `state.variable` aliases the user's model (gradient_descent.jl:11-13), and each
+step is ONE fused kernel over the parameter arena instead of 1-5 broadcast passes per leaf.
+Hyper-parameters given as Python floats are Float64 (per-element Float64 math);
+pass numpy float32 scalars to mirror `Float32` hyper-parameters.  fast=True selects the
+all-Float32 fused Adam (normwise ~1e-7 from the exact form).
+"""
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+from .capi import call
+from .device import dtype_code
+from .model import Model, _scalar_flags
+
+
+def _f64(x):
+    return capi.SCALAR_F64 if _scalar_flags(x) else 0
+
+
+class NesterovMomentumSequence:
+    """src/optimizers/nesterov_method.jl:1-8."""
+
+    def __iter__(self):
+        t = 1.0
+        while True:
+            t_next = (1 + math.sqrt(1 + 4 * t * t)) / 2
+            yield (t - 1) / t_next
+            t = t_next
+
+
+@dataclass
+class GradientDescent:
+    stepsize: float
+
+
+@dataclass
+class HeavyBallMethod:
+    stepsize: float
+    momentum: float
+
+
+@dataclass
+class NesterovMethod:
+    stepsize: float
+    momentum_sequence: object = field(default_factory=NesterovMomentumSequence)
+
+
+@dataclass
+class Adam:
+    stepsize: float
+    beta1: float = 0.9
+    beta2: float = 0.999
+    epsilon: float = 1e-8
+    fast: bool = False
+    keep_hats: bool = True   # materialise m_hat / v_hat like the reference's AdamState
+
+
+class _State:
+    def _arena(self, g):
+        v = self.variable
+        v._check_same(g)
+        ctx, p, n, leaves = v.arena()
+        _, pg, _, _ = g.arena()
+        return ctx, dtype_code(leaves[0].dtype), p, pg, n
+
+    @staticmethod
+    def _ptr(m):
+        return m.arena()[1]
+
+
+class GradientDescentState(_State):
+    def __init__(self, opt, variable):
+        self.optimizer, self.stepsize, self.variable = opt, opt.stepsize, variable
+
+    def step(self, g, shadow=None):
+        """gradient_descent.jl:15-17"""
+        ctx, code, p, pg, n = self._arena(g)
+        call("pg_opt_gd", ctx.h, code, p, pg, n, float(self.stepsize), _f64(self.stepsize), shadow)
+        return self.variable
+
+
+class HeavyBallMethodState(_State):
+    def __init__(self, opt, variable):
+        self.optimizer, self.stepsize, self.variable = opt, opt.stepsize, variable
+        self.step_ = variable.zero()      # `step` field of the reference (heavy_ball_method.jl:13-14)
+
+    def step(self, g, shadow=None):
+        """heavy_ball_method.jl:16-19"""
+        ctx, code, p, pg, n = self._arena(g)
+        fl = _f64(self.stepsize) | (capi.SCALAR2_F64 if _scalar_flags(self.optimizer.momentum) else 0)
+        call("pg_opt_heavyball", ctx.h, code, p, self._ptr(self.step_), pg, n, float(self.stepsize), float(self.optimizer.momentum), fl, shadow)
+        return self.variable
+
+
+class NesterovState(_State):
+    def __init__(self, opt, variable):
+        self.optimizer, self.stepsize, self.variable = opt, opt.stepsize, variable
+        self.variable_prev = variable.zero()
+        self.momentum_iterator = iter(opt.momentum_sequence)
+
+    def step(self, g, shadow=None):
+        """nesterov_method.jl:33-39 (momentum popped from the host-side stateful iterator)"""
+        ctx, code, p, pg, n = self._arena(g)
+        mu = next(self.momentum_iterator)
+        call("pg_opt_nesterov", ctx.h, code, p, self._ptr(self.variable_prev), pg, n, float(self.stepsize), float(mu), _f64(self.stepsize), shadow)
+        return self.variable
+
+
+class AdamState(_State):
+    def __init__(self, opt, variable):
+        self.optimizer, self.stepsize, self.variable = opt, opt.stepsize, variable
+        self.m, self.v = variable.zero(), variable.zero()
+        self.m_hat = variable.zero() if opt.keep_hats else None
+        self.v_hat = variable.zero() if opt.keep_hats else None
+        self.it = 1                                               # adam.jl:28
+
+    def step(self, g, shadow=None):
+        """adam.jl:32-41; returns the incremented iteration counter like the reference"""
+        ctx, code, p, pg, n = self._arena(g)
+        o = self.optimizer
+        fl = _f64(self.stepsize) | (capi.MATH_FAST if o.fast else 0)
+        call("pg_opt_adam", ctx.h, code, p, self._ptr(self.m), self._ptr(self.v),
+             self._ptr(self.m_hat) if self.m_hat is not None else None, self._ptr(self.v_hat) if self.v_hat is not None else None,
+             pg, n, float(self.stepsize), float(o.beta1), float(o.beta2), float(o.epsilon), self.it, fl, shadow)
+        self.it += 1
+        return self.it
+
+
+_STATES = {GradientDescent: GradientDescentState, HeavyBallMethod: HeavyBallMethodState, NesterovMethod: NesterovState, Adam: AdamState}
+
+
+def init(optimizer, variable):
+    """init(optimizer, variable) of src/optimizers/*.jl — the state aliases `variable`."""
+    if not isinstance(variable, Model):
+        raise TypeError("the B200 optimizers update arena-backed Models")
+    return _STATES[type(optimizer)](optimizer, variable)
+
+
+def step(state, gradient, shadow=None):
+    """step!(state, gradient)"""
+    return state.step(gradient, shadow)
