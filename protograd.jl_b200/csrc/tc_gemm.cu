@@ -1,7 +1,604 @@
-// placeholder until the tcgen05 kernel lands
+// tc_gemm.cu — BF16 tensor-core path of the Linear layer (src/layers.jl:28-34 and its pullback):
+// hand-written tcgen05.mma GEMM with TMEM accumulators, TMA-fed 4-stage shared-memory pipeline,
+// warp-specialised (1 TMA producer warp, 1 MMA-issuer warp, 4 epilogue warps), persistent over
+// 128x256 output tiles with double-buffered accumulators (2 x 256 TMEM columns) so the epilogue
+// of tile i overlaps the MMAs of tile i+1.  fp32 accumulation; epilogues fuse bias+ReLU (forward),
+// the ReLU' mask (data gradient) or write fp32 straight into the gradient arena (weight gradient).
+//
+// No physical transposes: the three products use K-major or MN-major shared-memory operand
+// descriptors directly on the row-major tensors:
+//   layout 0  Y  = X  W      A = X  [M][K] K-major     B = W  [K][N]  MN-major
+//   layout 1  dX = dY W^T    A = dY [M][K] K-major     B = W  [N][K]  K-major
+//   layout 2  dW = X^T dY    A = X  [K][M] MN-major    B = dY [K][N]  MN-major   (K = batch)
+// Layers with N <= 32 (the 10-class logits layer) are HBM-bound and use CUDA-core "skinny" kernels.
+#include <cuda.h>
+
 #include "common.cuh"
-extern "C" {
-int pg_tc_linear_fwd(pg_ctx* ctx, const void*, const void*, const void*, void*, int, int64_t, int64_t, int64_t, int) { PG_CHECK_CTX(ctx); pg_set_error("tc path not built"); return PG_ERR_UNSUPPORTED; }
-int pg_tc_linear_bwd(pg_ctx* ctx, const void*, const void*, const void*, int, void*, void*, void*, const void*, int64_t, int64_t, int64_t) { PG_CHECK_CTX(ctx); pg_set_error("tc path not built"); return PG_ERR_UNSUPPORTED; }
-int pg_tc_gemm(pg_ctx* ctx, int, const void*, const void*, void*, int, int64_t, int64_t, int64_t) { PG_CHECK_CTX(ctx); pg_set_error("tc path not built"); return PG_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16, STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+struct Epi {
+  const float* bias;            // forward: per-column bias (nullable)
+  const __nv_bfloat16* mask;    // data gradient: keep where mask[m][n] > 0 (nullable)
+  int relu;
+  int out_f32;                  // 1: float output, 0: bf16 output
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s at 2 GHz
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
+// [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in
+// [46,48), layout type SWIZZLE_128B (= 2) in [61,64).
+//  K-major  SW128: rows of 128 B (64 bf16 along K); 8-row groups 1024 B apart (SBO); LBO unused.
+//  MN-major SW128: rows of 128 B (64 bf16 along M/N) per k; 8-k groups 1024 B apart (SBO);
+//                  64-element M/N chunks LBO apart (= BLOCK_K * 128 B, one TMA box each).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bits 4-5 = 1), A,B = bf16
+// (bits 7-9, 10-12 = 1), a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 in [17,23), M>>4 in [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ C,
+               int M, int N, int K, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base address
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_aligned + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M, num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (1 CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % num_m) * BLOCK_M, n0 = (tile / num_m) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if (A_MN) {  // A stored [K][M]: boxes {64 m, 64 k}, one per 64-wide M chunk
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * (BLOCK_K * 128), &map_a, full_bar(stage), m0 + c * 64, k0);
+          } else {     // A stored [M][K]: one box {64 k, 128 m}
+            tma_load_2d(sa, &map_a, full_bar(stage), k0, m0);
+          }
+          if (B_MN) {  // B stored [K][N]
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c) tma_load_2d(sb + c * (BLOCK_K * 128), &map_b, full_bar(stage), n0 + c * 64, k0);
+          } else {     // B stored [N][K]: one box {64 k, 256 n}
+            tma_load_2d(sb, &map_b, full_bar(stage), k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);       // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);             // TMA bytes have landed
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: advance 16 elements = 32 B inside the 128 B swizzled row.
+            // MN-major: advance 16 k-rows = 2 swizzle atoms = 2048 B.
+            const uint64_t ad = A_MN ? make_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bd = B_MN ? make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          tcgen05_commit(empty_bar(stage));              // frees the smem slot once these MMAs retire
+          if (kb == num_kb - 1) tcgen05_commit(tfull_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps (TMEM -> registers -> global) =====
+    const int q = warp & 3;                              // TMEM lane quarter this warp may read
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % num_m) * BLOCK_M, n0 = (tile / num_m) * BLOCK_N;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c, r);
+        tmem_ld_wait();
+        const int col = n0 + c;
+        if (row < M && col < N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (epi.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (col + j < N) {
+                const float4 b4 = *reinterpret_cast<const float4*>(epi.bias + col + j);
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
+          }
+          if (epi.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          }
+          if (epi.mask != nullptr) {
+            const __nv_bfloat16* mp = epi.mask + (size_t)row * N + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col + j < N) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(mp + j);
+                const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[j + e] = (__bfloat162float(me[e]) > 0.0f) ? v[j + e] : 0.0f;
+              }
+            }
+          }
+          if (epi.out_f32) {
+            float* op = reinterpret_cast<float*>(C) + (size_t)row * N + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (col + j < N) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(C) + (size_t)row * N + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col + j < N) {
+                __nv_bfloat162 pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pk[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(op + j) = *reinterpret_cast<uint4*>(pk);
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- TMA descriptor encoding (driver entry point resolved at run time: no libcuda link) ------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encoder(pg_ctx* ctx, EncodeTiledFn* fn) {
+  if (!ctx->encode_tiled) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PG_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !p) {
+      pg_set_error("cuTensorMapEncodeTiled not available from the driver");
+      return PG_ERR_CUDA;
+    }
+    ctx->encode_tiled = p;
+  }
+  *fn = (EncodeTiledFn)ctx->encode_tiled;
+  return PG_OK;
+}
+
+// row-major bf16 matrix [rows][cols] (cols contiguous); box = {box_cols (<= 64), box_rows}
+int make_map(pg_ctx* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_cols, int box_rows) {
+  EncodeTiledFn enc;
+  int rc = get_encoder(ctx, &enc);
+  if (rc != PG_OK) return rc;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    pg_set_error("cuTensorMapEncodeTiled failed (%d) for [%lld][%lld] box {%d,%d}", (int)r, (long long)rows, (long long)cols, box_cols, box_rows);
+    return PG_ERR_CUDA;
+  }
+  return PG_OK;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, const Epi& epi) {
+  CUtensorMap ma, mb;
+  int rc;
+  // A: K-major stored [M][K] -> box {64 k, 128 m};  MN-major stored [K][M] -> box {64 m, 64 k}
+  rc = A_MN ? make_map(ctx, &ma, A, K, M, 64, BLOCK_K) : make_map(ctx, &ma, A, M, K, BLOCK_K, BLOCK_M);
+  if (rc != PG_OK) return rc;
+  rc = B_MN ? make_map(ctx, &mb, B, K, N, 64, BLOCK_K) : make_map(ctx, &mb, B, N, K, BLOCK_K, BLOCK_N);
+  if (rc != PG_OK) return rc;
+  auto kern = tc_gemm_kernel<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  int64_t tiles = pg_cdiv(M, BLOCK_M) * pg_cdiv(N, BLOCK_N);
+  int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi);
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+int tc_dispatch(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, const Epi& epi) {
+  PG_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
+  PG_REQUIRE(M % 8 == 0 || layout != 2, "weight-gradient GEMM needs M % 8 == 0 (TMA 16-byte pitch)");
+  PG_REQUIRE(N % 8 == 0 && K % 8 == 0, "tensor-core GEMM needs N % 8 == 0 and K % 8 == 0 (TMA 16-byte pitch)");
+  PG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "operands must be 16-byte aligned");
+  PG_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension too large");
+  switch (layout) {
+    case 0: return launch_tc<false, true>(ctx, A, B, C, M, N, K, epi);
+    case 1: return launch_tc<false, false>(ctx, A, B, C, M, N, K, epi);
+    case 2: return launch_tc<true, true>(ctx, A, B, C, M, N, K, epi);
+  }
+  pg_set_error("pg_tc_gemm: unknown layout %d", layout);
+  return PG_ERR_ARG;
+}
+
+// ================================================================================================
+// Skinny layers (N <= 32, e.g. the 4096 -> 10 logits layer): HBM-bound, CUDA cores.
+// W [K][N] bf16 is staged in shared memory as float rows padded to NP (NP/4 odd -> conflict-free
+// 128-bit reads when consecutive lanes read consecutive k).
+// ================================================================================================
+__host__ __device__ inline int skinny_np(int N) {
+  int np = (N + 3) / 4 * 4;
+  if (((np / 4) & 1) == 0) np += 4;
+  return np;
+}
+
+// Z[M][N] f32 = X[M][K] bf16 * W[K][N] bf16 + b ; one warp per row, lanes stride over k.
+template <int NP>
+__global__ void __launch_bounds__(256) skinny_fwd_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ W,
+                                                         const float* __restrict__ bias, float* __restrict__ Z, int M, int K, int N, int relu) {
+  extern __shared__ __align__(16) float Ws[];   // [K][NP]
+  for (int i = threadIdx.x; i < K * NP; i += blockDim.x) {
+    int k = i / NP, n = i % NP;
+    Ws[i] = n < N ? __bfloat162float(W[(size_t)k * N + n]) : 0.0f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
+    float acc[NP];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) acc[n] = 0.0f;
+    const __nv_bfloat16* xr = X + (size_t)row * K;
+    for (int k = lane; k < K; k += 32) {
+      const float xv = __bfloat162float(xr[k]);
+      const float4* wr = reinterpret_cast<const float4*>(Ws + (size_t)k * NP);
+#pragma unroll
+      for (int n4 = 0; n4 < NP / 4; ++n4) {
+        const float4 w4 = wr[n4];
+        acc[4 * n4] += xv * w4.x; acc[4 * n4 + 1] += xv * w4.y; acc[4 * n4 + 2] += xv * w4.z; acc[4 * n4 + 3] += xv * w4.w;
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NP; ++n) acc[n] = warp_sum(acc[n]);
+    float out = 0.0f;
+#pragma unroll
+    for (int n = 0; n < NP; ++n) out = (lane == n) ? acc[n] : out;
+    if (lane < N) {
+      out += bias ? bias[lane] : 0.0f;
+      if (relu) out = fmaxf(out, 0.0f);
+      Z[(size_t)row * N + lane] = out;
+    }
+  }
+}
+
+// dX[M][K] bf16 = (dZ[M][N] f32 * W[K][N]^T) .* [mask > 0]; block = one row chunk, lanes over k.
+template <int NP>
+__global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restrict__ dZ, const __nv_bfloat16* __restrict__ W,
+                                                           const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dX, int M, int K, int N) {
+  extern __shared__ __align__(16) float Ws[];   // [K][NP]
+  for (int i = threadIdx.x; i < K * NP; i += blockDim.x) {
+    int k = i / NP, n = i % NP;
+    Ws[i] = n < N ? __bfloat162float(W[(size_t)k * N + n]) : 0.0f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
+    float g[NP];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) g[n] = n < N ? dZ[(size_t)row * N + n] : 0.0f;
+    for (int k = lane; k < K; k += 32) {
+      const float4* wr = reinterpret_cast<const float4*>(Ws + (size_t)k * NP);
+      float s = 0.0f;
+#pragma unroll
+      for (int n4 = 0; n4 < NP / 4; ++n4) {
+        const float4 w4 = wr[n4];
+        s += g[4 * n4] * w4.x + g[4 * n4 + 1] * w4.y + g[4 * n4 + 2] * w4.z + g[4 * n4 + 3] * w4.w;
+      }
+      if (mask != nullptr && !(__bfloat162float(mask[(size_t)row * K + k]) > 0.0f)) s = 0.0f;
+      dX[(size_t)row * K + k] = __float2bfloat16_rn(s);
+    }
+  }
+}
+
+// partial dW[s][K][N] = sum_{b in split s} X[b][k] * dZ[b][n]; thread per k, dZ chunk staged in smem
+template <int NP>
+__global__ void __launch_bounds__(256) skinny_wgrad_kernel(const __nv_bfloat16* __restrict__ X, const float* __restrict__ dZ,
+                                                           float* __restrict__ part, int M, int K, int N, int rows_per_split) {
+  __shared__ __align__(16) float gs[64][NP];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int mb = blockIdx.y * rows_per_split;
+  const int me = min(mb + rows_per_split, M);
+  float acc[NP];
+#pragma unroll
+  for (int n = 0; n < NP; ++n) acc[n] = 0.0f;
+  for (int r0 = mb; r0 < me; r0 += 64) {
+    const int nr = min(64, me - r0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * NP; i += blockDim.x) {
+      int r = i / NP, n = i % NP;
+      gs[r][n] = (r < nr && n < N) ? dZ[(size_t)(r0 + r) * N + n] : 0.0f;
+    }
+    __syncthreads();
+    if (k < K) {
+      for (int r = 0; r < nr; ++r) {
+        const float xv = __bfloat162float(X[(size_t)(r0 + r) * K + k]);
+        const float4* g4 = reinterpret_cast<const float4*>(gs[r]);
+#pragma unroll
+        for (int n4 = 0; n4 < NP / 4; ++n4) {
+          const float4 gg = g4[n4];
+          acc[4 * n4] += xv * gg.x; acc[4 * n4 + 1] += xv * gg.y; acc[4 * n4 + 2] += xv * gg.z; acc[4 * n4 + 3] += xv * gg.w;
+        }
+      }
+    }
+  }
+  if (k < K) {
+    float* o = part + ((size_t)blockIdx.y * K + k) * N;
+    for (int n = 0; n < N; ++n) o[n] = acc[n];
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_f32_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int splits) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * n + i];
+  out[i] = s;
+}
+
+#define SKINNY_SWITCH(NPV, ...)                  \
+  switch (NPV) {                                 \
+    case 4: { constexpr int NP = 4; __VA_ARGS__; } break;   \
+    case 12: { constexpr int NP = 12; __VA_ARGS__; } break; \
+    case 20: { constexpr int NP = 20; __VA_ARGS__; } break; \
+    case 28: { constexpr int NP = 28; __VA_ARGS__; } break; \
+    case 36: { constexpr int NP = 36; __VA_ARGS__; } break; \
+    default: pg_set_error("skinny layer: unsupported N"); return PG_ERR_UNSUPPORTED; \
+  }
+
+int skinny_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, void* Z, int64_t M, int64_t K, int64_t N, int act) {
+  const int np = skinny_np((int)N);
+  size_t smem = (size_t)K * np * sizeof(float);
+  PG_REQUIRE(smem <= 200 * 1024, "skinny layer: K * N too large for shared-memory staging of W");
+  int blocks = (int)(pg_cdiv(M, 8) < (int64_t)ctx->num_sms ? pg_cdiv(M, 8) : ctx->num_sms);
+  SKINNY_SWITCH(np, {
+    auto kern = skinny_fwd_kernel<NP>;
+    PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, 256, smem, ctx->stream>>>((const __nv_bfloat16*)X, (const __nv_bfloat16*)W, (const float*)b, (float*)Z, (int)M, (int)K, (int)N, act == PG_ACT_RELU);
+  });
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+int skinny_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* dW, void* db, void* dX, const void* mask, int64_t M, int64_t K, int64_t N) {
+  const int np = skinny_np((int)N);
+  if (dW) {
+    int kb = (int)pg_cdiv(K, 256);
+    int64_t want = pg_cdiv(4 * (int64_t)ctx->num_sms, kb), maxs = pg_cdiv(M, 64);
+    int S = (int)(want < maxs ? want : maxs);
+    if (S < 1) S = 1;
+    int rps = (int)(pg_cdiv(pg_cdiv(M, S), 64) * 64);
+    S = (int)pg_cdiv(M, rps);
+    int rc = pg_ws_ensure(ctx, (size_t)S * K * N * sizeof(float));
+    if (rc != PG_OK) return rc;
+    dim3 grid(kb, S);
+    SKINNY_SWITCH(np, (skinny_wgrad_kernel<NP><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)X, (const float*)dZ, (float*)ctx->ws, (int)M, (int)K, (int)N, rps)));
+    PG_LAUNCHED(ctx);
+    reduce_f32_kernel<<<(unsigned)pg_cdiv(K * N, 256), 256, 0, ctx->stream>>>((const float*)ctx->ws, (float*)dW, K * N, S);
+    PG_LAUNCHED(ctx);
+  }
+  if (db) {
+    int rc = pg_colsum_launch(ctx, PG_F32, dZ, db, M, N);
+    if (rc != PG_OK) return rc;
+  }
+  if (dX) {
+    size_t smem = (size_t)K * np * sizeof(float);
+    PG_REQUIRE(smem <= 200 * 1024, "skinny layer: K * N too large for shared-memory staging of W");
+    int blocks = (int)(pg_cdiv(M, 8) < (int64_t)ctx->num_sms ? pg_cdiv(M, 8) : ctx->num_sms);
+    SKINNY_SWITCH(np, {
+      auto kern = skinny_dgrad_kernel<NP>;
+      PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<blocks, 256, smem, ctx->stream>>>((const float*)dZ, (const __nv_bfloat16*)W, (const __nv_bfloat16*)mask, (__nv_bfloat16*)dX, (int)M, (int)K, (int)N);
+    });
+    PG_LAUNCHED(ctx);
+  }
+  return PG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pg_tc_gemm(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, int c_dtype, int64_t M, int64_t N, int64_t K) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(A && B && C, "null pointer");
+  PG_REQUIRE(c_dtype == PG_F32 || c_dtype == PG_BF16, "C must be f32 or bf16");
+  Epi epi{nullptr, nullptr, 0, c_dtype == PG_F32};
+  return tc_dispatch(ctx, layout, A, B, C, M, N, K, epi);
+}
+
+int pg_tc_linear_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, void* Y, int y_dtype, int64_t M, int64_t K, int64_t N, int act) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(X && W && Y, "null pointer");
+  if (N <= 32) {
+    PG_REQUIRE(y_dtype == PG_F32, "skinny layers (N <= 32) produce f32 outputs");
+    return skinny_fwd(ctx, X, W, b, Y, M, K, N, act);
+  }
+  PG_REQUIRE(y_dtype == PG_BF16 || y_dtype == PG_F32, "Y must be bf16 or f32");
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, y_dtype == PG_F32};
+  return tc_dispatch(ctx, 0, X, W, Y, M, N, K, epi);
+}
+
+int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
+                     const void* relu_mask, int64_t M, int64_t K, int64_t N) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(dY != nullptr, "null dY");
+  PG_REQUIRE(!dW || X, "dW needs X");
+  PG_REQUIRE(!dX || W, "dX needs W");
+  if (N <= 32) {
+    PG_REQUIRE(dy_dtype == PG_F32, "skinny layers (N <= 32) take f32 dY");
+    return skinny_bwd(ctx, X, W, dY, dW, db, dX, relu_mask, M, K, N);
+  }
+  PG_REQUIRE(dy_dtype == PG_BF16, "wide layers take bf16 dY");
+  int rc;
+  if (dW) {  // dW[K][N] = X^T dY: GEMM (M'=K, N'=N, K'=M), A = X stored [M][K] (MN-major), B = dY stored [M][N] (MN-major)
+    Epi epi{nullptr, nullptr, 0, 1};
+    rc = tc_dispatch(ctx, 2, X, dY, dW, K, N, M, epi);
+    if (rc != PG_OK) return rc;
+  }
+  if (db) {
+    rc = pg_colsum_launch(ctx, PG_BF16, dY, db, M, N);
+    if (rc != PG_OK) return rc;
+  }
+  if (dX) {  // dX[M][K] = dY W^T: GEMM (M'=M, N'=K, K'=N), A = dY [M][N] K-major, B = W [K][N] K-major
+    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, 0};
+    rc = tc_dispatch(ctx, 1, dY, W, dX, M, K, N, epi);
+    if (rc != PG_OK) return rc;
+  }
+  return PG_OK;
+}
+
+}  // extern "C"

@@ -107,6 +107,8 @@ class Model:
                 break
             off += _pad(p.size) * isz
         total = sum(_pad(p.size) for p in leaves)
+        if packed and leaves[0].offset + total * isz > buf.nbytes:
+            packed = False                    # e.g. a lone leaf whose own buffer has no room for the padding
         if not packed:
             ctx = leaves[0].ctx
             nb = DeviceBuffer(ctx, total * isz, zero=True)

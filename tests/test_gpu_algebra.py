@@ -85,17 +85,19 @@ def test_axpy_update_is_bit_exact(pg, T):
     assert np.array_equal(m.vec(), exp.astype(T))
 
 
-class Vec:
-    pass
+_VM = {}
 
 
 def _vecmodel(pg, x):
-    class VecModel(pg.Model):
-        __fields__ = ("x",)
+    """a Model with one flat leaf (the reference's optimizer tests use a plain Vector)"""
+    if "cls" not in _VM:
+        class VecModel(pg.Model):
+            __fields__ = ("x",)
 
-        def __init__(self, x):
-            self.x = x if isinstance(x, pg.DeviceArray) else pg.DeviceArray.from_numpy(pg.Context.get(), x)
-    return VecModel(x)
+            def __init__(self, x):
+                self.x = x
+        _VM["cls"] = VecModel
+    return _VM["cls"](pg.DeviceArray.from_numpy(pg.Context.get(), x))
 
 
 @pytest.mark.parametrize("T", [np.float32, np.float64])

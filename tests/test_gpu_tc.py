@@ -1,0 +1,101 @@
+"""GPU parity of the BF16 tensor-core mode (tcgen05 GEMM + skinny kernels) through the C ABI.
+
+Tolerances (stated bound for the tensor-core mode, north_star): operands are rounded to bf16
+(rel 2^-9 per element), accumulation is fp32.  Against a float64 reference on the SAME bf16-rounded
+operands the GEMM must agree to 1e-5 normwise (it is then exact up to fp32 accumulation order);
+against the un-rounded float64 oracle, a whole training step must agree to 1e-2 normwise on
+gradients and 2e-3 on the loss (measured: ~3e-3 / ~1e-4)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import protograd_oracle as O
+from tests.helpers import rel_err
+
+
+@pytest.fixture(scope="module")
+def pg():
+    import protograd_b200 as pg
+    return pg
+
+
+def _bf(pg, a):
+    from protograd_b200.device import bf16_to_f32, f32_to_bf16
+    return bf16_to_f32(f32_to_bf16(np.ascontiguousarray(a, dtype=np.float32)))
+
+
+def _dev_bf16(pg, a):
+    from protograd_b200.device import f32_to_bf16
+    d = pg.DeviceArray.empty(pg.Context.get(), a.shape, pg.BF16)
+    d.upload(f32_to_bf16(np.ascontiguousarray(a, dtype=np.float32)))
+    return d
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (384, 768, 320), (136, 264, 72), (8, 8, 8), (1024, 784, 4096), (784, 4096, 1024)])
+def test_tc_gemm_layouts(pg, layout, M, N, K):
+    from protograd_b200.capi import call
+    rng = np.random.default_rng(M + N + K + layout)
+    A = _bf(pg, rng.standard_normal((M, K))); B = _bf(pg, rng.standard_normal((K, N)))
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    a_st = A.T if layout == 2 else A
+    b_st = B.T if layout == 1 else B
+    ctx = pg.Context.get()
+    ad, bd = _dev_bf16(pg, a_st), _dev_bf16(pg, b_st)
+    cd = pg.DeviceArray.empty(ctx, (M, N), np.float32)
+    call("pg_tc_gemm", ctx.h, layout, ad.ptr, bd.ptr, cd.ptr, 0, M, N, K)
+    assert rel_err(cd.numpy(), ref) <= 1e-5
+
+
+@pytest.mark.parametrize("M,K,N,act", [(256, 784, 512, 1), (1024, 512, 4096, 1), (200, 264, 72, 0), (512, 4096, 10, 0), (64, 128, 32, 0)])
+def test_tc_linear_fwd_bwd(pg, M, K, N, act):
+    """pg_tc_linear_fwd/bwd (wide: tcgen05; N <= 32: skinny) vs float64 on bf16-rounded operands."""
+    from protograd_b200.capi import call
+    from protograd_b200.device import bf16_to_f32
+    rng = np.random.default_rng(M + K + N)
+    X = _bf(pg, np.maximum(rng.standard_normal((M, K)), 0)); W = _bf(pg, rng.standard_normal((K, N)) / np.sqrt(K))
+    b = rng.standard_normal(N).astype(np.float32)
+    skinny = N <= 32
+    dY = rng.standard_normal((M, N)).astype(np.float32) if skinny else _bf(pg, rng.standard_normal((M, N)))
+    ctx = pg.Context.get()
+    Xd, Wd = _dev_bf16(pg, X), _dev_bf16(pg, W)
+    bd = pg.DeviceArray.from_numpy(ctx, b)
+    dYd = pg.DeviceArray.from_numpy(ctx, dY) if skinny else _dev_bf16(pg, dY)
+    Yd = pg.DeviceArray.empty(ctx, (M, N), np.float32 if skinny else pg.BF16)
+    dWd, dbd = pg.DeviceArray.empty(ctx, (K, N), np.float32), pg.DeviceArray.empty(ctx, (N,), np.float32)
+    dXd = pg.DeviceArray.empty(ctx, (M, K), pg.BF16)
+    call("pg_tc_linear_fwd", ctx.h, Xd.ptr, Wd.ptr, bd.ptr, Yd.ptr, 0 if skinny else 2, M, K, N, act)
+    call("pg_tc_linear_bwd", ctx.h, Xd.ptr, Wd.ptr, dYd.ptr, 0 if skinny else 2, dWd.ptr, dbd.ptr, dXd.ptr, Xd.ptr, M, K, N)
+    X64, W64, dY64 = X.astype(np.float64), W.astype(np.float64), dY.astype(np.float64)
+    Y = X64 @ W64 + b
+    if act:
+        Y = np.maximum(Y, 0)
+    dW, db, dX = O.linear_bwd(X64, W64, dY64)
+    dX = O.relu_bwd(X64, dX)
+    Yout = Yd.numpy() if skinny else bf16_to_f32(Yd.numpy())
+    assert rel_err(Yout, Y) <= (1e-5 if skinny else 4e-3)          # bf16 output rounding 2^-9
+    assert rel_err(dWd.numpy(), dW) <= 1e-5
+    assert rel_err(dbd.numpy(), db) <= 1e-5
+    assert rel_err(bf16_to_f32(dXd.numpy()), dX) <= 4e-3
+
+
+def test_tc_training_step_c4_shape_small_batch(pg):
+    """Wide MLP 784-4096-4096-10 (config C4's model) at batch 512 in bf16 mode vs the float64 oracle."""
+    spec = [("linear", 784, 4096), ("relu",), ("linear", 4096, 4096), ("relu",), ("linear", 4096, 10), ("softmax",)]
+    rng = np.random.default_rng(0)
+    p0 = O.init_params(spec, np.float32, seed=3)
+    B = 512
+    x = rng.random((B, 784)).astype(np.float32); lab = np.eye(10, dtype=np.float32)[rng.integers(0, 10, B)]
+    m = pg.Compose(pg.Linear(W=p0[0], b=p0[1]), pg.relu, pg.Linear(W=p0[2], b=p0[3]), pg.relu, pg.Linear(W=p0[4], b=p0[5]), pg.softmax)
+    out, pb = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(x), lab), m, math="bf16")
+    g = [p.numpy() for p in pb().allparams()]
+    v, gr = O.net_loss_and_grad(spec, [p.astype(np.float64) for p in p0], x.astype(np.float64), lab.astype(np.float64))
+    assert abs(float(out) - v) <= 2e-3 * abs(v)
+    errs = [rel_err(a, r) for a, r in zip(g, gr)]
+    assert max(errs) <= 1e-2, errs
+    # and the fp32 SIMT mode on the same model meets the 1e-5 bound
+    out32, pb32 = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(x), lab), m, math="fp32")
+    g32 = [p.numpy() for p in pb32().allparams()]
+    assert abs(float(out32) - v) <= 1e-5 * abs(v)
+    assert max(rel_err(a, r) for a, r in zip(g32, gr)) <= 1e-5
