@@ -84,12 +84,32 @@ class DeviceBuffer:
             call("pg_memset0", ctx.h, self.ptr, self.nbytes)
 
 
+_PINNED = {}  # base pointer -> nbytes of live pinned allocations
+
+
+def is_pinned(a):
+    """True if the numpy array's storage lies inside a live PinnedBuffer (async H2D is then safe)"""
+    p = a.ctypes.data
+    for base, n in _PINNED.items():
+        if base <= p and p + a.nbytes <= base + n:
+            return True
+    return False
+
+
+def _free_pinned(ptr):
+    _PINNED.pop(ptr, None)
+    capi.lib.pg_host_free(ctypes.c_void_p(ptr))
+
+
 class PinnedBuffer:
+    """Page-locked host memory (source of asynchronous H2D copies)."""
+
     def __init__(self, nbytes):
         p = ctypes.c_void_p()
         call("pg_host_alloc", int(max(nbytes, 16)), ctypes.byref(p))
         self.ptr, self.nbytes = p.value, int(nbytes)
-        weakref.finalize(self, capi.lib.pg_host_free, ctypes.c_void_p(self.ptr))
+        _PINNED[self.ptr] = self.nbytes
+        weakref.finalize(self, _free_pinned, self.ptr)
 
     def as_numpy(self, dtype, shape):
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import capi
 from .capi import ACT_NONE, ACT_RELU, PG_BF16, PG_F32, call
-from .device import BF16, Context, DeviceArray, DeviceBuffer, dtype_code
+from .device import BF16, Context, DeviceArray, DeviceBuffer, dtype_code, is_pinned
 
 _current = None  # the Trace being recorded (set by eval_with_pullback / forward)
 
@@ -399,7 +399,8 @@ class Plan:
                         buf = self.owned_inputs[t.id] = self._new(t.shape, t.dtype)
                     a = np.ascontiguousarray(src)
                     call("pg_upload", ctx.h, buf.ptr, a.ctypes.data, buf.nbytes)
-                    ctx.sync()  # pageable source may be a temporary
+                    if not is_pinned(a):
+                        ctx.sync()  # pageable source may be a temporary; pinned sources stay async
                     self.vals[t.id] = buf
                 else:
                     self.vals[t.id] = src
