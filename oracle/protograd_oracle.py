@@ -526,3 +526,67 @@ class TrainStep:
         val, grads = net_loss_and_grad(self.spec, self.leaves, x, label, self.loss)
         self.opt.step(vec(grads))
         return val
+
+
+# ----------------------------------------------------------------------------------------------
+# bf16 tensor-core mode restatement (what the B200 path computes when math="bf16")
+# ----------------------------------------------------------------------------------------------
+
+
+def bf16_round(a):
+    """round-to-nearest-even to bfloat16, returned as float64 (the value the tensor cores see)"""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return (((u + r) >> 16) << 16).astype(np.uint32).view(np.float32).astype(np.float64)
+
+
+def mlp_bf16_loss_and_grad(spec, params, x, label, global_batch=None):
+    """The same step with the tensor-core mode's number formats made explicit: operands (inputs,
+    weights, hidden activations, hidden-activation gradients) rounded to bf16, products accumulated
+    exactly (float64 here, fp32 on the device), wide-layer outputs stored in bf16, the N <= 32
+    logits layer / loss / dZ / dW / db kept in float.  Only linear/relu/softmax + cross-entropy.
+    The un-rounded float64 oracle differs from this by the bf16 operand rounding AND by ReLU gates
+    that flip sign under that rounding (a gate flip is an O(1) change of one gradient entry)."""
+    bf = bf16_round
+    acts = [bf(x)]
+    lin = [op for op in spec if op[0] == "linear"]
+    pi = 0
+    a = acts[0]
+    i = 0
+    ops = list(spec)
+    layer_inputs, relu_after = [], []
+    while i < len(ops):
+        op = ops[i]
+        if op[0] == "linear":
+            W, b = bf(params[pi]), params[pi + 1].astype(np.float64)
+            z = a @ W + b
+            has_relu = i + 1 < len(ops) and ops[i + 1][0] == "relu"
+            if has_relu:
+                z = np.maximum(z, 0); i += 1
+            wide = op[2] > 32
+            layer_inputs.append(a); relu_after.append(has_relu)
+            a = bf(z) if wide else z
+            pi += 2
+        elif op[0] == "softmax":
+            a = softmax_fwd(a)
+        else:
+            raise ValueError("mlp_bf16_loss_and_grad supports linear/relu/softmax only")
+        i += 1
+    p = a
+    eps = np.finfo(np.float32).eps
+    B = x.shape[0] if global_batch is None else global_batch
+    loss = float((-(label * np.log(p + eps)).sum(-1)).sum() / B)
+    dp = -label / (B * (p + eps))
+    d = softmax_bwd(p, dp)                                   # dZ (float)
+    grads = [None] * len(params)
+    for li in range(len(lin) - 1, -1, -1):
+        W = bf(params[2 * li])
+        xin = layer_inputs[li]
+        grads[2 * li] = xin.T @ d
+        grads[2 * li + 1] = d.sum(0)
+        if li > 0:
+            dx = d @ W.T
+            if relu_after[li - 1]:
+                dx = np.where(xin > 0, dx, 0.0)
+            d = bf(dx)                                       # hidden gradients are stored in bf16
+    return loss, grads

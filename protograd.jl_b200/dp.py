@@ -42,3 +42,21 @@ def broadcast_parameters(model, src=0):
 def arena_checksum(model):
     """float64 sum of the arena — replicas must agree bit-for-bit after identical updates"""
     return float(arena_tensor(model).double().sum().item())
+
+
+def shard_range(rank, world_size, global_batch):
+    """samples [lo, hi) of the global batch that `rank` takes (SURVEY.md §8e partitioning)"""
+    if global_batch % world_size:
+        raise ValueError(f"global batch {global_batch} is not divisible by {world_size} ranks")
+    per = global_batch // world_size
+    return rank * per, (rank + 1) * per
+
+
+def allreduce_host(flat, group=None):
+    """sum a host (numpy) gradient vector over ranks — the gloo/CPU form of the same exchange,
+    used by the world_size-2 CPU tests of the data-parallel host logic"""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(flat)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return flat
