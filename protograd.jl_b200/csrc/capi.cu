@@ -77,6 +77,7 @@ int pg_destroy(pg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->aux) cudaFree(ctx->aux);
   if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->result_slot) cudaFree(ctx->result_slot);
   if (ctx->result_host) cudaFreeHost(ctx->result_host);

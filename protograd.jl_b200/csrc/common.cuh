@@ -17,6 +17,9 @@ struct pg_ctx {
   // scratch: split-K partials, block partials for reductions
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  // padded bf16 operand copies of narrow (N <= 32) tensor-core layers
+  void* aux = nullptr;
+  size_t aux_bytes = 0;
   // small persistent scratch: [0..63] counters (zeroed), [64..] result slots
   unsigned int* counters = nullptr;
   double* result_slot = nullptr;     // device

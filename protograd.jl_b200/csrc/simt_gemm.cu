@@ -116,6 +116,40 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TI* __restrict__ X, T
     out[(int64_t)blockIdx.y * N + n] = s;
   }
 }
+// vectorised column sums for wide matrices: each thread owns VEC consecutive columns (16-byte loads),
+// 8 row-lanes per block; grid (ceil(N / (32*VEC)), S).  HBM-bound: one pass over X.
+template <typename TI, typename TO, int VEC>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const TI* __restrict__ X, TO* __restrict__ out, int64_t M, int64_t N, int64_t rows_per_split) {
+  __shared__ TO sm[8][32 * VEC + 1];
+  const int64_t n0 = ((int64_t)blockIdx.x * 32 + threadIdx.x) * VEC;
+  const int64_t mb = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t me = mb + rows_per_split < M ? mb + rows_per_split : M;
+  TO acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = TO(0);
+  if (n0 < N) {
+    for (int64_t m = mb + threadIdx.y; m < me; m += 8) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(X + m * N + n0);
+      const TI* e = reinterpret_cast<const TI*>(&raw);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] += cvt<TO>(e[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) sm[threadIdx.y][threadIdx.x * VEC + j] = acc[j];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  for (int c = t; c < 32 * VEC; c += 256) {
+    const int64_t n = (int64_t)blockIdx.x * 32 * VEC + c;
+    if (n < N) {
+      TO s = TO(0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += sm[i][c];
+      out[(int64_t)blockIdx.y * N + n] = s;
+    }
+  }
+}
+
 template <typename T>
 int gemm_launch(pg_ctx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, int64_t sam, int64_t sak, int64_t sbk,
                 int64_t sbn, int64_t ldc, int epi, const T* bias, const T* mask, bool allow_split) {
@@ -179,8 +213,10 @@ int linear_bwd_t(pg_ctx* ctx, const T* X, const T* W, const T* dY, T* dW, T* db,
 // shared with tc_gemm.cu (bf16 input, f32 output)
 int pg_colsum_launch(pg_ctx* ctx, int in_dtype, const void* X, void* out, int64_t M, int64_t N) {
   if (N <= 0) return PG_OK;
-  int64_t gx = pg_cdiv(N, 32);
-  int64_t want = pg_cdiv(2 * (int64_t)ctx->num_sms, gx);
+  const int vec = in_dtype == PG_BF16 ? 8 : in_dtype == PG_F32 ? 4 : 2;
+  const bool use_vec = N >= 256 && N % vec == 0 && ((uintptr_t)X & 15) == 0;
+  int64_t gx = use_vec ? pg_cdiv(N, 32 * vec) : pg_cdiv(N, 32);
+  int64_t want = pg_cdiv(4 * (int64_t)ctx->num_sms, gx);
   int64_t maxs = pg_cdiv(M, 64);
   int S = (int)(want < maxs ? want : maxs);
   if (S < 1) S = 1;
@@ -196,9 +232,15 @@ int pg_colsum_launch(pg_ctx* ctx, int in_dtype, const void* X, void* out, int64_
     tgt = ctx->ws;
   }
   dim3 grid((unsigned)gx, (unsigned)S), block(32, 8);
-  if (in_dtype == PG_F32) colsum_kernel<float, float><<<grid, block, 0, ctx->stream>>>((const float*)X, (float*)tgt, M, N, rps);
-  else if (in_dtype == PG_F64) colsum_kernel<double, double><<<grid, block, 0, ctx->stream>>>((const double*)X, (double*)tgt, M, N, rps);
-  else colsum_kernel<__nv_bfloat16, float><<<grid, block, 0, ctx->stream>>>((const __nv_bfloat16*)X, (float*)tgt, M, N, rps);
+  if (use_vec) {
+    if (in_dtype == PG_F32) colsum_vec_kernel<float, float, 4><<<grid, block, 0, ctx->stream>>>((const float*)X, (float*)tgt, M, N, rps);
+    else if (in_dtype == PG_F64) colsum_vec_kernel<double, double, 2><<<grid, block, 0, ctx->stream>>>((const double*)X, (double*)tgt, M, N, rps);
+    else colsum_vec_kernel<__nv_bfloat16, float, 8><<<grid, block, 0, ctx->stream>>>((const __nv_bfloat16*)X, (float*)tgt, M, N, rps);
+  } else {
+    if (in_dtype == PG_F32) colsum_kernel<float, float><<<grid, block, 0, ctx->stream>>>((const float*)X, (float*)tgt, M, N, rps);
+    else if (in_dtype == PG_F64) colsum_kernel<double, double><<<grid, block, 0, ctx->stream>>>((const double*)X, (double*)tgt, M, N, rps);
+    else colsum_kernel<__nv_bfloat16, float><<<grid, block, 0, ctx->stream>>>((const __nv_bfloat16*)X, (float*)tgt, M, N, rps);
+  }
   PG_LAUNCHED(ctx);
   if (S > 1) {
     if (in_dtype == PG_F64) splitk_reduce_kernel<double><<<(unsigned)pg_cdiv(N, 256), 256, 0, ctx->stream>>>((const double*)tgt, (double*)out, N, S);

@@ -10,26 +10,34 @@
 //   layout 0  Y  = X  W      A = X  [M][K] K-major     B = W  [K][N]  MN-major
 //   layout 1  dX = dY W^T    A = dY [M][K] K-major     B = W  [N][K]  K-major
 //   layout 2  dW = X^T dY    A = X  [K][M] MN-major    B = dY [K][N]  MN-major   (K = batch)
-// Layers with N <= 32 (the 10-class logits layer) are HBM-bound and use CUDA-core "skinny" kernels.
+// Layers with N <= 32 (the 10-class logits layer) are HBM-bound; they reuse the kernel with a 32-wide
+// N tile on small zero-padded operand copies (see "Narrow layers" below).
 #include <cuda.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16, STAGES = 4;
+constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 192;
-constexpr int TMEM_COLS = 512;
+
+// BN = 256: the wide layers (4 stages x 48 KB).  BN = 32: layers with N <= 32 (8 stages x 20 KB);
+// those are HBM-bound, the narrow tile only keeps the MMA pipe from becoming the limiter.
+template <int BN> struct Cfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 8;
+  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // power of two >= 32
+};
 
 struct Epi {
   const float* bias;            // forward: per-column bias (nullable)
   const __nv_bfloat16* mask;    // data gradient: keep where mask[m][n] > 0 (nullable)
   int relu;
   int out_f32;                  // 1: float output, 0: bf16 output
+  int narrow;                   // 1: N not a multiple of 8 -> scalar guarded loads/stores (f32 out only)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -115,15 +123,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bits 4-5 = 1), A,B = bf16
 // (bits 7-9, 10-12 = 1), a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 in [17,23), M>>4 in [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+         ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ C,
                int M, int N, int K, Epi epi) {
+  constexpr int STAGES = Cfg<BLOCK_N>::STAGES, B_STAGE_BYTES = Cfg<BLOCK_N>::B_STAGE_BYTES, STAGE_BYTES = Cfg<BLOCK_N>::STAGE_BYTES;
+  constexpr int TMEM_COLS = Cfg<BLOCK_N>::TMEM_COLS;
+  static_assert(!B_MN || BLOCK_N % 64 == 0, "MN-major B tiles are made of 64-wide TMA boxes");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -176,7 +187,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (B_MN) {  // B stored [K][N]
 #pragma unroll
             for (int c = 0; c < BLOCK_N / 64; ++c) tma_load_2d(sb + c * (BLOCK_K * 128), &map_b, full_bar(stage), n0 + c * 64, k0);
-          } else {     // B stored [N][K]: one box {64 k, 256 n}
+          } else {     // B stored [N][K]: one box {64 k, BLOCK_N n}
             tma_load_2d(sb, &map_b, full_bar(stage), k0, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -186,7 +197,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ===== MMA issuer (single thread) =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BLOCK_N);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -232,6 +243,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (epi.narrow) {
+            // N is not a multiple of 8 (e.g. 10 logits): scalar, fully guarded fp32 path
+            float* op = reinterpret_cast<float*>(C) + (size_t)row * N;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col + j < N) {
+                float o = v[j] + (epi.bias != nullptr ? epi.bias[col + j] : 0.0f);
+                if (epi.relu) o = fmaxf(o, 0.0f);
+                op[col + j] = o;
+              }
+            }
+            continue;
+          }
           if (epi.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -311,13 +335,13 @@ int get_encoder(pg_ctx* ctx, EncodeTiledFn* fn) {
   return PG_OK;
 }
 
-// row-major bf16 matrix [rows][cols] (cols contiguous); box = {box_cols (<= 64), box_rows}
-int make_map(pg_ctx* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_cols, int box_rows) {
+// row-major bf16 matrix [rows][cols] with row pitch `ld` elements; box = {box_cols (<= 64), box_rows}
+int make_map(pg_ctx* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
   EncodeTiledFn enc;
   int rc = get_encoder(ctx, &enc);
   if (rc != PG_OK) return rc;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -329,24 +353,26 @@ int make_map(pg_ctx* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64
   return PG_OK;
 }
 
-template <bool A_MN, bool B_MN>
-int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, const Epi& epi) {
+template <bool A_MN, bool B_MN, int BN>
+int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, const Epi& epi) {
+  // lda / ldb: row pitch (elements) of the stored operands; rows beyond the logical extent are
+  // zero-filled by TMA, so padded copies only need a 16-byte-multiple pitch.
   CUtensorMap ma, mb;
   int rc;
-  // A: K-major stored [M][K] -> box {64 k, 128 m};  MN-major stored [K][M] -> box {64 m, 64 k}
-  rc = A_MN ? make_map(ctx, &ma, A, K, M, 64, BLOCK_K) : make_map(ctx, &ma, A, M, K, BLOCK_K, BLOCK_M);
+  // A: K-major stored [M][lda>=K] -> box {64 k, 128 m};  MN-major stored [K][lda>=M] -> box {64 m, 64 k}
+  rc = A_MN ? make_map(ctx, &ma, A, K, M, lda, 64, BLOCK_K) : make_map(ctx, &ma, A, M, K, lda, BLOCK_K, BLOCK_M);
   if (rc != PG_OK) return rc;
-  rc = B_MN ? make_map(ctx, &mb, B, K, N, 64, BLOCK_K) : make_map(ctx, &mb, B, N, K, BLOCK_K, BLOCK_N);
+  rc = B_MN ? make_map(ctx, &mb, B, K, N, ldb, 64, BLOCK_K) : make_map(ctx, &mb, B, N, K, ldb, BLOCK_K, BN);
   if (rc != PG_OK) return rc;
-  auto kern = tc_gemm_kernel<A_MN, B_MN>;
+  auto kern = tc_gemm_kernel<A_MN, B_MN, BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  int64_t tiles = pg_cdiv(M, BLOCK_M) * pg_cdiv(N, BLOCK_N);
+  int64_t tiles = pg_cdiv(M, BLOCK_M) * pg_cdiv(N, BN);
   int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi);
+  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi);
   PG_LAUNCHED(ctx);
   return PG_OK;
 }
@@ -358,192 +384,105 @@ int tc_dispatch(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, 
   PG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "operands must be 16-byte aligned");
   PG_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension too large");
   switch (layout) {
-    case 0: return launch_tc<false, true>(ctx, A, B, C, M, N, K, epi);
-    case 1: return launch_tc<false, false>(ctx, A, B, C, M, N, K, epi);
-    case 2: return launch_tc<true, true>(ctx, A, B, C, M, N, K, epi);
+    case 0: return launch_tc<false, true, 256>(ctx, A, B, C, M, N, K, K, N, epi);
+    case 1: return launch_tc<false, false, 256>(ctx, A, B, C, M, N, K, K, K, epi);
+    case 2: return launch_tc<true, true, 256>(ctx, A, B, C, M, N, K, M, N, epi);
   }
   pg_set_error("pg_tc_gemm: unknown layout %d", layout);
   return PG_ERR_ARG;
 }
 
 // ================================================================================================
-// Skinny layers (N <= 32, e.g. the 4096 -> 10 logits layer): HBM-bound, CUDA cores.
-// W [K][N] bf16 is staged in shared memory as float rows padded to NP (NP/4 odd -> conflict-free
-// 128-bit reads when consecutive lanes read consecutive k).
+// Narrow layers (N <= 32, e.g. the 4096 -> 10 logits layer).  They are HBM-bound (one pass over the
+// [M][K] activations), so they run on the same tcgen05 kernel with a 32-wide N tile and tiny
+// zero-padded bf16 operand copies (pitch multiple of 16 B for TMA, K-major so N may be < 64):
+//   forward   Z  = X W      : A = X [M][K],            B = W^T padded  [32][K]       (K-major)
+//   data grad dX = dZ W^T   : A = dZ padded [M][64],   B = W   padded  [K][64]       (K-major, K' = 64)
+//   wt. grad  dW = X^T dZ   : A = X [M][K] (MN-major), B = dZ^T padded [32][M]       (K-major, K' = batch)
 // ================================================================================================
-__host__ __device__ inline int skinny_np(int N) {
-  int np = (N + 3) / 4 * 4;
-  if (((np / 4) & 1) == 0) np += 4;
-  return np;
-}
+constexpr int NARROW_N = 32, NARROW_K = 64;
 
-// Z[M][N] f32 = X[M][K] bf16 * W[K][N] bf16 + b ; one warp per row, lanes stride over k.
-template <int NP>
-__global__ void __launch_bounds__(256) skinny_fwd_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ W,
-                                                         const float* __restrict__ bias, float* __restrict__ Z, int M, int K, int N, int relu) {
-  extern __shared__ __align__(16) float Ws[];   // [K][NP]
-  for (int i = threadIdx.x; i < K * NP; i += blockDim.x) {
-    int k = i / NP, n = i % NP;
-    Ws[i] = n < N ? __bfloat162float(W[(size_t)k * N + n]) : 0.0f;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
-    float acc[NP];
-#pragma unroll
-    for (int n = 0; n < NP; ++n) acc[n] = 0.0f;
-    const __nv_bfloat16* xr = X + (size_t)row * K;
-    for (int k = lane; k < K; k += 32) {
-      const float xv = __bfloat162float(xr[k]);
-      const float4* wr = reinterpret_cast<const float4*>(Ws + (size_t)k * NP);
-#pragma unroll
-      for (int n4 = 0; n4 < NP / 4; ++n4) {
-        const float4 w4 = wr[n4];
-        acc[4 * n4] += xv * w4.x; acc[4 * n4 + 1] += xv * w4.y; acc[4 * n4 + 2] += xv * w4.z; acc[4 * n4 + 3] += xv * w4.w;
-      }
+// src [R][C] (float or bf16) -> dst [R][CP] bf16 zero padded (nullable), dstT [CP][R] bf16 (nullable)
+template <typename TS>
+__global__ void __launch_bounds__(256) pad_copy_kernel(const TS* __restrict__ src, __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dstT,
+                                                       int64_t R, int C, int CP, int CPT) {
+  const int cmax = CP > CPT ? CP : CPT;
+  const int64_t total = R * cmax;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / cmax;
+    const int c = (int)(idx % cmax);
+    float v = 0.0f;
+    if (c < C) {
+      if constexpr (sizeof(TS) == 4) v = (float)src[r * C + c]; else v = __bfloat162float(src[r * C + c]);
     }
-#pragma unroll
-    for (int n = 0; n < NP; ++n) acc[n] = warp_sum(acc[n]);
-    float out = 0.0f;
-#pragma unroll
-    for (int n = 0; n < NP; ++n) out = (lane == n) ? acc[n] : out;
-    if (lane < N) {
-      out += bias ? bias[lane] : 0.0f;
-      if (relu) out = fmaxf(out, 0.0f);
-      Z[(size_t)row * N + lane] = out;
-    }
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    if (dst != nullptr && c < CP) dst[r * CP + c] = b;
+    if (dstT != nullptr && c < CPT) dstT[(int64_t)c * R + r] = b;
   }
 }
 
-// dX[M][K] bf16 = (dZ[M][N] f32 * W[K][N]^T) .* [mask > 0]; block = one row chunk, lanes over k.
-template <int NP>
-__global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restrict__ dZ, const __nv_bfloat16* __restrict__ W,
-                                                           const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dX, int M, int K, int N) {
-  extern __shared__ __align__(16) float Ws[];   // [K][NP]
-  for (int i = threadIdx.x; i < K * NP; i += blockDim.x) {
-    int k = i / NP, n = i % NP;
-    Ws[i] = n < N ? __bfloat162float(W[(size_t)k * N + n]) : 0.0f;
+int aux_ensure(pg_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->aux_bytes) return PG_OK;
+  if (ctx->capturing) {
+    pg_set_error("narrow-layer scratch of %zu bytes needed during graph capture: run one eager step first", bytes);
+    return PG_ERR_NOMEM;
   }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
-    float g[NP];
-#pragma unroll
-    for (int n = 0; n < NP; ++n) g[n] = n < N ? dZ[(size_t)row * N + n] : 0.0f;
-    for (int k = lane; k < K; k += 32) {
-      const float4* wr = reinterpret_cast<const float4*>(Ws + (size_t)k * NP);
-      float s = 0.0f;
-#pragma unroll
-      for (int n4 = 0; n4 < NP / 4; ++n4) {
-        const float4 w4 = wr[n4];
-        s += g[4 * n4] * w4.x + g[4 * n4 + 1] * w4.y + g[4 * n4 + 2] * w4.z + g[4 * n4 + 3] * w4.w;
-      }
-      if (mask != nullptr && !(__bfloat162float(mask[(size_t)row * K + k]) > 0.0f)) s = 0.0f;
-      dX[(size_t)row * K + k] = __float2bfloat16_rn(s);
-    }
-  }
-}
-
-// partial dW[s][K][N] = sum_{b in split s} X[b][k] * dZ[b][n]; thread per k, dZ chunk staged in smem
-template <int NP>
-__global__ void __launch_bounds__(256) skinny_wgrad_kernel(const __nv_bfloat16* __restrict__ X, const float* __restrict__ dZ,
-                                                           float* __restrict__ part, int M, int K, int N, int rows_per_split) {
-  __shared__ __align__(16) float gs[64][NP];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int mb = blockIdx.y * rows_per_split;
-  const int me = min(mb + rows_per_split, M);
-  float acc[NP];
-#pragma unroll
-  for (int n = 0; n < NP; ++n) acc[n] = 0.0f;
-  for (int r0 = mb; r0 < me; r0 += 64) {
-    const int nr = min(64, me - r0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * NP; i += blockDim.x) {
-      int r = i / NP, n = i % NP;
-      gs[r][n] = (r < nr && n < N) ? dZ[(size_t)(r0 + r) * N + n] : 0.0f;
-    }
-    __syncthreads();
-    if (k < K) {
-      for (int r = 0; r < nr; ++r) {
-        const float xv = __bfloat162float(X[(size_t)(r0 + r) * K + k]);
-        const float4* g4 = reinterpret_cast<const float4*>(gs[r]);
-#pragma unroll
-        for (int n4 = 0; n4 < NP / 4; ++n4) {
-          const float4 gg = g4[n4];
-          acc[4 * n4] += xv * gg.x; acc[4 * n4 + 1] += xv * gg.y; acc[4 * n4 + 2] += xv * gg.z; acc[4 * n4 + 3] += xv * gg.w;
-        }
-      }
-    }
-  }
-  if (k < K) {
-    float* o = part + ((size_t)blockIdx.y * K + k) * N;
-    for (int n = 0; n < N; ++n) o[n] = acc[n];
-  }
-}
-
-__global__ void __launch_bounds__(256) reduce_f32_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int splits) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.0f;
-  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * n + i];
-  out[i] = s;
-}
-
-#define SKINNY_SWITCH(NPV, ...)                  \
-  switch (NPV) {                                 \
-    case 4: { constexpr int NP = 4; __VA_ARGS__; } break;   \
-    case 12: { constexpr int NP = 12; __VA_ARGS__; } break; \
-    case 20: { constexpr int NP = 20; __VA_ARGS__; } break; \
-    case 28: { constexpr int NP = 28; __VA_ARGS__; } break; \
-    case 36: { constexpr int NP = 36; __VA_ARGS__; } break; \
-    default: pg_set_error("skinny layer: unsupported N"); return PG_ERR_UNSUPPORTED; \
-  }
-
-int skinny_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, void* Z, int64_t M, int64_t K, int64_t N, int act) {
-  const int np = skinny_np((int)N);
-  size_t smem = (size_t)K * np * sizeof(float);
-  PG_REQUIRE(smem <= 200 * 1024, "skinny layer: K * N too large for shared-memory staging of W");
-  int blocks = (int)(pg_cdiv(M, 8) < (int64_t)ctx->num_sms ? pg_cdiv(M, 8) : ctx->num_sms);
-  SKINNY_SWITCH(np, {
-    auto kern = skinny_fwd_kernel<NP>;
-    PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, 256, smem, ctx->stream>>>((const __nv_bfloat16*)X, (const __nv_bfloat16*)W, (const float*)b, (float*)Z, (int)M, (int)K, (int)N, act == PG_ACT_RELU);
-  });
-  PG_LAUNCHED(ctx);
+  PG_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->aux) PG_CHECK_CUDA(cudaFree(ctx->aux));
+  ctx->aux = nullptr; ctx->aux_bytes = 0;
+  PG_CHECK_CUDA(cudaMalloc(&ctx->aux, bytes));
+  ctx->aux_bytes = bytes;
   return PG_OK;
 }
 
-int skinny_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* dW, void* db, void* dX, const void* mask, int64_t M, int64_t K, int64_t N) {
-  const int np = skinny_np((int)N);
-  if (dW) {
-    int kb = (int)pg_cdiv(K, 256);
-    int64_t want = pg_cdiv(4 * (int64_t)ctx->num_sms, kb), maxs = pg_cdiv(M, 64);
-    int S = (int)(want < maxs ? want : maxs);
-    if (S < 1) S = 1;
-    int rps = (int)(pg_cdiv(pg_cdiv(M, S), 64) * 64);
-    S = (int)pg_cdiv(M, rps);
-    int rc = pg_ws_ensure(ctx, (size_t)S * K * N * sizeof(float));
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int narrow_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, void* Z, int64_t M, int64_t K, int64_t N, int act) {
+  PG_REQUIRE(K % 8 == 0, "narrow tensor-core layer needs K % 8 == 0 (TMA 16-byte pitch)");
+  const size_t wt_bytes = align256((size_t)NARROW_N * K * 2);
+  int rc = aux_ensure(ctx, wt_bytes);
+  if (rc != PG_OK) return rc;
+  __nv_bfloat16* Wt = (__nv_bfloat16*)ctx->aux;           // [32][K]
+  int64_t total = K * NARROW_N;
+  pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, nullptr, Wt, K, (int)N, 0, NARROW_N);
+  PG_LAUNCHED(ctx);
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, 1, 1};
+  return launch_tc<false, false, NARROW_N>(ctx, X, Wt, Z, M, N, K, K, K, epi);
+}
+
+int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* dW, void* db, void* dX, const void* mask, int64_t M, int64_t K, int64_t N) {
+  PG_REQUIRE(K % 8 == 0 && M % 8 == 0, "narrow tensor-core layer needs K % 8 == 0 and batch % 8 == 0 (TMA 16-byte pitch)");
+  const size_t dzp_bytes = align256((size_t)M * NARROW_K * 2), dzt_bytes = align256((size_t)NARROW_N * M * 2), wp_bytes = align256((size_t)K * NARROW_K * 2);
+  // layout of the scratch: [W^T padded (forward)] [dZ padded] [dZ^T padded] [W padded]
+  const size_t wt_bytes = align256((size_t)NARROW_N * K * 2);
+  int rc = aux_ensure(ctx, wt_bytes + dzp_bytes + dzt_bytes + wp_bytes);
+  if (rc != PG_OK) return rc;
+  uint8_t* base = (uint8_t*)ctx->aux + wt_bytes;
+  __nv_bfloat16* dZp = (__nv_bfloat16*)base;                               // [M][64]
+  __nv_bfloat16* dZt = (__nv_bfloat16*)(base + dzp_bytes);                 // [32][M]
+  __nv_bfloat16* Wp = (__nv_bfloat16*)(base + dzp_bytes + dzt_bytes);      // [K][64]
+  {
+    int64_t total = M * NARROW_K;
+    pad_copy_kernel<float><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const float*)dZ, dX ? dZp : nullptr, dW ? dZt : nullptr, M, (int)N,
+                                                                                   dX ? NARROW_K : 0, dW ? NARROW_N : 0);
+    PG_LAUNCHED(ctx);
+  }
+  if (dW) {  // dW[K][N] f32 = X^T dZ : M' = K, N' = N (tile 32), K' = batch
+    Epi epi{nullptr, nullptr, 0, 1, 1};
+    rc = launch_tc<true, false, NARROW_N>(ctx, X, dZt, dW, K, N, M, K, M, epi);
     if (rc != PG_OK) return rc;
-    dim3 grid(kb, S);
-    SKINNY_SWITCH(np, (skinny_wgrad_kernel<NP><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)X, (const float*)dZ, (float*)ctx->ws, (int)M, (int)K, (int)N, rps)));
-    PG_LAUNCHED(ctx);
-    reduce_f32_kernel<<<(unsigned)pg_cdiv(K * N, 256), 256, 0, ctx->stream>>>((const float*)ctx->ws, (float*)dW, K * N, S);
-    PG_LAUNCHED(ctx);
   }
   if (db) {
-    int rc = pg_colsum_launch(ctx, PG_F32, dZ, db, M, N);
+    rc = pg_colsum_launch(ctx, PG_F32, dZ, db, M, N);
     if (rc != PG_OK) return rc;
   }
-  if (dX) {
-    size_t smem = (size_t)K * np * sizeof(float);
-    PG_REQUIRE(smem <= 200 * 1024, "skinny layer: K * N too large for shared-memory staging of W");
-    int blocks = (int)(pg_cdiv(M, 8) < (int64_t)ctx->num_sms ? pg_cdiv(M, 8) : ctx->num_sms);
-    SKINNY_SWITCH(np, {
-      auto kern = skinny_dgrad_kernel<NP>;
-      PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<blocks, 256, smem, ctx->stream>>>((const float*)dZ, (const __nv_bfloat16*)W, (const __nv_bfloat16*)mask, (__nv_bfloat16*)dX, (int)M, (int)K, (int)N);
-    });
+  if (dX) {  // dX[M][K] bf16 = dZ W^T : M' = M, N' = K, K' = 64 (zero padded beyond N)
+    int64_t total = K * NARROW_K;
+    pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, Wp, nullptr, K, (int)N, NARROW_K, 0);
     PG_LAUNCHED(ctx);
+    Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, 0, 0};
+    rc = launch_tc<false, false, 256>(ctx, dZp, Wp, dX, M, K, NARROW_K, NARROW_K, NARROW_K, epi);
+    if (rc != PG_OK) return rc;
   }
   return PG_OK;
 }
@@ -556,7 +495,7 @@ int pg_tc_gemm(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, i
   PG_CHECK_CTX(ctx);
   PG_REQUIRE(A && B && C, "null pointer");
   PG_REQUIRE(c_dtype == PG_F32 || c_dtype == PG_BF16, "C must be f32 or bf16");
-  Epi epi{nullptr, nullptr, 0, c_dtype == PG_F32};
+  Epi epi{nullptr, nullptr, 0, c_dtype == PG_F32, 0};
   return tc_dispatch(ctx, layout, A, B, C, M, N, K, epi);
 }
 
@@ -564,11 +503,11 @@ int pg_tc_linear_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, v
   PG_CHECK_CTX(ctx);
   PG_REQUIRE(X && W && Y, "null pointer");
   if (N <= 32) {
-    PG_REQUIRE(y_dtype == PG_F32, "skinny layers (N <= 32) produce f32 outputs");
-    return skinny_fwd(ctx, X, W, b, Y, M, K, N, act);
+    PG_REQUIRE(y_dtype == PG_F32, "narrow layers (N <= 32) produce f32 outputs");
+    return narrow_fwd(ctx, X, W, b, Y, M, K, N, act);
   }
   PG_REQUIRE(y_dtype == PG_BF16 || y_dtype == PG_F32, "Y must be bf16 or f32");
-  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, y_dtype == PG_F32};
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, y_dtype == PG_F32, 0};
   return tc_dispatch(ctx, 0, X, W, Y, M, N, K, epi);
 }
 
@@ -579,13 +518,13 @@ int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, 
   PG_REQUIRE(!dW || X, "dW needs X");
   PG_REQUIRE(!dX || W, "dX needs W");
   if (N <= 32) {
-    PG_REQUIRE(dy_dtype == PG_F32, "skinny layers (N <= 32) take f32 dY");
-    return skinny_bwd(ctx, X, W, dY, dW, db, dX, relu_mask, M, K, N);
+    PG_REQUIRE(dy_dtype == PG_F32, "narrow layers (N <= 32) take f32 dY");
+    return narrow_bwd(ctx, X, W, dY, dW, db, dX, relu_mask, M, K, N);
   }
   PG_REQUIRE(dy_dtype == PG_BF16, "wide layers take bf16 dY");
   int rc;
   if (dW) {  // dW[K][N] = X^T dY: GEMM (M'=K, N'=N, K'=M), A = X stored [M][K] (MN-major), B = dY stored [M][N] (MN-major)
-    Epi epi{nullptr, nullptr, 0, 1};
+    Epi epi{nullptr, nullptr, 0, 1, 0};
     rc = tc_dispatch(ctx, 2, X, dY, dW, K, N, M, epi);
     if (rc != PG_OK) return rc;
   }
@@ -594,7 +533,7 @@ int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, 
     if (rc != PG_OK) return rc;
   }
   if (dX) {  // dX[M][K] = dY W^T: GEMM (M'=M, N'=K, K'=N), A = dY [M][N] K-major, B = W [K][N] K-major
-    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, 0};
+    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, 0, 0};
     rc = tc_dispatch(ctx, 1, dY, W, dX, M, K, N, epi);
     if (rc != PG_OK) return rc;
   }
