@@ -189,7 +189,7 @@ def main():
         g = pb()
         if world > 1:
             dp.allreduce_gradients(g)
-        pg.step(state, g)
+        pg.step(state, g, shadow=(args.math == "bf16"))
         return out
 
     def barrier():

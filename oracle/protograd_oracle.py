@@ -582,10 +582,11 @@ def mlp_bf16_loss_and_grad(spec, params, x, label, global_batch=None):
     for li in range(len(lin) - 1, -1, -1):
         W = bf(params[2 * li])
         xin = layer_inputs[li]
-        grads[2 * li] = xin.T @ d
-        grads[2 * li + 1] = d.sum(0)
+        dq = bf(d)                                           # tensor-core operand copy of dY (bf16)
+        grads[2 * li] = xin.T @ dq
+        grads[2 * li + 1] = d.sum(0)                         # db sums the stored dY (float for the logits layer)
         if li > 0:
-            dx = d @ W.T
+            dx = dq @ W.T
             if relu_after[li - 1]:
                 dx = np.where(xin > 0, dx, 0.0)
             d = bf(dx)                                       # hidden gradients are stored in bf16

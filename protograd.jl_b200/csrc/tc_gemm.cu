@@ -20,7 +20,9 @@ namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                           // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;       // + TMA producer warp + MMA issuer warp
+constexpr int GROUP_M = 16;                            // tile rasterisation: 16 m-blocks x all n-blocks per group (L2 reuse)
 
 // BN = 256: the wide layers (4 stages x 48 KB).  BN = 32: layers with N <= 32 (8 stages x 20 KB);
 // those are HBM-bound, the narrow tile only keeps the MMA pipe from becoming the limiter.
@@ -38,6 +40,8 @@ struct Epi {
   int relu;
   int out_f32;                  // 1: float output, 0: bf16 output
   int narrow;                   // 1: N not a multiple of 8 -> scalar guarded loads/stores (f32 out only)
+  int splits;                   // split-K: work item = (tile, split); split s writes its fp32 partial to C + s*M*N
+  int kb_per_split;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -150,10 +154,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int num_m = (M + BLOCK_M - 1) / BLOCK_M, num_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int num_work = num_tiles * epi.splits;
+  // grouped rasterisation: co-resident CTAs cover ~GROUP_M m-blocks x ~9 n-blocks, so a wave re-reads
+  // few distinct A/B panels from HBM (m fastest inside a group, groups advance along M)
+  auto tile_coords = [&](int tile, int& m0, int& n0) {
+    const int per_group = GROUP_M * num_n;
+    const int g = tile / per_group, r = tile - g * per_group;
+    const int gm = min(GROUP_M, num_m - g * GROUP_M);      // m-blocks in this (possibly last, smaller) group
+    m0 = (g * GROUP_M + r % gm) * BLOCK_M;
+    n0 = (r / gm) * BLOCK_N;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -171,9 +185,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % num_m) * BLOCK_M, n0 = (tile / num_m) * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int tile = work % num_tiles, split = work / num_tiles;
+        const int kb0 = split * epi.kb_per_split, kb1 = min(num_kb, kb0 + epi.kb_per_split);
+        int m0, n0;
+        tile_coords(tile, m0, n0);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
@@ -200,11 +217,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BLOCK_N);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int tile = work % num_tiles, split = work / num_tiles;
+        const int kb0 = split * epi.kb_per_split, kb1 = min(num_kb, kb0 + epi.kb_per_split);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);       // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);             // TMA bytes have landed
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
@@ -214,10 +233,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // MN-major: advance 16 k-rows = 2 swizzle atoms = 2048 B.
             const uint64_t ad = A_MN ? make_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
             const uint64_t bd = B_MN ? make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            umma_bf16(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0);
           }
           tcgen05_commit(empty_bar(stage));              // frees the smem slot once these MMAs retire
-          if (kb == num_kb - 1) tcgen05_commit(tfull_bar(acc));
+          if (kb == kb1 - 1) tcgen05_commit(tfull_bar(acc));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -226,15 +245,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ===== epilogue warps (TMEM -> registers -> global) =====
     const int q = warp & 3;                              // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;                    // which half of the tile's columns this warp drains
+    constexpr int COLS_PER_WARP = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % num_m) * BLOCK_M, n0 = (tile / num_m) * BLOCK_N;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int tile = work % num_tiles, split = work / num_tiles;
+        const int kb0 = split * epi.kb_per_split, kb1 = min(num_kb, kb0 + epi.kb_per_split);
+      int m0, n0;
+      tile_coords(tile, m0, n0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = (BLOCK_N >= 64 ? half * COLS_PER_WARP : 0); c < (BLOCK_N >= 64 ? (half + 1) * COLS_PER_WARP : (half == 0 ? BLOCK_N : 0)); c += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         tmem_ld_wait();
@@ -245,7 +269,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (epi.narrow) {
             // N is not a multiple of 8 (e.g. 10 logits): scalar, fully guarded fp32 path
-            float* op = reinterpret_cast<float*>(C) + (size_t)row * N;
+            float* op = reinterpret_cast<float*>(C) + (size_t)split * M * N + (size_t)row * N;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (col + j < N) {
@@ -282,7 +306,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           if (epi.out_f32) {
-            float* op = reinterpret_cast<float*>(C) + (size_t)row * N + col;
+            float* op = reinterpret_cast<float*>(C) + (size_t)split * M * N + (size_t)row * N + col;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               if (col + j < N) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -370,7 +394,7 @@ int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int
     PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  int64_t tiles = pg_cdiv(M, BLOCK_M) * pg_cdiv(N, BN);
+  int64_t tiles = pg_cdiv(M, BLOCK_M) * pg_cdiv(N, BN) * epi.splits;
   int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
   kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi);
   PG_LAUNCHED(ctx);
@@ -421,6 +445,14 @@ __global__ void __launch_bounds__(256) pad_copy_kernel(const TS* __restrict__ sr
   }
 }
 
+__global__ void __launch_bounds__(256) reduce_f32_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int splits) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * n + i];
+  out[i] = s;
+}
+
 int aux_ensure(pg_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->aux_bytes) return PG_OK;
   if (ctx->capturing) {
@@ -446,7 +478,7 @@ int narrow_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, void* Z
   int64_t total = K * NARROW_N;
   pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, nullptr, Wt, K, (int)N, 0, NARROW_N);
   PG_LAUNCHED(ctx);
-  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, 1, 1};
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, 1, 1, 1, 1 << 30};
   return launch_tc<false, false, NARROW_N>(ctx, X, Wt, Z, M, N, K, K, K, epi);
 }
 
@@ -468,9 +500,26 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
     PG_LAUNCHED(ctx);
   }
   if (dW) {  // dW[K][N] f32 = X^T dZ : M' = K, N' = N (tile 32), K' = batch
-    Epi epi{nullptr, nullptr, 0, 1, 1};
-    rc = launch_tc<true, false, NARROW_N>(ctx, X, dZt, dW, K, N, M, K, M, epi);
+    // only K/128 output tiles: split the batch (K') over ~all SMs, fp32 partials, deterministic reduce
+    const int64_t tiles = pg_cdiv(K, BLOCK_M), num_kb = pg_cdiv(M, BLOCK_K);
+    int splits = (int)(ctx->num_sms / tiles);
+    if (splits < 1) splits = 1;
+    if (splits > 8) splits = 8;
+    int kb_per = (int)pg_cdiv(num_kb, splits);
+    splits = (int)pg_cdiv(num_kb, kb_per);
+    Epi epi{nullptr, nullptr, 0, 1, 1, splits, kb_per};
+    void* target = dW;
+    if (splits > 1) {
+      rc = pg_ws_ensure(ctx, (size_t)splits * K * N * sizeof(float));
+      if (rc != PG_OK) return rc;
+      target = ctx->ws;
+    }
+    rc = launch_tc<true, false, NARROW_N>(ctx, X, dZt, target, K, N, M, K, M, epi);
     if (rc != PG_OK) return rc;
+    if (splits > 1) {
+      reduce_f32_kernel<<<(unsigned)pg_cdiv(K * N, 256), 256, 0, ctx->stream>>>((const float*)ctx->ws, (float*)dW, K * N, splits);
+      PG_LAUNCHED(ctx);
+    }
   }
   if (db) {
     rc = pg_colsum_launch(ctx, PG_F32, dZ, db, M, N);
@@ -480,7 +529,7 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
     int64_t total = K * NARROW_K;
     pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, Wp, nullptr, K, (int)N, NARROW_K, 0);
     PG_LAUNCHED(ctx);
-    Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, 0, 0};
+    Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, 0, 0, 1, 1 << 30};
     rc = launch_tc<false, false, 256>(ctx, dZp, Wp, dX, M, K, NARROW_K, NARROW_K, NARROW_K, epi);
     if (rc != PG_OK) return rc;
   }
@@ -495,7 +544,7 @@ int pg_tc_gemm(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, i
   PG_CHECK_CTX(ctx);
   PG_REQUIRE(A && B && C, "null pointer");
   PG_REQUIRE(c_dtype == PG_F32 || c_dtype == PG_BF16, "C must be f32 or bf16");
-  Epi epi{nullptr, nullptr, 0, c_dtype == PG_F32, 0};
+  Epi epi{nullptr, nullptr, 0, c_dtype == PG_F32, 0, 1, 1 << 30};
   return tc_dispatch(ctx, layout, A, B, C, M, N, K, epi);
 }
 
@@ -507,7 +556,7 @@ int pg_tc_linear_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, v
     return narrow_fwd(ctx, X, W, b, Y, M, K, N, act);
   }
   PG_REQUIRE(y_dtype == PG_BF16 || y_dtype == PG_F32, "Y must be bf16 or f32");
-  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, y_dtype == PG_F32, 0};
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, y_dtype == PG_F32, 0, 1, 1 << 30};
   return tc_dispatch(ctx, 0, X, W, Y, M, N, K, epi);
 }
 
@@ -524,7 +573,7 @@ int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, 
   PG_REQUIRE(dy_dtype == PG_BF16, "wide layers take bf16 dY");
   int rc;
   if (dW) {  // dW[K][N] = X^T dY: GEMM (M'=K, N'=N, K'=M), A = X stored [M][K] (MN-major), B = dY stored [M][N] (MN-major)
-    Epi epi{nullptr, nullptr, 0, 1, 0};
+    Epi epi{nullptr, nullptr, 0, 1, 0, 1, 1 << 30};
     rc = tc_dispatch(ctx, 2, X, dY, dW, K, N, M, epi);
     if (rc != PG_OK) return rc;
   }
@@ -533,7 +582,7 @@ int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, 
     if (rc != PG_OK) return rc;
   }
   if (dX) {  // dX[M][K] = dY W^T: GEMM (M'=M, N'=K, K'=N), A = dY [M][N] K-major, B = W [K][N] K-major
-    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, 0, 0};
+    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, 0, 0, 1, 1 << 30};
     rc = tc_dispatch(ctx, 1, dY, W, dX, M, K, N, epi);
     if (rc != PG_OK) return rc;
   }

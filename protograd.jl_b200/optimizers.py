@@ -140,5 +140,11 @@ def init(optimizer, variable):
 
 
 def step(state, gradient, shadow=None):
-    """step!(state, gradient)"""
-    return state.step(gradient, shadow)
+    """step!(state, gradient).  shadow=True: the fused pass also writes the bf16 operand copy of the
+    updated parameters that the next bf16-mode forward will use (saves that forward's cast pass)."""
+    if shadow is True:
+        from .trace import shadow_target
+        arena_leaves = state.variable.arena()[3]
+        full = len(arena_leaves) and arena_leaves[0].offset == 0
+        shadow = shadow_target(state.variable) if full else None
+    return state.step(gradient, shadow or None)

@@ -200,6 +200,27 @@ def mse(output, label, denom=None):
 
 # ---- plan -------------------------------------------------------------------------------------
 
+
+def _shadow_entry(ctx, buf):
+    key = id(buf)
+    ent = _SHADOWS.get(key)
+    if ent is None or ent[0] is not buf:
+        ent = _SHADOWS[key] = [buf, DeviceBuffer(ctx, buf.nbytes // 2 + 16, zero=True), False]
+    return ent
+
+
+def shadow_target(model):
+    """Device pointer where a fused optimizer pass may write bf16(p_new) for `model`'s arena
+    (`pg.step(state, grad, shadow=True)`).  The next bf16-mode forward then skips its own cast.
+    Opt-in: parameters must not be modified by anything else between that step and the forward."""
+    ctx, base, total, leaves = model.arena()
+    if leaves[0].dtype != np.float32:
+        raise TypeError("bf16 shadows exist for Float32 models only")
+    ent = _shadow_entry(ctx, leaves[0].buf)
+    ent[2] = True
+    return ent[1].ptr + leaves[0].offset // 2
+
+
 _PLANS = {}
 _SHADOWS = {}  # id(DeviceBuffer) -> (buffer ref, bf16 shadow buffer)
 
@@ -407,14 +428,15 @@ class Plan:
 
     # ---- bf16 operand copies -------------------------------------------------------------------
     def _shadow(self, leaf):
-        """bf16 copy of the whole buffer a leaf lives in (refreshed once per forward)"""
+        """bf16 copy of the whole buffer a leaf lives in (refreshed once per forward, unless the
+        optimizer already wrote it in its fused pass — see `shadow_target`)"""
+        ent = _shadow_entry(self.ctx, leaf.buf)
         key = id(leaf.buf)
-        ent = _SHADOWS.get(key)
-        if ent is None or ent[0] is not leaf.buf:
-            sh = DeviceBuffer(self.ctx, leaf.buf.nbytes // 2 + 16, zero=True)
-            ent = _SHADOWS[key] = (leaf.buf, sh)
         if key not in self._fresh:
-            call("pg_vec_cast_bf16", self.ctx.h, ent[1].ptr, leaf.buf.ptr, leaf.buf.nbytes // 4)
+            if ent[2]:
+                ent[2] = False            # consume the optimizer-written copy (valid for one forward)
+            else:
+                call("pg_vec_cast_bf16", self.ctx.h, ent[1].ptr, leaf.buf.ptr, leaf.buf.nbytes // 4)
             self._fresh.add(key)
         return DeviceArray(ent[1], leaf.offset // 2, leaf.shape, BF16)
 
