@@ -61,6 +61,15 @@ int pg_download_async(pg_ctx* ctx, void* dst_host, const void* src_dev, size_t b
 int pg_host_alloc(size_t bytes, void** p);       /* pinned host memory */
 int pg_host_free(void* p);
 
+/* ---- input prefetch: a second (copy) stream + events, so the H2D copy of the next minibatch
+ * (the reference's `train_x_flat[:, idx]` gather, examples/01_mnist_mlp.jl:35-38) overlaps the step.
+ * which_stream: 0 = the compute stream, 1 = the context's copy stream. ---- */
+int pg_event_create(pg_ctx* ctx, void** event);
+int pg_event_destroy(pg_ctx* ctx, void* event);
+int pg_event_record(pg_ctx* ctx, void* event, int which_stream);
+int pg_stream_wait_event(pg_ctx* ctx, int which_stream, void* event);
+int pg_upload_on(pg_ctx* ctx, int which_stream, void* dst_dev, const void* src_host, size_t bytes);
+
 /* ---- CUDA-graph capture of a whole step (stream capture on the ctx stream) ---------------- */
 int pg_graph_begin(pg_ctx* ctx);
 int pg_graph_end(pg_ctx* ctx, void** graph_exec);

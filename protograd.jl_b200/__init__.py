@@ -24,10 +24,11 @@ def within_training_mode(f):
 
 from .broadcast import L  # noqa: E402
 from .device import BF16, Context, DeviceArray, PinnedBuffer  # noqa: E402
-from .gradient import Loss, eval_with_pullback  # noqa: E402
+from .gradient import Loss, eval_with_pullback, gradient_container  # noqa: E402
 from .layers import (Compose, Conv, Dropout, Linear, MaxPool, MeanPool, ReLU, Reshape, SoftMax, dropout, flatten,  # noqa: E402
                      maxpool, meanpool, relu, reshape, softmax, xavier_uniform)
 from .model import Model, allparams, dot, ldiv, overlap, vec  # noqa: E402
+from .pipeline import Prefetcher  # noqa: E402
 from .optimizers import Adam, GradientDescent, HeavyBallMethod, NesterovMethod, NesterovMomentumSequence, init, step  # noqa: E402
 from .trace import cross_entropy, mse  # noqa: E402
 

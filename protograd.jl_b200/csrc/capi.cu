@@ -62,6 +62,7 @@ int pg_init(int device, pg_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   PG_CHECK_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
+  PG_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   PG_CHECK_CUDA(cudaMalloc((void**)&c->counters, 64 * sizeof(unsigned int)));
   PG_CHECK_CUDA(cudaMemset(c->counters, 0, 64 * sizeof(unsigned int)));
   PG_CHECK_CUDA(cudaMalloc((void**)&c->result_slot, 16 * sizeof(double)));
@@ -81,6 +82,7 @@ int pg_destroy(pg_ctx* ctx) {
   if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->result_slot) cudaFree(ctx->result_slot);
   if (ctx->result_host) cudaFreeHost(ctx->result_host);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return PG_OK;
@@ -156,6 +158,37 @@ int pg_host_alloc(size_t bytes, void** p) {
 }
 int pg_host_free(void* p) {
   if (p) PG_CHECK_CUDA(cudaFreeHost(p));
+  return PG_OK;
+}
+
+static cudaStream_t pick_stream(pg_ctx* ctx, int which) { return which == 1 ? ctx->copy_stream : ctx->stream; }
+
+int pg_event_create(pg_ctx* ctx, void** event) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(event != nullptr, "null out pointer");
+  cudaEvent_t e;
+  PG_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *event = (void*)e;
+  return PG_OK;
+}
+int pg_event_destroy(pg_ctx* ctx, void* event) {
+  PG_CHECK_CTX(ctx);
+  if (event) PG_CHECK_CUDA(cudaEventDestroy((cudaEvent_t)event));
+  return PG_OK;
+}
+int pg_event_record(pg_ctx* ctx, void* event, int which_stream) {
+  PG_CHECK_CTX(ctx);
+  PG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)event, pick_stream(ctx, which_stream)));
+  return PG_OK;
+}
+int pg_stream_wait_event(pg_ctx* ctx, int which_stream, void* event) {
+  PG_CHECK_CTX(ctx);
+  PG_CHECK_CUDA(cudaStreamWaitEvent(pick_stream(ctx, which_stream), (cudaEvent_t)event, 0));
+  return PG_OK;
+}
+int pg_upload_on(pg_ctx* ctx, int which_stream, void* dst, const void* src, size_t bytes) {
+  PG_CHECK_CTX(ctx);
+  PG_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pick_stream(ctx, which_stream)));
   return PG_OK;
 }
 

@@ -13,6 +13,7 @@ struct pg_ctx {
   int num_sms = 148;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H2D prefetch of the next minibatch
   int64_t launches = 0;
   // scratch: split-K partials, block partials for reductions
   void* ws = nullptr;

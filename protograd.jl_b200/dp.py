@@ -60,3 +60,53 @@ def allreduce_host(flat, group=None):
     t = torch.from_numpy(flat)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return flat
+
+
+class GradientBuckets:
+    """Layer-bucketed, overlapped all-reduce of the gradient arena: backward finishes
+    layers last-to-first, i.e. the arena tail first; as soon as >= bucket_bytes of finished gradient
+    leaves have accumulated their slice is all-reduced asynchronously on NCCL's stream while the
+    remaining backward GEMMs run; finish() reduces the head slice and joins everything before the
+    optimizer pass.
+
+        buckets = dp.GradientBuckets(gradient_container(model))
+        grad = pb(on_ready=buckets.ready); buckets.finish(); step(state, grad)
+    """
+
+    def __init__(self, grad_model, bucket_bytes=24 << 20):
+        from .model import _pad
+        ctx, base, total, leaves = grad_model.arena()
+        self.flat = arena_tensor(grad_model)
+        self.offsets, off = [], 0
+        for p in leaves:
+            self.offsets.append(off)
+            off += _pad(p.size)
+        self.total = total
+        self.itemsize = leaves[0].dtype.itemsize
+        self.bucket_bytes = bucket_bytes
+        self.hi = total
+        self.lo_ready = total
+        self.works = []
+        self.enabled = world()[1] > 1
+
+    def ready(self, leaf_index):
+        if not self.enabled:
+            return
+        import torch.distributed as dist
+        lo = self.offsets[leaf_index]
+        assert lo <= self.lo_ready, "gradient leaves must complete last-to-first"
+        self.lo_ready = lo
+        if (self.hi - lo) * self.itemsize >= self.bucket_bytes and lo > 0:
+            self.works.append(dist.all_reduce(self.flat[lo:self.hi], op=dist.ReduceOp.SUM, async_op=True))
+            self.hi = lo
+
+    def finish(self):
+        if self.enabled:
+            import torch.distributed as dist
+            if self.hi > 0:
+                self.works.append(dist.all_reduce(self.flat[0:self.hi], op=dist.ReduceOp.SUM, async_op=True))
+            for w in self.works:
+                w.wait()          # the compute stream waits for NCCL's stream
+        self.works = []
+        self.hi = self.total
+        self.lo_ready = self.total

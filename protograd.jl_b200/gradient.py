@@ -62,6 +62,14 @@ class Loss:
     __radd__ = __add__
 
 
+def gradient_container(m):
+    """the (reused) arena-backed gradient model of `m`"""
+    g = _grad_cache.get(m)
+    if g is None:
+        g = _grad_cache[m] = m.zero()
+    return g
+
+
 def eval_with_pullback(f, m, backend="B200", math="fp32"):
     """src/gradient.jl:1-2.  `math`: "fp32" (FP32/FP64 SIMT, rel 1e-5) or "bf16" (tcgen05 tensor cores)."""
     if backend not in _BACKENDS:
@@ -81,12 +89,12 @@ def eval_with_pullback(f, m, backend="B200", math="fp32"):
     plan.forward(tr)
     loss = Loss(plan.vals[out.id])
 
-    def pullback():
-        g = _grad_cache.get(m)
-        if g is None:
-            g = _grad_cache[m] = m.zero()
+    def pullback(on_ready=None):
+        """pb(): zero arguments like the reference's; `on_ready` is the data-parallel hook
+        (see dp.GradientBuckets) and may be ignored by single-GPU callers."""
+        g = gradient_container(m)
         gleaves = g.allparams()
-        plan.backward(gleaves)
+        plan.backward(gleaves, on_ready)
         return g
 
     return loss, pullback

@@ -529,8 +529,10 @@ class Plan:
                 raise NotImplementedError(op)
 
     # ---- backward ------------------------------------------------------------------------------
-    def backward(self, grad_leaves):
-        """grad_leaves: DeviceArrays in vec(m) order receiving dW / db (written, not accumulated)."""
+    def backward(self, grad_leaves, on_ready=None):
+        """grad_leaves: DeviceArrays in vec(m) order receiving dW / db (written, not accumulated).
+        on_ready(i): called once the gradient kernels of leaves >= i have all been enqueued (layers
+        finish in reverse order), so a data-parallel caller can start reducing that bucket."""
         h = self.ctx.h
         P = lambda a: a.ptr if a is not None else None
         for i in range(self.n - 1, -1, -1):
@@ -558,13 +560,24 @@ class Plan:
                     if self.math == "bf16":
                         xv = self._as_bf16(x) if gW is not None else None
                         Wv = self._as_bf16(W) if gx is not None else None
-                        call("pg_tc_linear_bwd", h, P(xv), P(Wv), gy.ptr, PG_BF16 if gy.dtype == BF16 else PG_F32, P(gW), P(gb), P(gx), P(mask), M, K, N)
+                        gyc = PG_BF16 if gy.dtype == BF16 else PG_F32
+                        if on_ready is not None and gx is not None and (gW is not None or gb is not None):
+                            # data-parallel: parameter gradients first, so their bucket can start reducing
+                            # while this layer's data gradient (and everything upstream) still computes
+                            call("pg_tc_linear_bwd", h, P(xv), None, gy.ptr, gyc, P(gW), P(gb), None, None, M, K, N)
+                            on_ready(min(self.attrs[j]["grad_index"] for j in (W, b) if self.ng[j]))
+                            call("pg_tc_linear_bwd", h, None, P(Wv), gy.ptr, gyc, None, None, P(gx), P(mask), M, K, N)
+                            continue
+                        call("pg_tc_linear_bwd", h, P(xv), P(Wv), gy.ptr, gyc, P(gW), P(gb), P(gx), P(mask), M, K, N)
                     else:
                         call("pg_linear_bwd", h, code, self._val(x).ptr, self._val(W).ptr, gy.ptr, P(gW), P(gb), P(gx), P(mask), M, K, N)
                 else:
                     N_, Cin, H, W_ = self.shapes[x]
                     Cout, _, kH, kW = self.shapes[W]
                     call("pg_conv2d_bwd", h, code, self._val(x).ptr, self._val(W).ptr, gy.ptr, P(gW), P(gb), P(gx), N_, Cin, H, W_, Cout, kH, kW)
+                if on_ready is not None and (gW is not None or gb is not None):
+                    idx = [self.attrs[j]["grad_index"] for j in (W, b) if self.ng[j]]
+                    on_ready(min(idx))
             elif op == "relu":
                 if i in self.fused_into:
                     continue  # handled by the producer
