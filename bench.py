@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="samples per GPU")
     ap.add_argument("--math", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--dp-mode", default="bucket", choices=["bucket", "flat", "none"], help="gradient exchange: layer-bucketed overlapped all-reduce (default), one flat all-reduce, or none (diagnostic)")
+    ap.add_argument("--sm-limit", type=int, default=0, help="size persistent grids for this many SMs (0 = all)")
     ap.add_argument("--exact-adam", action="store_true", help="Float64-promoted Adam arithmetic (bit-exact with the reference's broadcast) instead of the fused Float32 form")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -185,15 +187,23 @@ def main():
     x_p[...] = x_h; lab_p[...] = lab_h
 
     buckets = dp.GradientBuckets(pg.gradient_container(model)) if world > 1 else None
+    if args.sm_limit:
+        ctx.set_sm_limit(args.sm_limit)
+    use_shadow = args.math == "bf16"
 
     def train_step(x, lab):
         out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(x), lab, global_batch=GB), model, math=args.math)
-        if buckets is not None:
+        if buckets is None:
+            pg.step(state, pb(), shadow=use_shadow)
+        elif args.dp_mode == "bucket":
             g = pb(on_ready=buckets.ready)      # tail buckets reduce while the remaining backward GEMMs run
-            buckets.finish()
-        else:
+            buckets.finish_and_step(state, g, shadow=use_shadow)
+        elif args.dp_mode == "flat":
             g = pb()
-        pg.step(state, g, shadow=(args.math == "bf16"))
+            dp.allreduce_gradients(g)
+            pg.step(state, g, shadow=use_shadow)
+        else:                                   # "none": no exchange (diagnostic only, replicas diverge)
+            pg.step(state, pb(), shadow=use_shadow)
         return out
 
     def barrier():
@@ -304,7 +314,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.math == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "wide MLP 784-4096-4096-10 (BASELINE configs[3]), softmax+cross-entropy, Adam(1e-3), %d samples/GPU" % B,
-                       "global_batch": GB, "parallelism": "dp%d" % world, "math": args.math, "adam": "float64-promoted (bit-exact)" if args.exact_adam else "fused float32 (normwise 1e-7 of the reference form)",
+                       "global_batch": GB, "parallelism": "dp%d" % world, "dp_mode": args.dp_mode if world > 1 else None, "math": args.math, "adam": "float64-promoted (bit-exact)" if args.exact_adam else "fused float32 (normwise 1e-7 of the reference form)",
                        "l2": "working set per step (>600 MB of activations, weights, gradients, optimizer state) exceeds the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(x_h.nbytes + lab_h.nbytes), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / e2e_steps},

@@ -59,7 +59,7 @@ int pg_init(int device, pg_ctx** out) {
   }
   pg_ctx* c = new pg_ctx();
   c->device = device;
-  c->num_sms = prop.multiProcessorCount;
+  c->num_sms = c->real_sms = prop.multiProcessorCount;
   PG_CHECK_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   PG_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -106,6 +106,11 @@ int pg_sync(pg_ctx* ctx) {
 int pg_launch_count(pg_ctx* ctx, int64_t* n) {
   PG_CHECK_CTX(ctx);
   *n = ctx->launches;
+  return PG_OK;
+}
+int pg_set_sm_limit(pg_ctx* ctx, int n) {
+  PG_CHECK_CTX(ctx);
+  ctx->num_sms = (n <= 0 || n > ctx->real_sms) ? ctx->real_sms : n;
   return PG_OK;
 }
 int pg_reserve_workspace(pg_ctx* ctx, size_t bytes) {

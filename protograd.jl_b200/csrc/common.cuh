@@ -10,7 +10,8 @@
 
 struct pg_ctx {
   int device = 0;
-  int num_sms = 148;
+  int num_sms = 148;       // SMs used to size grids (pg_set_sm_limit)
+  int real_sms = 148;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D prefetch of the next minibatch

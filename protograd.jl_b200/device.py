@@ -61,6 +61,10 @@ class Context:
         call("pg_launch_count", self.h, ctypes.byref(n))
         return n.value
 
+    def set_sm_limit(self, n):
+        """size persistent grids for n SMs (0 = all), e.g. to leave SMs to a concurrent NCCL kernel"""
+        call("pg_set_sm_limit", self.h, int(n))
+
     def reserve_workspace(self, nbytes):
         call("pg_reserve_workspace", self.h, int(nbytes))
 

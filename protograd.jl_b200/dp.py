@@ -86,7 +86,7 @@ class GradientBuckets:
         self.bucket_bytes = bucket_bytes
         self.hi = total
         self.lo_ready = total
-        self.works = []
+        self.works, self.ranges = [], []
         self.enabled = world()[1] > 1
 
     def ready(self, leaf_index):
@@ -98,7 +98,31 @@ class GradientBuckets:
         self.lo_ready = lo
         if (self.hi - lo) * self.itemsize >= self.bucket_bytes and lo > 0:
             self.works.append(dist.all_reduce(self.flat[lo:self.hi], op=dist.ReduceOp.SUM, async_op=True))
+            self.ranges.append((lo, self.hi - lo))
             self.hi = lo
+
+    def finish_and_step(self, state, grad, shadow=None):
+        """Join the buckets one by one and run the fused optimizer pass on each bucket's slice as soon
+        as its reduction has landed, so the last (head) bucket's all-reduce overlaps the update of the
+        others.  Single process: one whole-arena step."""
+        from .optimizers import step, step_range
+        if not self.enabled:
+            return step(state, grad, shadow)
+        import torch.distributed as dist
+        if self.hi > 0:
+            self.works.append(dist.all_reduce(self.flat[0:self.hi], op=dist.ReduceOp.SUM, async_op=True))
+            self.ranges.append((0, self.hi))
+        r = None
+        for k, (w, (lo, cnt)) in enumerate(zip(self.works, self.ranges)):
+            w.wait()
+            r = step_range(state, grad, lo, cnt, shadow=shadow, last=(k == len(self.works) - 1))
+        self._reset()
+        return r
+
+    def _reset(self):
+        self.works, self.ranges = [], []
+        self.hi = self.total
+        self.lo_ready = self.total
 
     def finish(self):
         if self.enabled:
@@ -107,6 +131,4 @@ class GradientBuckets:
                 self.works.append(dist.all_reduce(self.flat[0:self.hi], op=dist.ReduceOp.SUM, async_op=True))
             for w in self.works:
                 w.wait()          # the compute stream waits for NCCL's stream
-        self.works = []
-        self.hi = self.total
-        self.lo_ready = self.total
+        self._reset()

@@ -59,16 +59,27 @@ class Adam:
 
 
 class _State:
+    """`_range = (start, count)` (padded-arena elements) restricts a step to a slice of the arena:
+    the update is elementwise, so a data-parallel caller can update each gradient bucket as soon as
+    its all-reduce has landed (see step_range)."""
+    _range = None
+
     def _arena(self, g):
         v = self.variable
         v._check_same(g)
         ctx, p, n, leaves = v.arena()
         _, pg, _, _ = g.arena()
+        self._isz = leaves[0].dtype.itemsize
+        if self._range is not None:
+            start, count = self._range
+            p += start * self._isz; pg += start * self._isz; n = count
         return ctx, dtype_code(leaves[0].dtype), p, pg, n
 
-    @staticmethod
-    def _ptr(m):
-        return m.arena()[1]
+    def _ptr(self, m):
+        p = m.arena()[1]
+        if self._range is not None:
+            p += self._range[0] * self._isz
+        return p
 
 
 class GradientDescentState(_State):
@@ -137,6 +148,35 @@ def init(optimizer, variable):
     if not isinstance(variable, Model):
         raise TypeError("the B200 optimizers update arena-backed Models")
     return _STATES[type(optimizer)](optimizer, variable)
+
+
+def step_range(state, gradient, start, count, shadow=None, last=True):
+    """step! restricted to arena elements [start, start+count).  Call once per bucket; pass
+    last=False for all but the final bucket of a step so per-step scalars (Adam's `it`, Nesterov's
+    momentum) advance once per step."""
+    if shadow is True:
+        from .trace import shadow_target
+        shadow = shadow_target(state.variable) + start * 2
+    state._range = (int(start), int(count))
+    try:
+        if isinstance(state, AdamState) and not last:
+            it = state.it
+            r = state.step(gradient, shadow or None)
+            state.it = it
+        elif isinstance(state, NesterovState):
+            if not hasattr(state, "_mu_cached"):
+                state._mu_cached = next(state.momentum_iterator)
+            mu = state._mu_cached
+            ctx, code, p, pg, n = state._arena(gradient)
+            call("pg_opt_nesterov", ctx.h, code, p, state._ptr(state.variable_prev), pg, n, float(state.stepsize), float(mu), _f64(state.stepsize), shadow or None)
+            if last:
+                del state._mu_cached
+            r = state.variable
+        else:
+            r = state.step(gradient, shadow or None)
+    finally:
+        state._range = None
+    return r
 
 
 def step(state, gradient, shadow=None):
