@@ -190,14 +190,29 @@ def main():
     if args.sm_limit:
         ctx.set_sm_limit(args.sm_limit)
     use_shadow = args.math == "bf16"
+    timeline = [] if os.environ.get("PG_DP_TIMELINE") else None
 
     def train_step(x, lab):
         out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(x), lab, global_batch=GB), model, math=args.math)
         if buckets is None:
             pg.step(state, pb(), shadow=use_shadow)
         elif args.dp_mode == "bucket":
-            g = pb(on_ready=buckets.ready)      # tail buckets reduce while the remaining backward GEMMs run
-            buckets.finish_and_step(state, g, shadow=use_shadow)
+            if timeline is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record(stream)
+
+                def hook(i):
+                    buckets.ready(i)
+                    if i == 2:
+                        ev[1].record(stream)   # parameter gradients of layers 2,3 done; their bucket was just issued
+                g = pb(on_ready=hook)
+                ev[2].record(stream)           # end of backward compute
+                buckets.finish_and_step(state, g, shadow=use_shadow)
+                ev[3].record(stream)
+                timeline.append(ev)
+            else:
+                g = pb(on_ready=buckets.ready)      # tail buckets reduce while the remaining backward GEMMs run
+                buckets.finish_and_step(state, g, shadow=use_shadow)
         elif args.dp_mode == "flat":
             g = pb()
             dp.allreduce_gradients(g)
@@ -212,12 +227,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_enqueue = [0.0]
+
     def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
+        t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_enqueue[0] = (time.perf_counter() - t0) / steps * 1e3
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=f"cuda:{local}")
@@ -235,6 +254,11 @@ def main():
     n0 = ctx.launch_count()
     ms = timed(lambda: train_step(x_d, lab_d), args.steps)
     launches = ctx.launch_count() - n0
+    host_ms = host_enqueue[0]
+    if timeline and rank == 0:
+        torch.cuda.synchronize()
+        tl = np.array([[e[0].elapsed_time(e[k]) for k in (1, 2, 3)] for e in timeline[-20:]])
+        print("DP timeline (ms from step start: bucket issued, backward done, step done):", tl.mean(0).round(4).tolist(), file=sys.stderr)
     clk = clocks.stop() if rank == 0 else None
     value = GB * args.steps / (ms * 1e-3)
 
@@ -318,7 +342,7 @@ def main():
                        "l2": "working set per step (>600 MB of activations, weights, gradients, optimizer state) exceeds the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(x_h.nbytes + lab_h.nbytes), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / e2e_steps},
-            "gpu_launches": int(launches), "clocks": clk, "loss_after_warmup": first_loss,
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms, "clocks": clk, "loss_after_warmup": first_loss,
             "tflops_per_gpu": FLOP_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12,
         }
         if roofline:

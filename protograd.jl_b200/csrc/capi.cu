@@ -110,6 +110,7 @@ int pg_launch_count(pg_ctx* ctx, int64_t* n) {
 }
 int pg_set_sm_limit(pg_ctx* ctx, int n) {
   PG_CHECK_CTX(ctx);
+  if (n < 0) n = ctx->real_sms + n;            // negative: leave |n| SMs free
   ctx->num_sms = (n <= 0 || n > ctx->real_sms) ? ctx->real_sms : n;
   return PG_OK;
 }

@@ -73,7 +73,11 @@ class GradientBuckets:
         grad = pb(on_ready=buckets.ready); buckets.finish(); step(state, grad)
     """
 
-    def __init__(self, grad_model, bucket_bytes=24 << 20):
+    def __init__(self, grad_model, bucket_bytes=24 << 20, comm_sms=16):
+        # while a bucket is in flight the persistent GEMM grids are sized for (all - comm_sms) SMs, so
+        # NCCL's CTAs get SMs of their own instead of time-slicing with (and stalling) GEMM CTAs
+        self.comm_sms = comm_sms
+        self.ctx = grad_model.arena()[0]
         from .model import _pad
         ctx, base, total, leaves = grad_model.arena()
         self.flat = arena_tensor(grad_model)
@@ -100,6 +104,8 @@ class GradientBuckets:
             self.works.append(dist.all_reduce(self.flat[lo:self.hi], op=dist.ReduceOp.SUM, async_op=True))
             self.ranges.append((lo, self.hi - lo))
             self.hi = lo
+            if self.comm_sms:
+                self.ctx.set_sm_limit(-self.comm_sms)
 
     def finish_and_step(self, state, grad, shadow=None):
         """Join the buckets one by one and run the fused optimizer pass on each bucket's slice as soon
@@ -120,6 +126,8 @@ class GradientBuckets:
         return r
 
     def _reset(self):
+        if self.comm_sms:
+            self.ctx.set_sm_limit(0)
         self.works, self.ranges = [], []
         self.hi = self.total
         self.lo_ready = self.total

@@ -55,7 +55,7 @@ class Adam:
     beta2: float = 0.999
     epsilon: float = 1e-8
     fast: bool = False
-    keep_hats: bool = True   # materialise m_hat / v_hat like the reference's AdamState
+    keep_hats: bool = False  # True: rewrite m_hat / v_hat every step; False: materialise them on access
 
 
 class _State:
@@ -121,12 +121,31 @@ class NesterovState(_State):
 
 
 class AdamState(_State):
+    """adam.jl:8-17.  `m_hat` / `v_hat` are state fields in the reference; they are pure functions
+    of (m, v, it), so by default they are NOT rewritten every step (that would be 8 of 36 B/param of
+    HBM traffic) but materialised on access with the same arithmetic (m ./ (1 - beta1^it) with the
+    `it` of the last step).  Adam(keep_hats=True) restores the eager per-step materialisation."""
+
     def __init__(self, opt, variable):
         self.optimizer, self.stepsize, self.variable = opt, opt.stepsize, variable
         self.m, self.v = variable.zero(), variable.zero()
-        self.m_hat = variable.zero() if opt.keep_hats else None
-        self.v_hat = variable.zero() if opt.keep_hats else None
+        self._m_hat = variable.zero() if opt.keep_hats else None
+        self._v_hat = variable.zero() if opt.keep_hats else None
         self.it = 1                                               # adam.jl:28
+
+    def _hat(self, src, beta):
+        if self.it <= 1:
+            return self.variable.zero()                           # init value (adam.jl:26-27)
+        c = 1 - beta ** (self.it - 1)                             # the `it` the last step used
+        return src / (float(c) if _scalar_flags(self.stepsize) else np.float32(c))
+
+    @property
+    def m_hat(self):
+        return self._m_hat if self._m_hat is not None else self._hat(self.m, self.optimizer.beta1)
+
+    @property
+    def v_hat(self):
+        return self._v_hat if self._v_hat is not None else self._hat(self.v, self.optimizer.beta2)
 
     def step(self, g, shadow=None):
         """adam.jl:32-41; returns the incremented iteration counter like the reference"""
@@ -134,7 +153,7 @@ class AdamState(_State):
         o = self.optimizer
         fl = _f64(self.stepsize) | (capi.MATH_FAST if o.fast else 0)
         call("pg_opt_adam", ctx.h, code, p, self._ptr(self.m), self._ptr(self.v),
-             self._ptr(self.m_hat) if self.m_hat is not None else None, self._ptr(self.v_hat) if self.v_hat is not None else None,
+             self._ptr(self._m_hat) if self._m_hat is not None else None, self._ptr(self._v_hat) if self._v_hat is not None else None,
              pg, n, float(self.stepsize), float(o.beta1), float(o.beta2), float(o.epsilon), self.it, fl, shadow)
         self.it += 1
         return self.it
