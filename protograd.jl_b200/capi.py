@@ -105,5 +105,10 @@ def check(rc):
         raise PGError(f"protograd_b200 error {rc}: {lib.pg_last_error().decode(errors='replace')}")
 
 
+_FN = {name: getattr(lib, name) for name in _SIGS}
+_err = lib.pg_last_error
+
+
 def call(name, *args):
-    check(getattr(lib, name)(*args))
+    if _FN[name](*args):
+        raise PGError(f"protograd_b200 error in {name}: {_err().decode(errors='replace')}")

@@ -253,12 +253,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int kb0 = split * epi.kb_per_split, kb1 = min(num_kb, kb0 + epi.kb_per_split);
       int m0, n0;
       tile_coords(tile, m0, n0);
+      const int row = m0 + q * 32 + lane;
+      const int c_begin = BLOCK_N >= 64 ? half * COLS_PER_WARP : 0;
+      const bool active = BLOCK_N >= 64 || half == 0;
+      // ReLU' mask of this thread's row slice: issued BEFORE waiting for the accumulator, so its HBM
+      // latency overlaps the tile's MMAs instead of serialising with every 32-column chunk
+      uint4 mk[COLS_PER_WARP / 8];
+      if (epi.mask != nullptr && active) {
+        const __nv_bfloat16* mp = epi.mask + (size_t)row * N + n0 + c_begin;
+#pragma unroll
+        for (int j = 0; j < COLS_PER_WARP / 8; ++j)
+          mk[j] = (row < M && n0 + c_begin + 8 * j < N) ? __ldg(reinterpret_cast<const uint4*>(mp) + j) : make_uint4(0, 0, 0, 0);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const int row = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c = (BLOCK_N >= 64 ? half * COLS_PER_WARP : 0); c < (BLOCK_N >= 64 ? (half + 1) * COLS_PER_WARP : (half == 0 ? BLOCK_N : 0)); c += 32) {
+#pragma unroll
+      for (int ci = 0; ci < COLS_PER_WARP / 32; ++ci) {
+        if (!active) break;
+        const int c = c_begin + ci * 32;
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         tmem_ld_wait();
@@ -294,15 +307,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
           }
           if (epi.mask != nullptr) {
-            const __nv_bfloat16* mp = epi.mask + (size_t)row * N + col;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              if (col + j < N) {
-                const uint4 mk = *reinterpret_cast<const uint4*>(mp + j);
-                const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk);
+              const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk[ci * 4 + j / 8]);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[j + e] = (__bfloat162float(me[e]) > 0.0f) ? v[j + e] : 0.0f;
-              }
+              for (int e = 0; e < 8; ++e) v[j + e] = (__bfloat162float(me[e]) > 0.0f) ? v[j + e] : 0.0f;
             }
           }
           if (epi.out_f32) {

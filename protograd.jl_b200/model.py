@@ -47,7 +47,12 @@ class Model:
         return [getattr(self, k) for k in self.__fields__]
 
     def allparams(self):
-        """src/model.jl:9-24: DFS over fields / tuples collecting array leaves, skipping functions."""
+        """src/model.jl:9-24: DFS over fields / tuples collecting array leaves, skipping functions.
+        The leaf list is cached: like the reference's structs, a Model's fields are immutable once
+        it has been used (leaf CONTENTS change, leaf objects do not)."""
+        cached = self.__dict__.get("_leaves_cache")
+        if cached is not None:
+            return cached
         out = []
 
         def rec(v):
@@ -69,6 +74,7 @@ class Model:
             dt = out[0].dtype
             if any(p.dtype != dt for p in out):
                 raise TypeError("all leaves of a Model must share one eltype (src/model.jl:9)")
+        self.__dict__["_leaves_cache"] = out
         return out
 
     def _map(self, fun):
@@ -80,7 +86,7 @@ class Model:
             if isinstance(v, Model):
                 new = object.__new__(type(v))
                 new.__dict__.update(v.__dict__)
-                new.__dict__.pop("_arena_cache", None)
+                new.__dict__.pop("_leaves_cache", None)
                 for k in v.__fields__:
                     setattr(new, k, rec(getattr(v, k)))
                 return new
