@@ -133,6 +133,10 @@ int pg_maxpool2d_fwd(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t NC,
 int pg_maxpool2d_bwd(pg_ctx* ctx, int dtype, const void* x, const void* dy, void* dx, int64_t NC, int H, int W, int k);
 int pg_meanpool2d_fwd(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t NC, int H, int W, int k);
 int pg_meanpool2d_bwd(pg_ctx* ctx, int dtype, const void* dy, void* dx, int64_t NC, int H, int W, int k);
+/* dropout in training mode (layers.jl:109-138): y = x .* mask, mask_i = rand_i > p ? T(1/(1-p)) : 0.
+ * The mask is a pure function of (seed, stream_id, elem_offset + i) (Philox4x32-10): call it again on dY
+ * with the same arguments for the pullback.  elem_offset: global index of x[0] (data-parallel shards). */
+int pg_dropout(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t n, double p, uint64_t seed, uint32_t stream_id, uint64_t elem_offset);
 int pg_relu_fwd(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t n);
 int pg_relu_bwd(pg_ctx* ctx, int dtype, const void* y, const void* dy, void* dx, int64_t n);
 

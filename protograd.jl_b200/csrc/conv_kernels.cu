@@ -388,3 +388,59 @@ int pg_relu_bwd(pg_ctx* ctx, int dtype, const void* y, const void* dy, void* dx,
 }
 
 }  // extern "C"
+
+// ---- dropout (src/layers.jl:109-138) --------------------------------------------------------------
+// mask_i = rand_i > p ? T(1/(1-p)) : 0, y = x .* mask; the pullback multiplies by the SAME mask.
+// The mask is never stored: it is a pure function of (seed, stream, element index) through
+// Philox4x32-10, so the backward pass regenerates it, and data-parallel shards that pass their global
+// element offset draw exactly the masks the single-GPU full batch would.
+namespace {
+
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, float p, T scale,
+                                                      uint64_t seed, uint32_t stream_id, uint64_t elem_offset) {
+  const int64_t ngroups = (n + 3) / 4;
+  for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < ngroups; gidx += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t e0 = elem_offset + (uint64_t)gidx * 4;     // global index of the group's first element
+    const uint64_t ctr = e0 >> 2;
+    const uint4 r = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), stream_id, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = gidx * 4 + j;
+      if (i < n) {
+        const float u = (float)(rr[j] >> 8) * (1.0f / 16777216.0f);   // uniform [0,1), 24 bits like rand(Float32)
+        y[i] = u > p ? x[i] * scale : T(0);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int pg_dropout(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t n, double p, uint64_t seed, uint32_t stream_id, uint64_t elem_offset) {
+  PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
+  PG_REQUIRE(x && y, "null pointer");
+  PG_REQUIRE(p >= 0.0 && p < 1.0, "dropout probability must be in [0, 1)");
+  PG_REQUIRE((elem_offset & 3) == 0, "element offset must be a multiple of 4");
+  if (n <= 0) return PG_OK;
+  const double scale = 1.0 / (1.0 - p);                       // T(1 / (1 - p)), src/layers.jl:114
+  if (dtype == PG_F32) dropout_kernel<float><<<grid_for(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>((const float*)x, (float*)y, n, (float)p, (float)scale, seed, stream_id, elem_offset);
+  else dropout_kernel<double><<<grid_for(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>((const double*)x, (double*)y, n, (float)p, scale, seed, stream_id, elem_offset);
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}

@@ -70,14 +70,16 @@ def gradient_container(m):
     return g
 
 
-def eval_with_pullback(f, m, backend="B200", math="fp32"):
+def eval_with_pullback(f, m, backend="B200", math="fp32", sample_offset=0):
     """src/gradient.jl:1-2.  `math`: "fp32" (FP32/FP64 SIMT, rel 1e-5) or "bf16" (tcgen05 tensor cores)."""
     if backend not in _BACKENDS:
         raise ValueError(f"unknown AD backend {backend}")          # gradient.jl:1
     if not isinstance(m, Model):
         raise TypeError("the B200 backend differentiates with respect to a Model")
     ctx, base, total, leaves = m.arena()
-    tr = T.Trace(ctx or Context.get(), leaves, math)
+    # sample_offset: global index of this process's first sample (data-parallel shards draw the
+    # dropout masks the full batch would)
+    tr = T.Trace(ctx or Context.get(), leaves, math, sample_offset)
     prev = T.set_current(tr)
     try:
         out = f(m)

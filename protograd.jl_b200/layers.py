@@ -108,12 +108,12 @@ class Reshape(Model):
 
 
 class Dropout(Model):
-    """layers.jl:134-138 (identity outside training mode)"""
+    """layers.jl:134-138 (identity outside training mode; P and D are type parameters there)"""
     def __init__(self, p, dims=None):
-        self._p = p
+        self._p, self._dims = p, dims
 
     def __call__(self, x):
-        return T.dropout(x, self._p)
+        return T.dropout(x, self._p, self._dims)
 
 
 relu, softmax, maxpool, meanpool, flatten, reshape, dropout = T.relu, T.softmax, T.maxpool, T.meanpool, T.flatten, T.reshape, T.dropout

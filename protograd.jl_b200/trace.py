@@ -18,6 +18,13 @@ from .capi import ACT_NONE, ACT_RELU, PG_BF16, PG_F32, call
 from .device import BF16, Context, DeviceArray, DeviceBuffer, dtype_code, is_pinned
 
 _current = None  # the Trace being recorded (set by eval_with_pullback / forward)
+_rng = {"seed": 0x5EED5EED, "step": 0}
+
+
+def seed(s):
+    """seed the counter-based dropout generator (masks are a function of seed, step, layer, element)"""
+    _rng["seed"] = int(s) & 0xFFFFFFFFFFFFFFFF
+    _rng["step"] = 0
 
 
 class Tensor:
@@ -45,9 +52,14 @@ class Tensor:
 
 
 class Trace:
-    def __init__(self, ctx, trainable=(), math="fp32"):
+    def __init__(self, ctx, trainable=(), math="fp32", sample_offset=0):
         self.ctx, self.math = ctx, math
         self.nodes = []
+        # dropout masks are keyed by (seed, trace step, node, global element index)
+        self.rng_seed = _rng["seed"]
+        self.rng_step = _rng["step"]
+        _rng["step"] += 1
+        self.sample_offset = int(sample_offset)
         self.trainable = {id(p): i for i, p in enumerate(trainable)}  # id(leaf) -> index in vec(m) order
         self._leaf_nodes = {}
 
@@ -171,13 +183,18 @@ def softmax(x):
     return Tensor(tr, "softmax", (x,), x.shape, x.dtype)
 
 
-def dropout(x, p):
-    """src/layers.jl:118-124.  Identity outside training mode; training-mode masks are SURVEY §8(f)#1."""
+def dropout(x, p, dims=None):
+    """src/layers.jl:118-132.  Identity outside training mode; in training mode y = x .* mask with
+    mask = rand > p ? T(1/(1-p)) : 0, regenerated (not stored) for the pullback.  Julia's task-local
+    Xoshiro stream is not reproduced: parity is statistical (keep rate, scale) plus exact
+    forward/backward mask agreement."""
     from . import is_training_mode
     tr = _tr(x); x = tr.lift(x)
-    if is_training_mode() and p > 0:
-        raise NotImplementedError("training-mode dropout is not on the B200 path yet (SURVEY.md §8(f) #1); use p = 0 or eval mode")
-    return x
+    if not is_training_mode() or p <= 0:
+        return x
+    if dims is not None:
+        raise NotImplementedError("Dropout with dims other than `:` is not on the B200 path")
+    return Tensor(tr, "dropout", (x,), x.shape, x.dtype, {"p": float(p)})
 
 
 def cross_entropy(probs, label, global_batch=None):
@@ -236,6 +253,8 @@ def _sig(trace, root):
             extra = (a["k"],)
         elif n.op == "mse":
             extra = (a["denom"],)
+        elif n.op == "dropout":
+            extra = (a["p"],)
         elif n.op == "cross_entropy":
             extra = (a["global_batch"],)
         parts.append((n.op, n.shape, n.dtype.str, tuple(i.id for i in n.inputs), extra))
@@ -362,7 +381,7 @@ class Plan:
             elif op == "relu":
                 src = self.fused_into.get(i)
                 self.vals[i] = self._new(self.shapes[i], self._act_dtype(src) if src is not None else self.dtypes[i])
-            elif op in ("maxpool", "meanpool"):
+            elif op in ("maxpool", "meanpool", "dropout"):
                 self.vals[i] = self._new(self.shapes[i], self.dtypes[i])
             elif op == "softmax":
                 if i not in self.sce_softmax:
@@ -457,6 +476,13 @@ class Plan:
             self._cast_done.add(b)
         return buf.reshape(v.shape)
 
+    def _dropout(self, i, src, dst):
+        rows = self.shapes[i][0] if self.shapes[i] else 1
+        per_sample = src.size // max(rows, 1)
+        stream_id = ((self._rng_step & 0xFFFFF) << 12) | (i & 0xFFF)
+        call("pg_dropout", self.ctx.h, dtype_code(self.dtypes[i]), src.ptr, dst.ptr, src.size, self.attrs[i]["p"],
+             self._rng_seed, stream_id, self._sample_offset * per_sample)
+
     def _f(self, i):
         """value of node i for a non-tensor-core op: must not be a bf16 activation"""
         v = self._val(i)
@@ -466,6 +492,7 @@ class Plan:
 
     # ---- forward -------------------------------------------------------------------------------
     def forward(self, trace):
+        self._rng_seed, self._rng_step, self._sample_offset = trace.rng_seed, trace.rng_step, trace.sample_offset
         self._bind(trace)
         self._fresh, self._cast_done = set(), set()
         h = self.ctx.h
@@ -502,6 +529,8 @@ class Plan:
             elif op in ("maxpool", "meanpool"):
                 N_, C, H, W_ = self.shapes[ins[0]]
                 call("pg_%s2d_fwd" % op, h, code, self._f(ins[0]).ptr, self.vals[i].ptr, N_ * C, H, W_, self.attrs[i]["k"])
+            elif op == "dropout":
+                self._dropout(i, self._f(ins[0]), self.vals[i])
             elif op == "softmax":
                 if i in self.sce_softmax:
                     continue
@@ -595,6 +624,11 @@ class Plan:
                     call("pg_maxpool2d_bwd", h, code, self._val(x).ptr, self.grads[i].ptr, gx.ptr, N_ * C, H, W_, self.attrs[i]["k"])
                 else:
                     call("pg_meanpool2d_bwd", h, code, self.grads[i].ptr, gx.ptr, N_ * C, H, W_, self.attrs[i]["k"])
+            elif op == "dropout":
+                g, gx = self.grads[i], self._grad(ins[0])
+                if g.dtype == BF16 or gx.dtype == BF16:
+                    raise NotImplementedError("training-mode dropout next to a bf16 tensor-core layer: use math='fp32'")
+                self._dropout(i, g, gx)      # same (seed, step, node, element) key -> same mask
             elif op == "softmax":
                 if i in self.sce_softmax:
                     continue  # dZ was written by the fused loss kernel
