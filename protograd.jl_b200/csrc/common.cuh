@@ -64,6 +64,11 @@ int pg_ws_ensure(pg_ctx* ctx, size_t bytes);  // grow scratch (fails during grap
 // column sums out[n] = sum_m X[m][n]; in_dtype f32/f64 (out same type) or bf16 (out f32)
 int pg_colsum_launch(pg_ctx* ctx, int in_dtype, const void* X, void* out, int64_t M, int64_t N);
 
+// shared-memory-tiled direct convolutions (conv_tiled.cu): 1 = handled, 0 = shape outside envelope, <0 = error
+template <typename T> int pg_conv_fwd_tiled(pg_ctx* ctx, const T* x, const T* w, const T* b, T* y, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW, int act);
+template <typename T> int pg_conv_dgrad_tiled(pg_ctx* ctx, const T* dy, const T* w, T* dx, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW);
+template <typename T> int pg_conv_wgrad_tiled(pg_ctx* ctx, const T* x, const T* dy, T* dw, T* db, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW);
+
 static inline int64_t pg_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers ------------------------------------------------------------------------

@@ -231,6 +231,10 @@ int conv_fwd_t(pg_ctx* ctx, const T* x, const T* w, const T* b, T* y, int64_t N,
   const int Ho = H - kH + 1, Wo = W - kW + 1;
   int64_t total = N * Ho * Wo;
   if (total <= 0) return PG_OK;
+  {
+    int r = pg_conv_fwd_tiled<T>(ctx, x, w, b, y, N, Cin, H, W, Cout, kH, kW, act);
+    if (r != 0) return r < 0 ? r : PG_OK;
+  }
   size_t wbytes = (size_t)COT * Cin * kH * kW * sizeof(T);
   int in_smem = wbytes <= 48 * 1024;
   dim3 grid(grid_for(ctx, total), (unsigned)pg_cdiv(Cout, COT));
@@ -275,7 +279,13 @@ int conv_wgrad_t(pg_ctx* ctx, const T* x, const T* dy, T* dw, T* db, int64_t N, 
 template <typename T>
 int conv_bwd_t(pg_ctx* ctx, const T* x, const T* w, const T* dy, T* dw, T* db, T* dx, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW) {
   int rc = PG_OK;
-  if (dw || db) {
+  bool wgrad_done = false;
+  if ((dw || db) && N > 0) {
+    int r = pg_conv_wgrad_tiled<T>(ctx, x, dy, dw, db, N, Cin, H, W, Cout, kH, kW);
+    if (r < 0) return r;
+    wgrad_done = r == 1;
+  }
+  if ((dw || db) && !wgrad_done) {
     PG_REQUIRE(kH == kW, "conv weight gradient supports square filters only");
     switch (kH) {
       case 1: rc = conv_wgrad_t<T, 1>(ctx, x, dy, dw, db, N, Cin, H, W, Cout); break;
@@ -292,7 +302,9 @@ int conv_bwd_t(pg_ctx* ctx, const T* x, const T* w, const T* dy, T* dw, T* db, T
   }
   if (dx) {
     int64_t total = N * Cin * H * W;
-    if (total > 0) {
+    int r = total > 0 ? pg_conv_dgrad_tiled<T>(ctx, dy, w, dx, N, Cin, H, W, Cout, kH, kW) : 1;
+    if (r < 0) return r;
+    if (total > 0 && r == 0) {
       conv_dgrad_kernel<T><<<grid_for(ctx, total), 256, 0, ctx->stream>>>(dy, w, dx, N, Cin, H, W, Cout, kH, kW);
       PG_LAUNCHED(ctx);
     }
