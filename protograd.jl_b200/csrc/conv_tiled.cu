@@ -155,13 +155,13 @@ conv_dgrad_tiled_kernel(const T* __restrict__ dy, const T* __restrict__ w, T* __
 template <typename T, int KS>
 __global__ void __launch_bounds__(256)
 conv_wgrad_tiled_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dw_part, T* __restrict__ db_part,
-                        int N, int Cin, int H, int W, int Cout, int SPB, int RG, int samples_per_block) {
+                        int N, int Cin, int H, int W, int Cout, int SPB, int RG, int SB, int samples_per_block) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int Ho = H - KS + 1, Wo = W - KS + 1, chw = Cin * H * W, ych = Cout * Ho * Wo;
   const int nitem = Cout * Cin * KS;            // (co, ci, a)
-  T* xs = reinterpret_cast<T*>(smem_raw);       // [SPB][chw]
-  T* dys = xs + SPB * chw;                      // [SPB][ych]
-  T* red = dys + SPB * ych;                     // [nitem][KS + 1]  (block result, accumulated with atomics in smem)
+  T* xs = reinterpret_cast<T*>(smem_raw);       // [SB][chw]   SB staged samples per iteration
+  T* dys = xs + SB * chw;                       // [SB][ych]
+  T* red = dys + SB * ych;                     // [nitem][KS + 1]  (block result, accumulated with atomics in smem)
   for (int i = threadIdx.x; i < nitem * (KS + 1); i += blockDim.x) red[i] = T(0);
   // thread -> (slot, item, row-group).  nitem <= 256: one item per thread, RG row-groups, SPB sample slots.
   // nitem > 256: RG = SPB = 1 and each thread owns up to NI = ceil(nitem / 256) items (it, it + 256, ...).
@@ -183,22 +183,23 @@ conv_wgrad_tiled_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __
   }
   const int nb0 = blockIdx.x * samples_per_block;
   const int nb1 = min(N, nb0 + samples_per_block);
-  for (int n0 = nb0; n0 < nb1; n0 += SPB) {
-    const int ns = min(SPB, nb1 - n0);
+  for (int n0 = nb0; n0 < nb1; n0 += SB) {
+    const int ns = min(SB, nb1 - n0);
     __syncthreads();
     const T* xg = x + (size_t)n0 * chw;
     for (int i = threadIdx.x; i < ns * chw; i += blockDim.x) xs[i] = xg[i];
     const T* dg = dy + (size_t)n0 * ych;
     for (int i = threadIdx.x; i < ns * ych; i += blockDim.x) dys[i] = dg[i];
     __syncthreads();
-    if (live && slot < ns) {
+    if (live)
+    for (int sm_i = slot; sm_i < ns; sm_i += SPB) {     // this slot's samples among the staged ones
 #pragma unroll
       for (int p = 0; p < NIMAX; ++p) {
         const int it = it0 + p * 256;
         if (p < NI && it < nitem) {
           const int co = it / (Cin * KS), ci = (it / KS) % Cin, a = it % KS;
-          const T* xsamp = xs + slot * chw + (ci * H + KS - 1 - a) * W;
-          const T* dsamp = dys + slot * ych + co * Ho * Wo;
+          const T* xsamp = xs + sm_i * chw + (ci * H + KS - 1 - a) * W;
+          const T* dsamp = dys + sm_i * ych + co * Ho * Wo;
           const bool do_db = (ci == 0 && a == 0);
           for (int i = rg; i < Ho; i += RG) {
             for (int j0 = 0; j0 < Wo; j0 += JB) {
@@ -245,9 +246,14 @@ template <typename T>
 __global__ void __launch_bounds__(256) reduce_blocks_kernel(const T* __restrict__ part, T* __restrict__ out, int64_t n, int blocks) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  T s = T(0);
-  for (int z = 0; z < blocks; ++z) s += part[(int64_t)z * n + i];
-  out[i] = s;
+  T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+  int z = 0;
+  for (; z + 3 < blocks; z += 4) {
+    s0 += part[(int64_t)z * n + i]; s1 += part[(int64_t)(z + 1) * n + i];
+    s2 += part[(int64_t)(z + 2) * n + i]; s3 += part[(int64_t)(z + 3) * n + i];
+  }
+  for (; z < blocks; ++z) s0 += part[(int64_t)z * n + i];
+  out[i] = (s0 + s1) + (s2 + s3);
 }
 
 template <typename K>
@@ -264,17 +270,17 @@ int fwd_launch(pg_ctx* ctx, const T* x, const T* w, const T* b, T* y, int64_t N,
   const size_t wfl = ((size_t)Cout * Cin * KS * KS + 3) & ~(size_t)3;
   const size_t per_sample = (size_t)Cin * H * W * sizeof(T);
   if (wfl * sizeof(T) + per_sample > SMEM_CAP) return 0;
-  int SPB = 256 / IPS;
-  if (SPB < 1) SPB = 1;
-  const int cap = (int)((SMEM_CAP - wfl * sizeof(T)) / per_sample);
-  if (SPB > cap) SPB = cap;
+  // fat iterations: stage as many whole samples as fit (<= 32) so the coalesced global loads of one
+  // iteration are deep enough to hide HBM latency and the two barriers amortise over many passes
+  int SPB = (int)((SMEM_CAP - wfl * sizeof(T)) / per_sample);
   if (SPB > 32) SPB = 32;
+  if (SPB < 1) SPB = 1;
   const size_t smem = wfl * sizeof(T) + (size_t)SPB * per_sample;
   auto kern = conv_fwd_tiled_kernel<T, KS>;
   int rc = set_smem(kern, smem);
   if (rc != PG_OK) return rc;
   int64_t groups = pg_cdiv(N, SPB);
-  int blocks = (int)(groups < 2 * (int64_t)ctx->num_sms ? groups : 2 * (int64_t)ctx->num_sms);
+  int blocks = (int)(groups < (int64_t)ctx->num_sms ? groups : (int64_t)ctx->num_sms);
   kern<<<blocks, 256, smem, ctx->stream>>>(x, w, b, y, (int)N, Cin, H, W, Cout, act == PG_ACT_RELU, SPB, IPS, SEG, (int)wfl);
   ctx->launches++;
   PG_CHECK_CUDA(cudaGetLastError());
@@ -289,17 +295,15 @@ int dgrad_launch(pg_ctx* ctx, const T* dy, const T* w, T* dx, int64_t N, int Cin
   const size_t wfl = ((size_t)Cout * Cin * KS * KS + 3) & ~(size_t)3;
   const size_t per_sample = (size_t)Cout * Hp * Wp * sizeof(T);
   if (wfl * sizeof(T) + per_sample > SMEM_CAP) return 0;
-  int SPB = 256 / IPS;
-  if (SPB < 1) SPB = 1;
-  const int cap = (int)((SMEM_CAP - wfl * sizeof(T)) / per_sample);
-  if (SPB > cap) SPB = cap;
+  int SPB = (int)((SMEM_CAP - wfl * sizeof(T)) / per_sample);
   if (SPB > 32) SPB = 32;
+  if (SPB < 1) SPB = 1;
   const size_t smem = wfl * sizeof(T) + (size_t)SPB * per_sample;
   auto kern = conv_dgrad_tiled_kernel<T, KS>;
   int rc = set_smem(kern, smem);
   if (rc != PG_OK) return rc;
   int64_t groups = pg_cdiv(N, SPB);
-  int blocks = (int)(groups < 2 * (int64_t)ctx->num_sms ? groups : 2 * (int64_t)ctx->num_sms);
+  int blocks = (int)(groups < (int64_t)ctx->num_sms ? groups : (int64_t)ctx->num_sms);
   kern<<<blocks, 256, smem, ctx->stream>>>(dy, w, dx, (int)N, Cin, H, W, Cout, SPB, IPS, SEG, (int)wfl);
   ctx->launches++;
   PG_CHECK_CUDA(cudaGetLastError());
@@ -320,11 +324,13 @@ int wgrad_launch(pg_ctx* ctx, const T* x, const T* dy, T* dw, T* db, int64_t N, 
   if (RG < 1) RG = 1;
   int SPB = nitem > 256 ? 1 : 256 / (nitem * RG);
   if (SPB < 1) SPB = 1;
-  const int cap = (int)((SMEM_CAP - red_bytes) / per_sample);
-  if (SPB > cap) SPB = cap;
-  const size_t smem = (size_t)SPB * per_sample + red_bytes;
-  int blocks = (int)(pg_cdiv(N, SPB) < 4 * (int64_t)ctx->num_sms ? pg_cdiv(N, SPB) : 4 * (int64_t)ctx->num_sms);
-  int spb_total = (int)(pg_cdiv(pg_cdiv(N, blocks), SPB) * SPB);   // samples per block, multiple of SPB
+  int SB = (int)((SMEM_CAP - red_bytes) / per_sample);         // staged samples per iteration
+  if (SB > 32) SB = 32;
+  if (SB < SPB) SPB = SB;
+  SB = SB / SPB * SPB;
+  const size_t smem = (size_t)SB * per_sample + red_bytes;
+  int blocks = (int)(pg_cdiv(N, SB) < (int64_t)ctx->num_sms ? pg_cdiv(N, SB) : (int64_t)ctx->num_sms);
+  int spb_total = (int)(pg_cdiv(pg_cdiv(N, blocks), SB) * SB);   // samples per block, multiple of SB
   blocks = (int)pg_cdiv(N, spb_total);
   const size_t nw = (size_t)nitem * KS;
   int rc = pg_ws_ensure(ctx, (size_t)blocks * (nw + Cout) * sizeof(T));
@@ -334,7 +340,7 @@ int wgrad_launch(pg_ctx* ctx, const T* x, const T* dy, T* dw, T* db, int64_t N, 
   auto kern = conv_wgrad_tiled_kernel<T, KS>;
   rc = set_smem(kern, smem);
   if (rc != PG_OK) return rc;
-  kern<<<blocks, 256, smem, ctx->stream>>>(x, dy, dw_part, db ? db_part : nullptr, (int)N, Cin, H, W, Cout, SPB, RG, spb_total);
+  kern<<<blocks, 256, smem, ctx->stream>>>(x, dy, dw_part, db ? db_part : nullptr, (int)N, Cin, H, W, Cout, SPB, RG, SB, spb_total);
   ctx->launches++;
   PG_CHECK_CUDA(cudaGetLastError());
   if (dw) {
