@@ -131,6 +131,8 @@ int pg_conv2d_bwd(pg_ctx* ctx, int dtype, const void* x, const void* w, const vo
                   int64_t N, int Cin, int H, int W, int Cout, int kH, int kW);
 int pg_maxpool2d_fwd(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t NC, int H, int W, int k);
 int pg_maxpool2d_bwd(pg_ctx* ctx, int dtype, const void* x, const void* dy, void* dx, int64_t NC, int H, int W, int k);
+/* same, fused with relu' of the pool input (x = a ReLU output): dx is the gradient w.r.t. the pre-activation */
+int pg_maxpool2d_relu_bwd(pg_ctx* ctx, int dtype, const void* x, const void* dy, void* dx, int64_t NC, int H, int W, int k, int relu);
 int pg_meanpool2d_fwd(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t NC, int H, int W, int k);
 int pg_meanpool2d_bwd(pg_ctx* ctx, int dtype, const void* dy, void* dx, int64_t NC, int H, int W, int k);
 /* dropout in training mode (layers.jl:109-138): y = x .* mask, mask_i = rand_i > p ? T(1/(1-p)) : 0.

@@ -78,6 +78,7 @@ _SIGS = {
     "pg_conv2d_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I],
     "pg_maxpool2d_fwd": [_P, _I, _P, _P, _L, _I, _I, _I],
     "pg_maxpool2d_bwd": [_P, _I, _P, _P, _P, _L, _I, _I, _I],
+    "pg_maxpool2d_relu_bwd": [_P, _I, _P, _P, _P, _L, _I, _I, _I, _I],
     "pg_meanpool2d_fwd": [_P, _I, _P, _P, _L, _I, _I, _I],
     "pg_meanpool2d_bwd": [_P, _I, _P, _P, _L, _I, _I, _I],
     "pg_dropout": [_P, _I, _P, _P, _L, _D, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64],

@@ -158,9 +158,12 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ 
   }
 }
 
-// dx must be zero-filled beforehand (border rows/cols outside any window stay zero)
+// Writes every element of each window (dy at the FIRST max, 0 elsewhere); border rows/cols outside any
+// window must be zero-filled beforehand when H or W is not a multiple of k.  relu != 0 additionally
+// applies relu' of the pool's input (a fused conv+ReLU output): the routed gradient is kept only where
+// the max itself is > 0, which equals relu'(x) at the arg-max.
 template <typename T>
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int64_t NC, int H, int W, int k) {
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int64_t NC, int H, int W, int k, int relu) {
   const int Ho = (H - k) / k + 1, Wo = (W - k) / k + 1;
   const int64_t total = NC * Ho * Wo;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -172,7 +175,9 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
     int am = 0;
     for (int a = 0; a < k; ++a)
       for (int b = 0; b < k; ++b) { T v = xp[a * W + b]; if (v > m) { m = v; am = a * W + b; } }  // strict >: first max wins
-    dx[base + am] = dy[idx];
+    const T g = (relu && !(m > T(0))) ? T(0) : dy[idx];
+    for (int a = 0; a < k; ++a)
+      for (int b = 0; b < k; ++b) dx[base + a * W + b] = (a * W + b == am) ? g : T(0);
   }
 }
 
@@ -348,13 +353,18 @@ int pg_maxpool2d_fwd(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t NC,
 }
 
 int pg_maxpool2d_bwd(pg_ctx* ctx, int dtype, const void* x, const void* dy, void* dx, int64_t NC, int H, int W, int k) {
+  return pg_maxpool2d_relu_bwd(ctx, dtype, x, dy, dx, NC, H, W, k, 0);
+}
+
+int pg_maxpool2d_relu_bwd(pg_ctx* ctx, int dtype, const void* x, const void* dy, void* dx, int64_t NC, int H, int W, int k, int relu) {
   PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
   PG_REQUIRE(x && dy && dx && k >= 1 && H >= k && W >= k, "bad pool geometry");
   int64_t total = NC * ((H - k) / k + 1) * ((W - k) / k + 1);
   if (total <= 0) return PG_OK;
-  PG_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)NC * H * W * (dtype == PG_F64 ? 8 : 4), ctx->stream));
-  DISPATCH_T((maxpool_bwd_kernel<float><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const float*)x, (const float*)dy, (float*)dx, NC, H, W, k)),
-             (maxpool_bwd_kernel<double><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const double*)x, (const double*)dy, (double*)dx, NC, H, W, k)));
+  if (H % k != 0 || W % k != 0)   // windows do not tile the plane: rows/cols outside any window get zero gradient
+    PG_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)NC * H * W * (dtype == PG_F64 ? 8 : 4), ctx->stream));
+  DISPATCH_T((maxpool_bwd_kernel<float><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const float*)x, (const float*)dy, (float*)dx, NC, H, W, k, relu)),
+             (maxpool_bwd_kernel<double><<<grid_for(ctx, total), 256, 0, ctx->stream>>>((const double*)x, (const double*)dy, (double*)dx, NC, H, W, k, relu)));
   PG_LAUNCHED(ctx);
   return PG_OK;
 }

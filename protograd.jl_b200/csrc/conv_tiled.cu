@@ -20,7 +20,7 @@ constexpr int CIB = 8;   // input channels per thread (data gradient)
 constexpr size_t SMEM_CAP = 100 * 1024;
 
 template <typename T, int KS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
 conv_fwd_tiled_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b, T* __restrict__ y,
                       int N, int Cin, int H, int W, int Cout, int relu, int SPB, int IPS, int SEG, int woff) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -85,7 +85,7 @@ conv_fwd_tiled_kernel(const T* __restrict__ x, const T* __restrict__ w, const T*
 }
 
 template <typename T, int KS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
 conv_dgrad_tiled_kernel(const T* __restrict__ dy, const T* __restrict__ w, T* __restrict__ dx,
                         int N, int Cin, int H, int W, int Cout, int SPB, int IPS, int SEG, int woff) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -153,7 +153,7 @@ conv_dgrad_tiled_kernel(const T* __restrict__ dy, const T* __restrict__ w, T* __
 // weight gradient: thread item = (co, ci, a, row-group rg); it accumulates dw[co][ci][a][0..KS) over the
 // rows i = rg, rg+RG, ... of every sample of its slot; slots and row-groups are summed at the end.
 template <typename T, int KS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
 conv_wgrad_tiled_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dw_part, T* __restrict__ db_part,
                         int N, int Cin, int H, int W, int Cout, int SPB, int RG, int SB, int samples_per_block) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -270,17 +270,20 @@ int fwd_launch(pg_ctx* ctx, const T* x, const T* w, const T* b, T* y, int64_t N,
   const size_t wfl = ((size_t)Cout * Cin * KS * KS + 3) & ~(size_t)3;
   const size_t per_sample = (size_t)Cin * H * W * sizeof(T);
   if (wfl * sizeof(T) + per_sample > SMEM_CAP) return 0;
-  // fat iterations: stage as many whole samples as fit (<= 32) so the coalesced global loads of one
-  // iteration are deep enough to hide HBM latency and the two barriers amortise over many passes
-  int SPB = (int)((SMEM_CAP - wfl * sizeof(T)) / per_sample);
-  if (SPB > 32) SPB = 32;
+  // enough samples per iteration to give every thread one item; small tiles keep several blocks
+  // resident per SM so one block's load phase overlaps another's compute phase (measured: staging 32
+  // samples with one block per SM was 1.3-3x slower, profiles/r1_launches_c3_b8192_v3_fat.csv)
+  int SPB = 256 / IPS;
+  if (SPB < 1) SPB = 1;
+  const int cap = (int)((SMEM_CAP / 2 - wfl * sizeof(T)) / per_sample);
+  if (SPB > cap) SPB = cap;
   if (SPB < 1) SPB = 1;
   const size_t smem = wfl * sizeof(T) + (size_t)SPB * per_sample;
   auto kern = conv_fwd_tiled_kernel<T, KS>;
   int rc = set_smem(kern, smem);
   if (rc != PG_OK) return rc;
   int64_t groups = pg_cdiv(N, SPB);
-  int blocks = (int)(groups < (int64_t)ctx->num_sms ? groups : (int64_t)ctx->num_sms);
+  int blocks = (int)(groups < 4 * (int64_t)ctx->num_sms ? groups : 4 * (int64_t)ctx->num_sms);
   kern<<<blocks, 256, smem, ctx->stream>>>(x, w, b, y, (int)N, Cin, H, W, Cout, act == PG_ACT_RELU, SPB, IPS, SEG, (int)wfl);
   ctx->launches++;
   PG_CHECK_CUDA(cudaGetLastError());
@@ -295,15 +298,17 @@ int dgrad_launch(pg_ctx* ctx, const T* dy, const T* w, T* dx, int64_t N, int Cin
   const size_t wfl = ((size_t)Cout * Cin * KS * KS + 3) & ~(size_t)3;
   const size_t per_sample = (size_t)Cout * Hp * Wp * sizeof(T);
   if (wfl * sizeof(T) + per_sample > SMEM_CAP) return 0;
-  int SPB = (int)((SMEM_CAP - wfl * sizeof(T)) / per_sample);
-  if (SPB > 32) SPB = 32;
+  int SPB = 256 / IPS;
+  if (SPB < 1) SPB = 1;
+  const int cap = (int)((SMEM_CAP / 2 - wfl * sizeof(T)) / per_sample);
+  if (SPB > cap) SPB = cap;
   if (SPB < 1) SPB = 1;
   const size_t smem = wfl * sizeof(T) + (size_t)SPB * per_sample;
   auto kern = conv_dgrad_tiled_kernel<T, KS>;
   int rc = set_smem(kern, smem);
   if (rc != PG_OK) return rc;
   int64_t groups = pg_cdiv(N, SPB);
-  int blocks = (int)(groups < (int64_t)ctx->num_sms ? groups : (int64_t)ctx->num_sms);
+  int blocks = (int)(groups < 4 * (int64_t)ctx->num_sms ? groups : 4 * (int64_t)ctx->num_sms);
   kern<<<blocks, 256, smem, ctx->stream>>>(dy, w, dx, (int)N, Cin, H, W, Cout, SPB, IPS, SEG, (int)wfl);
   ctx->launches++;
   PG_CHECK_CUDA(cudaGetLastError());
@@ -324,12 +329,12 @@ int wgrad_launch(pg_ctx* ctx, const T* x, const T* dy, T* dw, T* db, int64_t N, 
   if (RG < 1) RG = 1;
   int SPB = nitem > 256 ? 1 : 256 / (nitem * RG);
   if (SPB < 1) SPB = 1;
-  int SB = (int)((SMEM_CAP - red_bytes) / per_sample);         // staged samples per iteration
-  if (SB > 32) SB = 32;
+  int SB = (int)((SMEM_CAP / 2 - red_bytes) / per_sample);     // staged samples per iteration
+  if (SB < 1) SB = 1;
   if (SB < SPB) SPB = SB;
-  SB = SB / SPB * SPB;
+  SB = SPB;                                                    // one sample per slot and iteration (several blocks per SM)
   const size_t smem = (size_t)SB * per_sample + red_bytes;
-  int blocks = (int)(pg_cdiv(N, SB) < (int64_t)ctx->num_sms ? pg_cdiv(N, SB) : (int64_t)ctx->num_sms);
+  int blocks = (int)(pg_cdiv(N, SB) < 4 * (int64_t)ctx->num_sms ? pg_cdiv(N, SB) : 4 * (int64_t)ctx->num_sms);
   int spb_total = (int)(pg_cdiv(pg_cdiv(N, blocks), SB) * SB);   // samples per block, multiple of SB
   blocks = (int)pg_cdiv(N, spb_total);
   const size_t nw = (size_t)nitem * KS;

@@ -353,8 +353,10 @@ class Plan:
         return i
 
     def _premasked(self, r):
+        """consumers that apply relu' of their input themselves: Linear (dX epilogue mask) and maxpool
+        (routes the gradient only where the window max is > 0)"""
         c = self._through_reshape_down(r)
-        return c is not None and self.ops[c] == "linear"
+        return c is not None and self.ops[c] in ("linear", "maxpool")
 
     def _consumer_is_tc_linear(self, i):
         c = self._through_reshape_down(i)
@@ -621,7 +623,8 @@ class Plan:
                 N_, C, H, W_ = self.shapes[x]
                 gx = self._grad(x)
                 if op == "maxpool":
-                    call("pg_maxpool2d_bwd", h, code, self._val(x).ptr, self.grads[i].ptr, gx.ptr, N_ * C, H, W_, self.attrs[i]["k"])
+                    fuse_relu = 1 if self.ops[self._base(x)] == "relu" else 0
+                    call("pg_maxpool2d_relu_bwd", h, code, self._val(x).ptr, self.grads[i].ptr, gx.ptr, N_ * C, H, W_, self.attrs[i]["k"], fuse_relu)
                 else:
                     call("pg_meanpool2d_bwd", h, code, self.grads[i].ptr, gx.ptr, N_ * C, H, W_, self.attrs[i]["k"])
             elif op == "dropout":
