@@ -85,7 +85,7 @@ conv_fwd_tiled_kernel(const T* __restrict__ x, const T* __restrict__ w, const T*
 }
 
 template <typename T, int KS>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
+__global__ void __launch_bounds__(256)
 conv_dgrad_tiled_kernel(const T* __restrict__ dy, const T* __restrict__ w, T* __restrict__ dx,
                         int N, int Cin, int H, int W, int Cout, int SPB, int IPS, int SEG, int woff) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -153,7 +153,7 @@ conv_dgrad_tiled_kernel(const T* __restrict__ dy, const T* __restrict__ w, T* __
 // weight gradient: thread item = (co, ci, a, row-group rg); it accumulates dw[co][ci][a][0..KS) over the
 // rows i = rg, rg+RG, ... of every sample of its slot; slots and row-groups are summed at the end.
 template <typename T, int KS>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
+__global__ void __launch_bounds__(256)
 conv_wgrad_tiled_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dw_part, T* __restrict__ db_part,
                         int N, int Cin, int H, int W, int Cout, int SPB, int RG, int SB, int samples_per_block) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -242,18 +242,24 @@ conv_wgrad_tiled_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __
     for (int c = threadIdx.x; c < Cout; c += blockDim.x) db_part[(size_t)blockIdx.x * Cout + c] = red[(c * Cin * KS) * (KS + 1) + KS];
 }
 
+// out[i] = sum_z part[z][i]: 64 outputs x 4 z-lanes per block, 4 independent accumulators per thread
 template <typename T>
 __global__ void __launch_bounds__(256) reduce_blocks_kernel(const T* __restrict__ part, T* __restrict__ out, int64_t n, int blocks) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  __shared__ T sm[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int64_t i = (int64_t)blockIdx.x * 64 + tx;
   T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
-  int z = 0;
-  for (; z + 3 < blocks; z += 4) {
-    s0 += part[(int64_t)z * n + i]; s1 += part[(int64_t)(z + 1) * n + i];
-    s2 += part[(int64_t)(z + 2) * n + i]; s3 += part[(int64_t)(z + 3) * n + i];
+  if (i < n) {
+    int z = ty;
+    for (; z + 12 < blocks; z += 16) {
+      s0 += part[(int64_t)z * n + i]; s1 += part[(int64_t)(z + 4) * n + i];
+      s2 += part[(int64_t)(z + 8) * n + i]; s3 += part[(int64_t)(z + 12) * n + i];
+    }
+    for (; z < blocks; z += 4) s0 += part[(int64_t)z * n + i];
   }
-  for (; z < blocks; ++z) s0 += part[(int64_t)z * n + i];
-  out[i] = (s0 + s1) + (s2 + s3);
+  sm[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && i < n) out[i] = (sm[0][tx] + sm[1][tx]) + (sm[2][tx] + sm[3][tx]);
 }
 
 template <typename K>
@@ -349,11 +355,11 @@ int wgrad_launch(pg_ctx* ctx, const T* x, const T* dy, T* dw, T* db, int64_t N, 
   ctx->launches++;
   PG_CHECK_CUDA(cudaGetLastError());
   if (dw) {
-    reduce_blocks_kernel<T><<<(unsigned)pg_cdiv((int64_t)nw, 256), 256, 0, ctx->stream>>>(dw_part, dw, (int64_t)nw, blocks);
+    reduce_blocks_kernel<T><<<(unsigned)pg_cdiv((int64_t)nw, 64), 256, 0, ctx->stream>>>(dw_part, dw, (int64_t)nw, blocks);
     ctx->launches++;
   }
   if (db) {
-    reduce_blocks_kernel<T><<<(unsigned)pg_cdiv(Cout, 256), 256, 0, ctx->stream>>>(db_part, db, Cout, blocks);
+    reduce_blocks_kernel<T><<<(unsigned)pg_cdiv(Cout, 64), 256, 0, ctx->stream>>>(db_part, db, Cout, blocks);
     ctx->launches++;
   }
   PG_CHECK_CUDA(cudaGetLastError());

@@ -125,15 +125,21 @@ class PinnedBuffer:
 class DeviceArray:
     """A typed, shaped view into a DeviceBuffer (a Model leaf, an activation, an input batch)."""
 
-    __slots__ = ("buf", "offset", "shape", "dtype", "__weakref__")
+    __slots__ = ("buf", "offset", "shape", "dtype", "size", "__weakref__")
 
     def __init__(self, buf, offset, shape, dtype):
         self.buf, self.offset, self.shape = buf, int(offset), tuple(int(s) for s in shape)
         self.dtype = dtype if dtype == BF16 else np.dtype(dtype)
+        n = 1
+        for d in self.shape:
+            n *= d
+        self.size = n
 
     @classmethod
     def empty(cls, ctx, shape, dtype, zero=True):
-        n = int(np.prod(shape)) if len(shape) else 1
+        n = 1
+        for d in shape:
+            n *= int(d)
         return cls(DeviceBuffer(ctx, n * itemsize(dtype), zero), 0, shape, dtype)
 
     @classmethod
@@ -150,10 +156,6 @@ class DeviceArray:
     @property
     def ptr(self):
         return self.buf.ptr + self.offset
-
-    @property
-    def size(self):
-        return int(np.prod(self.shape)) if len(self.shape) else 1
 
     @property
     def nbytes(self):

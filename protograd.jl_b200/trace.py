@@ -17,6 +17,13 @@ from . import capi
 from .capi import ACT_NONE, ACT_RELU, PG_BF16, PG_F32, call
 from .device import BF16, Context, DeviceArray, DeviceBuffer, dtype_code, is_pinned
 
+def _prod(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
 _current = None  # the Trace being recorded (set by eval_with_pullback / forward)
 _rng = {"seed": 0x5EED5EED, "step": 0}
 
@@ -28,17 +35,17 @@ def seed(s):
 
 
 class Tensor:
-    __slots__ = ("trace", "id", "op", "inputs", "shape", "dtype", "attrs")
+    __slots__ = ("trace", "id", "op", "inputs", "shape", "dtype", "attrs", "size")
 
     def __init__(self, trace, op, inputs, shape, dtype, attrs=None):
         self.trace, self.op, self.inputs = trace, op, tuple(inputs)
         self.shape, self.dtype, self.attrs = tuple(int(s) for s in shape), np.dtype(dtype), attrs or {}
+        n = 1
+        for d in self.shape:
+            n *= d
+        self.size = n
         self.id = len(trace.nodes)
         trace.nodes.append(self)
-
-    @property
-    def size(self):
-        return int(np.prod(self.shape)) if self.shape else 1
 
     def reshape(self, *shape):
         return reshape(self, *shape)
@@ -510,7 +517,7 @@ class Plan:
             if op == "linear":
                 x, W, b = ins
                 K, N = self.shapes[W]
-                M = int(np.prod(self.shapes[x][:-1]))
+                M = _prod(self.shapes[x][:-1])
                 act = ACT_RELU if i in self.fused_act else ACT_NONE
                 out = self._val(i)
                 if self.math == "bf16":
@@ -541,7 +548,7 @@ class Plan:
             elif op == "cross_entropy":
                 p, y = ins
                 C = self.shapes[p][-1]
-                B = int(np.prod(self.shapes[p][:-1]))
+                B = _prod(self.shapes[p][:-1])
                 gb = self.attrs[i]["global_batch"] or B
                 if i in self.fused_sce:
                     z = self.inputs[self.fused_sce[i]][0]
@@ -552,7 +559,7 @@ class Plan:
                     call("pg_cross_entropy_fwd_bwd", h, code, self._f(p).ptr, self._f(y).ptr, P(dp), self.vals[i].ptr, B, C, 1.0 / gb)
             elif op == "mse":
                 yh, y = ins
-                n_el = int(np.prod(self.shapes[yh]))
+                n_el = _prod(self.shapes[yh])
                 denom = self.attrs[i]["denom"] or n_el
                 dy = self._grad(yh) if self.ng[yh] else None
                 call("pg_mse_fwd_bwd", h, code, self._f(yh).ptr, self._f(y).ptr, P(dy), self.vals[i].ptr, n_el, 1.0 / denom)
@@ -586,7 +593,7 @@ class Plan:
                 gx = self._grad(x) if self.ng[x] else None
                 if op == "linear":
                     K, N = self.shapes[W]
-                    M = int(np.prod(self.shapes[x][:-1]))
+                    M = _prod(self.shapes[x][:-1])
                     mask = self._val(x) if (gx is not None and self.ops[self._base(x)] == "relu") else None
                     if self.math == "bf16":
                         xv = self._as_bf16(x) if gW is not None else None
