@@ -283,6 +283,8 @@ class Plan:
         key = _sig(trace, root)
         p = _PLANS.get(key)
         if p is None:
+            if len(_PLANS) >= 64:                      # bounded cache: drop the oldest plan (and its buffers)
+                _PLANS.pop(next(iter(_PLANS)))
             p = _PLANS[key] = cls(trace, root)
         return p
 
