@@ -103,6 +103,13 @@ int pg_opt_nesterov(pg_ctx* ctx, int dtype, void* p, void* prev, const void* g, 
 int pg_opt_adam(pg_ctx* ctx, int dtype, void* p, void* m, void* v, void* m_hat, void* v_hat, const void* g, int64_t n,
                 double stepsize, double beta1, double beta2, double epsilon, int64_t it, int flags, void* shadow_bf16);
 
+/* Graph-replayable forms: the per-step scalars live in `scalars_dev` (5 doubles: Adam it, 1-beta1^it,
+ * 1-beta2^it, Nesterov t, momentum; initialise to {1,0,0,1,0}) and are advanced by a one-thread kernel
+ * in front of the update, so a captured CUDA graph can be replayed without re-baking kernel arguments. */
+int pg_opt_adam_dev(pg_ctx* ctx, int dtype, void* p, void* m, void* v, void* m_hat, void* v_hat, const void* g, int64_t n,
+                    double stepsize, double beta1, double beta2, double epsilon, double* scalars_dev, int flags, void* shadow_bf16);
+int pg_opt_nesterov_dev(pg_ctx* ctx, int dtype, void* p, void* prev, const void* g, int64_t n, double stepsize, double* scalars_dev, int flags, void* shadow_bf16);
+
 /* ---- Linear layer, FP32/FP64 SIMT mode (src/layers.jl:28-34 and its Zygote pullback) ------- */
 /* Y = act(X W + b) */
 int pg_linear_fwd(pg_ctx* ctx, int dtype, const void* X, const void* W, const void* b, void* Y,

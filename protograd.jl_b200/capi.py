@@ -69,6 +69,8 @@ _SIGS = {
     "pg_opt_heavyball": [_P, _I, _P, _P, _P, _L, _D, _D, _I, _P],
     "pg_opt_nesterov": [_P, _I, _P, _P, _P, _L, _D, _D, _I, _P],
     "pg_opt_adam": [_P, _I, _P, _P, _P, _P, _P, _P, _L, _D, _D, _D, _D, _L, _I, _P],
+    "pg_opt_adam_dev": [_P, _I, _P, _P, _P, _P, _P, _P, _L, _D, _D, _D, _D, _P, _I, _P],
+    "pg_opt_nesterov_dev": [_P, _I, _P, _P, _P, _L, _D, _P, _I, _P],
     "pg_linear_fwd": [_P, _I, _P, _P, _P, _P, _L, _L, _L, _I],
     "pg_linear_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L],
     "pg_tc_linear_fwd": [_P, _P, _P, _P, _P, _I, _L, _L, _L, _I],

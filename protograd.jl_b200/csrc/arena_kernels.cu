@@ -151,7 +151,9 @@ template <typename T, typename PS, typename PM> struct HeavyBallF {
 // nesterov: in = {p, g}; out = {p, prev}
 template <typename T, typename P> struct NesterovF {
   P s; double mu;
+  const double* dev;   // non-null: momentum comes from device scalars (CUDA-graph replay), dev[4]
   __device__ __forceinline__ void operator()(const T* in, T* out) const {
+    const double mu = dev ? dev[4] : this->mu;
     T prev = in[0];
     T p1 = (T)Ar<P>::sub((P)in[0], Ar<P>::mul(s, (P)in[1]));
     T diff = Ar<T>::sub(p1, prev);
@@ -162,7 +164,9 @@ template <typename T, typename P> struct NesterovF {
 // adam: in = {p, m, v, g}; out = {p, m, v, m_hat, v_hat}
 template <typename T, typename P> struct AdamF {
   P s, b1, omb1, b2, omb2, c1, c2, eps;  // c1 = 1 - b1^it, c2 = 1 - b2^it
+  const double* dev;                     // non-null: c1, c2 come from device scalars dev[1], dev[2]
   __device__ __forceinline__ void operator()(const T* in, T* out) const {
+    const P c1 = dev ? (P)dev[1] : this->c1, c2 = dev ? (P)dev[2] : this->c2;
     T g = in[3];
     T m = (T)Ar<P>::add(Ar<P>::mul(b1, (P)in[1]), Ar<P>::mul(omb1, (P)g));
     T g2 = Ar<T>::mul(g, g);
@@ -178,7 +182,9 @@ template <typename T, typename P> struct AdamF {
 // fast f32 Adam: reciprocal bias corrections, approximate division (normwise ~1e-7 of exact)
 struct AdamFastF {
   float s, b1, omb1, b2, omb2, rc1, rc2, eps;
+  const double* dev;
   __device__ __forceinline__ void operator()(const float* in, float* out) const {
+    const float rc1 = dev ? (float)(1.0 / dev[1]) : this->rc1, rc2 = dev ? (float)(1.0 / dev[2]) : this->rc2;
     float g = in[3];
     float m = fmaf(b1, in[1], omb1 * g);
     float v = fmaf(b2, in[2], omb2 * g * g);
@@ -235,6 +241,23 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<uint4*>(r);
   }
   for (int64_t i = nvec * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __float2bfloat16_rn(x[i]);
+}
+
+// per-step scalars kept on the device so a captured CUDA graph can be replayed unchanged:
+// s[0] = Adam `it` (starts at 1), s[1] = 1 - beta1^it, s[2] = 1 - beta2^it  (adam.jl:36-40)
+// s[3] = Nesterov t (starts at 1.0), s[4] = momentum (nesterov_method.jl:3-6)
+__global__ void opt_tick_kernel(double* s, int kind, double b1, double b2) {
+  if (kind == 0) {
+    const double it = s[0];
+    s[1] = 1.0 - pow(b1, it);
+    s[2] = 1.0 - pow(b2, it);
+    s[0] = it + 1.0;
+  } else {
+    const double t = s[3];
+    const double t_next = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;
+    s[4] = (t - 1.0) / t_next;
+    s[3] = t_next;
+  }
 }
 
 template <typename T, int OP>
@@ -355,17 +378,29 @@ int pg_opt_heavyball(pg_ctx* ctx, int dtype, void* p, void* d, const void* g, in
   return ew_launch<float, 3, 2>(ctx, HeavyBallF<float, float, float>{(float)s, (float)mu}, in, o, shadow, n);
 }
 
-int pg_opt_nesterov(pg_ctx* ctx, int dtype, void* p, void* prev, const void* g, int64_t n, double s, double mu, int flags, void* shadow) {
+static int nesterov_impl(pg_ctx* ctx, int dtype, void* p, void* prev, const void* g, int64_t n, double s, double mu, int flags, void* shadow, const double* dev) {
   PG_CHECK_CTX(ctx); PG_DTYPE_FLOAT_ONLY(dtype);
   PG_REQUIRE(shadow == nullptr || dtype == PG_F32, "bf16 shadow needs an f32 arena");
   Ptrs<2> in{{p, g}}; MPtrs<2> o{{p, prev}};
-  if (dtype == PG_F64) return ew_launch<double, 2, 2>(ctx, NesterovF<double, double>{s, mu}, in, o, nullptr, n);
-  if (flags & PG_SCALAR_F64) return ew_launch<float, 2, 2>(ctx, NesterovF<float, double>{s, mu}, in, o, shadow, n);
-  return ew_launch<float, 2, 2>(ctx, NesterovF<float, float>{(float)s, mu}, in, o, shadow, n);
+  if (dtype == PG_F64) return ew_launch<double, 2, 2>(ctx, NesterovF<double, double>{s, mu, dev}, in, o, nullptr, n);
+  if (flags & PG_SCALAR_F64) return ew_launch<float, 2, 2>(ctx, NesterovF<float, double>{s, mu, dev}, in, o, shadow, n);
+  return ew_launch<float, 2, 2>(ctx, NesterovF<float, float>{(float)s, mu, dev}, in, o, shadow, n);
 }
 
-int pg_opt_adam(pg_ctx* ctx, int dtype, void* p, void* m, void* v, void* m_hat, void* v_hat, const void* g, int64_t n,
-                double s, double b1, double b2, double eps, int64_t it, int flags, void* shadow) {
+int pg_opt_nesterov(pg_ctx* ctx, int dtype, void* p, void* prev, const void* g, int64_t n, double s, double mu, int flags, void* shadow) {
+  return nesterov_impl(ctx, dtype, p, prev, g, n, s, mu, flags, shadow, nullptr);
+}
+
+int pg_opt_nesterov_dev(pg_ctx* ctx, int dtype, void* p, void* prev, const void* g, int64_t n, double s, double* scalars_dev, int flags, void* shadow) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(scalars_dev != nullptr, "null device scalars");
+  opt_tick_kernel<<<1, 1, 0, ctx->stream>>>(scalars_dev, 1, 0.0, 0.0);
+  PG_LAUNCHED(ctx);
+  return nesterov_impl(ctx, dtype, p, prev, g, n, s, 0.0, flags, shadow, scalars_dev);
+}
+
+static int adam_impl(pg_ctx* ctx, int dtype, void* p, void* m, void* v, void* m_hat, void* v_hat, const void* g, int64_t n,
+                     double s, double b1, double b2, double eps, int64_t it, int flags, void* shadow, const double* dev) {
   PG_CHECK_CTX(ctx); PG_DTYPE_FLOAT_ONLY(dtype);
   PG_REQUIRE(it >= 1, "Adam iteration counter starts at 1 (adam.jl:28)");
   PG_REQUIRE(shadow == nullptr || dtype == PG_F32, "bf16 shadow needs an f32 arena");
@@ -373,15 +408,29 @@ int pg_opt_adam(pg_ctx* ctx, int dtype, void* p, void* m, void* v, void* m_hat, 
   // Julia: beta^it with an Int exponent (power by squaring); host pow agrees to <= 1 ulp.
   double c1 = 1.0 - pow(b1, (double)it), c2 = 1.0 - pow(b2, (double)it);
   if (dtype == PG_F64)
-    return ew_launch<double, 4, 5>(ctx, AdamF<double, double>{s, b1, 1.0 - b1, b2, 1.0 - b2, c1, c2, eps}, in, o, nullptr, n);
+    return ew_launch<double, 4, 5>(ctx, AdamF<double, double>{s, b1, 1.0 - b1, b2, 1.0 - b2, c1, c2, eps, dev}, in, o, nullptr, n);
   if (flags & PG_MATH_FAST)
-    return ew_launch<float, 4, 5>(ctx, AdamFastF{(float)s, (float)b1, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)(1.0 / c1), (float)(1.0 / c2), (float)eps}, in, o, shadow, n);
+    return ew_launch<float, 4, 5>(ctx, AdamFastF{(float)s, (float)b1, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)(1.0 / c1), (float)(1.0 / c2), (float)eps, dev}, in, o, shadow, n);
   if (flags & PG_SCALAR_F64)
-    return ew_launch<float, 4, 5>(ctx, AdamF<float, double>{s, b1, 1.0 - b1, b2, 1.0 - b2, c1, c2, eps}, in, o, shadow, n);
+    return ew_launch<float, 4, 5>(ctx, AdamF<float, double>{s, b1, 1.0 - b1, b2, 1.0 - b2, c1, c2, eps, dev}, in, o, shadow, n);
   float fb1 = (float)b1, fb2 = (float)b2;
   // Float32 hyper-parameters: Julia computes 1 - beta and beta^it in Float32
   float fc1 = 1.0f - powf(fb1, (float)it), fc2 = 1.0f - powf(fb2, (float)it);
-  return ew_launch<float, 4, 5>(ctx, AdamF<float, float>{(float)s, fb1, 1.0f - fb1, fb2, 1.0f - fb2, fc1, fc2, (float)eps}, in, o, shadow, n);
+  return ew_launch<float, 4, 5>(ctx, AdamF<float, float>{(float)s, fb1, 1.0f - fb1, fb2, 1.0f - fb2, fc1, fc2, (float)eps, dev}, in, o, shadow, n);
+}
+
+int pg_opt_adam(pg_ctx* ctx, int dtype, void* p, void* m, void* v, void* m_hat, void* v_hat, const void* g, int64_t n,
+                double s, double b1, double b2, double eps, int64_t it, int flags, void* shadow) {
+  return adam_impl(ctx, dtype, p, m, v, m_hat, v_hat, g, n, s, b1, b2, eps, it, flags, shadow, nullptr);
+}
+
+int pg_opt_adam_dev(pg_ctx* ctx, int dtype, void* p, void* m, void* v, void* m_hat, void* v_hat, const void* g, int64_t n,
+                    double s, double b1, double b2, double eps, double* scalars_dev, int flags, void* shadow) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(scalars_dev != nullptr, "null device scalars");
+  opt_tick_kernel<<<1, 1, 0, ctx->stream>>>(scalars_dev, 0, b1, b2);
+  PG_LAUNCHED(ctx);
+  return adam_impl(ctx, dtype, p, m, v, m_hat, v_hat, g, n, s, b1, b2, eps, 1, flags, shadow, scalars_dev);
 }
 
 }  // extern "C"

@@ -248,3 +248,29 @@ def test_large_batch_c1_step_matches_oracle(pg):
     assert abs(float(out) - v) <= TOL * abs(v)
     for a, r in zip(g, gr):
         assert rel_err(a, r) <= TOL
+
+
+@pytest.mark.parametrize("opt", ["gd", "heavyball", "nesterov", "adam"])
+def test_graph_replay_matches_eager_steps(pg, opt):
+    """GraphStep (captured CUDA graph, device-resident optimizer scalars) == the eager step loop."""
+    spec = MG.C1_SPEC
+    x, lab = MG.class_data(spec, 64, np.float32, 41)
+    p0 = MG.biased_params(spec, np.float32, 41)
+    ctx = pg.Context.get()
+    xd, ld = pg.DeviceArray.from_numpy(ctx, x), pg.DeviceArray.from_numpy(ctx, lab)
+    mk = lambda: {"gd": pg.GradientDescent(0.1), "heavyball": pg.HeavyBallMethod(0.1, 0.5), "nesterov": pg.NesterovMethod(0.1), "adam": pg.Adam(1e-3)}[opt]
+    f = lambda mm: pg.cross_entropy(mm(xd), ld)
+    m_e = build_model(pg, spec, p0); st_e = pg.init(mk(), m_e)
+    losses_e = []
+    for _ in range(6):
+        out, pb = pg.eval_with_pullback(f, m_e)
+        pg.step(st_e, pb())
+        losses_e.append(float(out))
+    m_g = build_model(pg, spec, p0); st_g = pg.init(mk(), m_g)
+    gs = pg.GraphStep(f, m_g, st_g)
+    assert np.array_equal(m_g.vec(), np.concatenate([p.ravel() for p in p0]))     # warm-up steps were rolled back
+    losses_g = [float(gs()) for _ in range(6)]
+    assert np.allclose(losses_g, losses_e, rtol=1e-6)
+    assert rel_err(m_g.vec(), m_e.vec()) <= 1e-6
+    if opt == "adam":
+        assert st_g.it == st_e.it == 7
