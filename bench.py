@@ -325,11 +325,18 @@ def main():
         for k in kernels.values():
             k["tflops"] = k["flop"] / (k["ms"] * 1e-3) / 1e12
         achieved = tot_flop / (tot_ms * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of the same kernels
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["tc_gemm_kernel"]
+            if B == PER_GPU_BATCH:
+                traffic, traffic_src = tj["per_launch_bytes"], tj["source"]
+        except Exception:
+            pass
         peak = peaks.get("bf16_tflops_sustained") or 1400.0
         roofline = {"kernel": "tc_gemm_kernel (tcgen05 bf16, 5 launches/step)", "bound": "tensor", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
-                    "traffic": None, "avg_launch_ms": tot_ms / (reps * len(gemms)),
+                    "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": tot_ms / (reps * len(gemms)),
                     "share_of_step": (tot_ms / reps) / (ms / args.steps)}
 
     if rank == 0:

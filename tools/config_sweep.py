@@ -25,7 +25,7 @@ ctx.use_stream(stream.cuda_stream)
 FLOPS = {"c1": 319_600, "c3": 1_517_040, "c5": 490_240}
 
 
-def run(name, spec, B, opt, steps=30, warmup=5):
+def run(name, spec, B, opt, steps=30, warmup=5, graph=False):
     x, lab = MG.class_data(spec, B, np.float32, 1)
     p0 = MG.biased_params(spec, np.float32, 1)
     full = build_model(pg, spec, p0)
@@ -42,10 +42,13 @@ def run(name, spec, B, opt, steps=30, warmup=5):
         objective = lambda mm: pg.cross_entropy(mm(xd), ld)
     st = pg.init(opt, m)
 
-    def step():
-        out, pb = pg.eval_with_pullback(objective, m)
-        pg.step(st, pb())
-        return out
+    if graph:
+        step = pg.GraphStep(objective, m, st)          # one cudaGraphLaunch per step
+    else:
+        def step():
+            out, pb = pg.eval_with_pullback(objective, m)
+            pg.step(st, pb())
+            return out
     for _ in range(warmup):
         out = step()
     float(out)
@@ -60,12 +63,18 @@ def run(name, spec, B, opt, steps=30, warmup=5):
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     ms = e0.elapsed_time(e1) / steps
-    print(json.dumps({"config": name, "batch": B, "optimizer": type(opt).__name__, "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3),
+    print(json.dumps({"config": name, "batch": B, "optimizer": type(opt).__name__, "mode": "graph" if graph else "eager", "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3),
                       "gflops": FLOPS[name] * B / (ms * 1e-3) / 1e9, "launches_per_step": (ctx.launch_count() - n0) / steps,
                       "host_ms_per_step": wall / steps * 1e3, "loss": float(out)}), flush=True)
 
 
 if __name__ == "__main__":
+    for B in (128, 1024, 8192):
+        run("c1", MG.C1_SPEC, B, pg.GradientDescent(1e-1), graph=True)
+    run("c1", MG.C1_SPEC, 128, pg.Adam(1e-3), graph=True)
+    for B in (128, 1024):
+        run("c3", MG.C3_SPEC, B, pg.Adam(1e-3), graph=True)
+    run("c5", MG.C5_SPEC, 1024, pg.GradientDescent(0.1), graph=True)
     for B in (128, 1024, 8192, 65536):
         run("c1", MG.C1_SPEC, B, pg.GradientDescent(1e-1))
     run("c1", MG.C1_SPEC, 8192, pg.Adam(1e-3))
