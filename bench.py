@@ -186,7 +186,8 @@ def main():
     x_p, lab_p = pin_x.as_numpy(np.float32, x_h.shape), pin_l.as_numpy(np.float32, lab_h.shape)
     x_p[...] = x_h; lab_p[...] = lab_h
 
-    buckets = dp.GradientBuckets(pg.gradient_container(model)) if world > 1 else None
+    buckets = dp.GradientBuckets(pg.gradient_container(model), bucket_bytes=int(os.environ.get("PG_BUCKET_MB", "24")) << 20,
+                                 comm_sms=int(os.environ.get("PG_COMM_SMS", "16"))) if world > 1 else None
     if args.sm_limit:
         ctx.set_sm_limit(args.sm_limit)
     use_shadow = args.math == "bf16"
