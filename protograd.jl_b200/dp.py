@@ -73,9 +73,13 @@ class GradientBuckets:
         grad = pb(on_ready=buckets.ready); buckets.finish(); step(state, grad)
     """
 
-    def __init__(self, grad_model, bucket_bytes=24 << 20, comm_sms=16):
+    def __init__(self, grad_model, bucket_bytes=24 << 20, comm_sms=None):
         # while a bucket is in flight the persistent GEMM grids are sized for (all - comm_sms) SMs, so
-        # NCCL's CTAs get SMs of their own instead of time-slicing with (and stalling) GEMM CTAs
+        # NCCL's CTAs get SMs of their own instead of time-slicing with (and stalling) GEMM CTAs.
+        # Measured (tools/dp_timeline*.sh): 2 ranks want 16 SMs; at 8 ranks NCCL uses more channels and
+        # 0/8/16 reserved SMs all cost ~1.25 ms/step while 24 gives 1.14 ms/step.
+        if comm_sms is None:
+            comm_sms = 16 if world()[1] <= 2 else 24
         self.comm_sms = comm_sms
         self.ctx = grad_model.arena()[0]
         from .model import _pad
