@@ -270,15 +270,18 @@ def main():
 
     def e2e_loop(n):
         pf.submit(x_p, lab_p)
-        last = None
+        last, prev = None, None
         for i in range(n):
             xd, ld = pf.next()
             if i + 1 < n:
                 pf.submit(x_p, lab_p)
             out = train_step(xd, ld)
             pf.release()
-            last = float(out)
-        return last
+            out.fetch_async()              # D2H of this step's loss, queued right behind the step
+            if prev is not None:
+                last = float(prev)         # read step i-1's loss while step i runs
+            prev = out
+        return float(prev)
     e2e_loop(3)
     e2e_steps = max(5, args.steps // 2)
     ms_e2e = timed(lambda: e2e_loop(e2e_steps), 1)

@@ -69,6 +69,7 @@ int pg_event_create(pg_ctx* ctx, void** event);
 int pg_event_destroy(pg_ctx* ctx, void* event);
 int pg_event_record(pg_ctx* ctx, void* event, int which_stream);
 int pg_stream_wait_event(pg_ctx* ctx, int which_stream, void* event);
+int pg_event_sync(pg_ctx* ctx, void* event);      /* block the host until the event has completed */
 int pg_upload_on(pg_ctx* ctx, int which_stream, void* dst_dev, const void* src_host, size_t bytes);
 
 /* ---- CUDA-graph capture of a whole step (stream capture on the ctx stream) ---------------- */

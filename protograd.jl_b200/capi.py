@@ -54,6 +54,7 @@ _SIGS = {
     "pg_event_destroy": [_P, _P],
     "pg_event_record": [_P, _P, _I],
     "pg_stream_wait_event": [_P, _I, _P],
+    "pg_event_sync": [_P, _P],
     "pg_upload_on": [_P, _I, _P, _P, _Z],
     "pg_graph_begin": [_P],
     "pg_graph_end": [_P, POINTER(_P)],

@@ -192,6 +192,11 @@ int pg_stream_wait_event(pg_ctx* ctx, int which_stream, void* event) {
   PG_CHECK_CUDA(cudaStreamWaitEvent(pick_stream(ctx, which_stream), (cudaEvent_t)event, 0));
   return PG_OK;
 }
+int pg_event_sync(pg_ctx* ctx, void* event) {
+  PG_CHECK_CTX(ctx);
+  PG_CHECK_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+  return PG_OK;
+}
 int pg_upload_on(pg_ctx* ctx, int which_stream, void* dst, const void* src, size_t bytes) {
   PG_CHECK_CTX(ctx);
   PG_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pick_stream(ctx, which_stream)));

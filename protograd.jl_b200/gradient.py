@@ -24,17 +24,50 @@ _grad_cache = weakref.WeakKeyDictionary()
 
 
 class Loss:
-    """Device-resident scalar; float() synchronises and reads it (pg_loss_read)."""
+    """Device-resident scalar; float() synchronises and reads it (pg_loss_read).
+
+    fetch_async() starts the device->host copy of the value into pinned memory right behind the
+    step's kernels and returns immediately; a later float() then only waits for that copy, so a loop
+    can enqueue step i+1 before it looks at the loss of step i (the reference only looks at it on log
+    steps, examples/01_mnist_mlp.jl:49-51)."""
+
+    _pinned = None      # ring of pinned slots shared by all Loss objects
+    _ring, _next = 64, 0
 
     def __init__(self, buf):
         self._buf = buf
         self._val = None
+        self._pending = None
+
+    def fetch_async(self):
+        from .device import PinnedBuffer
+        ctx = self._buf.ctx
+        if Loss._pinned is None:
+            Loss._pinned = PinnedBuffer(8 * Loss._ring)
+            Loss._events = [None] * Loss._ring
+        k = Loss._next
+        Loss._next = (k + 1) % Loss._ring
+        if Loss._events[k] is None:
+            e = ctypes.c_void_p()
+            call("pg_event_create", ctx.h, ctypes.byref(e))
+            Loss._events[k] = e
+        call("pg_download_async", ctx.h, Loss._pinned.ptr + 8 * k, self._buf.ptr, self._buf.dtype.itemsize)
+        call("pg_event_record", ctx.h, Loss._events[k], 0)
+        self._pending = k
+        return self
 
     def __float__(self):
         if self._val is None:
-            r = ctypes.c_double()
-            call("pg_loss_read", self._buf.ctx.h, dtype_code(self._buf.dtype), self._buf.ptr, ctypes.byref(r))
-            self._val = r.value
+            if self._pending is not None:
+                k = self._pending
+                call("pg_event_sync", self._buf.ctx.h, Loss._events[k])
+                host = Loss._pinned.as_numpy(np.uint8, (8 * Loss._ring,))[8 * k:8 * k + self._buf.dtype.itemsize]
+                self._val = float(host.view(self._buf.dtype)[0])
+                self._pending = None
+            else:
+                r = ctypes.c_double()
+                call("pg_loss_read", self._buf.ctx.h, dtype_code(self._buf.dtype), self._buf.ptr, ctypes.byref(r))
+                self._val = r.value
         return self._val
 
     item = __float__

@@ -274,3 +274,37 @@ def test_graph_replay_matches_eager_steps(pg, opt):
     assert rel_err(m_g.vec(), m_e.vec()) <= 1e-6
     if opt == "adam":
         assert st_g.it == st_e.it == 7
+
+
+def test_loss_fetch_async_and_prefetcher(pg):
+    """Loss.fetch_async (pinned D2H behind the step) and Prefetcher (double-buffered H2D) give the same numbers as the plain path."""
+    spec = MG.C1_SPEC
+    p0 = MG.biased_params(spec, np.float32, 3)
+    ctx = pg.Context.get()
+    batches = [MG.class_data(spec, 32, np.float32, 50 + i) for i in range(5)]
+    m1 = build_model(pg, spec, p0); s1 = pg.init(pg.GradientDescent(0.1), m1)
+    ref = []
+    for x, lab in batches:
+        out, pb = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(x), lab), m1)
+        pg.step(s1, pb()); ref.append(float(out))
+    m2 = build_model(pg, spec, p0); s2 = pg.init(pg.GradientDescent(0.1), m2)
+    pin = [(pg.PinnedBuffer(x.nbytes), pg.PinnedBuffer(l.nbytes)) for x, l in batches]
+    host = []
+    for (px, pl), (x, l) in zip(pin, batches):
+        hx, hl = px.as_numpy(np.float32, x.shape), pl.as_numpy(np.float32, l.shape)
+        hx[...] = x; hl[...] = l
+        host.append((hx, hl))
+    pf = pg.Prefetcher(ctx, [(batches[0][0].shape, np.float32), (batches[0][1].shape, np.float32)])
+    pf.submit(*host[0])
+    outs = []
+    for i in range(5):
+        xd, ld = pf.next()
+        if i + 1 < 5:
+            pf.submit(*host[i + 1])
+        out, pb = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(xd), ld), m2)
+        pg.step(s2, pb())
+        pf.release()
+        outs.append(out.fetch_async())
+    got = [float(o) for o in outs]
+    assert got == ref
+    assert np.array_equal(m1.vec(), m2.vec())
