@@ -40,6 +40,7 @@ struct Epi {
   int relu;
   int out_f32;                  // 1: float output, 0: bf16 output
   int narrow;                   // 1: N not a multiple of 8 -> scalar guarded loads/stores (f32 out only)
+  float* db;                    // weight-gradient launches: fused bias gradient db[n] = sum_k B[k][n] (nullable)
   int splits;                   // split-K: work item = (tile, split); split s writes its fp32 partial to C + s*M*N
   int kb_per_split;
 };
@@ -132,8 +133,12 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) 
          ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN, int BLOCK_N>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// DBW: two extra "reducer" warps (weight-gradient launches) that read the B (= dY) tiles the TMA producer
+// already staged in shared memory and accumulate their column sums, so the bias gradient costs no extra
+// pass over dY.  Only the tiles of the first m-block do the arithmetic; for every stage the reducer
+// warps wait on the full barrier and arrive on the empty barrier like the MMA warp does.
+template <bool A_MN, bool B_MN, int BLOCK_N, bool DBW>
+__global__ void __launch_bounds__(NUM_THREADS + (DBW ? 64 : 0), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ C,
                int M, int N, int K, Epi epi) {
   constexpr int STAGES = Cfg<BLOCK_N>::STAGES, B_STAGE_BYTES = Cfg<BLOCK_N>::B_STAGE_BYTES, STAGE_BYTES = Cfg<BLOCK_N>::STAGE_BYTES;
@@ -166,7 +171,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), DBW ? 3 : 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -241,6 +246,46 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+    }
+  } else if (DBW && warp >= 2 + EPI_WARPS) {
+    // ===== bias-gradient reducer warps =====
+    static_assert(!DBW || (B_MN && BLOCK_N == 256), "reducer warps read MN-major 256-wide B tiles");
+    const int rw = warp - (2 + EPI_WARPS);               // columns [rw*128, rw*128 + 128) of the tile
+    const int col0 = rw * 128 + lane * 4;                // this lane's 4 consecutive columns
+    const uint32_t box_off = (uint32_t)(col0 >> 6) * (BLOCK_K * 128) + (uint32_t)(col0 & 7) * 2;
+    const int chunk = (col0 & 63) >> 3;                  // 16-byte chunk inside the 128-byte row
+    float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+    int stage = 0; uint32_t phase = 0;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int tile = work % num_tiles, split = work / num_tiles;
+        const int kb0 = split * epi.kb_per_split, kb1 = min(num_kb, kb0 + epi.kb_per_split);
+        int m0, n0;
+        tile_coords(tile, m0, n0);
+        const bool mine = (m0 == 0) && (epi.db != nullptr);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          if (mine) {
+            const uint8_t* sb = smem_aligned + stage * STAGE_BYTES + A_STAGE_BYTES + box_off;
+#pragma unroll 8
+            for (int r = 0; r < BLOCK_K; ++r) {           // SWIZZLE_128B: chunk index is XORed with (row & 7)
+              const uint2 v = *reinterpret_cast<const uint2*>(sb + r * 128 + ((chunk ^ (r & 7)) << 4));
+              const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+              const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+              acc4[0] += __low2float(p0); acc4[1] += __high2float(p0);
+              acc4[2] += __low2float(p1); acc4[3] += __high2float(p1);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (mine) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n0 + col0 + j < N) epi.db[n0 + col0 + j] = acc4[j];
+            acc4[j] = 0.f;
+          }
+        }
     }
   } else {
     // ===== epilogue warps (TMEM -> registers -> global) =====
@@ -386,7 +431,7 @@ int make_map(pg_ctx* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64
   return PG_OK;
 }
 
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, bool DBW = false>
 int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, const Epi& epi) {
   // lda / ldb: row pitch (elements) of the stored operands; rows beyond the logical extent are
   // zero-filled by TMA, so padded copies only need a 16-byte-multiple pitch.
@@ -397,7 +442,7 @@ int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int
   if (rc != PG_OK) return rc;
   rc = B_MN ? make_map(ctx, &mb, B, K, N, ldb, 64, BLOCK_K) : make_map(ctx, &mb, B, N, K, ldb, BLOCK_K, BN);
   if (rc != PG_OK) return rc;
-  auto kern = tc_gemm_kernel<A_MN, B_MN, BN>;
+  auto kern = tc_gemm_kernel<A_MN, B_MN, BN, DBW>;
   static bool attr_set = false;
   if (!attr_set) {
     PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
@@ -405,7 +450,7 @@ int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int
   }
   int64_t tiles = pg_cdiv(M, BLOCK_M) * pg_cdiv(N, BN) * epi.splits;
   int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
-  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi);
+  kern<<<grid, NUM_THREADS + (DBW ? 64 : 0), Cfg<BN>::SMEM_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi);
   PG_LAUNCHED(ctx);
   return PG_OK;
 }
@@ -419,7 +464,8 @@ int tc_dispatch(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, 
   switch (layout) {
     case 0: return launch_tc<false, true, 256>(ctx, A, B, C, M, N, K, K, N, epi);
     case 1: return launch_tc<false, false, 256>(ctx, A, B, C, M, N, K, K, K, epi);
-    case 2: return launch_tc<true, true, 256>(ctx, A, B, C, M, N, K, M, N, epi);
+    case 2: return epi.db != nullptr ? launch_tc<true, true, 256, true>(ctx, A, B, C, M, N, K, M, N, epi)
+                                     : launch_tc<true, true, 256>(ctx, A, B, C, M, N, K, M, N, epi);
   }
   pg_set_error("pg_tc_gemm: unknown layout %d", layout);
   return PG_ERR_ARG;
@@ -487,7 +533,7 @@ int narrow_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, void* Z
   int64_t total = K * NARROW_N;
   pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, nullptr, Wt, K, (int)N, 0, NARROW_N);
   PG_LAUNCHED(ctx);
-  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, 1, 1, 1, 1 << 30};
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, 1, 1, nullptr, 1, 1 << 30};
   return launch_tc<false, false, NARROW_N>(ctx, X, Wt, Z, M, N, K, K, K, epi);
 }
 
@@ -516,7 +562,7 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
     if (splits > 8) splits = 8;
     int kb_per = (int)pg_cdiv(num_kb, splits);
     splits = (int)pg_cdiv(num_kb, kb_per);
-    Epi epi{nullptr, nullptr, 0, 1, 1, splits, kb_per};
+    Epi epi{nullptr, nullptr, 0, 1, 1, nullptr, splits, kb_per};
     void* target = dW;
     if (splits > 1) {
       rc = pg_ws_ensure(ctx, (size_t)splits * K * N * sizeof(float));
@@ -538,7 +584,7 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
     int64_t total = K * NARROW_K;
     pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, Wp, nullptr, K, (int)N, NARROW_K, 0);
     PG_LAUNCHED(ctx);
-    Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, 0, 0, 1, 1 << 30};
+    Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, 0, 0, nullptr, 1, 1 << 30};
     rc = launch_tc<false, false, 256>(ctx, dZp, Wp, dX, M, K, NARROW_K, NARROW_K, NARROW_K, epi);
     if (rc != PG_OK) return rc;
   }
@@ -553,7 +599,7 @@ int pg_tc_gemm(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, i
   PG_CHECK_CTX(ctx);
   PG_REQUIRE(A && B && C, "null pointer");
   PG_REQUIRE(c_dtype == PG_F32 || c_dtype == PG_BF16, "C must be f32 or bf16");
-  Epi epi{nullptr, nullptr, 0, c_dtype == PG_F32, 0, 1, 1 << 30};
+  Epi epi{nullptr, nullptr, 0, c_dtype == PG_F32, 0, nullptr, 1, 1 << 30};
   return tc_dispatch(ctx, layout, A, B, C, M, N, K, epi);
 }
 
@@ -565,7 +611,7 @@ int pg_tc_linear_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, v
     return narrow_fwd(ctx, X, W, b, Y, M, K, N, act);
   }
   PG_REQUIRE(y_dtype == PG_BF16 || y_dtype == PG_F32, "Y must be bf16 or f32");
-  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, y_dtype == PG_F32, 0, 1, 1 << 30};
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, y_dtype == PG_F32, 0, nullptr, 1, 1 << 30};
   return tc_dispatch(ctx, 0, X, W, Y, M, N, K, epi);
 }
 
@@ -582,16 +628,18 @@ int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, 
   PG_REQUIRE(dy_dtype == PG_BF16, "wide layers take bf16 dY");
   int rc;
   if (dW) {  // dW[K][N] = X^T dY: GEMM (M'=K, N'=N, K'=M), A = X stored [M][K] (MN-major), B = dY stored [M][N] (MN-major)
-    Epi epi{nullptr, nullptr, 0, 1, 0, 1, 1 << 30};
+    // db = column sums of dY ride along: reducer warps sum the dY tiles already staged in shared memory
+    Epi epi{nullptr, nullptr, 0, 1, 0, (float*)db, 1, 1 << 30};
     rc = tc_dispatch(ctx, 2, X, dY, dW, K, N, M, epi);
     if (rc != PG_OK) return rc;
+    db = nullptr;
   }
   if (db) {
     rc = pg_colsum_launch(ctx, PG_BF16, dY, db, M, N);
     if (rc != PG_OK) return rc;
   }
   if (dX) {  // dX[M][K] = dY W^T: GEMM (M'=M, N'=K, K'=N), A = dY [M][N] K-major, B = W [K][N] K-major
-    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, 0, 0, 1, 1 << 30};
+    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, 0, 0, nullptr, 1, 1 << 30};
     rc = tc_dispatch(ctx, 1, dY, W, dX, M, K, N, epi);
     if (rc != PG_OK) return rc;
   }
