@@ -135,8 +135,10 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) 
 
 // DBW: two extra "reducer" warps (weight-gradient launches) that read the B (= dY) tiles the TMA producer
 // already staged in shared memory and accumulate their column sums, so the bias gradient costs no extra
-// pass over dY.  Only the tiles of the first m-block do the arithmetic; for every stage the reducer
-// warps wait on the full barrier and arrive on the empty barrier like the MMA warp does.
+// pass over dY.  The num_m tiles that share an n-block split the k-blocks between them (tile m_blk sums
+// the stages with kb % num_m == m_blk, ~1.6k cycles each, hidden behind num_m x 512 cycles of MMAs) and
+// add their partial sums to db with one atomicAdd per column; for every stage the reducer warps wait on
+// the full barrier and arrive on the empty barrier like the MMA warp does.  db must be zeroed first.
 template <bool A_MN, bool B_MN, int BLOCK_N, bool DBW>
 __global__ void __launch_bounds__(NUM_THREADS + (DBW ? 64 : 0), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ C,
@@ -261,10 +263,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int kb0 = split * epi.kb_per_split, kb1 = min(num_kb, kb0 + epi.kb_per_split);
         int m0, n0;
         tile_coords(tile, m0, n0);
-        const bool mine = (m0 == 0) && (epi.db != nullptr);
+        const int m_blk = m0 / BLOCK_M;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
-          if (mine) {
+          if (kb % num_m == m_blk) {
             const uint8_t* sb = smem_aligned + stage * STAGE_BYTES + A_STAGE_BYTES + box_off;
 #pragma unroll 8
             for (int r = 0; r < BLOCK_K; ++r) {           // SWIZZLE_128B: chunk index is XORed with (row & 7)
@@ -279,12 +281,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (lane == 0) mbar_arrive(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (mine) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n0 + col0 + j < N) epi.db[n0 + col0 + j] = acc4[j];
-            acc4[j] = 0.f;
-          }
+        for (int j = 0; j < 4; ++j) {
+          if (n0 + col0 + j < N) atomicAdd(epi.db + n0 + col0 + j, acc4[j]);
+          acc4[j] = 0.f;
         }
     }
   } else {
@@ -628,11 +628,14 @@ int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, 
   PG_REQUIRE(dy_dtype == PG_BF16, "wide layers take bf16 dY");
   int rc;
   if (dW) {  // dW[K][N] = X^T dY: GEMM (M'=K, N'=N, K'=M), A = X stored [M][K] (MN-major), B = dY stored [M][N] (MN-major)
-    // db = column sums of dY ride along: reducer warps sum the dY tiles already staged in shared memory
-    Epi epi{nullptr, nullptr, 0, 1, 0, (float*)db, 1, 1 << 30};
+    // db = column sums of dY ride along when enough m-blocks share the work: reducer warps sum the dY
+    // tiles already staged in shared memory (no extra pass over dY)
+    const bool fuse_db = db != nullptr && pg_cdiv(K, BLOCK_M) >= 4;
+    if (fuse_db) PG_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), ctx->stream));
+    Epi epi{nullptr, nullptr, 0, 1, 0, fuse_db ? (float*)db : nullptr, 1, 1 << 30};
     rc = tc_dispatch(ctx, 2, X, dY, dW, K, N, M, epi);
     if (rc != PG_OK) return rc;
-    db = nullptr;
+    if (fuse_db) db = nullptr;
   }
   if (db) {
     rc = pg_colsum_launch(ctx, PG_BF16, dY, db, M, N);
