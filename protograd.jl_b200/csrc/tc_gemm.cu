@@ -13,6 +13,7 @@
 // Layers with N <= 32 (the 10-class logits layer) are HBM-bound; they reuse the kernel with a 32-wide
 // N tile on small zero-padded operand copies (see "Narrow layers" below).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -131,6 +132,66 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// One 32-column chunk of one accumulator row: bias / ReLU / ReLU' mask / store (shared by both kernels).
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Epi& epi, void* __restrict__ C, int M, int N,
+                                               int row, int col, int split, const uint4* mk4) {
+  if (!(row < M && col < N)) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (epi.narrow) {
+    // N is not a multiple of 8 (e.g. 10 logits): scalar, fully guarded fp32 path
+    float* op = reinterpret_cast<float*>(C) + (size_t)split * M * N + (size_t)row * N;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (col + j < N) {
+        float o = v[j] + (epi.bias != nullptr ? epi.bias[col + j] : 0.0f);
+        if (epi.relu) o = fmaxf(o, 0.0f);
+        op[col + j] = o;
+      }
+    }
+    return;
+  }
+  if (epi.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (col + j < N) {
+        const float4 b4 = *reinterpret_cast<const float4*>(epi.bias + col + j);
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    }
+  }
+  if (epi.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (epi.mask != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk4[j / 8]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j + e] = (__bfloat162float(me[e]) > 0.0f) ? v[j + e] : 0.0f;
+    }
+  }
+  if (epi.out_f32) {
+    float* op = reinterpret_cast<float*>(C) + (size_t)split * M * N + (size_t)row * N + col;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      if (col + j < N) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(C) + (size_t)row * N + col;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (col + j < N) {
+        __nv_bfloat162 pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pk[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(op + j) = *reinterpret_cast<uint4*>(pk);
+      }
+    }
+  }
 }
 
 // DBW: two extra "reducer" warps (weight-gradient launches) that read the B (= dY) tiles the TMA producer
@@ -320,63 +381,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         tmem_ld_wait();
-        const int col = n0 + c;
-        if (row < M && col < N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (epi.narrow) {
-            // N is not a multiple of 8 (e.g. 10 logits): scalar, fully guarded fp32 path
-            float* op = reinterpret_cast<float*>(C) + (size_t)split * M * N + (size_t)row * N;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col + j < N) {
-                float o = v[j] + (epi.bias != nullptr ? epi.bias[col + j] : 0.0f);
-                if (epi.relu) o = fmaxf(o, 0.0f);
-                op[col + j] = o;
-              }
-            }
-            continue;
-          }
-          if (epi.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col + j < N) {
-                const float4 b4 = *reinterpret_cast<const float4*>(epi.bias + col + j);
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-              }
-            }
-          }
-          if (epi.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-          }
-          if (epi.mask != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk[ci * 4 + j / 8]);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[j + e] = (__bfloat162float(me[e]) > 0.0f) ? v[j + e] : 0.0f;
-            }
-          }
-          if (epi.out_f32) {
-            float* op = reinterpret_cast<float*>(C) + (size_t)split * M * N + (size_t)row * N + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (col + j < N) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(C) + (size_t)row * N + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col + j < N) {
-                __nv_bfloat162 pk[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) pk[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(op + j) = *reinterpret_cast<uint4*>(pk);
-              }
-            }
-          }
-        }
+        epilogue_chunk(r, epi, C, M, N, row, n0 + c, split, &mk[ci * 4]);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -390,6 +395,212 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ================================================================================================
+// 2-CTA kernel (tcgen05 cta_group::2): a cluster of two CTAs (one SM pair) computes a 256 x 256 tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 columns), so a stage
+// is 32 KB instead of 48 KB for the same 512 MMA cycles: the shared-memory ring becomes 6 stages deep
+// (~3000 cycles of prefetch distance instead of ~2000, the 1-CTA kernel's exposed DRAM latency was
+// ~25 % of its time, profiles/r1_ncu_full_prof_tc_final.csv) and L2->SM traffic drops by a third.
+// Protocol: both CTAs' TMA loads signal the LEADER's (rank 0) full barrier; the leader's single MMA
+// thread issues cta_group::2 MMAs (M = 256) and multicast-commits to the empty / tmem-full barriers of
+// both CTAs; each CTA's epilogue warps drain their own TMEM half and arrive on the leader's tmem-empty
+// barrier.
+// ================================================================================================
+constexpr int STAGES2 = 6;
+constexpr int B2_STAGE_BYTES = 128 * BLOCK_K * 2;
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;      // 32 KB per CTA
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr int GROUP_M2 = 8;                                        // rasterisation group, in 256-row blocks
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {   // shared::cluster address of `saddr` in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint32_t bar) {   // arrive on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc2(bool a_mn, bool b_mn) {   // M = 256 (across the pair), N = 256
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ C,
+                int M, int N, int K, Epi epi) {
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES2 * STAGE2_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES2 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_aligned + STAGES2 * STAGE2_BYTES + 8 * (2 * STAGES2 + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_m = (M + 255) / 256, num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  auto tile_coords = [&](int tile, int& m0, int& n0) {
+    const int per_group = GROUP_M2 * num_n;
+    const int g = tile / per_group, r = tile - g * per_group;
+    const int gm = min(GROUP_M2, num_m - g * GROUP_M2);
+    m0 = (g * GROUP_M2 + r % gm) * 256;
+    n0 = (r / gm) * BN;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {  // one warp of EACH CTA, same warp id, same smem slot
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();               // barriers of both CTAs are initialised before anyone signals them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own 128 rows of A, own 128 columns of B; bytes land on the leader's barrier =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int m0, n0;
+        tile_coords(tile, m0, n0);
+        const int my_m0 = m0 + (int)rank * 128, my_n0 = n0 + (int)rank * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
+          const uint32_t lbar = map_to_rank(full_bar(stage), 0);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE2_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_2sm(sa + c * (BLOCK_K * 128), &map_a, lbar, my_m0 + c * 64, k0);
+          } else {
+            tma_load_2d_2sm(sa, &map_a, lbar, k0, my_m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_2sm(sb + c * (BLOCK_K * 128), &map_b, lbar, my_n0 + c * 64, k0);
+          } else {
+            tma_load_2d_2sm(sb, &map_b, lbar, k0, my_n0);     // box {64 k, 128 n}
+          }
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives the tensor cores of both SMs =====
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc2(A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);             // both CTAs' bytes have landed
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t ad = A_MN ? make_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bd = B_MN ? make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          tcgen05_commit_2sm(empty_bar(stage));          // frees the slot in both CTAs
+          if (kb == num_kb - 1) tcgen05_commit_2sm(tfull_bar(acc));
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): own 128 rows x 256 columns from the local TMEM =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int COLS_PER_WARP = BN / 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int m0, n0;
+      tile_coords(tile, m0, n0);
+      const int row = m0 + (int)rank * 128 + q * 32 + lane;
+      const int c_begin = half * COLS_PER_WARP;
+      uint4 mk[COLS_PER_WARP / 8];
+      if (epi.mask != nullptr) {
+        const __nv_bfloat16* mp = epi.mask + (size_t)row * N + n0 + c_begin;
+#pragma unroll
+        for (int j = 0; j < COLS_PER_WARP / 8; ++j)
+          mk[j] = (row < M && n0 + c_begin + 8 * j < N) ? __ldg(reinterpret_cast<const uint4*>(mp) + j) : make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll
+      for (int ci = 0; ci < COLS_PER_WARP / 32; ++ci) {
+        const int c = c_begin + ci * 32;
+        uint32_t r[32];
+        tmem_ld32(taddr + c, r);
+        tmem_ld_wait();
+        epilogue_chunk(r, epi, C, M, N, row, n0 + c, 0, &mk[ci * 4]);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_rank(tempty_bar(acc), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();               // neither CTA frees TMEM / exits while its peer may still touch it
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -455,12 +666,46 @@ int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int
   return PG_OK;
 }
 
+template <bool A_MN, bool B_MN>
+int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, const Epi& epi) {
+  CUtensorMap ma, mb;
+  int rc;
+  rc = A_MN ? make_map(ctx, &ma, A, K, M, lda, 64, BLOCK_K) : make_map(ctx, &ma, A, M, K, lda, BLOCK_K, 128);
+  if (rc != PG_OK) return rc;
+  rc = B_MN ? make_map(ctx, &mb, B, K, N, ldb, 64, BLOCK_K) : make_map(ctx, &mb, B, N, K, ldb, BLOCK_K, 128);
+  if (rc != PG_OK) return rc;
+  auto kern = tc_gemm2_kernel<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    attr_set = true;
+  }
+  int64_t tiles = pg_cdiv(M, 256) * pg_cdiv(N, 256);
+  int clusters = (int)(tiles < ctx->num_sms / 2 ? tiles : ctx->num_sms / 2);
+  kern<<<2 * clusters, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi);
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+bool use_2cta(int64_t M, int64_t N) {
+  static int mode = -1;                        // PG_TC_1CTA=1 forces the single-CTA kernel
+  if (mode < 0) { const char* e = getenv("PG_TC_1CTA"); mode = (e && e[0] == '1') ? 0 : 1; }
+  return mode == 1 && M >= 512 && N >= 512;
+}
+
 int tc_dispatch(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, const Epi& epi) {
   PG_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
   PG_REQUIRE(M % 8 == 0 || layout != 2, "weight-gradient GEMM needs M % 8 == 0 (TMA 16-byte pitch)");
   PG_REQUIRE(N % 8 == 0 && K % 8 == 0, "tensor-core GEMM needs N % 8 == 0 and K % 8 == 0 (TMA 16-byte pitch)");
   PG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "operands must be 16-byte aligned");
   PG_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension too large");
+  if (epi.db == nullptr && epi.splits == 1 && use_2cta(M, N)) {
+    switch (layout) {
+      case 0: return launch_tc2<false, true>(ctx, A, B, C, M, N, K, K, N, epi);
+      case 1: return launch_tc2<false, false>(ctx, A, B, C, M, N, K, K, K, epi);
+      case 2: return launch_tc2<true, true>(ctx, A, B, C, M, N, K, M, N, epi);
+    }
+  }
   switch (layout) {
     case 0: return launch_tc<false, true, 256>(ctx, A, B, C, M, N, K, K, N, epi);
     case 1: return launch_tc<false, false, 256>(ctx, A, B, C, M, N, K, K, K, epi);

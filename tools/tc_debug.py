@@ -52,7 +52,7 @@ def run(layout, M, N, K, seed=0, c_dtype=0):
 
 
 if __name__ == "__main__":
-    shapes = [(128, 256, 64), (128, 256, 128), (128, 256, 512), (256, 512, 256), (384, 768, 320), (136, 264, 72), (1024, 1024, 1024)]
+    shapes = [(128, 256, 64), (256, 512, 256), (136, 264, 72), (512, 512, 64), (512, 512, 128), (512, 768, 320), (520, 1032, 72), (1024, 1024, 1024), (784, 4096, 1024)]
     worst = 0
     for layout in (1, 0, 2):
         for (M, N, K) in shapes:
