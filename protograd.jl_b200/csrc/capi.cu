@@ -206,7 +206,7 @@ int pg_upload_on(pg_ctx* ctx, int which_stream, void* dst, const void* src, size
 int pg_graph_begin(pg_ctx* ctx) {
   PG_CHECK_CTX(ctx);
   PG_REQUIRE(!ctx->capturing, "already capturing");
-  PG_CHECK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  PG_CHECK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
   ctx->capturing = true;
   return PG_OK;
 }

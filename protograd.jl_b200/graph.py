@@ -40,12 +40,22 @@ class GraphStep:
             self._one_step()
         self._restore(snap)
         self.ctx.sync()
+        # no Python garbage collection while capturing: a finalizer freeing device memory (cudaFree)
+        # in the middle of a stream capture would invalidate it
+        import gc
+        gc_was_enabled = gc.isenabled()
+        gc.collect()
+        gc.disable()
         call("pg_graph_begin", self.ctx.h)
         try:
             self._one_step()
         finally:
             ge = ctypes.c_void_p()
-            call("pg_graph_end", self.ctx.h, ctypes.byref(ge))
+            try:
+                call("pg_graph_end", self.ctx.h, ctypes.byref(ge))
+            finally:
+                if gc_was_enabled:
+                    gc.enable()
         self._graph = ge
         self.steps = 0
 
