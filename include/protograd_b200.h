@@ -127,6 +127,10 @@ int pg_tc_linear_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, v
 /* dY bf16 (or f32 when N <= 32); dW/db f32 (straight into the gradient arena); dX bf16. */
 int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
                      const void* relu_mask, int64_t M, int64_t K, int64_t N);
+/* same, plus dx_colsum (nullable, f32 [K]): column sums of the masked dX, i.e. the bias gradient of the
+ * layer that produced X — accumulated in the data-gradient epilogue instead of a separate pass over dX. */
+int pg_tc_linear_bwd_ex(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
+                        const void* relu_mask, void* dx_colsum, int64_t M, int64_t K, int64_t N);
 /* raw GEMM entry for unit tests: C[M][N] (f32 or bf16) = A op B, bf16 operands, fp32 accumulate.
  * layout 0: A[M][K] B[K][N]   (forward)      1: A[M][K] B[N][K]^T (data gradient)
  * layout 2: A[K][M]^T B[K][N] (weight gradient) */

@@ -76,6 +76,7 @@ _SIGS = {
     "pg_linear_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L],
     "pg_tc_linear_fwd": [_P, _P, _P, _P, _P, _I, _L, _L, _L, _I],
     "pg_tc_linear_bwd": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _L, _L],
+    "pg_tc_linear_bwd_ex": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _L, _L],
     "pg_tc_gemm": [_P, _I, _P, _P, _P, _I, _L, _L, _L],
     "pg_conv2d_fwd": [_P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I],
     "pg_conv2d_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I],

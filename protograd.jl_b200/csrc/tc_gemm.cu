@@ -41,6 +41,8 @@ struct Epi {
   int relu;
   int out_f32;                  // 1: float output, 0: bf16 output
   int narrow;                   // 1: N not a multiple of 8 -> scalar guarded loads/stores (f32 out only)
+  float* colsum;                // data-gradient launches: also accumulate column sums of the (masked, bf16-rounded) output
+                                // = the bias gradient of the layer that produced the masking activation (nullable, pre-zeroed)
   float* db;                    // weight-gradient launches: fused bias gradient db[n] = sum_k B[k][n] (nullable)
   int splits;                   // split-K: work item = (tile, split); split s writes its fp32 partial to C + s*M*N
   int kb_per_split;
@@ -137,6 +139,33 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) 
 // One 32-column chunk of one accumulator row: bias / ReLU / ReLU' mask / store (shared by both kernels).
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Epi& epi, void* __restrict__ C, int M, int N,
                                                int row, int col, int split, const uint4* mk4) {
+  if (epi.colsum != nullptr) {
+    // column sums of this warp's 32 x 32 block (rows = lanes): butterfly transpose-reduce, 31 shuffles;
+    // afterwards lane l holds the sum of column l.  Values are masked and bf16-rounded exactly like the
+    // stored output, rows beyond M contribute zero.  All 32 lanes take part (no early exit above).
+    float t[32];
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(r[j]);
+      if (epi.mask != nullptr) {
+        const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk4[j / 8]);
+        x = (__bfloat162float(me[j & 7]) > 0.0f) ? x : 0.0f;
+      }
+      t[j] = (row < M) ? __bfloat162float(__float2bfloat16_rn(x)) : 0.0f;
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const float send = up ? t[i] : t[i + s];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+        t[i] = (up ? t[i + s] : t[i]) + recv;
+      }
+    }
+    if (col + lane < N) atomicAdd(epi.colsum + col + lane, t[0]);
+  }
   if (!(row < M && col < N)) return;
   float v[32];
 #pragma unroll
@@ -778,11 +807,11 @@ int narrow_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, void* Z
   int64_t total = K * NARROW_N;
   pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, nullptr, Wt, K, (int)N, 0, NARROW_N);
   PG_LAUNCHED(ctx);
-  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, 1, 1, nullptr, 1, 1 << 30};
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, 1, 1, nullptr, nullptr, 1, 1 << 30};
   return launch_tc<false, false, NARROW_N>(ctx, X, Wt, Z, M, N, K, K, K, epi);
 }
 
-int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* dW, void* db, void* dX, const void* mask, int64_t M, int64_t K, int64_t N) {
+int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* dW, void* db, void* dX, const void* mask, void* dx_colsum, int64_t M, int64_t K, int64_t N) {
   PG_REQUIRE(K % 8 == 0 && M % 8 == 0, "narrow tensor-core layer needs K % 8 == 0 and batch % 8 == 0 (TMA 16-byte pitch)");
   const size_t dzp_bytes = align256((size_t)M * NARROW_K * 2), dzt_bytes = align256((size_t)NARROW_N * M * 2), wp_bytes = align256((size_t)K * NARROW_K * 2);
   // layout of the scratch: [W^T padded (forward)] [dZ padded] [dZ^T padded] [W padded]
@@ -807,7 +836,7 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
     if (splits > 8) splits = 8;
     int kb_per = (int)pg_cdiv(num_kb, splits);
     splits = (int)pg_cdiv(num_kb, kb_per);
-    Epi epi{nullptr, nullptr, 0, 1, 1, nullptr, splits, kb_per};
+    Epi epi{nullptr, nullptr, 0, 1, 1, nullptr, nullptr, splits, kb_per};
     void* target = dW;
     if (splits > 1) {
       rc = pg_ws_ensure(ctx, (size_t)splits * K * N * sizeof(float));
@@ -829,7 +858,8 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
     int64_t total = K * NARROW_K;
     pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, Wp, nullptr, K, (int)N, NARROW_K, 0);
     PG_LAUNCHED(ctx);
-    Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, 0, 0, nullptr, 1, 1 << 30};
+    if (dx_colsum) PG_CHECK_CUDA(cudaMemsetAsync(dx_colsum, 0, (size_t)K * sizeof(float), ctx->stream));
+    Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, 0, 0, (float*)dx_colsum, nullptr, 1, 1 << 30};
     rc = launch_tc<false, false, 256>(ctx, dZp, Wp, dX, M, K, NARROW_K, NARROW_K, NARROW_K, epi);
     if (rc != PG_OK) return rc;
   }
@@ -844,7 +874,7 @@ int pg_tc_gemm(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, i
   PG_CHECK_CTX(ctx);
   PG_REQUIRE(A && B && C, "null pointer");
   PG_REQUIRE(c_dtype == PG_F32 || c_dtype == PG_BF16, "C must be f32 or bf16");
-  Epi epi{nullptr, nullptr, 0, c_dtype == PG_F32, 0, nullptr, 1, 1 << 30};
+  Epi epi{nullptr, nullptr, 0, c_dtype == PG_F32, 0, nullptr, nullptr, 1, 1 << 30};
   return tc_dispatch(ctx, layout, A, B, C, M, N, K, epi);
 }
 
@@ -856,19 +886,20 @@ int pg_tc_linear_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, v
     return narrow_fwd(ctx, X, W, b, Y, M, K, N, act);
   }
   PG_REQUIRE(y_dtype == PG_BF16 || y_dtype == PG_F32, "Y must be bf16 or f32");
-  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, y_dtype == PG_F32, 0, nullptr, 1, 1 << 30};
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, y_dtype == PG_F32, 0, nullptr, nullptr, 1, 1 << 30};
   return tc_dispatch(ctx, 0, X, W, Y, M, N, K, epi);
 }
 
-int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
-                     const void* relu_mask, int64_t M, int64_t K, int64_t N) {
+int pg_tc_linear_bwd_ex(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
+                        const void* relu_mask, void* dx_colsum, int64_t M, int64_t K, int64_t N) {
   PG_CHECK_CTX(ctx);
   PG_REQUIRE(dY != nullptr, "null dY");
   PG_REQUIRE(!dW || X, "dW needs X");
   PG_REQUIRE(!dX || W, "dX needs W");
+  PG_REQUIRE(!dx_colsum || dX, "dx_colsum needs dX");
   if (N <= 32) {
     PG_REQUIRE(dy_dtype == PG_F32, "narrow layers (N <= 32) take f32 dY");
-    return narrow_bwd(ctx, X, W, dY, dW, db, dX, relu_mask, M, K, N);
+    return narrow_bwd(ctx, X, W, dY, dW, db, dX, relu_mask, dx_colsum, M, K, N);
   }
   PG_REQUIRE(dy_dtype == PG_BF16, "wide layers take bf16 dY");
   int rc;
@@ -877,7 +908,7 @@ int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, 
     // tiles already staged in shared memory (no extra pass over dY)
     const bool fuse_db = db != nullptr && pg_cdiv(K, BLOCK_M) >= 4;
     if (fuse_db) PG_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), ctx->stream));
-    Epi epi{nullptr, nullptr, 0, 1, 0, fuse_db ? (float*)db : nullptr, 1, 1 << 30};
+    Epi epi{nullptr, nullptr, 0, 1, 0, nullptr, fuse_db ? (float*)db : nullptr, 1, 1 << 30};
     rc = tc_dispatch(ctx, 2, X, dY, dW, K, N, M, epi);
     if (rc != PG_OK) return rc;
     if (fuse_db) db = nullptr;
@@ -887,11 +918,17 @@ int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, 
     if (rc != PG_OK) return rc;
   }
   if (dX) {  // dX[M][K] = dY W^T: GEMM (M'=M, N'=K, K'=N), A = dY [M][N] K-major, B = W [K][N] K-major
-    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, 0, 0, nullptr, 1, 1 << 30};
+    if (dx_colsum) PG_CHECK_CUDA(cudaMemsetAsync(dx_colsum, 0, (size_t)K * sizeof(float), ctx->stream));
+    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, 0, 0, (float*)dx_colsum, nullptr, 1, 1 << 30};
     rc = tc_dispatch(ctx, 1, dY, W, dX, M, K, N, epi);
     if (rc != PG_OK) return rc;
   }
   return PG_OK;
+}
+
+int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
+                     const void* relu_mask, int64_t M, int64_t K, int64_t N) {
+  return pg_tc_linear_bwd_ex(ctx, X, W, dY, dy_dtype, dW, db, dX, relu_mask, nullptr, M, K, N);
 }
 
 }  // extern "C"

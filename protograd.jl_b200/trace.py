@@ -575,6 +575,7 @@ class Plan:
         finish in reverse order), so a data-parallel caller can start reducing that bucket."""
         h = self.ctx.h
         P = lambda a: a.ptr if a is not None else None
+        db_done = set()    # linear nodes whose bias gradient was produced by a downstream epilogue
         for i in range(self.n - 1, -1, -1):
             if not self.need[i] or not self.ng[i]:
                 continue
@@ -601,14 +602,27 @@ class Plan:
                         xv = self._as_bf16(x) if gW is not None else None
                         Wv = self._as_bf16(W) if gx is not None else None
                         gyc = PG_BF16 if gy.dtype == BF16 else PG_F32
+                        if i in db_done:
+                            gb = None                       # already produced by the downstream layer's dX epilogue
+                        # bias gradient of the layer that produced x = column sums of (masked) dX: let this
+                        # layer's data-gradient epilogue accumulate them instead of a separate pass over dX
+                        prev_db = None
+                        if gx is not None and gx.dtype == BF16:
+                            xb = self._base(x)
+                            prod = self.fused_into.get(xb) if self.ops[xb] == "relu" else (xb if self.ops[xb] == "linear" else None)
+                            if prod is not None and self.ops[prod] == "linear" and (self.ops[xb] != "relu" or mask is not None):
+                                pb_ = self.inputs[prod][2]
+                                if self.ng[pb_]:
+                                    prev_db = grad_leaves[self.attrs[pb_]["grad_index"]]
+                                    db_done.add(prod)
                         if on_ready is not None and gx is not None and (gW is not None or gb is not None):
                             # data-parallel: parameter gradients first, so their bucket can start reducing
                             # while this layer's data gradient (and everything upstream) still computes
-                            call("pg_tc_linear_bwd", h, P(xv), None, gy.ptr, gyc, P(gW), P(gb), None, None, M, K, N)
+                            call("pg_tc_linear_bwd_ex", h, P(xv), None, gy.ptr, gyc, P(gW), P(gb), None, None, None, M, K, N)
                             on_ready(min(self.attrs[j]["grad_index"] for j in (W, b) if self.ng[j]))
-                            call("pg_tc_linear_bwd", h, None, P(Wv), gy.ptr, gyc, None, None, P(gx), P(mask), M, K, N)
+                            call("pg_tc_linear_bwd_ex", h, None, P(Wv), gy.ptr, gyc, None, None, P(gx), P(mask), P(prev_db), M, K, N)
                             continue
-                        call("pg_tc_linear_bwd", h, P(xv), P(Wv), gy.ptr, gyc, P(gW), P(gb), P(gx), P(mask), M, K, N)
+                        call("pg_tc_linear_bwd_ex", h, P(xv), P(Wv), gy.ptr, gyc, P(gW), P(gb), P(gx), P(mask), P(prev_db), M, K, N)
                     else:
                         call("pg_linear_bwd", h, code, self._val(x).ptr, self._val(W).ptr, gy.ptr, P(gW), P(gb), P(gx), P(mask), M, K, N)
                 else:
