@@ -136,88 +136,53 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) 
          ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-// ---- epilogue -----------------------------------------------------------------------------------
-// tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns per chunk).  Storing rows
-// thread-by-thread makes every warp-level 16-byte store touch 32 different cache lines, which costs ~14k
-// cycles per 128x256 tile and made short-K launches epilogue-bound.  For bf16 outputs the four lanes of a
-// quad therefore exchange 16-byte pieces (3 xor-shuffles): afterwards lane j of a quad holds piece j
-// (8 columns) of the quad's 4 rows, so each store / mask-load instruction covers 8 rows x 64 contiguous
-// bytes (4x fewer line requests).  The ReLU' mask is fetched in the same transposed distribution and
-// applied on the packed pieces; column sums (bias gradient of the upstream layer) are reduced from there.
-__device__ __forceinline__ uint4 sel4(const uint4 (&p)[4], int idx) {
-  uint4 r = p[0];
-  r = idx == 1 ? p[1] : r;
-  r = idx == 2 ? p[2] : r;
-  r = idx == 3 ? p[3] : r;
-  return r;
-}
-__device__ __forceinline__ uint4 shfl_xor_u4(uint4 v, int d) {
-  v.x = __shfl_xor_sync(0xffffffffu, v.x, d); v.y = __shfl_xor_sync(0xffffffffu, v.y, d);
-  v.z = __shfl_xor_sync(0xffffffffu, v.z, d); v.w = __shfl_xor_sync(0xffffffffu, v.w, d);
-  return v;
-}
-// keep x where m > 0 (packed bf16 pairs)
-__device__ __forceinline__ uint32_t mask_pair(uint32_t x, uint32_t m) {
-  const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(&x);
-  const __nv_bfloat162 mv = *reinterpret_cast<const __nv_bfloat162*>(&m);
-  const float lo = __low2float(mv) > 0.0f ? __low2float(xv) : 0.0f;
-  const float hi = __high2float(mv) > 0.0f ? __high2float(xv) : 0.0f;
-  const __nv_bfloat162 o = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&o);
-}
-
-// transposed mask prefetch for one 32-column chunk: mkT[d] = piece (lane & 3) of row (row ^ d)
-__device__ __forceinline__ void load_mask_chunk(uint4 (&mkT)[4], const __nv_bfloat16* mask, int M, int N, int row, int col) {
-  const int lj = threadIdx.x & 3;
-#pragma unroll
-  for (int d = 0; d < 4; ++d) {
-    const int rr = row ^ d;
-    mkT[d] = (rr < M && col + 8 * lj < N) ? __ldg(reinterpret_cast<const uint4*>(mask + (size_t)rr * N + col + 8 * lj)) : make_uint4(0, 0, 0, 0);
-  }
-}
-
-// One 32-column chunk of one accumulator row: bias / ReLU / ReLU' mask / column sums / store.
-// Must be called by all 32 lanes of the warp (shuffles); mkT as produced by load_mask_chunk.
+// One 32-column chunk of one accumulator row: bias / ReLU / ReLU' mask / store (shared by both kernels).
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Epi& epi, void* __restrict__ C, int M, int N,
-                                               int row, int col, int split, const uint4 (&mkT)[4]) {
+                                               int row, int col, int split, const uint4* mk4) {
+  if (epi.colsum != nullptr) {
+    // column sums of this warp's 32 x 32 block (rows = lanes): butterfly transpose-reduce, 31 shuffles;
+    // afterwards lane l holds the sum of column l.  Values are masked and bf16-rounded exactly like the
+    // stored output, rows beyond M contribute zero.  All 32 lanes take part (no early exit above).
+    float t[32];
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(r[j]);
+      if (epi.mask != nullptr) {
+        const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk4[j / 8]);
+        x = (__bfloat162float(me[j & 7]) > 0.0f) ? x : 0.0f;
+      }
+      t[j] = (row < M) ? __bfloat162float(__float2bfloat16_rn(x)) : 0.0f;
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const float send = up ? t[i] : t[i + s];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+        t[i] = (up ? t[i + s] : t[i]) + recv;
+      }
+    }
+    if (col + lane < N) atomicAdd(epi.colsum + col + lane, t[0]);
+  }
+  if (!(row < M && col < N)) return;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  if (epi.out_f32) {
-    if (!(row < M && col < N)) return;
-    if (epi.narrow) {
-      // N is not a multiple of 8 (e.g. 10 logits): scalar, fully guarded fp32 path
-      float* op = reinterpret_cast<float*>(C) + (size_t)split * M * N + (size_t)row * N;
+  if (epi.narrow) {
+    // N is not a multiple of 8 (e.g. 10 logits): scalar, fully guarded fp32 path
+    float* op = reinterpret_cast<float*>(C) + (size_t)split * M * N + (size_t)row * N;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (col + j < N) {
-          float o = v[j] + (epi.bias != nullptr ? epi.bias[col + j] : 0.0f);
-          if (epi.relu) o = fmaxf(o, 0.0f);
-          op[col + j] = o;
-        }
-      }
-      return;
-    }
-    if (epi.bias != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (col + j < N) {
-          const float4 b4 = *reinterpret_cast<const float4*>(epi.bias + col + j);
-          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-        }
+    for (int j = 0; j < 32; ++j) {
+      if (col + j < N) {
+        float o = v[j] + (epi.bias != nullptr ? epi.bias[col + j] : 0.0f);
+        if (epi.relu) o = fmaxf(o, 0.0f);
+        op[col + j] = o;
       }
     }
-    if (epi.relu) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-    }
-    float* op = reinterpret_cast<float*>(C) + (size_t)split * M * N + (size_t)row * N + col;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      if (col + j < N) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     return;
   }
-  // ---- bf16 output ----
   if (epi.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -231,54 +196,29 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
-  uint4 pc[4];
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    __nv_bfloat162 pk[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) pk[e] = __floats2bfloat162_rn(v[8 * p + 2 * e], v[8 * p + 2 * e + 1]);
-    pc[p] = *reinterpret_cast<uint4*>(pk);
-  }
-  const int lj = threadIdx.x & 3;
-  uint4 T[4];                                   // T[d] = piece lj of row (row ^ d)
-  T[0] = sel4(pc, lj);
-#pragma unroll
-  for (int d = 1; d < 4; ++d) T[d] = shfl_xor_u4(sel4(pc, lj ^ d), d);
   if (epi.mask != nullptr) {
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      T[d].x = mask_pair(T[d].x, mkT[d].x); T[d].y = mask_pair(T[d].y, mkT[d].y);
-      T[d].z = mask_pair(T[d].z, mkT[d].z); T[d].w = mask_pair(T[d].w, mkT[d].w);
+    for (int j = 0; j < 32; j += 8) {
+      const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk4[j / 8]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j + e] = (__bfloat162float(me[e]) > 0.0f) ? v[j + e] : 0.0f;
     }
   }
-  if (epi.colsum != nullptr) {
-    // this lane's 8 columns summed over the quad's 4 rows, then over the 8 quads of the warp
-    float cs[8];
+  if (epi.out_f32) {
+    float* op = reinterpret_cast<float*>(C) + (size_t)split * M * N + (size_t)row * N + col;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) cs[e] = 0.0f;
+    for (int j = 0; j < 32; j += 4)
+      if (col + j < N) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(C) + (size_t)row * N + col;
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      if ((row ^ d) < M) {
-        const __nv_bfloat162* q = reinterpret_cast<const __nv_bfloat162*>(&T[d]);
+    for (int j = 0; j < 32; j += 8) {
+      if (col + j < N) {
+        __nv_bfloat162 pk[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { cs[2 * e] += __low2float(q[e]); cs[2 * e + 1] += __high2float(q[e]); }
+        for (int e = 0; e < 4; ++e) pk[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(op + j) = *reinterpret_cast<uint4*>(pk);
       }
-    }
-#pragma unroll
-    for (int s = 4; s <= 16; s <<= 1)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], s);
-    if ((threadIdx.x & 31) < 4 && col + 8 * lj < N) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(epi.colsum + col + 8 * lj + e, cs[e]);
-    }
-  }
-  if (col + 8 * lj < N) {
-    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(C) + col + 8 * lj;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      const int rr = row ^ d;
-      if (rr < M) *reinterpret_cast<uint4*>(base + (size_t)rr * N) = T[d];
     }
   }
 }
@@ -453,10 +393,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool active = BLOCK_N >= 64 || half == 0;
       // ReLU' mask of this thread's row slice: issued BEFORE waiting for the accumulator, so its HBM
       // latency overlaps the tile's MMAs instead of serialising with every 32-column chunk
-      uint4 mk[COLS_PER_WARP / 32][4];
+      uint4 mk[COLS_PER_WARP / 8];
       if (epi.mask != nullptr && active) {
+        const __nv_bfloat16* mp = epi.mask + (size_t)row * N + n0 + c_begin;
 #pragma unroll
-        for (int ci = 0; ci < COLS_PER_WARP / 32; ++ci) load_mask_chunk(mk[ci], epi.mask, M, N, row, n0 + c_begin + ci * 32);
+        for (int j = 0; j < COLS_PER_WARP / 8; ++j)
+          mk[j] = (row < M && n0 + c_begin + 8 * j < N) ? __ldg(reinterpret_cast<const uint4*>(mp) + j) : make_uint4(0, 0, 0, 0);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
@@ -468,7 +410,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         tmem_ld_wait();
-        epilogue_chunk(r, epi, C, M, N, row, n0 + c, split, mk[ci]);
+        epilogue_chunk(r, epi, C, M, N, row, n0 + c, split, &mk[ci * 4]);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -657,10 +599,12 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tile_coords(tile, m0, n0);
       const int row = m0 + (int)rank * 128 + q * 32 + lane;
       const int c_begin = half * COLS_PER_WARP;
-      uint4 mk[COLS_PER_WARP / 32][4];
+      uint4 mk[COLS_PER_WARP / 8];
       if (epi.mask != nullptr) {
+        const __nv_bfloat16* mp = epi.mask + (size_t)row * N + n0 + c_begin;
 #pragma unroll
-        for (int ci = 0; ci < COLS_PER_WARP / 32; ++ci) load_mask_chunk(mk[ci], epi.mask, M, N, row, n0 + c_begin + ci * 32);
+        for (int j = 0; j < COLS_PER_WARP / 8; ++j)
+          mk[j] = (row < M && n0 + c_begin + 8 * j < N) ? __ldg(reinterpret_cast<const uint4*>(mp) + j) : make_uint4(0, 0, 0, 0);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
@@ -671,7 +615,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         tmem_ld_wait();
-        epilogue_chunk(r, epi, C, M, N, row, n0 + c, 0, mk[ci]);
+        epilogue_chunk(r, epi, C, M, N, row, n0 + c, 0, &mk[ci * 4]);
       }
       tcgen05_fence_before();
       __syncwarp();
