@@ -24,6 +24,7 @@ def _prod(shape):
     return n
 
 
+FUSE_PREV_DB = False   # bias gradients of hidden layers from the downstream dX epilogue (see Plan.backward)
 _current = None  # the Trace being recorded (set by eval_with_pullback / forward)
 _rng = {"seed": 0x5EED5EED, "step": 0}
 
@@ -607,7 +608,10 @@ class Plan:
                         # bias gradient of the layer that produced x = column sums of (masked) dX: let this
                         # layer's data-gradient epilogue accumulate them instead of a separate pass over dX
                         prev_db = None
-                        if gx is not None and gx.dtype == BF16:
+                        # (measured: a wash on C4 — the narrow data-gradient launch is epilogue-bound and pays
+                        #  +18 us for it, the wide one +6 us, vs ~25 us saved in the weight-gradient launches — so
+                        #  it stays off by default; tools/colsum_bench.py)
+                        if FUSE_PREV_DB and gx is not None and gx.dtype == BF16:
                             xb = self._base(x)
                             prod = self.fused_into.get(xb) if self.ops[xb] == "relu" else (xb if self.ops[xb] == "linear" else None)
                             if prod is not None and self.ops[prod] == "linear" and (self.ops[xb] != "relu" or mask is not None):

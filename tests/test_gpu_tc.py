@@ -129,5 +129,6 @@ def test_tc_steps_with_fused_shadow_match_plain_steps(pg):
             pg.step(st, pb(), shadow=use_shadow)
             losses.append(float(out))
         res.append((losses, m.vec()))
-    assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1])
+    # bias gradients are accumulated with fp32 atomics, so two runs agree to rounding, not bit for bit
+    assert np.allclose(res[0][0], res[1][0], rtol=1e-5) and rel_err(res[0][1], res[1][1]) <= 1e-5
     assert res[0][0][-1] < res[0][0][0]
