@@ -171,6 +171,11 @@ int pg_cross_entropy_fwd_bwd(pg_ctx* ctx, int dtype, const void* P, const void* 
 int pg_mse_fwd_bwd(pg_ctx* ctx, int dtype, const void* Yhat, const void* Y, void* dY, void* loss_dev, int64_t n, double inv_denom);
 /* class_error (losses.jl:12-16): fraction of rows whose argmax differs; synchronising */
 int pg_class_error(pg_ctx* ctx, int dtype, const void* P, const void* Y, int64_t B, int C, double* result);
+/* ---- data step next to the path (examples/01_mnist_mlp.jl:17,35-38) -------------------- */
+/* dst[r][:] = src[idx[r]][:]  — on-device minibatch gather from a dataset resident in HBM */
+int pg_gather_rows(pg_ctx* ctx, int dtype, const void* src, const int32_t* idx, void* dst, int64_t rows, int64_t row_elems);
+/* dense one-hot labels [B][C] from integer classes (Flux.onehotbatch) */
+int pg_onehot(pg_ctx* ctx, int dtype, const int32_t* labels, void* out, int64_t B, int C);
 /* read a device loss scalar of type T (the step's only host sync) */
 int pg_loss_read(pg_ctx* ctx, int dtype, const void* loss_dev, double* result);
 

@@ -95,6 +95,8 @@ _SIGS = {
     "pg_cross_entropy_fwd_bwd": [_P, _I, _P, _P, _P, _P, _L, _I, _D],
     "pg_mse_fwd_bwd": [_P, _I, _P, _P, _P, _P, _L, _D],
     "pg_class_error": [_P, _I, _P, _P, _L, _I, POINTER(c_double)],
+    "pg_gather_rows": [_P, _I, _P, _P, _P, _L, _L],
+    "pg_onehot": [_P, _I, _P, _P, _L, _I],
     "pg_loss_read": [_P, _I, _P, POINTER(c_double)],
 }
 

@@ -266,3 +266,55 @@ int pg_class_error(pg_ctx* ctx, int dtype, const void* P, const void* Y, int64_t
 }
 
 }  // extern "C"
+
+// ---- data step next to the path: the reference materialises every minibatch on the
+// host as `train_x_flat[:, idx]` / `train_y_onehot[:, idx]` (examples/01_mnist_mlp.jl:35-38).  With the
+// dataset resident in HBM the gather becomes one coalesced kernel and labels can stay integers.
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ src, const int32_t* __restrict__ idx, T* __restrict__ dst, int64_t rows, int64_t row_elems) {
+  const int64_t total = rows * row_elems;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / row_elems, c = i - r * row_elems;
+    dst[i] = src[(int64_t)idx[r] * row_elems + c];
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) onehot_kernel(const int32_t* __restrict__ labels, T* __restrict__ out, int64_t B, int C) {
+  const int64_t total = B * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int)(i % C) == labels[i / C] ? T(1) : T(0);
+}
+}  // namespace
+
+extern "C" {
+
+int pg_gather_rows(pg_ctx* ctx, int dtype, const void* src, const int32_t* idx, void* dst, int64_t rows, int64_t row_elems) {
+  PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
+  PG_REQUIRE(src && idx && dst, "null pointer");
+  const int64_t total = rows * row_elems;
+  if (total <= 0) return PG_OK;
+  int64_t blocks = pg_cdiv(total, 256);
+  const int64_t cap = (int64_t)ctx->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (dtype == PG_F32) gather_rows_kernel<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const float*)src, idx, (float*)dst, rows, row_elems);
+  else gather_rows_kernel<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const double*)src, idx, (double*)dst, rows, row_elems);
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+int pg_onehot(pg_ctx* ctx, int dtype, const int32_t* labels, void* out, int64_t B, int C) {
+  PG_CHECK_CTX(ctx); PG_FLOAT_DTYPE(dtype);
+  PG_REQUIRE(labels && out && C > 0, "null pointer or C <= 0");
+  const int64_t total = B * C;
+  if (total <= 0) return PG_OK;
+  int64_t blocks = pg_cdiv(total, 256);
+  const int64_t cap = (int64_t)ctx->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (dtype == PG_F32) onehot_kernel<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(labels, (float*)out, B, C);
+  else onehot_kernel<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(labels, (double*)out, B, C);
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+}  // extern "C"

@@ -308,3 +308,30 @@ def test_loss_fetch_async_and_prefetcher(pg):
     got = [float(o) for o in outs]
     assert got == ref
     assert np.array_equal(m1.vec(), m2.vec())
+
+
+def test_device_dataset_and_checkpoint(pg, tmp_path):
+    """on-device minibatch gather + one-hot, and a vec(m)-order checkpoint round trip
+    (test/test_models.jl:244-273 checks `out_copy == out` after Serialization)."""
+    rng = np.random.default_rng(0)
+    n = 1000
+    X = rng.random((n, 784)).astype(np.float32); labels = rng.integers(0, 10, n)
+    ds = pg.DeviceDataset(X, labels, 10)
+    idx = rng.choice(n, 128, replace=False)
+    xb, yb = ds.batch(idx)
+    assert np.array_equal(xb.numpy(), X[idx]) and np.array_equal(yb.numpy(), np.eye(10, dtype=np.float32)[labels[idx]])
+    spec = MG.C1_SPEC
+    m = build_model(pg, spec, MG.biased_params(spec, np.float32, 9))
+    st = pg.init(pg.Adam(1e-3), m)
+    for _ in range(3):
+        out, pb = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(xb), yb), m)
+        pg.step(st, pb())
+    before = m(X[:64]).numpy()
+    pg.save(tmp_path / "ckpt", m, st)
+    m2 = build_model(pg, spec, MG.biased_params(spec, np.float32, 10)); st2 = pg.init(pg.Adam(1e-3), m2)
+    pg.load(tmp_path / "ckpt", m2, st2)
+    assert np.array_equal(m2(X[:64]).numpy(), before) and st2.it == st.it
+    for s_, mm_ in ((st, m), (st2, m2)):                      # resumed training continues identically
+        out, pb = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(xb), yb), mm_)
+        pg.step(s_, pb())
+    assert np.array_equal(m.vec(), m2.vec())
