@@ -485,8 +485,11 @@ __host__ __device__ constexpr uint32_t make_idesc2(bool a_mn, bool b_mn) {   // 
          ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// DBW (weight-gradient launches): one extra reducer warp per CTA sums the CTA's half of the staged dY
+// tiles (see the 1-CTA kernel).  The peer CTA cannot wait on the leader's full barrier, so the leader's
+// MMA thread forwards every "stage landed" to the peer's ready[] barrier with a remote arrive.
+template <bool A_MN, bool B_MN, bool DBW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS + (DBW ? 32 : 0), 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ C,
                 int M, int N, int K, Epi epi) {
   constexpr int BN = 256;
@@ -498,7 +501,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES2 + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_aligned + STAGES2 * STAGE2_BYTES + 8 * (2 * STAGES2 + 4));
+  auto ready_bar = [&](int s) { return bar_base + 8u * (2 * STAGES2 + 4 + s); };     // peer CTA: "stage s has landed"
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_aligned + STAGES2 * STAGE2_BYTES + 8 * (3 * STAGES2 + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -515,7 +519,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), DBW ? 2 : 1); mbar_init(ready_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -573,6 +577,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);             // both CTAs' bytes have landed
+          if (DBW) mbar_arrive_cluster(map_to_rank(ready_bar(stage), 1));   // tell the peer's reducer warp
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
 #pragma unroll
@@ -586,6 +591,42 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (DBW && warp >= 2 + EPI_WARPS) {
+    // ===== bias-gradient reducer warp (one per CTA): this CTA's 128 columns of the dY tile =====
+    static_assert(!DBW || B_MN, "reducer warps read MN-major B tiles");
+    const int col0 = lane * 4;                           // 4 consecutive columns of the CTA's half
+    const uint32_t box_off = (uint32_t)(col0 >> 6) * (BLOCK_K * 128) + (uint32_t)(col0 & 7) * 2;
+    const int chunk = (col0 & 63) >> 3;
+    float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int m0, n0;
+      tile_coords(tile, m0, n0);
+      const int m_blk = m0 / 256;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(rank == 0 ? full_bar(stage) : ready_bar(stage), phase);
+        if (kb % num_m == m_blk) {
+          const uint8_t* sb = smem_aligned + stage * STAGE2_BYTES + A_STAGE_BYTES + box_off;
+#pragma unroll 8
+          for (int r = 0; r < BLOCK_K; ++r) {
+            const uint2 v = *reinterpret_cast<const uint2*>(sb + r * 128 + ((chunk ^ (r & 7)) << 4));
+            const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+            const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+            acc4[0] += __low2float(p0); acc4[1] += __high2float(p0);
+            acc4[2] += __low2float(p1); acc4[3] += __high2float(p1);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(stage));
+        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+      }
+      const int cbase = n0 + (int)rank * 128 + col0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (cbase + j < N) atomicAdd(epi.db + cbase + j, acc4[j]);
+        acc4[j] = 0.f;
       }
     }
   } else {
@@ -695,7 +736,7 @@ int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int
   return PG_OK;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool DBW = false>
 int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, const Epi& epi) {
   CUtensorMap ma, mb;
   int rc;
@@ -703,7 +744,7 @@ int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, in
   if (rc != PG_OK) return rc;
   rc = B_MN ? make_map(ctx, &mb, B, K, N, ldb, 64, BLOCK_K) : make_map(ctx, &mb, B, N, K, ldb, BLOCK_K, 128);
   if (rc != PG_OK) return rc;
-  auto kern = tc_gemm2_kernel<A_MN, B_MN>;
+  auto kern = tc_gemm2_kernel<A_MN, B_MN, DBW>;
   static bool attr_set = false;
   if (!attr_set) {
     PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -711,7 +752,7 @@ int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, in
   }
   int64_t tiles = pg_cdiv(M, 256) * pg_cdiv(N, 256);
   int clusters = (int)(tiles < ctx->num_sms / 2 ? tiles : ctx->num_sms / 2);
-  kern<<<2 * clusters, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi);
+  kern<<<2 * clusters, NUM_THREADS + (DBW ? 32 : 0), SMEM2_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi);
   PG_LAUNCHED(ctx);
   return PG_OK;
 }
@@ -728,11 +769,12 @@ int tc_dispatch(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, 
   PG_REQUIRE(N % 8 == 0 && K % 8 == 0, "tensor-core GEMM needs N % 8 == 0 and K % 8 == 0 (TMA 16-byte pitch)");
   PG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "operands must be 16-byte aligned");
   PG_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension too large");
-  if (epi.db == nullptr && epi.splits == 1 && use_2cta(M, N)) {
+  if (epi.splits == 1 && use_2cta(M, N)) {
     switch (layout) {
       case 0: return launch_tc2<false, true>(ctx, A, B, C, M, N, K, K, N, epi);
       case 1: return launch_tc2<false, false>(ctx, A, B, C, M, N, K, K, K, epi);
-      case 2: return launch_tc2<true, true>(ctx, A, B, C, M, N, K, M, N, epi);
+      case 2: return epi.db != nullptr ? launch_tc2<true, true, true>(ctx, A, B, C, M, N, K, M, N, epi)
+                                       : launch_tc2<true, true>(ctx, A, B, C, M, N, K, M, N, epi);
     }
   }
   switch (layout) {
@@ -906,7 +948,7 @@ int pg_tc_linear_bwd_ex(pg_ctx* ctx, const void* X, const void* W, const void* d
   if (dW) {  // dW[K][N] = X^T dY: GEMM (M'=K, N'=N, K'=M), A = X stored [M][K] (MN-major), B = dY stored [M][N] (MN-major)
     // db = column sums of dY ride along when enough m-blocks share the work: reducer warps sum the dY
     // tiles already staged in shared memory (no extra pass over dY)
-    const bool fuse_db = db != nullptr && pg_cdiv(K, BLOCK_M) >= 4;
+    const bool fuse_db = db != nullptr && (use_2cta(K, N) ? pg_cdiv(K, 256) >= 4 : pg_cdiv(K, BLOCK_M) >= 4);
     if (fuse_db) PG_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), ctx->stream));
     Epi epi{nullptr, nullptr, 0, 1, 0, nullptr, fuse_db ? (float*)db : nullptr, 1, 1 << 30};
     rc = tc_dispatch(ctx, 2, X, dY, dW, K, N, M, epi);
