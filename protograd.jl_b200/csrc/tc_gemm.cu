@@ -772,7 +772,8 @@ int tc_dispatch(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, 
   PG_REQUIRE(N % 8 == 0 && K % 8 == 0, "tensor-core GEMM needs N % 8 == 0 and K % 8 == 0 (TMA 16-byte pitch)");
   PG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "operands must be 16-byte aligned");
   PG_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension too large");
-  if (epi.splits == 1 && use_2cta(M, N)) {
+  static const bool dbw_1cta = getenv("PG_DBW_1CTA") != nullptr;        // A/B switch for the fused bias gradient
+  if (epi.splits == 1 && use_2cta(M, N) && !(epi.db != nullptr && dbw_1cta)) {
     switch (layout) {
       case 0: return launch_tc2<false, true>(ctx, A, B, C, M, N, K, K, N, epi);
       case 1: return launch_tc2<false, false>(ctx, A, B, C, M, N, K, K, K, epi);
@@ -951,7 +952,7 @@ int pg_tc_linear_bwd_ex(pg_ctx* ctx, const void* X, const void* W, const void* d
   if (dW) {  // dW[K][N] = X^T dY: GEMM (M'=K, N'=N, K'=M), A = X stored [M][K] (MN-major), B = dY stored [M][N] (MN-major)
     // db = column sums of dY ride along when enough m-blocks share the work: reducer warps sum the dY
     // tiles already staged in shared memory (no extra pass over dY)
-    const bool fuse_db = db != nullptr && (use_2cta(K, N) ? pg_cdiv(K, 256) >= 4 : pg_cdiv(K, BLOCK_M) >= 4);
+    const bool fuse_db = db != nullptr && (use_2cta(K, N) && getenv("PG_DBW_1CTA") == nullptr ? pg_cdiv(K, 256) >= 4 : pg_cdiv(K, BLOCK_M) >= 4);
     if (fuse_db) PG_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), ctx->stream));
     Epi epi{nullptr, nullptr, 0, 1, 0, nullptr, fuse_db ? (float*)db : nullptr, 1, 1 << 30};
     rc = tc_dispatch(ctx, 2, X, dY, dW, K, N, M, epi);
