@@ -226,7 +226,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
 // DBW: two extra "reducer" warps (weight-gradient launches) that read the B (= dY) tiles the TMA producer
 // already staged in shared memory and accumulate their column sums, so the bias gradient costs no extra
 // pass over dY.  The num_m tiles that share an n-block split the k-blocks between them (tile m_blk sums
-// the rows whose sample index is congruent to m_blk modulo num_m: a few rows of every stage) and
+// the stages with kb % num_m == m_blk, ~1.6k cycles each, hidden behind num_m x 512 cycles of MMAs) and
 // add their partial sums to db with one atomicAdd per column; for every stage the reducer warps wait on
 // the full barrier and arrive on the empty barrier like the MMA warp does.  db must be zeroed first.
 template <bool A_MN, bool B_MN, int BLOCK_N, bool DBW>
@@ -356,12 +356,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int m_blk = m0 / BLOCK_M;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
-          {
-            // rows (samples) whose global index is congruent to m_blk modulo num_m: a few rows of every stage
+          if (kb % num_m == m_blk) {
             const uint8_t* sb = smem_aligned + stage * STAGE_BYTES + A_STAGE_BYTES + box_off;
-            int r = (m_blk - (kb * BLOCK_K) % num_m + num_m) % num_m;
-#pragma unroll 4
-            for (; r < BLOCK_K; r += num_m) {             // SWIZZLE_128B: chunk index is XORed with (row & 7)
+#pragma unroll 8
+            for (int r = 0; r < BLOCK_K; ++r) {           // SWIZZLE_128B: chunk index is XORed with (row & 7)
               const uint2 v = *reinterpret_cast<const uint2*>(sb + r * 128 + ((chunk ^ (r & 7)) << 4));
               const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
               const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
@@ -609,11 +607,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int m_blk = m0 / 256;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(rank == 0 ? full_bar(stage) : ready_bar(stage), phase);
-        {
+        if (kb % num_m == m_blk) {
           const uint8_t* sb = smem_aligned + stage * STAGE2_BYTES + A_STAGE_BYTES + box_off;
-          int r = (m_blk - (kb * BLOCK_K) % num_m + num_m) % num_m;
-#pragma unroll 4
-          for (; r < BLOCK_K; r += num_m) {
+#pragma unroll 8
+          for (int r = 0; r < BLOCK_K; ++r) {
             const uint2 v = *reinterpret_cast<const uint2*>(sb + r * 128 + ((chunk ^ (r & 7)) << 4));
             const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
             const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
