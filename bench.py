@@ -192,6 +192,7 @@ def main():
         ctx.set_sm_limit(args.sm_limit)
     use_shadow = args.math == "bf16"
     timeline = [] if os.environ.get("PG_DP_TIMELINE") else None
+    timeline_leaves = []
 
     def train_step(x, lab):
         out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(x), lab, global_batch=GB), model, math=args.math)
@@ -200,10 +201,13 @@ def main():
         elif args.dp_mode == "bucket":
             if timeline is not None:
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                leaf_ev = {}
                 ev[0].record(stream)
 
                 def hook(i):
                     buckets.ready(i)
+                    leaf_ev[i] = torch.cuda.Event(enable_timing=True)
+                    leaf_ev[i].record(stream)  # gradient leaf i has been produced
                     if i == 2:
                         ev[1].record(stream)   # parameter gradients of layers 2,3 done; their bucket was just issued
                 g = pb(on_ready=hook)
@@ -211,6 +215,7 @@ def main():
                 buckets.finish_and_step(state, g, shadow=use_shadow)
                 ev[3].record(stream)
                 timeline.append(ev)
+                timeline_leaves.append((ev[0], leaf_ev))
             else:
                 g = pb(on_ready=buckets.ready)      # tail buckets reduce while the remaining backward GEMMs run
                 buckets.finish_and_step(state, g, shadow=use_shadow)
@@ -260,6 +265,9 @@ def main():
         torch.cuda.synchronize()
         tl = np.array([[e[0].elapsed_time(e[k]) for k in (1, 2, 3)] for e in timeline[-20:]])
         print("DP timeline (ms from step start: bucket issued, backward done, step done):", tl.mean(0).round(4).tolist(), file=sys.stderr)
+        keys = sorted(timeline_leaves[-1][1], reverse=True)
+        lv = np.array([[e0.elapsed_time(le[k]) for k in keys] for e0, le in timeline_leaves[-20:]])
+        print("DP timeline leaves (ms from backward start, gradient leaf done):", dict(zip(keys, lv.mean(0).round(4).tolist())), file=sys.stderr)
     clk = clocks.stop() if rank == 0 else None
     value = GB * args.steps / (ms * 1e-3)
 

@@ -31,7 +31,7 @@ template <int BN> struct Cfg {
   static constexpr int STAGES = BN == 256 ? 4 : 8;
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 256 /*tile ring*/;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // power of two >= 32
 };
 
@@ -112,6 +112,59 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- dynamic tile scheduler ----------------------------------------------------------------------
+// Work items are handed out by an atomic counter instead of the static `work += gridDim.x` stride, so
+// a CTA (pair) that becomes resident late — its SM was busy with a concurrent kernel, e.g. an NCCL
+// all-reduce overlapped with the backward pass — simply takes fewer tiles instead of running its whole
+// static share after everyone else has finished.  One scheduler thread per CTA (pair) fetches the ids
+// (the fetch for tile i+1 is in flight while tile i's loads are issued) and publishes them through a
+// small shared-memory ring with one mbarrier per slot; every other role reads the ring.  Slots need
+// no "empty" barrier: the producer leads the MMA issuer by <= STAGES tiles and the issuer leads the
+// epilogue by <= 2 (accumulator double buffering), so RING >= STAGES + 4 slots are never overwritten
+// early.  An id >= num_work ends every role.  The last scheduler to finish re-zeroes the counters.
+constexpr int RING = 16;
+constexpr int SCHED_SLOT = 32;        // pg_ctx::counters[32] = next work item, [33] = schedulers that have finished
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope: data written by the peer CTA
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+struct TileFeed {            // consumer side of the ring (any thread of any role)
+  uint32_t base;             // RING barriers (8 B each), then RING ids (4 B each)
+  int slot = 0;
+  uint32_t phase = 0;
+  bool remote;               // ids are written by the peer CTA of the cluster
+  __device__ TileFeed(uint32_t b, bool r) : base(b), remote(r) {}
+  __device__ __forceinline__ int next() {
+    const uint32_t bar = base + 8u * slot;
+    if (remote) mbar_wait_cluster(bar, phase); else mbar_wait(bar, phase);
+    const int t = (int)ld_shared_u32(base + 8u * RING + 4u * slot);
+    if (++slot == RING) { slot = 0; phase ^= 1; }
+    return t;
+  }
+};
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
 // [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in
@@ -232,10 +285,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
 template <bool A_MN, bool B_MN, int BLOCK_N, bool DBW>
 __global__ void __launch_bounds__(NUM_THREADS + (DBW ? 64 : 0), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ C,
-               int M, int N, int K, Epi epi) {
+               int M, int N, int K, Epi epi, unsigned int* __restrict__ sched) {
   constexpr int STAGES = Cfg<BLOCK_N>::STAGES, B_STAGE_BYTES = Cfg<BLOCK_N>::B_STAGE_BYTES, STAGE_BYTES = Cfg<BLOCK_N>::STAGE_BYTES;
   constexpr int TMEM_COLS = Cfg<BLOCK_N>::TMEM_COLS;
   static_assert(!B_MN || BLOCK_N % 64 == 0, "MN-major B tiles are made of 64-wide TMA boxes");
+  static_assert(RING >= STAGES + 4, "tile ring shorter than the producer's lead over the epilogue");
+  // the scheduler thread's first fetch is in flight while the barriers / TMEM are set up
+  unsigned int first_work = 0;
+  if (threadIdx.x == 0) first_work = atomicAdd(sched, 1u);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -246,6 +303,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_aligned + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  const uint32_t ring_base = bar_base + 256;             // tile ring: RING barriers + RING ids
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + BLOCK_M - 1) / BLOCK_M, num_n = (N + BLOCK_N - 1) / BLOCK_N;
@@ -265,6 +323,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), DBW ? 3 : 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    for (int i = 0; i < RING; ++i) mbar_init(ring_base + 8u * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -282,7 +341,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      int slot = 0;
+      auto publish = [&](int id) {
+        st_shared_u32(ring_base + 8u * RING + 4u * slot, (uint32_t)id);
+        mbar_arrive(ring_base + 8u * slot);
+        if (++slot == RING) slot = 0;
+      };
+      int work = (int)first_work;
+      publish(work);
+      while (work < num_work) {
+        const int next_work = (int)atomicAdd(sched, 1u);   // consumed after this tile's loads have been issued
         const int tile = work % num_tiles, split = work / num_tiles;
         const int kb0 = split * epi.kb_per_split, kb1 = min(num_kb, kb0 + epi.kb_per_split);
         int m0, n0;
@@ -306,7 +374,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        publish(next_work);
+        work = next_work;
       }
+      // every CTA fetches exactly one terminal id; the last one to do so re-arms the counters
+      if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (single thread) =====
@@ -314,8 +386,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BLOCK_N);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-        const int tile = work % num_tiles, split = work / num_tiles;
+      TileFeed feed(ring_base, false);
+      for (int work = feed.next(); work < num_work; work = feed.next()) {
+        const int split = work / num_tiles;
         const int kb0 = split * epi.kb_per_split, kb1 = min(num_kb, kb0 + epi.kb_per_split);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);       // epilogue has drained this accumulator
         tcgen05_fence_after();
@@ -348,7 +421,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int chunk = (col0 & 63) >> 3;                  // 16-byte chunk inside the 128-byte row
     float acc4[4] = {0.f, 0.f, 0.f, 0.f};
     int stage = 0; uint32_t phase = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+    TileFeed feed(ring_base, false);
+    for (int work = feed.next(); work < num_work; work = feed.next()) {
         const int tile = work % num_tiles, split = work / num_tiles;
         const int kb0 = split * epi.kb_per_split, kb1 = min(num_kb, kb0 + epi.kb_per_split);
         int m0, n0;
@@ -383,9 +457,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int half = (warp - 2) >> 2;                    // which half of the tile's columns this warp drains
     constexpr int COLS_PER_WARP = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-        const int tile = work % num_tiles, split = work / num_tiles;
-        const int kb0 = split * epi.kb_per_split, kb1 = min(num_kb, kb0 + epi.kb_per_split);
+    TileFeed feed(ring_base, false);
+    for (int work = feed.next(); work < num_work; work = feed.next()) {
+      const int tile = work % num_tiles, split = work / num_tiles;
       int m0, n0;
       tile_coords(tile, m0, n0);
       const int row = m0 + q * 32 + lane;
@@ -441,7 +515,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 constexpr int STAGES2 = 6;
 constexpr int B2_STAGE_BYTES = 128 * BLOCK_K * 2;
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;      // 32 KB per CTA
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + 256;
 constexpr int GROUP_M2 = 8;                                        // rasterisation group, in 256-row blocks
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -491,8 +565,13 @@ __host__ __device__ constexpr uint32_t make_idesc2(bool a_mn, bool b_mn) {   // 
 template <bool A_MN, bool B_MN, bool DBW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS + (DBW ? 32 : 0), 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ C,
-                int M, int N, int K, Epi epi) {
+                int M, int N, int K, Epi epi, unsigned int* __restrict__ sched) {
   constexpr int BN = 256;
+  static_assert(RING >= STAGES2 + 4, "tile ring shorter than the producer's lead over the epilogue");
+  const uint32_t rank = cluster_ctarank();
+  // the leader's scheduler thread fetches the pair's first tile while the barriers / TMEM are set up
+  unsigned int first_tile = 0;
+  if (threadIdx.x == 0 && rank == 0) first_tile = atomicAdd(sched, 1u);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -503,10 +582,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + 2 + a); };
   auto ready_bar = [&](int s) { return bar_base + 8u * (2 * STAGES2 + 4 + s); };     // peer CTA: "stage s has landed"
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_aligned + STAGES2 * STAGE2_BYTES + 8 * (3 * STAGES2 + 4));
+  const uint32_t ring_base = bar_base + 256;             // tile ring (same offset in both CTAs): RING barriers + RING ids
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
   const int num_m = (M + 255) / 256, num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
@@ -521,6 +600,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), DBW ? 2 : 1); mbar_init(ready_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
+    for (int i = 0; i < RING; ++i) mbar_init(ring_base + 8u * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -539,7 +619,21 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ===== TMA producer (both CTAs): own 128 rows of A, own 128 columns of B; bytes land on the leader's barrier =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int slot = 0;
+      auto publish = [&](int id) {                       // leader only: the id goes to both CTAs' rings
+        const uint32_t id_addr = ring_base + 8u * RING + 4u * slot, bar = ring_base + 8u * slot;
+        st_shared_u32(id_addr, (uint32_t)id);
+        mbar_arrive(bar);
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(map_to_rank(id_addr, 1)), "r"((uint32_t)id) : "memory");
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_rank(bar, 1)) : "memory");
+        if (++slot == RING) slot = 0;
+      };
+      TileFeed feed(ring_base, true);                    // peer: reads what the leader published
+      int tile;
+      if (rank == 0) { tile = (int)first_tile; publish(tile); } else { tile = feed.next(); }
+      while (tile < num_tiles) {
+        int next_tile = 0;
+        if (rank == 0) next_tile = (int)atomicAdd(sched, 1u);   // consumed after this tile's loads have been issued
         int m0, n0;
         tile_coords(tile, m0, n0);
         const int my_m0 = m0 + (int)rank * 128, my_n0 = n0 + (int)rank * 128;
@@ -563,7 +657,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
+        if (rank == 0) { publish(next_tile); tile = next_tile; } else { tile = feed.next(); }
       }
+      // every pair fetches exactly one terminal id; the last one to do so re-arms the counters
+      if (rank == 0 && atomicAdd(sched + 1, 1u) == (unsigned)num_clusters - 1) { sched[0] = 0; sched[1] = 0; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the leader CTA drives the tensor cores of both SMs =====
@@ -571,7 +668,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       constexpr uint32_t idesc = make_idesc2(A_MN, B_MN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      TileFeed feed(ring_base, false);
+      for (int tile = feed.next(); tile < num_tiles; tile = feed.next()) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -601,7 +699,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int chunk = (col0 & 63) >> 3;
     float acc4[4] = {0.f, 0.f, 0.f, 0.f};
     int stage = 0; uint32_t phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    TileFeed feed(ring_base, rank != 0);
+    for (int tile = feed.next(); tile < num_tiles; tile = feed.next()) {
       int m0, n0;
       tile_coords(tile, m0, n0);
       const int m_blk = m0 / 256;
@@ -635,7 +734,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int half = (warp - 2) >> 2;
     constexpr int COLS_PER_WARP = BN / 2;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    TileFeed feed(ring_base, rank != 0);
+    for (int tile = feed.next(); tile < num_tiles; tile = feed.next()) {
       int m0, n0;
       tile_coords(tile, m0, n0);
       const int row = m0 + (int)rank * 128 + q * 32 + lane;
@@ -731,7 +831,7 @@ int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int
   }
   int64_t tiles = pg_cdiv(M, BLOCK_M) * pg_cdiv(N, BN) * epi.splits;
   int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
-  kern<<<grid, NUM_THREADS + (DBW ? 64 : 0), Cfg<BN>::SMEM_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi);
+  kern<<<grid, NUM_THREADS + (DBW ? 64 : 0), Cfg<BN>::SMEM_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi, ctx->counters + SCHED_SLOT);
   PG_LAUNCHED(ctx);
   return PG_OK;
 }
@@ -752,7 +852,7 @@ int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, in
   }
   int64_t tiles = pg_cdiv(M, 256) * pg_cdiv(N, 256);
   int clusters = (int)(tiles < ctx->num_sms / 2 ? tiles : ctx->num_sms / 2);
-  kern<<<2 * clusters, NUM_THREADS + (DBW ? 32 : 0), SMEM2_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi);
+  kern<<<2 * clusters, NUM_THREADS + (DBW ? 32 : 0), SMEM2_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi, ctx->counters + SCHED_SLOT);
   PG_LAUNCHED(ctx);
   return PG_OK;
 }
