@@ -187,7 +187,8 @@ def main():
     x_p[...] = x_h; lab_p[...] = lab_h
 
     buckets = dp.GradientBuckets(pg.gradient_container(model), bucket_bytes=int(os.environ.get("PG_BUCKET_MB", "24")) << 20,
-                                 comm_sms=(int(os.environ["PG_COMM_SMS"]) if "PG_COMM_SMS" in os.environ else None)) if world > 1 else None
+                                 comm_sms=(int(os.environ["PG_COMM_SMS"]) if "PG_COMM_SMS" in os.environ else None),
+                                 delay_us=(float(os.environ["PG_COMM_DELAY_US"]) if "PG_COMM_DELAY_US" in os.environ else None)) if world > 1 else None
     if args.sm_limit:
         ctx.set_sm_limit(args.sm_limit)
     use_shadow = args.math == "bf16"

@@ -50,6 +50,7 @@ int pg_sync(pg_ctx* ctx);
 int pg_launch_count(pg_ctx* ctx, int64_t* n);    /* kernels launched through this ctx so far */
 int pg_reserve_workspace(pg_ctx* ctx, size_t bytes); /* pre-size scratch (needed before graph capture) */
 int pg_set_sm_limit(pg_ctx* ctx, int n_sms);     /* size persistent grids for n_sms SMs (0 = all, negative = all but |n|): leaves SMs to a concurrent NCCL kernel */
+int pg_delay_on(pg_ctx* ctx, void* stream, long long ns);   /* enqueue a one-thread kernel that sleeps ns (<= 1 ms) on `stream`: orders a collective behind the GEMM that becomes runnable at the same moment (protograd dp.py) */
 
 /* ---- device / pinned memory (arena storage; replaces Julia Array allocation for leaves) ---- */
 int pg_malloc(pg_ctx* ctx, size_t bytes, void** dptr);

@@ -41,6 +41,7 @@ _SIGS = {
     "pg_launch_count": [_P, POINTER(c_int64)],
     "pg_reserve_workspace": [_P, _Z],
     "pg_set_sm_limit": [_P, _I],
+    "pg_delay_on": [_P, _P, ctypes.c_longlong],
     "pg_malloc": [_P, _Z, POINTER(_P)],
     "pg_free": [_P, _P],
     "pg_memset0": [_P, _P, _Z],

@@ -857,9 +857,15 @@ int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, in
   return PG_OK;
 }
 
-bool use_2cta(int64_t M, int64_t N) {
+// The pair kernel needs both SMs of a TPC.  A concurrent kernel (NCCL's all-reduce CTAs during the data-
+// parallel backward pass) that becomes resident FIRST lands on arbitrary SMs and breaks pairs; the pairs
+// that cannot be placed only become resident — and let the GEMM launch complete — once the collective
+// has finished.  dp.GradientBuckets therefore reserves whole TPCs (pg_set_sm_limit) and starts the
+// collective a few microseconds after the GEMM (pg_delay_on), so the collective fills the free TPCs.
+bool use_2cta(const pg_ctx* ctx, int64_t M, int64_t N) {
   static int mode = -1;                        // PG_TC_1CTA=1 forces the single-CTA kernel
   if (mode < 0) { const char* e = getenv("PG_TC_1CTA"); mode = (e && e[0] == '1') ? 0 : 1; }
+  (void)ctx;
   return mode == 1 && M >= 512 && N >= 512;
 }
 
@@ -870,7 +876,7 @@ int tc_dispatch(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, 
   PG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "operands must be 16-byte aligned");
   PG_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension too large");
   static const bool dbw_1cta = getenv("PG_DBW_1CTA") != nullptr;        // A/B switch for the fused bias gradient
-  if (epi.splits == 1 && use_2cta(M, N) && !(epi.db != nullptr && dbw_1cta)) {
+  if (epi.splits == 1 && use_2cta(ctx, M, N) && !(epi.db != nullptr && dbw_1cta)) {
     switch (layout) {
       case 0: return launch_tc2<false, true>(ctx, A, B, C, M, N, K, K, N, epi);
       case 1: return launch_tc2<false, false>(ctx, A, B, C, M, N, K, K, K, epi);
@@ -1049,7 +1055,7 @@ int pg_tc_linear_bwd_ex(pg_ctx* ctx, const void* X, const void* W, const void* d
   if (dW) {  // dW[K][N] = X^T dY: GEMM (M'=K, N'=N, K'=M), A = X stored [M][K] (MN-major), B = dY stored [M][N] (MN-major)
     // db = column sums of dY ride along when enough m-blocks share the work: reducer warps sum the dY
     // tiles already staged in shared memory (no extra pass over dY)
-    const bool fuse_db = db != nullptr && (use_2cta(K, N) && getenv("PG_DBW_1CTA") == nullptr ? pg_cdiv(K, 256) >= 4 : pg_cdiv(K, BLOCK_M) >= 4);
+    const bool fuse_db = db != nullptr && (use_2cta(ctx, K, N) && getenv("PG_DBW_1CTA") == nullptr ? pg_cdiv(K, 256) >= 4 : pg_cdiv(K, BLOCK_M) >= 4);
     if (fuse_db) PG_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), ctx->stream));
     Epi epi{nullptr, nullptr, 0, 1, 0, nullptr, fuse_db ? (float*)db : nullptr, 1, 1 << 30};
     rc = tc_dispatch(ctx, 2, X, dY, dW, K, N, M, epi);

@@ -73,14 +73,23 @@ class GradientBuckets:
         grad = pb(on_ready=buckets.ready); buckets.finish(); step(state, grad)
     """
 
-    def __init__(self, grad_model, bucket_bytes=24 << 20, comm_sms=None):
-        # while a bucket is in flight the persistent GEMM grids are sized for (all - comm_sms) SMs, so
-        # NCCL's CTAs get SMs of their own instead of time-slicing with (and stalling) GEMM CTAs.
-        # Measured (tools/dp_timeline*.sh): 2 ranks want 16 SMs; at 8 ranks NCCL uses more channels and
-        # 0/8/16 reserved SMs all cost ~1.25 ms/step while 24 gives 1.14 ms/step.
+    def __init__(self, grad_model, bucket_bytes=24 << 20, comm_sms=None, delay_us=None):
+        # A bucket's all-reduce becomes runnable at the same moment as the next backward GEMM.  The
+        # GEMMs are persistent CTA pairs (one pair per TPC); if NCCL's CTAs become resident first they
+        # land on arbitrary SMs, break pairs, and the GEMM launch cannot complete before the collective
+        # does (measured at 8 ranks: +0.13 ms per step, tools/dp_sms8.sh).  So for > 2 ranks the GEMM
+        # grids are sized for (all - comm_sms) SMs while a bucket is in flight — comm_sms = 24 = NCCL's
+        # NVLS channel count, i.e. 12 whole TPCs — and the collective is issued from a side stream behind
+        # a `delay_us` sleep (pg_delay_on), after the next GEMM has been enqueued: the GEMM claims its
+        # pairs, NCCL fills the TPCs left free.  With 2 ranks the all-reduce is short and the dynamic
+        # tile scheduler absorbs it: nothing is reserved or delayed.
+        ws = world()[1]
         if comm_sms is None:
-            comm_sms = 16 if world()[1] <= 2 else 24
+            comm_sms = 0 if ws <= 2 else 24
+        if delay_us is None:
+            delay_us = 0 if ws <= 2 else 10
         self.comm_sms = comm_sms
+        self.delay_us = delay_us
         self.ctx = grad_model.arena()[0]
         from .model import _pad
         ctx, base, total, leaves = grad_model.arena()
@@ -95,18 +104,47 @@ class GradientBuckets:
         self.hi = total
         self.lo_ready = total
         self.works, self.ranges = [], []
-        self.enabled = world()[1] > 1
+        self.pending = None
+        self.side = None
+        self.enabled = ws > 1
+
+    def _issue(self, lo, hi, event=None):
+        """all-reduce flat[lo:hi]; with `event` (recorded when the slice was complete) the collective is
+        ordered behind event + delay on a side stream instead of behind everything enqueued so far"""
+        import torch
+        import torch.distributed as dist
+        if event is None or not self.delay_us:
+            w = dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+        else:
+            from .capi import call
+            if self.side is None:
+                self.side = torch.cuda.Stream(device=self.flat.device)
+            self.side.wait_event(event)
+            call("pg_delay_on", self.ctx.h, self.side.cuda_stream, int(self.delay_us * 1000))
+            with torch.cuda.stream(self.side):
+                w = dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+        self.works.append(w)
+        self.ranges.append((lo, hi - lo))
+
+    def _flush_pending(self):
+        if self.pending is not None:
+            lo, hi, ev = self.pending
+            self.pending = None
+            self._issue(lo, hi, ev)
 
     def ready(self, leaf_index):
         if not self.enabled:
             return
-        import torch.distributed as dist
+        import torch
+        self._flush_pending()       # the GEMMs enqueued since the bucket completed are ahead of it on the host side
         lo = self.offsets[leaf_index]
         assert lo <= self.lo_ready, "gradient leaves must complete last-to-first"
         self.lo_ready = lo
         if (self.hi - lo) * self.itemsize >= self.bucket_bytes and lo > 0:
-            self.works.append(dist.all_reduce(self.flat[lo:self.hi], op=dist.ReduceOp.SUM, async_op=True))
-            self.ranges.append((lo, self.hi - lo))
+            if self.delay_us:
+                self.pending = (lo, self.hi, torch.cuda.current_stream().record_event())
+            else:
+                self._issue(lo, self.hi)
             self.hi = lo
             if self.comm_sms:
                 self.ctx.set_sm_limit(-self.comm_sms)
@@ -118,10 +156,9 @@ class GradientBuckets:
         from .optimizers import step, step_range
         if not self.enabled:
             return step(state, grad, shadow)
-        import torch.distributed as dist
+        self._flush_pending()
         if self.hi > 0:
-            self.works.append(dist.all_reduce(self.flat[0:self.hi], op=dist.ReduceOp.SUM, async_op=True))
-            self.ranges.append((0, self.hi))
+            self._issue(0, self.hi)
         r = None
         for k, (w, (lo, cnt)) in enumerate(zip(self.works, self.ranges)):
             w.wait()
@@ -138,9 +175,9 @@ class GradientBuckets:
 
     def finish(self):
         if self.enabled:
-            import torch.distributed as dist
+            self._flush_pending()
             if self.hi > 0:
-                self.works.append(dist.all_reduce(self.flat[0:self.hi], op=dist.ReduceOp.SUM, async_op=True))
+                self._issue(0, self.hi)
             for w in self.works:
                 w.wait()          # the compute stream waits for NCCL's stream
         self._reset()
