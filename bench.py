@@ -188,12 +188,29 @@ def main():
 
     buckets = dp.GradientBuckets(pg.gradient_container(model), bucket_bytes=int(os.environ.get("PG_BUCKET_MB", "24")) << 20,
                                  comm_sms=(int(os.environ["PG_COMM_SMS"]) if "PG_COMM_SMS" in os.environ else None),
-                                 delay_us=(float(os.environ["PG_COMM_DELAY_US"]) if "PG_COMM_DELAY_US" in os.environ else None)) if world > 1 else None
+                                 delay_us=(float(os.environ["PG_COMM_DELAY_US"]) if "PG_COMM_DELAY_US" in os.environ else None),
+                                 overlap_update=(os.environ["PG_DP_OVERLAP_UPDATE"] == "1" if "PG_DP_OVERLAP_UPDATE" in os.environ else None)) if world > 1 else None
     if args.sm_limit:
         ctx.set_sm_limit(args.sm_limit)
     use_shadow = args.math == "bf16"
     timeline = [] if os.environ.get("PG_DP_TIMELINE") else None
     timeline_leaves = []
+
+    klog = {"cur": None, "steps": []}
+    if os.environ.get("PG_DP_TIMELINE") == "2":
+        # per-call device timeline of the backward + update kernels (diagnostic): an event after every C-ABI call
+        from protograd_b200 import trace as _trace, optimizers as _optimizers
+        _orig_call = _trace.call
+
+        def _logged_call(name, *a):
+            r = _orig_call(name, *a)
+            if klog["cur"] is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                klog["cur"].append((name, e))
+            return r
+        _trace.call = _logged_call
+        _optimizers.call = _logged_call
 
     def train_step(x, lab):
         out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(x), lab, global_batch=GB), model, math=args.math)
@@ -211,10 +228,15 @@ def main():
                     leaf_ev[i].record(stream)  # gradient leaf i has been produced
                     if i == 2:
                         ev[1].record(stream)   # parameter gradients of layers 2,3 done; their bucket was just issued
+                if os.environ.get("PG_DP_TIMELINE") == "2":
+                    klog["cur"] = []
                 g = pb(on_ready=hook)
                 ev[2].record(stream)           # end of backward compute
                 buckets.finish_and_step(state, g, shadow=use_shadow)
                 ev[3].record(stream)
+                if klog["cur"] is not None:
+                    klog["steps"].append((ev[0], klog["cur"]))
+                    klog["cur"] = None
                 timeline.append(ev)
                 timeline_leaves.append((ev[0], leaf_ev))
             else:
@@ -266,6 +288,15 @@ def main():
         torch.cuda.synchronize()
         tl = np.array([[e[0].elapsed_time(e[k]) for k in (1, 2, 3)] for e in timeline[-20:]])
         print("DP timeline (ms from step start: bucket issued, backward done, step done):", tl.mean(0).round(4).tolist(), file=sys.stderr)
+        if klog["steps"]:
+            last = klog["steps"][-20:]
+            names = [n for n, _ in last[-1][1]]
+            t = np.array([[e0.elapsed_time(e) for _, e in log] for e0, log in last if len(log) == len(names)]).mean(0)
+            print("DP kernel timeline (ms from backward start, call finished):", file=sys.stderr)
+            prev = 0.0
+            for n, x in zip(names, t):
+                print(f"   {n:28s} done {x:7.4f}  (+{x - prev:6.4f})", file=sys.stderr)
+                prev = x
         keys = sorted(timeline_leaves[-1][1], reverse=True)
         lv = np.array([[e0.elapsed_time(le[k]) for k in keys] for e0, le in timeline_leaves[-20:]])
         print("DP timeline leaves (ms from backward start, gradient leaf done):", dict(zip(keys, lv.mean(0).round(4).tolist())), file=sys.stderr)

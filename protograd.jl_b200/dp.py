@@ -73,7 +73,7 @@ class GradientBuckets:
         grad = pb(on_ready=buckets.ready); buckets.finish(); step(state, grad)
     """
 
-    def __init__(self, grad_model, bucket_bytes=24 << 20, comm_sms=None, delay_us=None):
+    def __init__(self, grad_model, bucket_bytes=24 << 20, comm_sms=None, delay_us=None, overlap_update=None):
         # A bucket's all-reduce becomes runnable at the same moment as the next backward GEMM.  The
         # GEMMs are persistent CTA pairs (one pair per TPC); if NCCL's CTAs become resident first they
         # land on arbitrary SMs, break pairs, and the GEMM launch cannot complete before the collective
@@ -85,11 +85,17 @@ class GradientBuckets:
         # tile scheduler absorbs it: nothing is reserved or delayed.
         ws = world()[1]
         if comm_sms is None:
-            comm_sms = 0 if ws <= 2 else 24
+            comm_sms = 0
         if delay_us is None:
-            delay_us = 0 if ws <= 2 else 10
+            delay_us = 0
+        if overlap_update is None:
+            overlap_update = True
         self.comm_sms = comm_sms
         self.delay_us = delay_us
+        # True: the optimizer pass of the buckets that have landed runs while the head bucket is still being
+        # reduced.  The update is HBM-bound and starves the collective's memory traffic, so with many ranks
+        # joining everything first and updating the whole arena once can be faster (tools/dp_cta8.sh).
+        self.overlap_update = overlap_update
         self.ctx = grad_model.arena()[0]
         from .model import _pad
         ctx, base, total, leaves = grad_model.arena()
@@ -159,6 +165,11 @@ class GradientBuckets:
         self._flush_pending()
         if self.hi > 0:
             self._issue(0, self.hi)
+        if not self.overlap_update:
+            for w in self.works:
+                w.wait()
+            self._reset()
+            return step(state, grad, shadow)
         r = None
         for k, (w, (lo, cnt)) in enumerate(zip(self.works, self.ranges)):
             w.wait()
