@@ -258,7 +258,10 @@ def init_params(spec, dtype=np.float32, seed=0):
     return ps
 
 
-def net_forward(spec, params, x, keep=False):
+def net_forward(spec, params, x, keep=False, conv_round=None):
+    """conv_round: optional rounding applied to the operands of every conv (x, w) — `bf16_round` restates
+    the B200 path's tensor-core conv mode (bf16 operands, exact accumulation, float outputs)."""
+    cr = conv_round if conv_round is not None else (lambda a: a)
     acts = [x]
     pi = 0
     y = x
@@ -267,7 +270,7 @@ def net_forward(spec, params, x, keep=False):
         if kind == "linear":
             y = linear_fwd(y, params[pi], params[pi + 1]); pi += 2
         elif kind == "conv":
-            y = conv2d_fwd(y, params[pi], params[pi + 1]); pi += 2
+            y = conv2d_fwd(cr(y), cr(params[pi]), params[pi + 1]); pi += 2
         elif kind == "relu":
             y = relu_fwd(y)
         elif kind == "maxpool":
@@ -284,11 +287,13 @@ def net_forward(spec, params, x, keep=False):
     return (y, acts) if keep else y
 
 
-def net_loss_and_grad(spec, params, x, label, loss="ce", global_batch=None, mse_denom=None):
+def net_loss_and_grad(spec, params, x, label, loss="ce", global_batch=None, mse_denom=None, conv_round=None):
     """One eval_with_pullback(f, m) + pb(): returns (loss, grads) with grads in vec(m) leaf order.
     Non-trainable leaves get a zero gradient and back-propagation stops below the first
-    trainable layer (the reference computes-and-discards that dX; values are identical)."""
-    out, acts = net_forward(spec, params, x, keep=True)
+    trainable layer (the reference computes-and-discards that dX; values are identical).
+    conv_round: see net_forward; the conv pullbacks then see rounded x, w and dy as well."""
+    cr = conv_round if conv_round is not None else (lambda a: a)
+    out, acts = net_forward(spec, params, x, keep=True, conv_round=conv_round)
     if loss == "ce":
         val = cross_entropy(out, label, global_batch)
         d = cross_entropy_bwd(out, label, global_batch)
@@ -321,7 +326,7 @@ def net_loss_and_grad(spec, params, x, label, loss="ce", global_batch=None, mse_
         elif kind == "conv":
             pi -= 2
             need_dx = pi > first_train_pi
-            dw, db, dx = conv2d_bwd(xin, params[pi], d, need_dx)
+            dw, db, dx = conv2d_bwd(cr(xin), cr(params[pi]), cr(d), need_dx)
             grads[pi], grads[pi + 1] = (dw, db) if train[pi] else (np.zeros_like(params[pi]), np.zeros_like(params[pi + 1]))
             if not need_dx:
                 break

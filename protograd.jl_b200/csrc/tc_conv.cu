@@ -1,0 +1,427 @@
+// tc_conv.cu — BF16 tensor-core path of the Conv layer (src/layers.jl:59-67: NNlib `conv`, i.e. a true
+// convolution with a flipped kernel, and its pullbacks ∇conv_filter / ∇conv_data): implicit GEMM on
+// tcgen05 with TMEM accumulators.  The im2col matrix is never materialised in HBM: producer warps gather
+// fp32 NCHW activations, round them to bf16 and write them straight into the SWIZZLE_128B shared-memory
+// operand tiles the UMMA descriptors expect (the same tile formats tc_gemm.cu receives from TMA).
+//
+//   forward    Y[p][co]   = sum_k  A[p][k] Wf[co][k]     p = (n, oy, ox),  k = (ci, i, j),  A = x[n][ci][oy+i][ox+j]
+//                                                         Wf[co][(ci,i,j)] = w[co][ci][kH-1-i][kW-1-j]
+//   data grad  dX[p][ci]  = sum_k  G[p][k] Wd[ci][k]     p = (n, iy, ix),  k = (co, i, j),  G = dY[n][co][iy+i-(kH-1)][ix+j-(kW-1)] or 0
+//                                                         Wd[ci][(co,i,j)] = w[co][ci][i][j]
+//   wt. grad   dW[co][k]  = sum_p  dY[p][co] A[p][k]     (k = Ktot is a column of ones: its sum is db[co])
+//
+// Forward / data gradient: M = 128 pixels per tile, N = 16 channels, K in 64-wide blocks; the (tiny)
+// weight matrix lives in shared memory for the whole kernel; double-buffered 16-column accumulators so the
+// epilogue (bias + ReLU, coalesced NCHW stores) overlaps the next tile.  Weight gradient: M = 128 rows of
+// dY^T (only Cout <= 16 are non-zero), N = the im2col width (<= 256), K = 64 pixels per block; every CTA
+// accumulates its share of the pixels in TMEM and adds its partial dW / db with fp32 atomics at the end.
+// Tensors stay fp32 in HBM (these layers are issue/latency-bound, not bandwidth-bound: 26 KB of
+// activations per sample at the LeNet shapes), products are bf16 x bf16 with fp32 accumulation.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+#include "tc_ptx.cuh"
+
+constexpr int BLOCK_K = 64, UMMA_K = 16;
+constexpr int TILE_BYTES = 128 * 128;                  // 128 rows x 64 bf16
+constexpr int PROD_WARPS = 8, PROD_THREADS = 32 * PROD_WARPS;
+constexpr int EPI_WARPS = 4;
+constexpr int THREADS = 32 * (1 + EPI_WARPS + PROD_WARPS);   // warp 0: MMA issuer; 1..4: epilogue; 5..12: producers
+constexpr int MAX_K = 512;                             // im2col width limit (lookup table size)
+constexpr int NCH = 16;                                // channel tile (UMMA N of the forward / data-gradient products)
+
+struct ConvArgs {
+  const float* src;        // im2col source [n][Cs][Hs][Ws]
+  const float* w;          // filters [Cout][Cin][kH][kW]
+  const float* bias;       // forward only (nullable)
+  const float* dy;         // weight gradient: [n][Cout][Hp][Wp]
+  float* out;              // forward: y [n][Cout][Hp][Wp]; data gradient: dx [n][Cin][Hp][Wp]
+  float* dw;               // weight gradient (pre-zeroed)
+  float* db;               // weight gradient (pre-zeroed, nullable)
+  long long Ptot;          // n * Hp * Wp positions
+  int Cs, Hs, Ws;          // source channels / height / width
+  int Hp, Wp;              // positions per sample
+  int kH, kW, pad_h, pad_w;
+  int Cin, Cout;
+  int Nout;                // output channels of the forward / data-gradient product (Cout resp. Cin)
+  int Ktot;                // Cs * kH * kW
+  int nkb;                 // 64-wide k-blocks (forward / data gradient), 64-wide im2col boxes (weight gradient)
+  int dgrad;               // 1: data gradient (zero padding, unflipped filters)
+  int relu;
+};
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// One 16-byte chunk (8 consecutive k) of one im2col row.  `tab[k]` = (offset of tap k relative to the patch
+// origin, (i << 16) | j); `origin` = offset of the patch origin in the source sample (may be "negative" for
+// the padded data-gradient patches, hence the bounds test on (py + i - pad, px + j - pad)).
+template <bool PAD, bool ONES>
+__device__ __forceinline__ void im2col_chunk(uint32_t dst, const float* __restrict__ sample, const int2* __restrict__ tab, int k0, int Ktot,
+                                             bool valid, int origin, int py, int px, int Hs, int Ws, int pad_h, int pad_w) {
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k0 + e;
+    float x = 0.f;
+    if (valid && k < Ktot) {
+      const int2 t = tab[k];
+      if (PAD) {
+        const int iy = py + (t.y >> 16) - pad_h, ix = px + (t.y & 0xffff) - pad_w;
+        if (iy >= 0 && iy < Hs && ix >= 0 && ix < Ws) x = __ldg(sample + origin + t.x);
+      } else {
+        x = __ldg(sample + origin + t.x);
+      }
+    } else if (ONES && valid && k == Ktot) {
+      x = 1.f;
+    }
+    v[e] = x;
+  }
+  st_shared_v4(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+// MODE 0: forward / data gradient.  MODE 1: weight gradient.
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a, int stages, int tmem_cols) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  // layout: [stages] operand stages | [MODE 0: nkb x 2 KB filter tiles] | k lookup table | barriers
+  const int stage_bytes = MODE == 0 ? TILE_BYTES : TILE_BYTES + a.nkb * (BLOCK_K * 128);
+  const uint32_t wm_base = smem_base + stages * stage_bytes;                 // MODE 0 only
+  const uint32_t tab_off = stages * stage_bytes + (MODE == 0 ? a.nkb * 2048 : 0);
+  int2* tab = reinterpret_cast<int2*>(smem + tab_off);
+  const uint32_t bar_base = smem_base + tab_off + MAX_K * 8;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (16 + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (18 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tab_off + MAX_K * 8 + 8 * 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HWp = a.Hp * a.Wp, HWs = a.Hs * a.Ws, kk = a.kH * a.kW;
+  const int Kcols = MODE == 0 ? a.nkb * BLOCK_K : a.nkb * 64;                // padded im2col width
+
+  // ---- one-time setup ----
+  for (int k = threadIdx.x; k < Kcols && k < MAX_K; k += THREADS) {
+    int2 t = make_int2(0, 0);
+    if (k < a.Ktot) {
+      const int c = k / kk, r = k - c * kk, i = r / a.kW, j = r - i * a.kW;
+      t = make_int2(c * HWs + i * a.Ws + j, (i << 16) | j);
+    }
+    tab[k] = t;
+  }
+  if (MODE == 0) {
+    // filter tiles: [nkb][16 rows][64 k] bf16, K-major SWIZZLE_128B (row r at r*128, 16-byte chunk c at (c ^ (r & 7)) * 16)
+    for (int idx = threadIdx.x; idx < a.nkb * NCH * BLOCK_K; idx += THREADS) {
+      const int kb = idx / (NCH * BLOCK_K), r = (idx / BLOCK_K) % NCH, kc = idx % BLOCK_K, k = kb * BLOCK_K + kc;
+      float v = 0.f;
+      if (r < a.Nout && k < a.Ktot) {
+        const int c = k / kk, rr = k - c * kk, i = rr / a.kW, j = rr - i * a.kW;
+        v = a.dgrad ? a.w[((c * a.Cin + r) * a.kH + i) * a.kW + j]
+                    : a.w[((r * a.Cin + c) * a.kH + (a.kH - 1 - i)) * a.kW + (a.kW - 1 - j)];
+      }
+      const uint32_t off = kb * 2048 + r * 128 + (((kc >> 3) ^ (r & 7)) << 4) + (kc & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(smem + (wm_base - smem_base) + off) = __float2bfloat16_rn(v);
+    }
+  } else {
+    // dY^T operand tiles: rows >= Cout stay zero for the whole kernel
+    for (int s = 0; s < stages; ++s)
+      for (int i = threadIdx.x; i < TILE_BYTES / 16; i += THREADS)
+        *reinterpret_cast<uint4*>(smem + s * stage_bytes + i * 16) = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), PROD_THREADS); mbar_init(empty_bar(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();                 // generic-proxy writes above (filter tiles, zeroed rows) -> visible to the tensor core
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (MODE == 0) {
+    const long long num_tiles = (a.Ptot + 127) / 128;
+    if (warp == 0) {
+      // ===== MMA issuer =====
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_mn(false, false, 128, NCH);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 32;
+          for (int kb = 0; kb < a.nkb; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_base + stage * stage_bytes, sb = wm_base + kb * 2048;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16(d_tmem, make_desc(sa + k * (UMMA_K * 2), 16, 1024), make_desc(sb + k * (UMMA_K * 2), 16, 1024), idesc, (kb | k) != 0);
+            tcgen05_commit(empty_bar(stage));
+            if (kb == a.nkb - 1) tcgen05_commit(tfull_bar(acc));
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    } else if (warp <= EPI_WARPS) {
+      // ===== epilogue: one accumulator row (= one position) per thread, 16 channels =====
+      const int q = warp & 3;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long P = tile * 128 + q * 32 + lane;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32, r);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));     // values are in registers: the accumulator is free again
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (P < a.Ptot) {
+          const long long n = P / HWp;
+          const int rem = (int)(P - n * HWp);
+          float* o = a.out + n * a.Nout * (long long)HWp + rem;
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            if (ch < a.Nout) {
+              float v = __uint_as_float(r[ch]);
+              if (a.bias != nullptr) v += __ldg(a.bias + ch);
+              if (a.relu) v = fmaxf(v, 0.f);
+              o[(long long)ch * HWp] = v;                // lanes = consecutive positions: coalesced per channel
+            }
+          }
+        }
+      }
+    } else {
+      // ===== im2col producers: thread -> (row = position, every other 16-byte chunk) =====
+      const int t = threadIdx.x - 32 * (1 + EPI_WARPS);
+      const int row = t & 127, chunk0 = t >> 7;
+      int stage = 0; uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long P = tile * 128 + row;
+        const bool valid = P < a.Ptot;
+        const long long n = valid ? P / HWp : 0;
+        const int rem = valid ? (int)(P - n * HWp) : 0;
+        const int py = rem / a.Wp, px = rem - py * a.Wp;
+        const float* sample = a.src + n * a.Cs * (long long)HWs;
+        const int origin = (py - a.pad_h) * a.Ws + (px - a.pad_w);
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t srow = smem_base + stage * stage_bytes + row * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int chunk = chunk0 + 2 * c;
+            const uint32_t dst = srow + ((chunk ^ (row & 7)) << 4);
+            if (a.dgrad) im2col_chunk<true, false>(dst, sample, tab, kb * BLOCK_K + chunk * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, a.pad_h, a.pad_w);
+            else im2col_chunk<false, false>(dst, sample, tab, kb * BLOCK_K + chunk * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, 0, 0);
+          }
+          fence_async_smem();
+          mbar_arrive(full_bar(stage));
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================= weight gradient =================
+    const long long num_blocks = (a.Ptot + 63) / 64;     // K blocks of 64 positions
+    const int N = a.nkb * 64;
+    if (warp == 0) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_mn(false, true, 128, N);
+        int stage = 0; uint32_t phase = 0;
+        bool first = true;
+        for (long long pb = blockIdx.x; pb < num_blocks; pb += gridDim.x) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(tmem_base, make_desc(sa + k * (UMMA_K * 2), 16, 1024), make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024), idesc,
+                      (first && k == 0) ? 0u : 1u);
+          first = false;
+          tcgen05_commit(empty_bar(stage));
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        if (!first) tcgen05_commit(tfull_bar(0));
+      }
+    } else if (warp <= EPI_WARPS) {
+      // ===== epilogue (once): rows 0..Cout-1 of the accumulator live in TMEM lane quarter 0 =====
+      if ((warp & 3) == 0 && (long long)blockIdx.x < num_blocks) {
+        mbar_wait(tfull_bar(0), 0);
+        tcgen05_fence_after();
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + c0, r);
+          tmem_ld_wait();
+          if (lane < a.Cout) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int k = c0 + j;
+              const float v = __uint_as_float(r[j]);
+              if (k < a.Ktot) {
+                const int2 t = tab[k];
+                const int ci = k / kk, i = t.y >> 16, jj = t.y & 0xffff;
+                atomicAdd(a.dw + ((lane * a.Cin + ci) * a.kH + (a.kH - 1 - i)) * a.kW + (a.kW - 1 - jj), v);
+              } else if (k == a.Ktot && a.db != nullptr) {
+                atomicAdd(a.db + lane, v);
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+      }
+    } else {
+      // ===== producers: im2col rows (B operand, MN-major boxes of 64 k) and dY^T rows (A operand) =====
+      const int t = threadIdx.x - 32 * (1 + EPI_WARPS);
+      const int row = t & 63, chunk0 = t >> 6;           // 4 chunk lanes per row
+      const int units = a.nkb * 8;                        // 16-byte chunks per im2col row
+      int stage = 0; uint32_t phase = 0;
+      for (long long pb = blockIdx.x; pb < num_blocks; pb += gridDim.x) {
+        const long long P = pb * 64 + row;
+        const bool valid = P < a.Ptot;
+        const long long n = valid ? P / HWp : 0;
+        const int rem = valid ? (int)(P - n * HWp) : 0;
+        const int py = rem / a.Wp, px = rem - py * a.Wp;
+        const float* sample = a.src + n * a.Cs * (long long)HWs;
+        const int origin = py * a.Ws + px;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + TILE_BYTES;
+        for (int u = chunk0; u < units; u += 4) {
+          const int box = u >> 3, chunk = u & 7;
+          const uint32_t dst = sb + box * (BLOCK_K * 128) + row * 128 + ((chunk ^ (row & 7)) << 4);
+          im2col_chunk<false, true>(dst, sample, tab, u * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, 0, 0);
+        }
+        // dY^T: row co, 64 positions of this block (8 per unit)
+        for (int u = t; u < a.Cout * 8; u += PROD_THREADS) {
+          const int co = u >> 3, chunk = u & 7;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const long long Pe = pb * 64 + chunk * 8 + e;
+            float x = 0.f;
+            if (Pe < a.Ptot) {
+              const long long ne = Pe / HWp;
+              x = __ldg(a.dy + (ne * a.Cout + co) * (long long)HWp + (Pe - ne * HWp));
+            }
+            v[e] = x;
+          }
+          st_shared_v4(sa + co * 128 + ((chunk ^ (co & 7)) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+        fence_async_smem();
+        mbar_arrive(full_bar(stage));
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+int smem_bytes(int mode, int stages, int nkb) {
+  const int stage_bytes = mode == 0 ? TILE_BYTES : TILE_BYTES + nkb * (BLOCK_K * 128);
+  return stages * stage_bytes + (mode == 0 ? nkb * 2048 : 0) + MAX_K * 8 + 8 * 20 + 16 + 1024;
+}
+
+template <int MODE>
+int launch(pg_ctx* ctx, const ConvArgs& a, long long work) {
+  const int stages = MODE == 0 ? 8 : 4;
+  const int bytes = smem_bytes(MODE, stages, a.nkb);
+  PG_REQUIRE(bytes <= 227 * 1024, "tensor-core conv: shared-memory budget exceeded");
+  static int attr_bytes = 0;
+  if (bytes > attr_bytes) {
+    PG_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    attr_bytes = bytes;
+  }
+  int tmem_cols = 64;
+  if (MODE == 1) { tmem_cols = 32; while (tmem_cols < a.nkb * 64) tmem_cols *= 2; }
+  const int grid = (int)(work < ctx->num_sms ? work : ctx->num_sms);
+  tc_conv_kernel<MODE><<<grid, THREADS, bytes, ctx->stream>>>(a, stages, tmem_cols);
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+bool supported(int Cin, int Cout, int kH, int kW) {
+  return Cin >= 1 && Cout >= 1 && Cin <= NCH && Cout <= NCH && kH >= 1 && kW >= 1 && kH < 256 && kW < 256 &&
+         Cin * kH * kW + 1 <= 256 &&         // weight gradient: im2col width (+ ones column) = UMMA N <= 256
+         Cout * kH * kW <= 448;              // data gradient: 7 k-blocks of filters in shared memory
+}
+
+}  // namespace
+
+extern "C" {
+
+int pg_tc_conv2d_supported(int Cin, int Cout, int kH, int kW) { return supported(Cin, Cout, kH, kW) ? 1 : 0; }
+
+int pg_tc_conv2d_fwd(pg_ctx* ctx, const void* x, const void* w, const void* b, void* y, int64_t N, int Cin, int H, int W, int Cout,
+                     int kH, int kW, int act) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(supported(Cin, Cout, kH, kW), "pg_tc_conv2d_fwd: shape outside the tensor-core envelope (channels <= 16, Cin*kH*kW < 256)");
+  PG_REQUIRE(N > 0 && H >= kH && W >= kW, "pg_tc_conv2d_fwd: empty output");
+  PG_REQUIRE(act == PG_ACT_NONE || act == PG_ACT_RELU, "pg_tc_conv2d_fwd: unknown activation");
+  ConvArgs a{};
+  a.src = (const float*)x; a.w = (const float*)w; a.bias = (const float*)b; a.out = (float*)y;
+  a.Cs = Cin; a.Hs = H; a.Ws = W; a.Hp = H - kH + 1; a.Wp = W - kW + 1;
+  a.kH = kH; a.kW = kW; a.Cin = Cin; a.Cout = Cout; a.Nout = Cout;
+  a.Ktot = Cin * kH * kW; a.nkb = (int)pg_cdiv(a.Ktot, BLOCK_K);
+  a.Ptot = (long long)N * a.Hp * a.Wp; a.relu = act == PG_ACT_RELU;
+  return launch<0>(ctx, a, (a.Ptot + 127) / 128);
+}
+
+int pg_tc_conv2d_bwd(pg_ctx* ctx, const void* x, const void* w, const void* dy, void* dw, void* db, void* dx, int64_t N, int Cin, int H,
+                     int W, int Cout, int kH, int kW) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(supported(Cin, Cout, kH, kW), "pg_tc_conv2d_bwd: shape outside the tensor-core envelope (channels <= 16, Cin*kH*kW < 256)");
+  PG_REQUIRE(N > 0 && H >= kH && W >= kW, "pg_tc_conv2d_bwd: empty output");
+  const int Ho = H - kH + 1, Wo = W - kW + 1;
+  if (dw != nullptr || db != nullptr) {
+    PG_REQUIRE(dw != nullptr, "pg_tc_conv2d_bwd: db without dw is not supported on the tensor-core path");
+    PG_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * kH * kW * sizeof(float), ctx->stream));
+    if (db != nullptr) PG_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), ctx->stream));
+    ConvArgs a{};
+    a.src = (const float*)x; a.dy = (const float*)dy; a.dw = (float*)dw; a.db = (float*)db;
+    a.Cs = Cin; a.Hs = H; a.Ws = W; a.Hp = Ho; a.Wp = Wo;
+    a.kH = kH; a.kW = kW; a.Cin = Cin; a.Cout = Cout;
+    a.Ktot = Cin * kH * kW; a.nkb = (int)pg_cdiv(a.Ktot + 1, 64);
+    a.Ptot = (long long)N * Ho * Wo;
+    int rc = launch<1>(ctx, a, (a.Ptot + 63) / 64);
+    if (rc != PG_OK) return rc;
+  }
+  if (dx != nullptr) {
+    ConvArgs a{};
+    a.src = (const float*)dy; a.w = (const float*)w; a.out = (float*)dx;
+    a.Cs = Cout; a.Hs = Ho; a.Ws = Wo; a.Hp = H; a.Wp = W;
+    a.kH = kH; a.kW = kW; a.pad_h = kH - 1; a.pad_w = kW - 1; a.Cin = Cin; a.Cout = Cout; a.Nout = Cin;
+    a.Ktot = Cout * kH * kW; a.nkb = (int)pg_cdiv(a.Ktot, BLOCK_K); a.dgrad = 1;
+    a.Ptot = (long long)N * H * W;
+    int rc = launch<0>(ctx, a, (a.Ptot + 127) / 128);
+    if (rc != PG_OK) return rc;
+  }
+  return PG_OK;
+}
+
+}  // extern "C"

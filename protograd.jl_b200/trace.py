@@ -341,6 +341,7 @@ class Plan:
                 if p.op == "softmax" and consumers[p.id] == [t.id] and p.id != root.id:
                     self.fused_sce[t.id] = p.id
         self.sce_softmax = set(self.fused_sce.values())
+        self.tc_linear, self.tc_conv = self._select_tensor_core_ops()
         self.vals = [None] * n
         self.grads = [None] * n
         self.owned_inputs = {}
@@ -368,16 +369,65 @@ class Plan:
         c = self._through_reshape_down(r)
         return c is not None and self.ops[c] in ("linear", "maxpool")
 
+    def _select_tensor_core_ops(self):
+        """Which Linear / Conv nodes run on the tcgen05 kernels in math="bf16" mode.
+        Linear: bf16 operands, so its input must be a trace input (cast once) or the bf16 activation of
+        another tensor-core Linear, K % 8 == 0 and N % 8 == 0 (16-byte TMA pitch) or N <= 32 (padded
+        narrow path); a wide (N > 32) layer stores a bf16 activation and expects a bf16 gradient back, so
+        its consumer must be a tensor-core Linear too (otherwise the layer stays on the fp32 SIMT GEMM).
+        Conv: Float32 tensors in and out (csrc/tc_conv.cu rounds operands on the way into shared memory),
+        any position in the graph, shapes inside pg_tc_conv2d_supported."""
+        tc_lin, tc_conv = set(), set()
+        if self.math != "bf16":
+            return tc_lin, tc_conv
+        from . import capi
+        for i in range(self.n):
+            if not self.need[i]:
+                continue
+            if self.ops[i] == "conv" and self.dtypes[i] == np.float32:
+                Cout, Cin, kH, kW = self.shapes[self.inputs[i][1]]
+                if capi._FN["pg_tc_conv2d_supported"](Cin, Cout, kH, kW) == 1:
+                    tc_conv.add(i)
+            if self.ops[i] != "linear" or self.dtypes[i] != np.float32:
+                continue
+            x, W, b = self.inputs[i]
+            K, N = self.shapes[W]
+            if K % 8 or (N > 32 and N % 8):
+                continue
+            src = self._base(x)
+            prod = self.fused_into.get(src, src) if self.ops[src] == "relu" else src
+            if self.ops[src] == "input" or (self.ops[prod] == "linear" and prod in tc_lin and self.shapes[prod][-1] > 32):
+                tc_lin.add(i)
+        changed = True
+        while changed:                        # demote wide layers whose consumer left the tensor-core chain
+            changed = False
+            for i in sorted(tc_lin, reverse=True):
+                if self.shapes[i][-1] <= 32:
+                    continue
+                out = self.fused_act.get(i, i)
+                c = self._through_reshape_down(out)
+                if c is not None and c not in tc_lin:
+                    tc_lin.discard(i)
+                    changed = True
+            for i in sorted(tc_lin):          # ... and layers fed by a demoted one
+                x = self.inputs[i][0]
+                src = self._base(x)
+                prod = self.fused_into.get(src, src) if self.ops[src] == "relu" else src
+                if self.ops[src] != "input" and prod not in tc_lin:
+                    tc_lin.discard(i)
+                    changed = True
+        return tc_lin, tc_conv
+
     def _consumer_is_tc_linear(self, i):
         c = self._through_reshape_down(i)
-        return self.math == "bf16" and c is not None and self.ops[c] == "linear"
+        return c is not None and c in self.tc_linear
 
     # ---- buffers -------------------------------------------------------------------------------
     def _new(self, shape, dtype):
         return DeviceArray.empty(self.ctx, shape, dtype, zero=True)
 
     def _act_dtype(self, lin):
-        if self.math == "bf16" and self.ops[lin] == "linear" and self.shapes[lin][-1] > 32:
+        if lin in self.tc_linear and self.shapes[lin][-1] > 32:
             return BF16
         return self.dtypes[lin]
 
@@ -523,7 +573,7 @@ class Plan:
                 M = _prod(self.shapes[x][:-1])
                 act = ACT_RELU if i in self.fused_act else ACT_NONE
                 out = self._val(i)
-                if self.math == "bf16":
+                if i in self.tc_linear:
                     xv, Wv = self._as_bf16(x), self._as_bf16(W)
                     call("pg_tc_linear_fwd", h, xv.ptr, Wv.ptr, self._val(b).ptr, out.ptr, PG_BF16 if out.dtype == BF16 else PG_F32, M, K, N, act)
                 else:
@@ -533,7 +583,10 @@ class Plan:
                 N_, Cin, H, W_ = self.shapes[x]
                 Cout, _, kH, kW = self.shapes[w]
                 act = ACT_RELU if i in self.fused_act else ACT_NONE
-                call("pg_conv2d_fwd", h, code, self._f(x).ptr, self._val(w).ptr, self._val(b).ptr, self._val(i).ptr, N_, Cin, H, W_, Cout, kH, kW, act)
+                if i in self.tc_conv:
+                    call("pg_tc_conv2d_fwd", h, self._f(x).ptr, self._val(w).ptr, self._val(b).ptr, self._val(i).ptr, N_, Cin, H, W_, Cout, kH, kW, act)
+                else:
+                    call("pg_conv2d_fwd", h, code, self._f(x).ptr, self._val(w).ptr, self._val(b).ptr, self._val(i).ptr, N_, Cin, H, W_, Cout, kH, kW, act)
             elif op == "relu":
                 if i in self.fused_into:
                     continue
@@ -599,7 +652,7 @@ class Plan:
                     K, N = self.shapes[W]
                     M = _prod(self.shapes[x][:-1])
                     mask = self._val(x) if (gx is not None and self.ops[self._base(x)] == "relu") else None
-                    if self.math == "bf16":
+                    if i in self.tc_linear:
                         xv = self._as_bf16(x) if gW is not None else None
                         Wv = self._as_bf16(W) if gx is not None else None
                         gyc = PG_BF16 if gy.dtype == BF16 else PG_F32
@@ -632,7 +685,10 @@ class Plan:
                 else:
                     N_, Cin, H, W_ = self.shapes[x]
                     Cout, _, kH, kW = self.shapes[W]
-                    call("pg_conv2d_bwd", h, code, self._val(x).ptr, self._val(W).ptr, gy.ptr, P(gW), P(gb), P(gx), N_, Cin, H, W_, Cout, kH, kW)
+                    if i in self.tc_conv and (gW is not None or gb is None):
+                        call("pg_tc_conv2d_bwd", h, self._val(x).ptr, self._val(W).ptr, gy.ptr, P(gW), P(gb), P(gx), N_, Cin, H, W_, Cout, kH, kW)
+                    else:
+                        call("pg_conv2d_bwd", h, code, self._val(x).ptr, self._val(W).ptr, gy.ptr, P(gW), P(gb), P(gx), N_, Cin, H, W_, Cout, kH, kW)
                 if on_ready is not None and (gW is not None or gb is not None):
                     idx = [self.attrs[j]["grad_index"] for j in (W, b) if self.ng[j]]
                     on_ready(min(idx))
