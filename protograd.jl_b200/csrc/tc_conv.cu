@@ -31,9 +31,12 @@ constexpr int BLOCK_K = 64, UMMA_K = 16;
 constexpr int TILE_BYTES = 128 * 128;                  // 128 rows x 64 bf16
 constexpr int PROD_WARPS = 8, PROD_THREADS = 32 * PROD_WARPS;
 constexpr int EPI_WARPS = 4;
-constexpr int THREADS = 32 * (1 + EPI_WARPS + PROD_WARPS);   // warp 0: MMA issuer; 1..4: epilogue; 5..12: producers
+constexpr int THREADS = 32 * (2 + EPI_WARPS + PROD_WARPS);   // warp 0: MMA issuer; 1..4: epilogue; 5: bulk-copy loader; 6..13: producers
+constexpr int FIRST_PROD_WARP = 2 + EPI_WARPS;
 constexpr int MAX_K = 512;                             // im2col width limit (lookup table size)
 constexpr int NCH = 16;                                // channel tile (UMMA N of the forward / data-gradient products)
+constexpr int NACC = 8;                                // TMEM accumulator ring of the forward / data-gradient kernel (32 columns each)
+constexpr int MAX_STAGES = 8, MAX_SLOTS = 4;
 
 struct ConvArgs {
   const float* src;        // im2col source [n][Cs][Hs][Ws]
@@ -43,7 +46,8 @@ struct ConvArgs {
   float* out;              // forward: y [n][Cout][Hp][Wp]; data gradient: dx [n][Cin][Hp][Wp]
   float* dw;               // weight gradient (pre-zeroed)
   float* db;               // weight gradient (pre-zeroed, nullable)
-  long long Ptot;          // n * Hp * Wp positions
+  long long nsamples;
+  int G;                   // samples per group: one bulk copy of G whole samples feeds G*Hp*Wp positions
   int Cs, Hs, Ws;          // source channels / height / width
   int Hp, Wp;              // positions per sample
   int kH, kW, pad_h, pad_w;
@@ -53,6 +57,9 @@ struct ConvArgs {
   int nkb;                 // 64-wide k-blocks (forward / data gradient), 64-wide im2col boxes (weight gradient)
   int dgrad;               // 1: data gradient (zero padding, unflipped filters)
   int relu;
+  int stages, slots;       // operand-tile ring / staged-sample ring depths
+  int slot_bytes, dy_off;  // bytes per staged group (source, then dY at dy_off for the weight gradient)
+  int tmem_cols;
 };
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -63,12 +70,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 
-// One 16-byte chunk (8 consecutive k) of one im2col row.  `tab[k]` = (offset of tap k relative to the patch
-// origin, (i << 16) | j); `origin` = offset of the patch origin in the source sample (may be "negative" for
-// the padded data-gradient patches, hence the bounds test on (py + i - pad, px + j - pad)).
+// One 16-byte chunk (8 consecutive k) of one im2col row, gathered from the sample staged in shared memory.
+// `tab[k]` = (offset of tap k relative to the patch origin, (i << 16) | j); `origin` = offset of the patch
+// origin in the staged group (may point before the sample for the padded data-gradient patches, hence the
+// bounds test on (py + i - pad, px + j - pad)).
 template <bool PAD, bool ONES>
-__device__ __forceinline__ void im2col_chunk(uint32_t dst, const float* __restrict__ sample, const int2* __restrict__ tab, int k0, int Ktot,
+__device__ __forceinline__ void im2col_chunk(uint32_t dst, const float* __restrict__ staged, const int2* __restrict__ tab, int k0, int Ktot,
                                              bool valid, int origin, int py, int px, int Hs, int Ws, int pad_h, int pad_w) {
   float v[8];
 #pragma unroll
@@ -79,9 +91,9 @@ __device__ __forceinline__ void im2col_chunk(uint32_t dst, const float* __restri
       const int2 t = tab[k];
       if (PAD) {
         const int iy = py + (t.y >> 16) - pad_h, ix = px + (t.y & 0xffff) - pad_w;
-        if (iy >= 0 && iy < Hs && ix >= 0 && ix < Ws) x = __ldg(sample + origin + t.x);
+        if (iy >= 0 && iy < Hs && ix >= 0 && ix < Ws) x = staged[origin + t.x];
       } else {
-        x = __ldg(sample + origin + t.x);
+        x = staged[origin + t.x];
       }
     } else if (ONES && valid && k == Ktot) {
       x = 1.f;
@@ -92,26 +104,37 @@ __device__ __forceinline__ void im2col_chunk(uint32_t dst, const float* __restri
 }
 
 // MODE 0: forward / data gradient.  MODE 1: weight gradient.
+// Work item = a group of G consecutive samples.  The loader thread bulk-copies the group's source
+// activations (and dY for the weight gradient) into a shared-memory slot (cp.async.bulk + mbarrier, a few
+// groups ahead), the producer warps expand them into operand tiles, one thread issues the MMAs, the
+// epilogue warps drain TMEM.
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a, int stages, int tmem_cols) {
+__global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  // layout: [stages] operand stages | [MODE 0: nkb x 2 KB filter tiles] | k lookup table | barriers
+  // layout: operand stages | [MODE 0: nkb x 2 KB filter tiles] | staged-sample slots | k lookup table | barriers
+  const int stages = a.stages, slots = a.slots;
   const int stage_bytes = MODE == 0 ? TILE_BYTES : TILE_BYTES + a.nkb * (BLOCK_K * 128);
-  const uint32_t wm_base = smem_base + stages * stage_bytes;                 // MODE 0 only
-  const uint32_t tab_off = stages * stage_bytes + (MODE == 0 ? a.nkb * 2048 : 0);
+  const uint32_t wm_off = stages * stage_bytes;                              // MODE 0 only
+  const uint32_t slot_off = wm_off + (MODE == 0 ? a.nkb * 2048 : 0);
+  const uint32_t tab_off = slot_off + slots * a.slot_bytes;
   int2* tab = reinterpret_cast<int2*>(smem + tab_off);
   const uint32_t bar_base = smem_base + tab_off + MAX_K * 8;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
-  auto tfull_bar = [&](int i) { return bar_base + 8u * (16 + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (18 + i); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tab_off + MAX_K * 8 + 8 * 20);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                                   // operand tile written
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };                   // operand tile consumed by the MMAs
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + i); };               // accumulator complete
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + NACC + i); };       // accumulator drained
+  auto sfull_bar = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + 2 * NACC + i); };    // staged group landed
+  auto sempty_bar = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + 2 * NACC + MAX_SLOTS + i); };   // staged group expanded
+  constexpr int NUM_BARS = 2 * MAX_STAGES + 2 * NACC + 2 * MAX_SLOTS;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tab_off + MAX_K * 8 + 8 * NUM_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HWp = a.Hp * a.Wp, HWs = a.Hs * a.Ws, kk = a.kH * a.kW;
-  const int Kcols = MODE == 0 ? a.nkb * BLOCK_K : a.nkb * 64;                // padded im2col width
+  const int Kcols = a.nkb * 64;                                              // padded im2col width
+  const long long num_groups = (a.nsamples + a.G - 1) / a.G;
+  const int src_per_sample = a.Cs * HWs;                                     // floats
 
   // ---- one-time setup ----
   for (int k = threadIdx.x; k < Kcols && k < MAX_K; k += THREADS) {
@@ -133,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a, int sta
                     : a.w[((r * a.Cin + c) * a.kH + (a.kH - 1 - i)) * a.kW + (a.kW - 1 - j)];
       }
       const uint32_t off = kb * 2048 + r * 128 + (((kc >> 3) ^ (r & 7)) << 4) + (kc & 7) * 2;
-      *reinterpret_cast<__nv_bfloat16*>(smem + (wm_base - smem_base) + off) = __float2bfloat16_rn(v);
+      *reinterpret_cast<__nv_bfloat16*>(smem + wm_off + off) = __float2bfloat16_rn(v);
     }
   } else {
     // dY^T operand tiles: rows >= Cout stay zero for the whole kernel
@@ -142,12 +165,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a, int sta
         *reinterpret_cast<uint4*>(smem + s * stage_bytes + i * 16) = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), PROD_THREADS); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), EPI_WARPS); }
+    for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), PROD_WARPS); mbar_init(empty_bar(s), 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), EPI_WARPS); }
+    for (int i = 0; i < slots; ++i) { mbar_init(sfull_bar(i), 1); mbar_init(sempty_bar(i), PROD_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   fence_async_smem();                 // generic-proxy writes above (filter tiles, zeroed rows) -> visible to the tensor core
@@ -156,117 +180,152 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a, int sta
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (MODE == 0) {
-    const long long num_tiles = (a.Ptot + 127) / 128;
+  // positions / tiles / k-blocks of group `grp` (the last group may hold fewer samples)
+  auto group_samples = [&](long long grp) { return (int)min((long long)a.G, a.nsamples - grp * a.G); };
+
+  if (warp == 1 + EPI_WARPS) {
+    // ===== loader: one thread bulk-copies whole groups into the slot ring =====
+    if (lane == 0) {
+      int slot = 0; uint32_t sphase = 0;
+      for (long long grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+        const int gs = group_samples(grp);
+        mbar_wait(sempty_bar(slot), sphase ^ 1);
+        const uint32_t dst = smem_base + slot_off + slot * a.slot_bytes;
+        const uint32_t sbytes = ((uint32_t)(gs * src_per_sample) * 4u + 15u) & ~15u;
+        const uint32_t dbytes = MODE == 1 ? (((uint32_t)(gs * a.Cout * HWp) * 4u + 15u) & ~15u) : 0u;
+        mbar_expect_tx(sfull_bar(slot), sbytes + dbytes);
+        bulk_copy_g2s(dst, a.src + grp * a.G * (long long)src_per_sample, sbytes, sfull_bar(slot));
+        if (MODE == 1) bulk_copy_g2s(dst + a.dy_off, a.dy + grp * a.G * (long long)a.Cout * HWp, dbytes, sfull_bar(slot));
+        if (++slot == slots) { slot = 0; sphase ^= 1; }
+      }
+    }
+  } else if (MODE == 0) {
     if (warp == 0) {
       // ===== MMA issuer =====
       if (lane == 0) {
         const uint32_t idesc = make_idesc_mn(false, false, 128, NCH);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-          tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * 32;
-          for (int kb = 0; kb < a.nkb; ++kb) {
-            mbar_wait(full_bar(stage), phase);
+        for (long long grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+          const int tiles = (group_samples(grp) * HWp + 127) / 128;
+          for (int tile = 0; tile < tiles; ++tile) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1);
             tcgen05_fence_after();
-            const uint32_t sa = smem_base + stage * stage_bytes, sb = wm_base + kb * 2048;
+            const uint32_t d_tmem = tmem_base + acc * 32;
+            for (int kb = 0; kb < a.nkb; ++kb) {
+              mbar_wait(full_bar(stage), phase);
+              tcgen05_fence_after();
+              const uint32_t sa = smem_base + stage * stage_bytes, sb = smem_base + wm_off + kb * 2048;
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_bf16(d_tmem, make_desc(sa + k * (UMMA_K * 2), 16, 1024), make_desc(sb + k * (UMMA_K * 2), 16, 1024), idesc, (kb | k) != 0);
-            tcgen05_commit(empty_bar(stage));
-            if (kb == a.nkb - 1) tcgen05_commit(tfull_bar(acc));
-            if (++stage == stages) { stage = 0; phase ^= 1; }
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                umma_bf16(d_tmem, make_desc(sa + k * (UMMA_K * 2), 16, 1024), make_desc(sb + k * (UMMA_K * 2), 16, 1024), idesc, (kb | k) != 0);
+              tcgen05_commit(empty_bar(stage));
+              if (kb == a.nkb - 1) tcgen05_commit(tfull_bar(acc));
+              if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
           }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
     } else if (warp <= EPI_WARPS) {
       // ===== epilogue: one accumulator row (= one position) per thread, 16 channels =====
       const int q = warp & 3;
       int acc = 0; uint32_t acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const long long P = tile * 128 + q * 32 + lane;
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tcgen05_fence_after();
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32, r);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));     // values are in registers: the accumulator is free again
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        if (P < a.Ptot) {
-          const long long n = P / HWp;
-          const int rem = (int)(P - n * HWp);
-          float* o = a.out + n * a.Nout * (long long)HWp + rem;
+      for (long long grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+        const int npos = group_samples(grp) * HWp;
+        const int tiles = (npos + 127) / 128;
+        for (int tile = 0; tile < tiles; ++tile) {
+          const int pl = tile * 128 + q * 32 + lane;       // position inside the group
+          mbar_wait(tfull_bar(acc), acc_phase);
+          tcgen05_fence_after();
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32, r);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));     // values are in registers: the accumulator is free again
+          if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+          if (pl < npos) {
+            const int gl = pl / HWp, rem = pl - gl * HWp;
+            float* o = a.out + (grp * a.G + gl) * a.Nout * (long long)HWp + rem;
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) {
-            if (ch < a.Nout) {
-              float v = __uint_as_float(r[ch]);
-              if (a.bias != nullptr) v += __ldg(a.bias + ch);
-              if (a.relu) v = fmaxf(v, 0.f);
-              o[(long long)ch * HWp] = v;                // lanes = consecutive positions: coalesced per channel
+            for (int ch = 0; ch < NCH; ++ch) {
+              if (ch < a.Nout) {
+                float v = __uint_as_float(r[ch]);
+                if (a.bias != nullptr) v += __ldg(a.bias + ch);
+                if (a.relu) v = fmaxf(v, 0.f);
+                o[(long long)ch * HWp] = v;                // lanes = consecutive positions: coalesced per channel
+              }
             }
           }
         }
       }
     } else {
       // ===== im2col producers: thread -> (row = position, every other 16-byte chunk) =====
-      const int t = threadIdx.x - 32 * (1 + EPI_WARPS);
+      const int t = threadIdx.x - 32 * FIRST_PROD_WARP;
       const int row = t & 127, chunk0 = t >> 7;
       int stage = 0; uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const long long P = tile * 128 + row;
-        const bool valid = P < a.Ptot;
-        const long long n = valid ? P / HWp : 0;
-        const int rem = valid ? (int)(P - n * HWp) : 0;
-        const int py = rem / a.Wp, px = rem - py * a.Wp;
-        const float* sample = a.src + n * a.Cs * (long long)HWs;
-        const int origin = (py - a.pad_h) * a.Ws + (px - a.pad_w);
-        for (int kb = 0; kb < a.nkb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t srow = smem_base + stage * stage_bytes + row * 128;
+      int slot = 0; uint32_t sphase = 0;
+      for (long long grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+        const int npos = group_samples(grp) * HWp;
+        const int tiles = (npos + 127) / 128;
+        mbar_wait(sfull_bar(slot), sphase);
+        const float* staged = reinterpret_cast<const float*>(smem + slot_off + slot * a.slot_bytes);
+        for (int tile = 0; tile < tiles; ++tile) {
+          const int pl = tile * 128 + row;
+          const bool valid = pl < npos;
+          const int gl = valid ? pl / HWp : 0, rem = valid ? pl - gl * HWp : 0;
+          const int py = rem / a.Wp, px = rem - py * a.Wp;
+          const int origin = gl * src_per_sample + (py - a.pad_h) * a.Ws + (px - a.pad_w);
+          for (int kb = 0; kb < a.nkb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t srow = smem_base + stage * stage_bytes + row * 128;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int chunk = chunk0 + 2 * c;
-            const uint32_t dst = srow + ((chunk ^ (row & 7)) << 4);
-            if (a.dgrad) im2col_chunk<true, false>(dst, sample, tab, kb * BLOCK_K + chunk * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, a.pad_h, a.pad_w);
-            else im2col_chunk<false, false>(dst, sample, tab, kb * BLOCK_K + chunk * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, 0, 0);
+            for (int c = 0; c < 4; ++c) {
+              const int chunk = chunk0 + 2 * c;
+              const uint32_t dst = srow + ((chunk ^ (row & 7)) << 4);
+              if (a.dgrad) im2col_chunk<true, false>(dst, staged, tab, kb * BLOCK_K + chunk * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, a.pad_h, a.pad_w);
+              else im2col_chunk<false, false>(dst, staged, tab, kb * BLOCK_K + chunk * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, 0, 0);
+            }
+            fence_async_smem();                            // own writes -> async proxy, then one arrive per warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(stage));
+            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
-          fence_async_smem();
-          mbar_arrive(full_bar(stage));
-          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sempty_bar(slot));      // this warp no longer reads the staged group
+        if (++slot == slots) { slot = 0; sphase ^= 1; }
       }
     }
   } else {
     // ================= weight gradient =================
-    const long long num_blocks = (a.Ptot + 63) / 64;     // K blocks of 64 positions
     const int N = a.nkb * 64;
     if (warp == 0) {
       if (lane == 0) {
         const uint32_t idesc = make_idesc_mn(false, true, 128, N);
         int stage = 0; uint32_t phase = 0;
         bool first = true;
-        for (long long pb = blockIdx.x; pb < num_blocks; pb += gridDim.x) {
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + TILE_BYTES;
+        for (long long grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+          const int blocks = (group_samples(grp) * HWp + 63) / 64;
+          for (int pb = 0; pb < blocks; ++pb) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + TILE_BYTES;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_bf16(tmem_base, make_desc(sa + k * (UMMA_K * 2), 16, 1024), make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024), idesc,
-                      (first && k == 0) ? 0u : 1u);
-          first = false;
-          tcgen05_commit(empty_bar(stage));
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16(tmem_base, make_desc(sa + k * (UMMA_K * 2), 16, 1024), make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024), idesc,
+                        (first && k == 0) ? 0u : 1u);
+            first = false;
+            tcgen05_commit(empty_bar(stage));
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
         }
         if (!first) tcgen05_commit(tfull_bar(0));
       }
     } else if (warp <= EPI_WARPS) {
       // ===== epilogue (once): rows 0..Cout-1 of the accumulator live in TMEM lane quarter 0 =====
-      if ((warp & 3) == 0 && (long long)blockIdx.x < num_blocks) {
+      if ((warp & 3) == 0 && (long long)blockIdx.x < num_groups) {
         mbar_wait(tfull_bar(0), 0);
         tcgen05_fence_after();
         for (int c0 = 0; c0 < N; c0 += 32) {
@@ -292,44 +351,54 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a, int sta
       }
     } else {
       // ===== producers: im2col rows (B operand, MN-major boxes of 64 k) and dY^T rows (A operand) =====
-      const int t = threadIdx.x - 32 * (1 + EPI_WARPS);
+      const int t = threadIdx.x - 32 * FIRST_PROD_WARP;
       const int row = t & 63, chunk0 = t >> 6;           // 4 chunk lanes per row
       const int units = a.nkb * 8;                        // 16-byte chunks per im2col row
       int stage = 0; uint32_t phase = 0;
-      for (long long pb = blockIdx.x; pb < num_blocks; pb += gridDim.x) {
-        const long long P = pb * 64 + row;
-        const bool valid = P < a.Ptot;
-        const long long n = valid ? P / HWp : 0;
-        const int rem = valid ? (int)(P - n * HWp) : 0;
-        const int py = rem / a.Wp, px = rem - py * a.Wp;
-        const float* sample = a.src + n * a.Cs * (long long)HWs;
-        const int origin = py * a.Ws + px;
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + TILE_BYTES;
-        for (int u = chunk0; u < units; u += 4) {
-          const int box = u >> 3, chunk = u & 7;
-          const uint32_t dst = sb + box * (BLOCK_K * 128) + row * 128 + ((chunk ^ (row & 7)) << 4);
-          im2col_chunk<false, true>(dst, sample, tab, u * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, 0, 0);
-        }
-        // dY^T: row co, 64 positions of this block (8 per unit)
-        for (int u = t; u < a.Cout * 8; u += PROD_THREADS) {
-          const int co = u >> 3, chunk = u & 7;
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const long long Pe = pb * 64 + chunk * 8 + e;
-            float x = 0.f;
-            if (Pe < a.Ptot) {
-              const long long ne = Pe / HWp;
-              x = __ldg(a.dy + (ne * a.Cout + co) * (long long)HWp + (Pe - ne * HWp));
-            }
-            v[e] = x;
+      int slot = 0; uint32_t sphase = 0;
+      for (long long grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+        const int npos = group_samples(grp) * HWp;
+        const int blocks = (npos + 63) / 64;
+        mbar_wait(sfull_bar(slot), sphase);
+        const float* staged = reinterpret_cast<const float*>(smem + slot_off + slot * a.slot_bytes);
+        const float* dys = reinterpret_cast<const float*>(smem + slot_off + slot * a.slot_bytes + a.dy_off);
+        for (int pb = 0; pb < blocks; ++pb) {
+          const int pl = pb * 64 + row;
+          const bool valid = pl < npos;
+          const int gl = valid ? pl / HWp : 0, rem = valid ? pl - gl * HWp : 0;
+          const int py = rem / a.Wp, px = rem - py * a.Wp;
+          const int origin = gl * src_per_sample + py * a.Ws + px;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + TILE_BYTES;
+          for (int u = chunk0; u < units; u += 4) {
+            const int box = u >> 3, chunk = u & 7;
+            const uint32_t dst = sb + box * (BLOCK_K * 128) + row * 128 + ((chunk ^ (row & 7)) << 4);
+            im2col_chunk<false, true>(dst, staged, tab, u * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, 0, 0);
           }
-          st_shared_v4(sa + co * 128 + ((chunk ^ (co & 7)) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          // dY^T: row co, 64 positions of this block (8 per unit)
+          for (int u = t; u < a.Cout * 8; u += PROD_THREADS) {
+            const int co = u >> 3, chunk = u & 7;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int pe = pb * 64 + chunk * 8 + e;
+              float x = 0.f;
+              if (pe < npos) {
+                const int ge = pe / HWp;
+                x = dys[(ge * a.Cout + co) * HWp + (pe - ge * HWp)];
+              }
+              v[e] = x;
+            }
+            st_shared_v4(sa + co * 128 + ((chunk ^ (co & 7)) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar(stage));
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        fence_async_smem();
-        mbar_arrive(full_bar(stage));
-        if (++stage == stages) { stage = 0; phase ^= 1; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sempty_bar(slot));
+        if (++slot == slots) { slot = 0; sphase ^= 1; }
       }
     }
   }
@@ -338,29 +407,55 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a, int sta
   __syncthreads();
   if (warp == 0) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
 }
 
-int smem_bytes(int mode, int stages, int nkb) {
-  const int stage_bytes = mode == 0 ? TILE_BYTES : TILE_BYTES + nkb * (BLOCK_K * 128);
-  return stages * stage_bytes + (mode == 0 ? nkb * 2048 : 0) + MAX_K * 8 + 8 * 20 + 16 + 1024;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+// samples per group: whole samples, 16-byte aligned group starts, <= 32 KB of source (+ dY) per slot,
+// and as few padded rows as possible in the last 128-position tile (64-position block) of a group
+int choose_group(int src_floats, int dy_floats, int HWp, int unit, int max_bytes) {
+  int best = 0;
+  double best_eff = -1.0;
+  for (int g = 1; g <= 32; ++g) {
+    if ((g * src_floats) % 4 != 0 || (g * dy_floats) % 4 != 0) continue;
+    if ((long long)g * (src_floats + dy_floats) * 4 > max_bytes) break;
+    const int pos = g * HWp;
+    const double eff = (double)pos / (double)(((pos + unit - 1) / unit) * unit);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = g; }
+  }
+  return best;
 }
 
 template <int MODE>
-int launch(pg_ctx* ctx, const ConvArgs& a, long long work) {
-  const int stages = MODE == 0 ? 8 : 4;
-  const int bytes = smem_bytes(MODE, stages, a.nkb);
-  PG_REQUIRE(bytes <= 227 * 1024, "tensor-core conv: shared-memory budget exceeded");
+int launch(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
+  const int HWp = a.Hp * a.Wp, src_floats = a.Cs * a.Hs * a.Ws;
+  a.G = choose_group(src_floats, dy_floats_per_sample, HWp, MODE == 0 ? 128 : 64, 40 * 1024);
+  PG_REQUIRE(a.G > 0, "tensor-core conv: a sample (with its output gradient) does not fit a shared-memory slot");
+  const int src_bytes = (a.G * src_floats * 4 + 127) & ~127;
+  const int dy_bytes = (a.G * dy_floats_per_sample * 4 + 127) & ~127;
+  a.dy_off = src_bytes;
+  a.slot_bytes = src_bytes + dy_bytes;
+  const int stage_bytes = MODE == 0 ? TILE_BYTES : TILE_BYTES + a.nkb * (BLOCK_K * 128);
+  const int fixed = (MODE == 0 ? a.nkb * 2048 : 0) + MAX_K * 8 + 8 * (2 * MAX_STAGES + 2 * NACC + 2 * MAX_SLOTS) + 16 + 1024;
+  a.slots = 2;
+  a.stages = MODE == 0 ? 6 : 3;
+  while (a.stages > 2 && fixed + a.stages * stage_bytes + a.slots * a.slot_bytes > SMEM_LIMIT) --a.stages;
+  while (a.slots < 3 && fixed + a.stages * stage_bytes + (a.slots + 1) * a.slot_bytes <= SMEM_LIMIT) ++a.slots;
+  while (a.stages < (MODE == 0 ? MAX_STAGES : 4) && fixed + (a.stages + 1) * stage_bytes + a.slots * a.slot_bytes <= SMEM_LIMIT) ++a.stages;
+  const int bytes = fixed + a.stages * stage_bytes + a.slots * a.slot_bytes;
+  PG_REQUIRE(bytes <= SMEM_LIMIT, "tensor-core conv: shared-memory budget exceeded");
   static int attr_bytes = 0;
   if (bytes > attr_bytes) {
     PG_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     attr_bytes = bytes;
   }
-  int tmem_cols = 64;
-  if (MODE == 1) { tmem_cols = 32; while (tmem_cols < a.nkb * 64) tmem_cols *= 2; }
-  const int grid = (int)(work < ctx->num_sms ? work : ctx->num_sms);
-  tc_conv_kernel<MODE><<<grid, THREADS, bytes, ctx->stream>>>(a, stages, tmem_cols);
+  a.tmem_cols = NACC * 32;
+  if (MODE == 1) { a.tmem_cols = 32; while (a.tmem_cols < a.nkb * 64) a.tmem_cols *= 2; }
+  const long long groups = (a.nsamples + a.G - 1) / a.G;
+  const int grid = (int)(groups < ctx->num_sms ? groups : ctx->num_sms);
+  tc_conv_kernel<MODE><<<grid, THREADS, bytes, ctx->stream>>>(a);
   PG_LAUNCHED(ctx);
   return PG_OK;
 }
@@ -388,8 +483,8 @@ int pg_tc_conv2d_fwd(pg_ctx* ctx, const void* x, const void* w, const void* b, v
   a.Cs = Cin; a.Hs = H; a.Ws = W; a.Hp = H - kH + 1; a.Wp = W - kW + 1;
   a.kH = kH; a.kW = kW; a.Cin = Cin; a.Cout = Cout; a.Nout = Cout;
   a.Ktot = Cin * kH * kW; a.nkb = (int)pg_cdiv(a.Ktot, BLOCK_K);
-  a.Ptot = (long long)N * a.Hp * a.Wp; a.relu = act == PG_ACT_RELU;
-  return launch<0>(ctx, a, (a.Ptot + 127) / 128);
+  a.nsamples = N; a.relu = act == PG_ACT_RELU;
+  return launch<0>(ctx, a, 0);
 }
 
 int pg_tc_conv2d_bwd(pg_ctx* ctx, const void* x, const void* w, const void* dy, void* dw, void* db, void* dx, int64_t N, int Cin, int H,
@@ -407,8 +502,8 @@ int pg_tc_conv2d_bwd(pg_ctx* ctx, const void* x, const void* w, const void* dy, 
     a.Cs = Cin; a.Hs = H; a.Ws = W; a.Hp = Ho; a.Wp = Wo;
     a.kH = kH; a.kW = kW; a.Cin = Cin; a.Cout = Cout;
     a.Ktot = Cin * kH * kW; a.nkb = (int)pg_cdiv(a.Ktot + 1, 64);
-    a.Ptot = (long long)N * Ho * Wo;
-    int rc = launch<1>(ctx, a, (a.Ptot + 63) / 64);
+    a.nsamples = N;
+    int rc = launch<1>(ctx, a, Cout * Ho * Wo);
     if (rc != PG_OK) return rc;
   }
   if (dx != nullptr) {
@@ -417,8 +512,8 @@ int pg_tc_conv2d_bwd(pg_ctx* ctx, const void* x, const void* w, const void* dy, 
     a.Cs = Cout; a.Hs = Ho; a.Ws = Wo; a.Hp = H; a.Wp = W;
     a.kH = kH; a.kW = kW; a.pad_h = kH - 1; a.pad_w = kW - 1; a.Cin = Cin; a.Cout = Cout; a.Nout = Cin;
     a.Ktot = Cout * kH * kW; a.nkb = (int)pg_cdiv(a.Ktot, BLOCK_K); a.dgrad = 1;
-    a.Ptot = (long long)N * H * W;
-    int rc = launch<0>(ctx, a, (a.Ptot + 127) / 128);
+    a.nsamples = N;
+    int rc = launch<0>(ctx, a, 0);
     if (rc != PG_OK) return rc;
   }
   return PG_OK;
