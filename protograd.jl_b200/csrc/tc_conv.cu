@@ -34,6 +34,7 @@ constexpr int EPI_WARPS = 4;
 constexpr int THREADS = 32 * (2 + EPI_WARPS + PROD_WARPS);   // warp 0: MMA issuer; 1..4: epilogue; 5: bulk-copy loader; 6..13: producers
 constexpr int FIRST_PROD_WARP = 2 + EPI_WARPS;
 constexpr int MAX_K = 512;                             // im2col width limit (lookup table size)
+constexpr int MAX_POS = 2048;                          // positions per group (position table size)
 constexpr int NCH = 16;                                // channel tile (UMMA N of the forward / data-gradient products)
 constexpr int NACC = 8;                                // TMEM accumulator ring of the forward / data-gradient kernel (32 columns each)
 constexpr int MAX_STAGES = 8, MAX_SLOTS = 4;
@@ -59,6 +60,7 @@ struct ConvArgs {
   int relu;
   int stages, slots;       // operand-tile ring / staged-sample ring depths
   int slot_bytes, dy_off;  // bytes per staged group (source, then dY at dy_off for the weight gradient)
+  int padded_bytes;        // data gradient: zero-padded copy of one group (0 otherwise)
   int tmem_cols;
 };
 
@@ -74,53 +76,46 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory"); }
 
-// One 16-byte chunk (8 consecutive k) of one im2col row, gathered from the sample staged in shared memory.
-// `tab[k]` = (offset of tap k relative to the patch origin, (i << 16) | j); `origin` = offset of the patch
-// origin in the staged group (may point before the sample for the padded data-gradient patches, hence the
-// bounds test on (py + i - pad, px + j - pad)).
-template <bool PAD, bool ONES>
-__device__ __forceinline__ void im2col_chunk(uint32_t dst, const float* __restrict__ staged, const int2* __restrict__ tab, int k0, int Ktot,
-                                             bool valid, int origin, int py, int px, int Hs, int Ws, int pad_h, int pad_w) {
+// One 16-byte chunk (8 consecutive k) of one im2col row.  off[e] = offset of tap e relative to the patch
+// origin (thread-constant registers), `mask` bit e = tap exists, `ones` bit e = the constant-1 column.
+__device__ __forceinline__ void im2col_chunk(uint32_t dst, const float* __restrict__ staged, int origin, const int (&off)[8], uint32_t mask,
+                                             uint32_t ones) {
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int k = k0 + e;
-    float x = 0.f;
-    if (valid && k < Ktot) {
-      const int2 t = tab[k];
-      if (PAD) {
-        const int iy = py + (t.y >> 16) - pad_h, ix = px + (t.y & 0xffff) - pad_w;
-        if (iy >= 0 && iy < Hs && ix >= 0 && ix < Ws) x = staged[origin + t.x];
-      } else {
-        x = staged[origin + t.x];
-      }
-    } else if (ONES && valid && k == Ktot) {
-      x = 1.f;
-    }
+    float x = ((ones >> e) & 1u) ? 1.f : 0.f;
+    if ((mask >> e) & 1u) x = staged[origin + off[e]];
     v[e] = x;
   }
   st_shared_v4(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
-// MODE 0: forward / data gradient.  MODE 1: weight gradient.
+// MODE 0: forward / data gradient.  MODE 1: weight gradient.  NKB: 64-wide k-blocks (MODE 0) / im2col boxes (MODE 1).
 // Work item = a group of G consecutive samples.  The loader thread bulk-copies the group's source
 // activations (and dY for the weight gradient) into a shared-memory slot (cp.async.bulk + mbarrier, a few
-// groups ahead), the producer warps expand them into operand tiles, one thread issues the MMAs, the
-// epilogue warps drain TMEM.
-template <int MODE>
+// groups ahead); the 8 producer warps expand them into SWIZZLE_128B operand tiles: warp w owns the w-th
+// 16-byte chunk of every 64-wide k-block (its 8 tap offsets per block live in registers), lanes are 32
+// consecutive positions (conflict-free shared-memory gathers), the patch origin of a position comes from a
+// table built once per kernel.  One thread issues the MMAs, the epilogue warps drain TMEM.  The data
+// gradient gathers from a zero-padded copy of the group (built by the producers), so it needs no bounds tests.
+template <int MODE, int NKB>
 __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  // layout: operand stages | [MODE 0: nkb x 2 KB filter tiles] | staged-sample slots | k lookup table | barriers
+  // layout: operand stages | [MODE 0: NKB x 2 KB filter tiles] | staged-sample slots | [padded group] | tables | barriers
   const int stages = a.stages, slots = a.slots;
-  const int stage_bytes = MODE == 0 ? TILE_BYTES : TILE_BYTES + a.nkb * (BLOCK_K * 128);
+  constexpr int stage_bytes = MODE == 0 ? TILE_BYTES : TILE_BYTES + NKB * (BLOCK_K * 128);
   const uint32_t wm_off = stages * stage_bytes;                              // MODE 0 only
-  const uint32_t slot_off = wm_off + (MODE == 0 ? a.nkb * 2048 : 0);
-  const uint32_t tab_off = slot_off + slots * a.slot_bytes;
-  int2* tab = reinterpret_cast<int2*>(smem + tab_off);
-  const uint32_t bar_base = smem_base + tab_off + MAX_K * 8;
+  const uint32_t slot_off = wm_off + (MODE == 0 ? NKB * 2048 : 0);
+  const uint32_t pad_off = slot_off + slots * a.slot_bytes;
+  const uint32_t tab_off = pad_off + a.padded_bytes;
+  int2* tab = reinterpret_cast<int2*>(smem + tab_off);                       // [MAX_K] tap table
+  int* origin_tab = reinterpret_cast<int*>(smem + tab_off + MAX_K * 8);      // [MAX_POS] patch origin of a position (source offset)
+  int* dybase_tab = origin_tab + MAX_POS;                                    // [MAX_POS] MODE 1: offset of (position, co = 0) in the staged dY
+  const uint32_t bar_base = smem_base + tab_off + MAX_K * 8 + 2 * MAX_POS * 4;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                                   // operand tile written
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };                   // operand tile consumed by the MMAs
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + i); };               // accumulator complete
@@ -128,26 +123,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
   auto sfull_bar = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + 2 * NACC + i); };    // staged group landed
   auto sempty_bar = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + 2 * NACC + MAX_SLOTS + i); };   // staged group expanded
   constexpr int NUM_BARS = 2 * MAX_STAGES + 2 * NACC + 2 * MAX_SLOTS;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tab_off + MAX_K * 8 + 8 * NUM_BARS);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tab_off + MAX_K * 8 + 2 * MAX_POS * 4 + 8 * NUM_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HWp = a.Hp * a.Wp, HWs = a.Hs * a.Ws, kk = a.kH * a.kW;
-  const int Kcols = a.nkb * 64;                                              // padded im2col width
+  // geometry of the buffer the gathers read: the raw staged group, or its zero-padded copy (data gradient)
+  const int gW = a.Ws + 2 * a.pad_w, gH = a.Hs + 2 * a.pad_h, gplane = gW * gH, gsample = a.Cs * gplane;
   const long long num_groups = (a.nsamples + a.G - 1) / a.G;
   const int src_per_sample = a.Cs * HWs;                                     // floats
+  const int max_pos = a.G * HWp;
 
   // ---- one-time setup ----
-  for (int k = threadIdx.x; k < Kcols && k < MAX_K; k += THREADS) {
+  for (int k = threadIdx.x; k < NKB * 64; k += THREADS) {
     int2 t = make_int2(0, 0);
     if (k < a.Ktot) {
       const int c = k / kk, r = k - c * kk, i = r / a.kW, j = r - i * a.kW;
-      t = make_int2(c * HWs + i * a.Ws + j, (i << 16) | j);
+      t = make_int2(c * gplane + i * gW + j, (i << 16) | j);
     }
     tab[k] = t;
   }
+  for (int pl = threadIdx.x; pl < max_pos; pl += THREADS) {
+    const int gl = pl / HWp, rem = pl - gl * HWp, py = rem / a.Wp, px = rem - py * a.Wp;
+    origin_tab[pl] = gl * gsample + py * gW + px;
+    dybase_tab[pl] = gl * a.Cout * HWp + rem;
+  }
   if (MODE == 0) {
-    // filter tiles: [nkb][16 rows][64 k] bf16, K-major SWIZZLE_128B (row r at r*128, 16-byte chunk c at (c ^ (r & 7)) * 16)
-    for (int idx = threadIdx.x; idx < a.nkb * NCH * BLOCK_K; idx += THREADS) {
+    // filter tiles: [NKB][16 rows][64 k] bf16, K-major SWIZZLE_128B (row r at r*128, 16-byte chunk c at (c ^ (r & 7)) * 16)
+    for (int idx = threadIdx.x; idx < NKB * NCH * BLOCK_K; idx += THREADS) {
       const int kb = idx / (NCH * BLOCK_K), r = (idx / BLOCK_K) % NCH, kc = idx % BLOCK_K, k = kb * BLOCK_K + kc;
       float v = 0.f;
       if (r < a.Nout && k < a.Ktot) {
@@ -158,6 +160,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
       const uint32_t off = kb * 2048 + r * 128 + (((kc >> 3) ^ (r & 7)) << 4) + (kc & 7) * 2;
       *reinterpret_cast<__nv_bfloat16*>(smem + wm_off + off) = __float2bfloat16_rn(v);
     }
+    // zero borders of the padded copy (interiors are rewritten for every group)
+    for (int i = threadIdx.x; i < a.padded_bytes / 16; i += THREADS)
+      *reinterpret_cast<uint4*>(smem + pad_off + i * 16) = make_uint4(0, 0, 0, 0);
   } else {
     // dY^T operand tiles: rows >= Cout stay zero for the whole kernel
     for (int s = 0; s < stages; ++s)
@@ -180,7 +185,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // positions / tiles / k-blocks of group `grp` (the last group may hold fewer samples)
   auto group_samples = [&](long long grp) { return (int)min((long long)a.G, a.nsamples - grp * a.G); };
 
   if (warp == 1 + EPI_WARPS) {
@@ -199,6 +203,114 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
         if (++slot == slots) { slot = 0; sphase ^= 1; }
       }
     }
+  } else if (warp >= FIRST_PROD_WARP) {
+    // ===== producers =====
+    const int cu = warp - FIRST_PROD_WARP;                // this warp's 16-byte chunk of every 64-wide k-block
+    int off[NKB][8];
+    uint32_t mask[NKB], ones[NKB];
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb) {
+      mask[kb] = 0; ones[kb] = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = kb * 64 + cu * 8 + e;
+        off[kb][e] = tab[k].x;
+        if (k < a.Ktot) mask[kb] |= 1u << e;
+        if (MODE == 1 && k == a.Ktot) ones[kb] |= 1u << e;
+      }
+    }
+    const int t = threadIdx.x - 32 * FIRST_PROD_WARP;
+    int stage = 0; uint32_t phase = 0;
+    int slot = 0; uint32_t sphase = 0;
+    for (long long grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+      const int gs = group_samples(grp);
+      const int npos = gs * HWp;
+      mbar_wait(sfull_bar(slot), sphase);
+      const float* raw = reinterpret_cast<const float*>(smem + slot_off + slot * a.slot_bytes);
+      const float* staged = raw;
+      if (MODE == 0 && a.padded_bytes != 0) {
+        // data gradient: copy the group's rows into the interior of the zero-padded buffer
+        float* padded = reinterpret_cast<float*>(smem + pad_off);
+        producers_sync();                                  // everyone has finished gathering the previous group
+        const int rows = gs * a.Cs * a.Hs;
+        for (int r = t; r < rows; r += PROD_THREADS) {
+          const int pc = r / a.Hs, y = r - pc * a.Hs;      // pc = (sample, channel)
+          const float* srow = raw + r * a.Ws;
+          float* drow = padded + pc * gplane + (y + a.pad_h) * gW + a.pad_w;
+          for (int x = 0; x < a.Ws; ++x) drow[x] = srow[x];
+        }
+        producers_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sempty_bar(slot));      // the raw slot can be refilled already
+        staged = padded;
+      }
+      if (MODE == 0) {
+        const int tiles = (npos + 127) / 128;
+        for (int tile = 0; tile < tiles; ++tile) {
+          int origin[4];
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int pl = tile * 128 + ps * 32 + lane;
+            origin[ps] = pl < npos ? origin_tab[pl] : -1;
+          }
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t sbase = smem_base + stage * stage_bytes;
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              const int row = ps * 32 + lane;
+              const uint32_t dst = sbase + row * 128 + ((cu ^ (row & 7)) << 4);
+              if (origin[ps] >= 0 && mask[kb] != 0) im2col_chunk(dst, staged, origin[ps], off[kb], mask[kb], 0u);
+              else st_shared_v4(dst, 0u, 0u, 0u, 0u);
+            }
+            fence_async_smem();                            // own writes -> async proxy, then one arrive per warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(stage));
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else {
+        const float* dys = reinterpret_cast<const float*>(smem + slot_off + slot * a.slot_bytes + a.dy_off);
+        const int blocks = (npos + 63) / 64;
+        for (int pb = 0; pb < blocks; ++pb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + TILE_BYTES;
+          // im2col rows (B operand: MN-major boxes of 64 k, rows = positions)
+#pragma unroll
+          for (int ps = 0; ps < 2; ++ps) {
+            const int row = ps * 32 + lane, pl = pb * 64 + row;
+            const int origin = pl < npos ? origin_tab[pl] : -1;
+#pragma unroll
+            for (int box = 0; box < NKB; ++box) {
+              const uint32_t dst = sb + box * (BLOCK_K * 128) + row * 128 + ((cu ^ (row & 7)) << 4);
+              if (origin >= 0 && (mask[box] | ones[box]) != 0) im2col_chunk(dst, staged, origin, off[box], mask[box], ones[box]);
+              else st_shared_v4(dst, 0u, 0u, 0u, 0u);
+            }
+          }
+          // dY^T rows (A operand): row co, 64 positions of this block, 8 per unit
+          for (int u = t; u < a.Cout * 8; u += PROD_THREADS) {
+            const int co = u >> 3, chunk = u & 7;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int pe = pb * 64 + chunk * 8 + e;
+              v[e] = pe < npos ? dys[dybase_tab[pe] + co * HWp] : 0.f;
+            }
+            st_shared_v4(sa + co * 128 + ((chunk ^ (co & 7)) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar(stage));
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (!(MODE == 0 && a.padded_bytes != 0)) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sempty_bar(slot));      // this warp no longer reads the staged group
+      }
+      if (++slot == slots) { slot = 0; sphase ^= 1; }
+    }
   } else if (MODE == 0) {
     if (warp == 0) {
       // ===== MMA issuer =====
@@ -212,7 +324,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
             mbar_wait(tempty_bar(acc), acc_phase ^ 1);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 32;
-            for (int kb = 0; kb < a.nkb; ++kb) {
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
               mbar_wait(full_bar(stage), phase);
               tcgen05_fence_after();
               const uint32_t sa = smem_base + stage * stage_bytes, sb = smem_base + wm_off + kb * 2048;
@@ -220,14 +333,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                 umma_bf16(d_tmem, make_desc(sa + k * (UMMA_K * 2), 16, 1024), make_desc(sb + k * (UMMA_K * 2), 16, 1024), idesc, (kb | k) != 0);
               tcgen05_commit(empty_bar(stage));
-              if (kb == a.nkb - 1) tcgen05_commit(tfull_bar(acc));
+              if (kb == NKB - 1) tcgen05_commit(tfull_bar(acc));
               if (++stage == stages) { stage = 0; phase ^= 1; }
             }
             if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
           }
         }
       }
-    } else if (warp <= EPI_WARPS) {
+    } else {
       // ===== epilogue: one accumulator row (= one position) per thread, 16 channels =====
       const int q = warp & 3;
       int acc = 0; uint32_t acc_phase = 0;
@@ -260,47 +373,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
           }
         }
       }
-    } else {
-      // ===== im2col producers: thread -> (row = position, every other 16-byte chunk) =====
-      const int t = threadIdx.x - 32 * FIRST_PROD_WARP;
-      const int row = t & 127, chunk0 = t >> 7;
-      int stage = 0; uint32_t phase = 0;
-      int slot = 0; uint32_t sphase = 0;
-      for (long long grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
-        const int npos = group_samples(grp) * HWp;
-        const int tiles = (npos + 127) / 128;
-        mbar_wait(sfull_bar(slot), sphase);
-        const float* staged = reinterpret_cast<const float*>(smem + slot_off + slot * a.slot_bytes);
-        for (int tile = 0; tile < tiles; ++tile) {
-          const int pl = tile * 128 + row;
-          const bool valid = pl < npos;
-          const int gl = valid ? pl / HWp : 0, rem = valid ? pl - gl * HWp : 0;
-          const int py = rem / a.Wp, px = rem - py * a.Wp;
-          const int origin = gl * src_per_sample + (py - a.pad_h) * a.Ws + (px - a.pad_w);
-          for (int kb = 0; kb < a.nkb; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            const uint32_t srow = smem_base + stage * stage_bytes + row * 128;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int chunk = chunk0 + 2 * c;
-              const uint32_t dst = srow + ((chunk ^ (row & 7)) << 4);
-              if (a.dgrad) im2col_chunk<true, false>(dst, staged, tab, kb * BLOCK_K + chunk * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, a.pad_h, a.pad_w);
-              else im2col_chunk<false, false>(dst, staged, tab, kb * BLOCK_K + chunk * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, 0, 0);
-            }
-            fence_async_smem();                            // own writes -> async proxy, then one arrive per warp
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(stage));
-            if (++stage == stages) { stage = 0; phase ^= 1; }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sempty_bar(slot));      // this warp no longer reads the staged group
-        if (++slot == slots) { slot = 0; sphase ^= 1; }
-      }
     }
   } else {
-    // ================= weight gradient =================
-    const int N = a.nkb * 64;
+    // ================= weight gradient: MMA issuer / epilogue =================
+    constexpr int N = NKB * 64;
     if (warp == 0) {
       if (lane == 0) {
         const uint32_t idesc = make_idesc_mn(false, true, 128, N);
@@ -323,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
         }
         if (!first) tcgen05_commit(tfull_bar(0));
       }
-    } else if (warp <= EPI_WARPS) {
+    } else {
       // ===== epilogue (once): rows 0..Cout-1 of the accumulator live in TMEM lane quarter 0 =====
       if ((warp & 3) == 0 && (long long)blockIdx.x < num_groups) {
         mbar_wait(tfull_bar(0), 0);
@@ -349,57 +425,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
         }
         tcgen05_fence_before();
       }
-    } else {
-      // ===== producers: im2col rows (B operand, MN-major boxes of 64 k) and dY^T rows (A operand) =====
-      const int t = threadIdx.x - 32 * FIRST_PROD_WARP;
-      const int row = t & 63, chunk0 = t >> 6;           // 4 chunk lanes per row
-      const int units = a.nkb * 8;                        // 16-byte chunks per im2col row
-      int stage = 0; uint32_t phase = 0;
-      int slot = 0; uint32_t sphase = 0;
-      for (long long grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
-        const int npos = group_samples(grp) * HWp;
-        const int blocks = (npos + 63) / 64;
-        mbar_wait(sfull_bar(slot), sphase);
-        const float* staged = reinterpret_cast<const float*>(smem + slot_off + slot * a.slot_bytes);
-        const float* dys = reinterpret_cast<const float*>(smem + slot_off + slot * a.slot_bytes + a.dy_off);
-        for (int pb = 0; pb < blocks; ++pb) {
-          const int pl = pb * 64 + row;
-          const bool valid = pl < npos;
-          const int gl = valid ? pl / HWp : 0, rem = valid ? pl - gl * HWp : 0;
-          const int py = rem / a.Wp, px = rem - py * a.Wp;
-          const int origin = gl * src_per_sample + py * a.Ws + px;
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + TILE_BYTES;
-          for (int u = chunk0; u < units; u += 4) {
-            const int box = u >> 3, chunk = u & 7;
-            const uint32_t dst = sb + box * (BLOCK_K * 128) + row * 128 + ((chunk ^ (row & 7)) << 4);
-            im2col_chunk<false, true>(dst, staged, tab, u * 8, a.Ktot, valid, origin, py, px, a.Hs, a.Ws, 0, 0);
-          }
-          // dY^T: row co, 64 positions of this block (8 per unit)
-          for (int u = t; u < a.Cout * 8; u += PROD_THREADS) {
-            const int co = u >> 3, chunk = u & 7;
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int pe = pb * 64 + chunk * 8 + e;
-              float x = 0.f;
-              if (pe < npos) {
-                const int ge = pe / HWp;
-                x = dys[(ge * a.Cout + co) * HWp + (pe - ge * HWp)];
-              }
-              v[e] = x;
-            }
-            st_shared_v4(sa + co * 128 + ((chunk ^ (co & 7)) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-          }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_bar(stage));
-          if (++stage == stages) { stage = 0; phase ^= 1; }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sempty_bar(slot));
-        if (++slot == slots) { slot = 0; sphase ^= 1; }
-      }
     }
   }
 
@@ -413,14 +438,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
 
 constexpr int SMEM_LIMIT = 227 * 1024;
 
-// samples per group: whole samples, 16-byte aligned group starts, <= 32 KB of source (+ dY) per slot,
-// and as few padded rows as possible in the last 128-position tile (64-position block) of a group
-int choose_group(int src_floats, int dy_floats, int HWp, int unit, int max_bytes) {
+// samples per group: whole samples, 16-byte aligned group starts, bounded bytes per slot, <= MAX_POS
+// positions, and as few padded rows as possible in the last 128-position tile (64-position block)
+int choose_group(int src_floats, int dy_floats, int padded_floats, int HWp, int unit, int max_bytes) {
   int best = 0;
   double best_eff = -1.0;
   for (int g = 1; g <= 32; ++g) {
     if ((g * src_floats) % 4 != 0 || (g * dy_floats) % 4 != 0) continue;
-    if ((long long)g * (src_floats + dy_floats) * 4 > max_bytes) break;
+    if ((long long)g * (src_floats + dy_floats + padded_floats) * 4 > max_bytes || g * HWp > MAX_POS) break;
     const int pos = g * HWp;
     const double eff = (double)pos / (double)(((pos + unit - 1) / unit) * unit);
     if (eff > best_eff + 1e-9) { best_eff = eff; best = g; }
@@ -428,17 +453,20 @@ int choose_group(int src_floats, int dy_floats, int HWp, int unit, int max_bytes
   return best;
 }
 
-template <int MODE>
-int launch(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
+template <int MODE, int NKB>
+int launch_nkb(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
   const int HWp = a.Hp * a.Wp, src_floats = a.Cs * a.Hs * a.Ws;
-  a.G = choose_group(src_floats, dy_floats_per_sample, HWp, MODE == 0 ? 128 : 64, 40 * 1024);
+  const int padded_floats = a.dgrad ? a.Cs * (a.Hs + 2 * a.pad_h) * (a.Ws + 2 * a.pad_w) : 0;
+  a.G = choose_group(src_floats, dy_floats_per_sample, padded_floats, HWp, MODE == 0 ? 128 : 64, a.dgrad ? 80 * 1024 : 40 * 1024);
   PG_REQUIRE(a.G > 0, "tensor-core conv: a sample (with its output gradient) does not fit a shared-memory slot");
   const int src_bytes = (a.G * src_floats * 4 + 127) & ~127;
   const int dy_bytes = (a.G * dy_floats_per_sample * 4 + 127) & ~127;
   a.dy_off = src_bytes;
   a.slot_bytes = src_bytes + dy_bytes;
-  const int stage_bytes = MODE == 0 ? TILE_BYTES : TILE_BYTES + a.nkb * (BLOCK_K * 128);
-  const int fixed = (MODE == 0 ? a.nkb * 2048 : 0) + MAX_K * 8 + 8 * (2 * MAX_STAGES + 2 * NACC + 2 * MAX_SLOTS) + 16 + 1024;
+  a.padded_bytes = (a.G * padded_floats * 4 + 127) & ~127;
+  constexpr int stage_bytes = MODE == 0 ? TILE_BYTES : TILE_BYTES + NKB * (BLOCK_K * 128);
+  const int fixed = (MODE == 0 ? NKB * 2048 : 0) + a.padded_bytes + MAX_K * 8 + 2 * MAX_POS * 4 +
+                    8 * (2 * MAX_STAGES + 2 * NACC + 2 * MAX_SLOTS) + 16 + 1024;
   a.slots = 2;
   a.stages = MODE == 0 ? 6 : 3;
   while (a.stages > 2 && fixed + a.stages * stage_bytes + a.slots * a.slot_bytes > SMEM_LIMIT) --a.stages;
@@ -448,16 +476,35 @@ int launch(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
   PG_REQUIRE(bytes <= SMEM_LIMIT, "tensor-core conv: shared-memory budget exceeded");
   static int attr_bytes = 0;
   if (bytes > attr_bytes) {
-    PG_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    PG_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<MODE, NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     attr_bytes = bytes;
   }
   a.tmem_cols = NACC * 32;
-  if (MODE == 1) { a.tmem_cols = 32; while (a.tmem_cols < a.nkb * 64) a.tmem_cols *= 2; }
+  if (MODE == 1) { a.tmem_cols = 32; while (a.tmem_cols < NKB * 64) a.tmem_cols *= 2; }
   const long long groups = (a.nsamples + a.G - 1) / a.G;
   const int grid = (int)(groups < ctx->num_sms ? groups : ctx->num_sms);
-  tc_conv_kernel<MODE><<<grid, THREADS, bytes, ctx->stream>>>(a);
+  tc_conv_kernel<MODE, NKB><<<grid, THREADS, bytes, ctx->stream>>>(a);
   PG_LAUNCHED(ctx);
   return PG_OK;
+}
+
+template <int MODE>
+int launch(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
+  switch (a.nkb) {
+    case 1: return launch_nkb<MODE, 1>(ctx, a, dy_floats_per_sample);
+    case 2: return launch_nkb<MODE, 2>(ctx, a, dy_floats_per_sample);
+    case 3: return launch_nkb<MODE, 3>(ctx, a, dy_floats_per_sample);
+    case 4: return launch_nkb<MODE, 4>(ctx, a, dy_floats_per_sample);
+  }
+  if (MODE == 0) {
+    switch (a.nkb) {
+      case 5: return launch_nkb<0, 5>(ctx, a, dy_floats_per_sample);
+      case 6: return launch_nkb<0, 6>(ctx, a, dy_floats_per_sample);
+      case 7: return launch_nkb<0, 7>(ctx, a, dy_floats_per_sample);
+    }
+  }
+  pg_set_error("tensor-core conv: %d k-blocks not instantiated", a.nkb);
+  return PG_ERR_ARG;
 }
 
 bool supported(int Cin, int Cout, int kH, int kW) {
