@@ -144,9 +144,10 @@ int pg_conv2d_bwd(pg_ctx* ctx, int dtype, const void* x, const void* w, const vo
                   int64_t N, int Cin, int H, int W, int Cout, int kH, int kW);
 /* Conv layer, BF16 tensor-core mode (tcgen05 implicit GEMM, csrc/tc_conv.cu): same tensors as pg_conv2d_* in
  * Float32 NCHW; operands are rounded to bf16 on the way into shared memory, products accumulate in fp32.
- * Envelope: Cin, Cout <= 16 and Cin*kH*kW < 256 (pg_tc_conv2d_supported); other shapes use pg_conv2d_*.
+ * Envelope (pg_tc_conv2d_supported returns 1): Cin, Cout <= 16, Cin*kH*kW < 256, Cout*kH*kW <= 448 and one
+ * sample (plus its output gradient / zero-padded copy) fits a shared-memory slot; other shapes use pg_conv2d_*.
  * The weight-gradient launch adds per-CTA partial sums with fp32 atomics (dw / db are zeroed first). */
-int pg_tc_conv2d_supported(int Cin, int Cout, int kH, int kW);
+int pg_tc_conv2d_supported(int Cin, int H, int W, int Cout, int kH, int kW);
 int pg_tc_conv2d_fwd(pg_ctx* ctx, const void* x, const void* w, const void* b, void* y,
                      int64_t N, int Cin, int H, int W, int Cout, int kH, int kW, int act);
 int pg_tc_conv2d_bwd(pg_ctx* ctx, const void* x, const void* w, const void* dy, void* dw, void* db, void* dx,

@@ -81,7 +81,7 @@ _SIGS = {
     "pg_tc_gemm": [_P, _I, _P, _P, _P, _I, _L, _L, _L],
     "pg_conv2d_fwd": [_P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I],
     "pg_conv2d_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I],
-    "pg_tc_conv2d_supported": [_I, _I, _I, _I],
+    "pg_tc_conv2d_supported": [_I, _I, _I, _I, _I, _I],
     "pg_tc_conv2d_fwd": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I],
     "pg_tc_conv2d_bwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I],
     "pg_maxpool2d_fwd": [_P, _I, _P, _P, _L, _I, _I, _I],

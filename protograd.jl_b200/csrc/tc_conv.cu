@@ -29,9 +29,9 @@ namespace {
 
 constexpr int BLOCK_K = 64, UMMA_K = 16;
 constexpr int TILE_BYTES = 128 * 128;                  // 128 rows x 64 bf16
-constexpr int PROD_WARPS = 8, PROD_THREADS = 32 * PROD_WARPS;
-constexpr int EPI_WARPS = 4;
-constexpr int THREADS = 32 * (2 + EPI_WARPS + PROD_WARPS);   // warp 0: MMA issuer; 1..4: epilogue; 5: bulk-copy loader; 6..13: producers
+constexpr int PROD_WARPS = 16, PROD_THREADS = 32 * PROD_WARPS;   // 8 chunk lanes x 2 row halves
+constexpr int EPI_WARPS = 8;                           // two groups of 4 (one warp per TMEM lane quarter) alternate tiles
+constexpr int THREADS = 32 * (2 + EPI_WARPS + PROD_WARPS);   // warp 0: MMA issuer; 1..8: epilogue; 9: bulk-copy loader; 10..25: producers
 constexpr int FIRST_PROD_WARP = 2 + EPI_WARPS;
 constexpr int MAX_K = 512;                             // im2col width limit (lookup table size)
 constexpr int MAX_POS = 2048;                          // positions per group (position table size)
@@ -76,17 +76,27 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory"); }
 
-// One 16-byte chunk (8 consecutive k) of one im2col row.  off[e] = offset of tap e relative to the patch
-// origin (thread-constant registers), `mask` bit e = tap exists, `ones` bit e = the constant-1 column.
-__device__ __forceinline__ void im2col_chunk(uint32_t dst, const float* __restrict__ staged, int origin, const int (&off)[8], uint32_t mask,
+// One 16-byte chunk (8 consecutive k) of one im2col row.  off2[e/2] packs the offsets of taps e, e+1 relative
+// to the patch origin (16 bits each, thread-constant registers), `mask` bit e = tap exists, `ones` bit e =
+// the constant-1 column.
+__device__ __forceinline__ void im2col_chunk(uint32_t dst, const float* __restrict__ staged, int origin, const uint32_t (&off2)[4], uint32_t mask,
                                              uint32_t ones) {
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     float x = ((ones >> e) & 1u) ? 1.f : 0.f;
-    if ((mask >> e) & 1u) x = staged[origin + off[e]];
+    const int o = (e & 1) ? (int)(off2[e >> 1] >> 16) : (int)(off2[e >> 1] & 0xffffu);
+    if ((mask >> e) & 1u) x = staged[origin + o];
     v[e] = x;
   }
   st_shared_v4(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -115,7 +125,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
   int2* tab = reinterpret_cast<int2*>(smem + tab_off);                       // [MAX_K] tap table
   int* origin_tab = reinterpret_cast<int*>(smem + tab_off + MAX_K * 8);      // [MAX_POS] patch origin of a position (source offset)
   int* dybase_tab = origin_tab + MAX_POS;                                    // [MAX_POS] MODE 1: offset of (position, co = 0) in the staged dY
-  const uint32_t bar_base = smem_base + tab_off + MAX_K * 8 + 2 * MAX_POS * 4;
+  uint4* offp = reinterpret_cast<uint4*>(smem + tab_off + MAX_K * 8 + 2 * MAX_POS * 4);   // [MAX_K / 8] per 16-byte chunk: 8 tap offsets, 16 bits each
+  uint32_t* maskp = reinterpret_cast<uint32_t*>(offp + MAX_K / 8);           // [MAX_K / 8] bits 0-7: tap exists, bits 8-15: constant-1 column
+  const uint32_t bar_base = smem_base + tab_off + MAX_K * 8 + 2 * MAX_POS * 4 + (MAX_K / 8) * 20;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                                   // operand tile written
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };                   // operand tile consumed by the MMAs
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + i); };               // accumulator complete
@@ -123,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
   auto sfull_bar = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + 2 * NACC + i); };    // staged group landed
   auto sempty_bar = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + 2 * NACC + MAX_SLOTS + i); };   // staged group expanded
   constexpr int NUM_BARS = 2 * MAX_STAGES + 2 * NACC + 2 * MAX_SLOTS;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tab_off + MAX_K * 8 + 2 * MAX_POS * 4 + 8 * NUM_BARS);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tab_off + MAX_K * 8 + 2 * MAX_POS * 4 + (MAX_K / 8) * 20 + 8 * NUM_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HWp = a.Hp * a.Wp, HWs = a.Hs * a.Ws, kk = a.kH * a.kW;
@@ -141,6 +153,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
       t = make_int2(c * gplane + i * gW + j, (i << 16) | j);
     }
     tab[k] = t;
+  }
+  for (int c8 = threadIdx.x; c8 < NKB * 8; c8 += THREADS) {
+    uint32_t w[4] = {0, 0, 0, 0}, m = 0;
+    for (int e = 0; e < 8; ++e) {
+      const int k = c8 * 8 + e;
+      if (k < a.Ktot) {
+        const int c = k / kk, r = k - c * kk, i = r / a.kW, j = r - i * a.kW;
+        w[e >> 1] |= ((uint32_t)(c * gplane + i * gW + j) & 0xffffu) << (16 * (e & 1));
+        m |= 1u << e;
+      } else if (MODE == 1 && k == a.Ktot) {
+        m |= 1u << (8 + e);
+      }
+    }
+    offp[c8] = make_uint4(w[0], w[1], w[2], w[3]);
+    maskp[c8] = m;
   }
   for (int pl = threadIdx.x; pl < max_pos; pl += THREADS) {
     const int gl = pl / HWp, rem = pl - gl * HWp, py = rem / a.Wp, px = rem - py * a.Wp;
@@ -171,7 +198,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), PROD_WARPS); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), EPI_WARPS); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
     for (int i = 0; i < slots; ++i) { mbar_init(sfull_bar(i), 1); mbar_init(sempty_bar(i), PROD_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -186,6 +213,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
   const uint32_t tmem_base = *tmem_slot;
 
   auto group_samples = [&](long long grp) { return (int)min((long long)a.G, a.nsamples - grp * a.G); };
+  // 16-wide k slices of k-block kb that contain taps (MODE 0): the MMAs of the remaining slices are skipped
+  auto kslices = [&](int kb) { return min(BLOCK_K / UMMA_K, (a.Ktot - kb * BLOCK_K + UMMA_K - 1) / UMMA_K); };
 
   if (warp == 1 + EPI_WARPS) {
     // ===== loader: one thread bulk-copies whole groups into the slot ring =====
@@ -204,21 +233,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
       }
     }
   } else if (warp >= FIRST_PROD_WARP) {
-    // ===== producers =====
-    const int cu = warp - FIRST_PROD_WARP;                // this warp's 16-byte chunk of every 64-wide k-block
-    int off[NKB][8];
-    uint32_t mask[NKB], ones[NKB];
-#pragma unroll
-    for (int kb = 0; kb < NKB; ++kb) {
-      mask[kb] = 0; ones[kb] = 0;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = kb * 64 + cu * 8 + e;
-        off[kb][e] = tab[k].x;
-        if (k < a.Ktot) mask[kb] |= 1u << e;
-        if (MODE == 1 && k == a.Ktot) ones[kb] |= 1u << e;
-      }
-    }
+    // ===== producers: warp = (chunk lane cu, row half) =====
+    const int pw = warp - FIRST_PROD_WARP;
+    const int cu = pw & 7;                                // this warp's 16-byte chunk of every 64-wide k-block
+    const int half = pw >> 3;                             // which half of a tile's rows
     const int t = threadIdx.x - 32 * FIRST_PROD_WARP;
     int stage = 0; uint32_t phase = 0;
     int slot = 0; uint32_t sphase = 0;
@@ -247,24 +265,30 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
       if (MODE == 0) {
         const int tiles = (npos + 127) / 128;
         for (int tile = 0; tile < tiles; ++tile) {
-          int origin[4];
+          int origin[2];
 #pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            const int pl = tile * 128 + ps * 32 + lane;
+          for (int ps = 0; ps < 2; ++ps) {
+            const int pl = tile * 128 + (half * 2 + ps) * 32 + lane;
             origin[ps] = pl < npos ? origin_tab[pl] : -1;
           }
 #pragma unroll
           for (int kb = 0; kb < NKB; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            const uint32_t sbase = smem_base + stage * stage_bytes;
+            // 16-wide k slices beyond the last tap are never read by the MMAs (see the issuer): no stores needed
+            if (cu * 8 < kslices(kb) * UMMA_K) {
+              const uint32_t sbase = smem_base + stage * stage_bytes;
+              const uint4 o4 = offp[kb * 8 + cu];
+              const uint32_t off2[4] = {o4.x, o4.y, o4.z, o4.w};
+              const uint32_t mk = maskp[kb * 8 + cu];
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-              const int row = ps * 32 + lane;
-              const uint32_t dst = sbase + row * 128 + ((cu ^ (row & 7)) << 4);
-              if (origin[ps] >= 0 && mask[kb] != 0) im2col_chunk(dst, staged, origin[ps], off[kb], mask[kb], 0u);
-              else st_shared_v4(dst, 0u, 0u, 0u, 0u);
+              for (int ps = 0; ps < 2; ++ps) {
+                const int row = (half * 2 + ps) * 32 + lane;
+                const uint32_t dst = sbase + row * 128 + ((cu ^ (row & 7)) << 4);
+                if (origin[ps] >= 0 && mk != 0) im2col_chunk(dst, staged, origin[ps], off2, mk, 0u);
+                else st_shared_v4(dst, 0u, 0u, 0u, 0u);
+              }
+              fence_async_smem();                          // own writes -> async proxy, then one arrive per warp
             }
-            fence_async_smem();                            // own writes -> async proxy, then one arrive per warp
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(stage));
             if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -277,14 +301,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + TILE_BYTES;
           // im2col rows (B operand: MN-major boxes of 64 k, rows = positions)
-#pragma unroll
-          for (int ps = 0; ps < 2; ++ps) {
-            const int row = ps * 32 + lane, pl = pb * 64 + row;
+          {
+            const int row = half * 32 + lane, pl = pb * 64 + row;
             const int origin = pl < npos ? origin_tab[pl] : -1;
 #pragma unroll
             for (int box = 0; box < NKB; ++box) {
               const uint32_t dst = sb + box * (BLOCK_K * 128) + row * 128 + ((cu ^ (row & 7)) << 4);
-              if (origin >= 0 && (mask[box] | ones[box]) != 0) im2col_chunk(dst, staged, origin, off[box], mask[box], ones[box]);
+              const uint4 o4 = offp[box * 8 + cu];
+              const uint32_t off2[4] = {o4.x, o4.y, o4.z, o4.w};
+              const uint32_t mk = maskp[box * 8 + cu];
+              if (origin >= 0 && mk != 0) im2col_chunk(dst, staged, origin, off2, mk & 0xffu, mk >> 8);
               else st_shared_v4(dst, 0u, 0u, 0u, 0u);
             }
           }
@@ -329,9 +355,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
               mbar_wait(full_bar(stage), phase);
               tcgen05_fence_after();
               const uint32_t sa = smem_base + stage * stage_bytes, sb = smem_base + wm_off + kb * 2048;
+              const int ks = kslices(kb);
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                umma_bf16(d_tmem, make_desc(sa + k * (UMMA_K * 2), 16, 1024), make_desc(sb + k * (UMMA_K * 2), 16, 1024), idesc, (kb | k) != 0);
+                if (k < ks) umma_bf16(d_tmem, make_desc(sa + k * (UMMA_K * 2), 16, 1024), make_desc(sb + k * (UMMA_K * 2), 16, 1024), idesc, (kb | k) != 0);
               tcgen05_commit(empty_bar(stage));
               if (kb == NKB - 1) tcgen05_commit(tfull_bar(acc));
               if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -341,36 +368,44 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
         }
       }
     } else {
-      // ===== epilogue: one accumulator row (= one position) per thread, 16 channels =====
-      const int q = warp & 3;
+      // ===== epilogue: one accumulator row (= one position) per thread, 16 channels; the two groups of four
+      //       warps take alternate tiles =====
+      const int q = warp & 3, parity = (warp - 1) >> 2;
+      float bias_r[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) bias_r[ch] = (a.bias != nullptr && ch < a.Nout) ? __ldg(a.bias + ch) : 0.f;
       int acc = 0; uint32_t acc_phase = 0;
+      int tcount = 0;
       for (long long grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
         const int npos = group_samples(grp) * HWp;
         const int tiles = (npos + 127) / 128;
-        for (int tile = 0; tile < tiles; ++tile) {
-          const int pl = tile * 128 + q * 32 + lane;       // position inside the group
-          mbar_wait(tfull_bar(acc), acc_phase);
-          tcgen05_fence_after();
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32, r);
-          tmem_ld_wait();
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));     // values are in registers: the accumulator is free again
-          if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
-          if (pl < npos) {
-            const int gl = pl / HWp, rem = pl - gl * HWp;
-            float* o = a.out + (grp * a.G + gl) * a.Nout * (long long)HWp + rem;
+        int pl = q * 32 + lane;                            // position inside the group
+        int gl = pl / HWp, rem = pl - gl * HWp;
+        for (int tile = 0; tile < tiles; ++tile, ++tcount) {
+          if ((tcount & 1) == parity) {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tcgen05_fence_after();
+            uint32_t r[NCH];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32, r);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));   // values are in registers: the accumulator is free again
+            if (pl < npos) {
+              float* o = a.out + (grp * a.G + gl) * a.Nout * (long long)HWp + rem;
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-              if (ch < a.Nout) {
-                float v = __uint_as_float(r[ch]);
-                if (a.bias != nullptr) v += __ldg(a.bias + ch);
-                if (a.relu) v = fmaxf(v, 0.f);
-                o[(long long)ch * HWp] = v;                // lanes = consecutive positions: coalesced per channel
+              for (int ch = 0; ch < NCH; ++ch) {
+                if (ch < a.Nout) {
+                  float v = __uint_as_float(r[ch]) + bias_r[ch];
+                  if (a.relu) v = fmaxf(v, 0.f);
+                  o[ch * HWp] = v;                         // lanes = consecutive positions: coalesced per channel
+                }
               }
             }
           }
+          if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+          pl += 128; rem += 128;
+          while (rem >= HWp) { rem -= HWp; ++gl; }
         }
       }
     }
@@ -401,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
       }
     } else {
       // ===== epilogue (once): rows 0..Cout-1 of the accumulator live in TMEM lane quarter 0 =====
-      if ((warp & 3) == 0 && (long long)blockIdx.x < num_groups) {
+      if (warp == 4 && (long long)blockIdx.x < num_groups) {
         mbar_wait(tfull_bar(0), 0);
         tcgen05_fence_after();
         for (int c0 = 0; c0 < N; c0 += 32) {
@@ -465,7 +500,7 @@ int launch_nkb(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
   a.slot_bytes = src_bytes + dy_bytes;
   a.padded_bytes = (a.G * padded_floats * 4 + 127) & ~127;
   constexpr int stage_bytes = MODE == 0 ? TILE_BYTES : TILE_BYTES + NKB * (BLOCK_K * 128);
-  const int fixed = (MODE == 0 ? NKB * 2048 : 0) + a.padded_bytes + MAX_K * 8 + 2 * MAX_POS * 4 +
+  const int fixed = (MODE == 0 ? NKB * 2048 : 0) + a.padded_bytes + MAX_K * 8 + 2 * MAX_POS * 4 + (MAX_K / 8) * 20 +
                     8 * (2 * MAX_STAGES + 2 * NACC + 2 * MAX_SLOTS) + 16 + 1024;
   a.slots = 2;
   a.stages = MODE == 0 ? 6 : 3;
@@ -507,23 +542,30 @@ int launch(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
   return PG_ERR_ARG;
 }
 
-bool supported(int Cin, int Cout, int kH, int kW) {
-  return Cin >= 1 && Cout >= 1 && Cin <= NCH && Cout <= NCH && kH >= 1 && kW >= 1 && kH < 256 && kW < 256 &&
-         Cin * kH * kW + 1 <= 256 &&         // weight gradient: im2col width (+ ones column) = UMMA N <= 256
-         Cout * kH * kW <= 448;              // data gradient: 7 k-blocks of filters in shared memory
+bool supported(int Cin, int H, int W, int Cout, int kH, int kW) {
+  if (!(Cin >= 1 && Cout >= 1 && Cin <= NCH && Cout <= NCH && kH >= 1 && kW >= 1 && kH < 256 && kW < 256 && H >= kH && W >= kW &&
+        Cin * kH * kW + 1 <= 256 &&         // weight gradient: im2col width (+ ones column) = UMMA N <= 256
+        Cout * kH * kW <= 448))             // data gradient: 7 k-blocks of filters in shared memory
+    return false;
+  const int Ho = H - kH + 1, Wo = W - kW + 1;
+  const int padded = Cout * (Ho + 2 * (kH - 1)) * (Wo + 2 * (kW - 1));
+  if (Cin * H * W >= 65536 || padded >= 65536) return false;                       // 16-bit tap offsets
+  return choose_group(Cin * H * W, 0, 0, Ho * Wo, 128, 40 * 1024) > 0 &&            // forward
+         choose_group(Cin * H * W, Cout * Ho * Wo, 0, Ho * Wo, 64, 40 * 1024) > 0 && // weight gradient
+         choose_group(Cout * Ho * Wo, 0, padded, H * W, 128, 80 * 1024) > 0;         // data gradient
 }
 
 }  // namespace
 
 extern "C" {
 
-int pg_tc_conv2d_supported(int Cin, int Cout, int kH, int kW) { return supported(Cin, Cout, kH, kW) ? 1 : 0; }
+int pg_tc_conv2d_supported(int Cin, int H, int W, int Cout, int kH, int kW) { return supported(Cin, H, W, Cout, kH, kW) ? 1 : 0; }
 
 int pg_tc_conv2d_fwd(pg_ctx* ctx, const void* x, const void* w, const void* b, void* y, int64_t N, int Cin, int H, int W, int Cout,
                      int kH, int kW, int act) {
   PG_CHECK_CTX(ctx);
-  PG_REQUIRE(supported(Cin, Cout, kH, kW), "pg_tc_conv2d_fwd: shape outside the tensor-core envelope (channels <= 16, Cin*kH*kW < 256)");
   PG_REQUIRE(N > 0 && H >= kH && W >= kW, "pg_tc_conv2d_fwd: empty output");
+  PG_REQUIRE(supported(Cin, H, W, Cout, kH, kW), "pg_tc_conv2d_fwd: shape outside the tensor-core envelope (pg_tc_conv2d_supported)");
   PG_REQUIRE(act == PG_ACT_NONE || act == PG_ACT_RELU, "pg_tc_conv2d_fwd: unknown activation");
   ConvArgs a{};
   a.src = (const float*)x; a.w = (const float*)w; a.bias = (const float*)b; a.out = (float*)y;
@@ -537,8 +579,8 @@ int pg_tc_conv2d_fwd(pg_ctx* ctx, const void* x, const void* w, const void* b, v
 int pg_tc_conv2d_bwd(pg_ctx* ctx, const void* x, const void* w, const void* dy, void* dw, void* db, void* dx, int64_t N, int Cin, int H,
                      int W, int Cout, int kH, int kW) {
   PG_CHECK_CTX(ctx);
-  PG_REQUIRE(supported(Cin, Cout, kH, kW), "pg_tc_conv2d_bwd: shape outside the tensor-core envelope (channels <= 16, Cin*kH*kW < 256)");
   PG_REQUIRE(N > 0 && H >= kH && W >= kW, "pg_tc_conv2d_bwd: empty output");
+  PG_REQUIRE(supported(Cin, H, W, Cout, kH, kW), "pg_tc_conv2d_bwd: shape outside the tensor-core envelope (pg_tc_conv2d_supported)");
   const int Ho = H - kH + 1, Wo = W - kW + 1;
   if (dw != nullptr || db != nullptr) {
     PG_REQUIRE(dw != nullptr, "pg_tc_conv2d_bwd: db without dw is not supported on the tensor-core path");

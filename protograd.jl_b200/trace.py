@@ -386,7 +386,8 @@ class Plan:
                 continue
             if self.ops[i] == "conv" and self.dtypes[i] == np.float32:
                 Cout, Cin, kH, kW = self.shapes[self.inputs[i][1]]
-                if capi._FN["pg_tc_conv2d_supported"](Cin, Cout, kH, kW) == 1:
+                H, W = self.shapes[self.inputs[i][0]][2:]
+                if capi._FN["pg_tc_conv2d_supported"](Cin, H, W, Cout, kH, kW) == 1:
                     tc_conv.add(i)
             if self.ops[i] != "linear" or self.dtypes[i] != np.float32:
                 continue

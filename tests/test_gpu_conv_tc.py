@@ -69,8 +69,9 @@ def test_tc_conv_fwd_bwd(pg, geom):
 def test_tc_conv_envelope(pg):
     from protograd_b200 import capi
     sup = capi._FN["pg_tc_conv2d_supported"]
-    assert sup(1, 6, 5, 5) == 1 and sup(6, 16, 5, 5) == 1 and sup(16, 16, 3, 3) == 1
-    assert sup(17, 4, 3, 3) == 0 and sup(4, 17, 3, 3) == 0 and sup(16, 16, 5, 5) == 0   # 16*25 + 1 > 256
+    assert sup(1, 28, 28, 6, 5, 5) == 1 and sup(6, 12, 12, 16, 5, 5) == 1 and sup(16, 6, 6, 16, 3, 3) == 1
+    assert sup(17, 8, 8, 4, 3, 3) == 0 and sup(4, 8, 8, 17, 3, 3) == 0 and sup(16, 12, 12, 16, 5, 5) == 0   # 16*25 + 1 > 256
+    assert sup(3, 224, 224, 8, 3, 3) == 0        # a sample does not fit a shared-memory slot
     ctx = pg.Context.get()
     a = pg.DeviceArray.empty(ctx, (1,), np.float32)
     with pytest.raises(capi.PGError):
