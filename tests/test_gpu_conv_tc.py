@@ -20,6 +20,8 @@ GEOMS = [
     (130, 6, 12, 12, 16, 5),     # more tiles than one wave of k-blocks per CTA
     (2, 16, 6, 6, 16, 3),        # full channel tile
     (5, 3, 10, 10, 4, 1),        # 1x1 filters
+    (4096, 1, 28, 28, 6, 5),     # many groups per CTA: every ring / slot / accumulator barrier wraps many times
+    (2048, 6, 12, 12, 16, 5),
 ]
 
 
