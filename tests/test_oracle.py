@@ -301,3 +301,25 @@ def test_golden_fixtures_reproduce(name):
         assert a.shape == b.shape and a.dtype == b.dtype, k
         tol = 1e-6 if a.dtype == np.float32 else 1e-12  # BLAS summation order may differ across hosts
         assert np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) <= tol * max(np.linalg.norm(a.astype(np.float64)), 1e-30), k
+
+
+def test_conv_operand_rounding_option():
+    """net_loss_and_grad(conv_round=...) restates the B200 tensor-core conv mode (bf16 operands for conv
+    only).  Identity rounding reproduces the plain step; bf16 rounding stays within bf16's 2^-8 relative
+    operand error of it and equals the plain step evaluated on operands that are already bf16 values."""
+    from tests.golden import make_golden as MG
+    spec = MG.C3_SPEC
+    x, lab = MG.class_data(spec, 6, np.float64, 5)
+    params = [p.astype(np.float64) for p in MG.biased_params(spec, np.float32, 5)]
+    l0, g0 = O.net_loss_and_grad(spec, params, x, lab)
+    l1, g1 = O.net_loss_and_grad(spec, params, x, lab, conv_round=lambda a: a)
+    assert l0 == l1 and all(np.array_equal(a, b) for a, b in zip(g0, g1))
+    l2, g2 = O.net_loss_and_grad(spec, params, x, lab, conv_round=O.bf16_round)
+    assert abs(l2 - l0) <= 2e-2 * abs(l0)
+    for a, b in zip(g0, g2):
+        assert np.linalg.norm(a - b) <= 0.1 * np.linalg.norm(a) + 1e-12
+    assert any(not np.array_equal(a, b) for a, b in zip(g0, g2))
+    # forward: rounding is idempotent, so pre-rounded conv operands give the same first conv output
+    y_plain = O.conv2d_fwd(O.bf16_round(x), O.bf16_round(params[0]), params[1])
+    y_opt = O.net_forward(spec[:1], params[:2], x, conv_round=O.bf16_round)
+    assert np.array_equal(y_plain, y_opt)
