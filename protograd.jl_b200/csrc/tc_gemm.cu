@@ -786,8 +786,13 @@ int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, in
 bool use_2cta(const pg_ctx* ctx, int64_t M, int64_t N) {
   static int mode = -1;                        // PG_TC_1CTA=1 forces the single-CTA kernel
   if (mode < 0) { const char* e = getenv("PG_TC_1CTA"); mode = (e && e[0] == '1') ? 0 : 1; }
-  (void)ctx;
-  return mode == 1 && M >= 512 && N >= 512;
+  if (mode != 1 || M < 512 || N < 512) return false;
+  // While SMs are reserved for a concurrent collective (pg_set_sm_limit), a launch whose pair tiles fit one
+  // wave (e.g. the first layer's weight gradient: 64 tiles for 74 pairs) would push every tile whose pair was
+  // broken by a collective CTA into a second wave and double its time (measured at 8 ranks: 152 us instead
+  // of 63 us); 128-row single-CTA tiles fit whichever SMs are left, in one wave.
+  if (ctx->num_sms < ctx->real_sms && pg_cdiv(M, 256) * pg_cdiv(N, 256) <= ctx->real_sms / 2) return false;
+  return true;
 }
 
 int tc_dispatch(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, const Epi& epi) {

@@ -74,18 +74,17 @@ class GradientBuckets:
     """
 
     def __init__(self, grad_model, bucket_bytes=24 << 20, comm_sms=None, delay_us=None, overlap_update=None):
-        # A bucket's all-reduce becomes runnable at the same moment as the next backward GEMM.  The
-        # GEMMs are persistent CTA pairs (one pair per TPC); if NCCL's CTAs become resident first they
-        # land on arbitrary SMs, break pairs, and the GEMM launch cannot complete before the collective
-        # does (measured at 8 ranks: +0.13 ms per step, tools/dp_sms8.sh).  So for > 2 ranks the GEMM
-        # grids are sized for (all - comm_sms) SMs while a bucket is in flight — comm_sms = 24 = NCCL's
-        # NVLS channel count, i.e. 12 whole TPCs — and the collective is issued from a side stream behind
-        # a `delay_us` sleep (pg_delay_on), after the next GEMM has been enqueued: the GEMM claims its
-        # pairs, NCCL fills the TPCs left free.  With 2 ranks the all-reduce is short and the dynamic
-        # tile scheduler absorbs it: nothing is reserved or delayed.
+        # A bucket's all-reduce runs next to the remaining backward GEMMs (persistent CTA pairs with a dynamic
+        # tile scheduler, so a pair that becomes resident late just takes fewer tiles).  Knobs, all measured
+        # (DESIGN.md section 5): `comm_sms` sizes the GEMM grids for (all - comm_sms) SMs while a bucket is in
+        # flight; `delay_us` > 0 issues the collective from a side stream behind a short sleep (pg_delay_on) so
+        # the next GEMM claims its SM pairs first (no gain measured, off); `overlap_update` (below).
         ws = world()[1]
         if comm_sms is None:
-            comm_sms = 0
+            # 8 ranks: NCCL's NVLS all-reduce runs 24 CTAs next to the backward GEMMs; with 24 SMs reserved the
+            # single-wave weight-gradient launch switches to 128-row single-CTA tiles (tc_gemm.cu use_2cta),
+            # which fit the SMs NCCL leaves.  Fewer ranks: short collectives, the dynamic scheduler absorbs them.
+            comm_sms = 24 if ws >= 8 else 0
         if delay_us is None:
             delay_us = 0
         if overlap_update is None:
