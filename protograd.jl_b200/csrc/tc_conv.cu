@@ -10,13 +10,14 @@
 //                                                         Wd[ci][(co,i,j)] = w[co][ci][i][j]
 //   wt. grad   dW[co][k]  = sum_p  dY[p][co] A[p][k]     (k = Ktot is a column of ones: its sum is db[co])
 //
-// Forward / data gradient: M = 128 pixels per tile, N = 16 channels, K in 64-wide blocks; the (tiny)
-// weight matrix lives in shared memory for the whole kernel; double-buffered 16-column accumulators so the
-// epilogue (bias + ReLU, coalesced NCHW stores) overlaps the next tile.  Weight gradient: M = 128 rows of
-// dY^T (only Cout <= 16 are non-zero), N = the im2col width (<= 256), K = 64 pixels per block; every CTA
-// accumulates its share of the pixels in TMEM and adds its partial dW / db with fp32 atomics at the end.
-// Tensors stay fp32 in HBM (these layers are issue/latency-bound, not bandwidth-bound: 26 KB of
-// activations per sample at the LeNet shapes), products are bf16 x bf16 with fp32 accumulation.
+// Forward / data gradient: M = 128 positions per tile, N = 16 channels, K in 64-wide blocks; the (tiny) filter
+// matrix lives in shared memory for the whole kernel; an 8-deep ring of TMEM accumulators lets the epilogue
+// warps (bias + ReLU, coalesced NCHW stores) run several tiles behind the MMA issuer.  Weight gradient: M = 128
+// rows of dY^T (only Cout <= 16 are non-zero), N = the im2col width (<= 256), K = 64 positions per block; every
+// CTA accumulates its share of the positions in TMEM and adds its partial dW / db with fp32 atomics at the end.
+// Tensors stay fp32 in HBM (26 KB of activations per sample at the LeNet shapes: these layers are not
+// bandwidth-bound), products are bf16 x bf16 with fp32 accumulation.  Measured behaviour and what bounds it:
+// profiles/r1_tc_conv_ablation.md (the stage round trip producer -> MMA -> commit -> producer, not the gathers).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
