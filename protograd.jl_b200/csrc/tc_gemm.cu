@@ -1,9 +1,14 @@
 // tc_gemm.cu — BF16 tensor-core path of the Linear layer (src/layers.jl:28-34 and its pullback):
-// hand-written tcgen05.mma GEMM with TMEM accumulators, TMA-fed 4-stage shared-memory pipeline,
-// warp-specialised (1 TMA producer warp, 1 MMA-issuer warp, 4 epilogue warps), persistent over
-// 128x256 output tiles with double-buffered accumulators (2 x 256 TMEM columns) so the epilogue
-// of tile i overlaps the MMAs of tile i+1.  fp32 accumulation; epilogues fuse bias+ReLU (forward),
-// the ReLU' mask (data gradient) or write fp32 straight into the gradient arena (weight gradient).
+// hand-written tcgen05.mma GEMMs with TMEM accumulators and TMA-fed shared-memory pipelines, warp-specialised
+// (1 TMA producer warp, 1 MMA-issuer warp, 8 epilogue warps, optional bias-gradient reducer warps) and
+// persistent, with double-buffered accumulators (2 x 256 TMEM columns) so the epilogue of tile i overlaps the
+// MMAs of tile i+1.  Two kernels share the epilogue code:
+//   tc_gemm2_kernel  wide layers: a cluster of two CTAs (one SM pair) owns a 256x256 tile (cta_group::2),
+//                    6 stages of 32 KB per CTA;
+//   tc_gemm_kernel   128 x 256 (or 128 x 32) tiles on one CTA: narrow layers, small shapes, split-K.
+// Tiles are handed out by a dynamic scheduler (atomic work counter + shared-memory id ring, see below).
+// fp32 accumulation; epilogues fuse bias+ReLU (forward), the ReLU' mask (data gradient) or write fp32 straight
+// into the gradient arena (weight gradient, with the bias gradient summed from the staged dY tiles).
 //
 // No physical transposes: the three products use K-major or MN-major shared-memory operand
 // descriptors directly on the row-major tensors:
