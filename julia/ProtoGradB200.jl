@@ -137,15 +137,38 @@ function ProtoGrad.step!(state::ProtoGrad.AdamState{R,V}, g::V) where {R,V<:Mode
                 base_ptr(g), padded_length(g), Float64(state.stepsize), Float64(o.beta1), Float64(o.beta2), Float64(o.epsilon), state.it, isf64(state.stepsize), C_NULL))
     return state.it += 1                              # adam.jl:40
 end
-# HeavyBallMethodState -> pg_opt_heavyball, NesterovState -> pg_opt_nesterov (momentum popped from
-# state.momentum_iterator on the host, nesterov_method.jl:36) follow the same pattern.
+
+# d = mu*d - s*g ; p += d                                  (src/optimizers/heavy_ball_method.jl:16-19)
+function ProtoGrad.step!(state::ProtoGrad.HeavyBallMethodState{S,V}, g::V) where {S,V<:Model}
+    T = eltype(first(allparams(g)))
+    mu = state.optimizer.momentum
+    flags = isf64(state.stepsize) | (mu isa Float64 ? Cint(2) : Cint(0))     # PG_SCALAR_F64 | PG_SCALAR2_F64
+    check(ccall((:pg_opt_heavyball, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cdouble, Cdouble, Cint, Ptr{Cvoid}),
+                ctx().h, code(T), base_ptr(state.variable), base_ptr(state.step), base_ptr(g), padded_length(g),
+                Float64(state.stepsize), Float64(mu), flags, C_NULL))
+    return state.variable
+end
+
+# prev = p ; p -= s*g ; p += mu*(p - prev), mu popped from the stateful host-side iterator
+# (src/optimizers/nesterov_method.jl:33-39; the sequence itself is :3-6)
+function ProtoGrad.step!(state::ProtoGrad.NesterovState{S,V,M}, g::V) where {S,V<:Model,M}
+    T = eltype(first(allparams(g)))
+    mu = popfirst!(state.momentum_iterator)                                   # Float64
+    check(ccall((:pg_opt_nesterov, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cdouble, Cdouble, Cint, Ptr{Cvoid}),
+                ctx().h, code(T), base_ptr(state.variable), base_ptr(state.variable_prev), base_ptr(g), padded_length(g),
+                Float64(state.stepsize), Float64(mu), isf64(state.stepsize) | Cint(2), C_NULL))
+    return state.variable
+end
 
 # ---- eval_with_pullback(f, m, ::Val{:B200}) ------------------------------------------------------
 # f(m) is run once on Tracer values: `*`(::DeviceLeaf, ::Tracer), broadcast `.+`, relu., NNlib.conv,
 # maxpool, reshape, softmax, cross_entropy and mse record ops into a plan (same scheme as
 # protograd.jl_b200/trace.py); the plan fuses Linear+bias+ReLU, softmax+cross_entropy and ReLU' into
 # the data-gradient epilogue, then calls pg_linear_fwd / pg_tc_linear_fwd / pg_conv2d_fwd /
-# pg_softmax_ce_fwd_bwd ... and, in pb(), pg_linear_bwd / pg_tc_linear_bwd / pg_conv2d_bwd, writing
+# pg_tc_conv2d_fwd (when pg_tc_conv2d_supported) / pg_softmax_ce_fwd_bwd ... and, in pb(),
+# pg_linear_bwd / pg_tc_linear_bwd / pg_conv2d_bwd / pg_tc_conv2d_bwd, writing
 # dW/db straight into a gradient model built by `zero(m)` so that typeof(grad) == typeof(m)
 # (test/test_models.jl:148).
 function ProtoGrad.eval_with_pullback(f, m::Model, ::Val{:B200})
