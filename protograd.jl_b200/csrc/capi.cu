@@ -77,6 +77,7 @@ int pg_destroy(pg_ctx* ctx) {
   if (!ctx) return PG_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->switch_event) cudaEventDestroy(ctx->switch_event);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->aux) cudaFree(ctx->aux);
   if (ctx->counters) cudaFree(ctx->counters);
@@ -90,7 +91,20 @@ int pg_destroy(pg_ctx* ctx) {
 
 int pg_set_stream(pg_ctx* ctx, void* s) {
   PG_CHECK_CTX(ctx);
-  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  cudaStream_t next = s ? (cudaStream_t)s : ctx->own_stream;
+  if (next != ctx->stream && !ctx->capturing) {
+    // The context's scratch (workspace, padded operand copies, reduction and tile-scheduler counters) assumes
+    // ONE queue of work: whatever was enqueued on the previous stream must finish before anything enqueued on
+    // the new one starts.
+    if (!ctx->switch_event) PG_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->switch_event, cudaEventDisableTiming));
+    // (a borrowed stream may have been destroyed by its owner since: then there is nothing to wait for)
+    if (cudaEventRecord(ctx->switch_event, ctx->stream) == cudaSuccess) {
+      PG_CHECK_CUDA(cudaStreamWaitEvent(next, ctx->switch_event, 0));
+    } else {
+      cudaGetLastError();
+    }
+  }
+  ctx->stream = next;
   return PG_OK;
 }
 int pg_get_stream(pg_ctx* ctx, void** s) {

@@ -15,6 +15,7 @@ struct pg_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D prefetch of the next minibatch
+  cudaEvent_t switch_event = nullptr;   // orders a newly borrowed stream behind the previous one (pg_set_stream)
   int64_t launches = 0;
   // scratch: split-K partials, block partials for reductions
   void* ws = nullptr;
