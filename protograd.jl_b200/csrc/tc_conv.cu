@@ -30,15 +30,27 @@ namespace {
 
 constexpr int BLOCK_K = 64, UMMA_K = 16;
 constexpr int TILE_BYTES = 128 * 128;                  // 128 rows x 64 bf16
-constexpr int PROD_WARPS = 16, PROD_THREADS = 32 * PROD_WARPS;   // 8 chunk lanes x 2 row halves
-constexpr int EPI_WARPS = 8;                           // two groups of 4 (one warp per TMEM lane quarter) alternate tiles
-constexpr int THREADS = 32 * (2 + EPI_WARPS + PROD_WARPS);   // warp 0: MMA issuer; 1..8: epilogue; 9: bulk-copy loader; 10..25: producers
-constexpr int FIRST_PROD_WARP = 2 + EPI_WARPS;
 constexpr int MAX_K = 512;                             // im2col width limit (lookup table size)
-constexpr int MAX_POS = 2048;                          // positions per group (position table size)
 constexpr int NCH = 16;                                // channel tile (UMMA N of the forward / data-gradient products)
-constexpr int NACC = 8;                                // TMEM accumulator ring of the forward / data-gradient kernel (32 columns each)
 constexpr int MAX_STAGES = 8, MAX_SLOTS = 4;
+
+// Warp roles of a CTA: warp 0 issues the MMAs, then EPI_WARPS epilogue warps (groups of four, one warp per TMEM
+// lane quarter, the groups taking alternate tiles), one bulk-copy loader warp, PROD_WARPS producer warps
+// (8 chunk lanes x HALVES row halves).  The regular geometry runs one CTA per SM; SMALL (PG_TCCONV_SMALL=1,
+// experimental) halves everything so that two CTAs — two independent pipelines and MMA issuers — share an SM.
+template <bool SMALL>
+struct Geo {
+  static constexpr int PROD_WARPS = SMALL ? 8 : 16;
+  static constexpr int EPI_WARPS = SMALL ? 4 : 8;
+  static constexpr int NACC = SMALL ? 4 : 8;           // TMEM accumulator ring of the forward / data-gradient kernel (32 columns each)
+  static constexpr int MAX_POS = SMALL ? 1280 : 2048;  // positions per group (position table size)
+  static constexpr int THREADS = 32 * (2 + EPI_WARPS + PROD_WARPS);
+  static constexpr int PROD_THREADS = 32 * PROD_WARPS;
+  static constexpr int FIRST_PROD_WARP = 2 + EPI_WARPS;
+  static constexpr int HALVES = PROD_WARPS / 8;
+  static constexpr int CTAS_PER_SM = SMALL ? 2 : 1;
+  static constexpr int SMEM_LIMIT = SMALL ? 112 * 1024 : 227 * 1024;
+};
 
 struct ConvArgs {
   const float* src;        // im2col source [n][Cs][Hs][Ws]
@@ -85,7 +97,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
-__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory"); }
+template <int N>
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
 // One 16-byte chunk (8 consecutive k) of one im2col row.  off2[e/2] packs the offsets of taps e, e+1 relative
 // to the patch origin (16 bits each, thread-constant registers), `mask` bit e = tap exists, `ones` bit e =
@@ -111,8 +124,12 @@ __device__ __forceinline__ void im2col_chunk(uint32_t dst, const float* __restri
 // consecutive positions (conflict-free shared-memory gathers), the patch origin of a position comes from a
 // table built once per kernel.  One thread issues the MMAs, the epilogue warps drain TMEM.  The data
 // gradient gathers from a zero-padded copy of the group (built by the producers), so it needs no bounds tests.
-template <int MODE, int NKB>
-__global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
+template <int MODE, int NKB, bool SMALL>
+__global__ void __launch_bounds__(Geo<SMALL>::THREADS, Geo<SMALL>::CTAS_PER_SM) tc_conv_kernel(ConvArgs a) {
+  using G_ = Geo<SMALL>;
+  constexpr int PROD_WARPS = G_::PROD_WARPS, EPI_WARPS = G_::EPI_WARPS, NACC = G_::NACC, MAX_POS = G_::MAX_POS;
+  constexpr int THREADS = G_::THREADS, PROD_THREADS = G_::PROD_THREADS, FIRST_PROD_WARP = G_::FIRST_PROD_WARP;
+  constexpr int HALVES = G_::HALVES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -250,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
       if (MODE == 0 && a.padded_bytes != 0) {
         // data gradient: copy the group's rows into the interior of the zero-padded buffer
         float* padded = reinterpret_cast<float*>(smem + pad_off);
-        producers_sync();                                  // everyone has finished gathering the previous group
+        producers_sync<PROD_THREADS>();                                  // everyone has finished gathering the previous group
         const int rows = gs * a.Cs * a.Hs;
         for (int r = t; r < rows; r += PROD_THREADS) {
           const int pc = r / a.Hs, y = r - pc * a.Hs;      // pc = (sample, channel)
@@ -258,18 +275,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
           float* drow = padded + pc * gplane + (y + a.pad_h) * gW + a.pad_w;
           for (int x = 0; x < a.Ws; ++x) drow[x] = srow[x];
         }
-        producers_sync();
+        producers_sync<PROD_THREADS>();
         __syncwarp();
         if (lane == 0) mbar_arrive(sempty_bar(slot));      // the raw slot can be refilled already
         staged = padded;
       }
       if (MODE == 0) {
         const int tiles = (npos + 127) / 128;
+        constexpr int RQ = 4 / HALVES;                    // 32-row quarters of a tile per producer warp
         for (int tile = 0; tile < tiles; ++tile) {
-          int origin[2];
+          int origin[RQ];
 #pragma unroll
-          for (int ps = 0; ps < 2; ++ps) {
-            const int pl = tile * 128 + (half * 2 + ps) * 32 + lane;
+          for (int ps = 0; ps < RQ; ++ps) {
+            const int pl = tile * 128 + (half * RQ + ps) * 32 + lane;
             origin[ps] = pl < npos ? origin_tab[pl] : -1;
           }
 #pragma unroll
@@ -282,8 +300,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
               const uint32_t off2[4] = {o4.x, o4.y, o4.z, o4.w};
               const uint32_t mk = maskp[kb * 8 + cu];
 #pragma unroll
-              for (int ps = 0; ps < 2; ++ps) {
-                const int row = (half * 2 + ps) * 32 + lane;
+              for (int ps = 0; ps < RQ; ++ps) {
+                const int row = (half * RQ + ps) * 32 + lane;
                 const uint32_t dst = sbase + row * 128 + ((cu ^ (row & 7)) << 4);
                 if (origin[ps] >= 0 && mk != 0) im2col_chunk(dst, staged, origin[ps], off2, mk, 0u);
                 else st_shared_v4(dst, 0u, 0u, 0u, 0u);
@@ -302,8 +320,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + TILE_BYTES;
           // im2col rows (B operand: MN-major boxes of 64 k, rows = positions)
-          {
-            const int row = half * 32 + lane, pl = pb * 64 + row;
+          constexpr int RH = 2 / HALVES;                  // 32-row halves of a block per producer warp
+#pragma unroll
+          for (int ps = 0; ps < RH; ++ps) {
+            const int row = (half * RH + ps) * 32 + lane, pl = pb * 64 + row;
             const int origin = pl < npos ? origin_tab[pl] : -1;
 #pragma unroll
             for (int box = 0; box < NKB; ++box) {
@@ -383,7 +403,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
         int pl = q * 32 + lane;                            // position inside the group
         int gl = pl / HWp, rem = pl - gl * HWp;
         for (int tile = 0; tile < tiles; ++tile, ++tcount) {
-          if ((tcount & 1) == parity) {
+          if ((tcount & (EPI_WARPS / 4 - 1)) == parity) {
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
             uint32_t r[NCH];
@@ -472,16 +492,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(ConvArgs a) {
   }
 }
 
-constexpr int SMEM_LIMIT = 227 * 1024;
-
-// samples per group: whole samples, 16-byte aligned group starts, bounded bytes per slot, <= MAX_POS
+// samples per group: whole samples, 16-byte aligned group starts, bounded bytes per slot, <= max_pos
 // positions, and as few padded rows as possible in the last 128-position tile (64-position block)
-int choose_group(int src_floats, int dy_floats, int padded_floats, int HWp, int unit, int max_bytes) {
+int choose_group(int src_floats, int dy_floats, int padded_floats, int HWp, int unit, int max_bytes, int max_pos = Geo<false>::MAX_POS) {
   int best = 0;
   double best_eff = -1.0;
   for (int g = 1; g <= 32; ++g) {
     if ((g * src_floats) % 4 != 0 || (g * dy_floats) % 4 != 0) continue;
-    if ((long long)g * (src_floats + dy_floats + padded_floats) * 4 > max_bytes || g * HWp > MAX_POS) break;
+    if ((long long)g * (src_floats + dy_floats + padded_floats) * 4 > max_bytes || g * HWp > max_pos) break;
     const int pos = g * HWp;
     const double eff = (double)pos / (double)(((pos + unit - 1) / unit) * unit);
     if (eff > best_eff + 1e-9) { best_eff = eff; best = g; }
@@ -489,39 +507,62 @@ int choose_group(int src_floats, int dy_floats, int padded_floats, int HWp, int 
   return best;
 }
 
-template <int MODE, int NKB>
-int launch_nkb(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
+// Sizes the group, the rings and the shared-memory footprint for one geometry; false = does not fit.
+template <int MODE, int NKB, bool SMALL>
+bool plan_launch(ConvArgs& a, int dy_floats_per_sample, int* bytes_out) {
+  using G_ = Geo<SMALL>;
   const int HWp = a.Hp * a.Wp, src_floats = a.Cs * a.Hs * a.Ws;
   const int padded_floats = a.dgrad ? a.Cs * (a.Hs + 2 * a.pad_h) * (a.Ws + 2 * a.pad_w) : 0;
-  a.G = choose_group(src_floats, dy_floats_per_sample, padded_floats, HWp, MODE == 0 ? 128 : 64, a.dgrad ? 80 * 1024 : 40 * 1024);
-  PG_REQUIRE(a.G > 0, "tensor-core conv: a sample (with its output gradient) does not fit a shared-memory slot");
+  const int slot_budget = SMALL ? (a.dgrad ? 36 * 1024 : 20 * 1024) : (a.dgrad ? 80 * 1024 : 40 * 1024);
+  a.G = choose_group(src_floats, dy_floats_per_sample, padded_floats, HWp, MODE == 0 ? 128 : 64, slot_budget, G_::MAX_POS);
+  if (a.G <= 0) return false;
   const int src_bytes = (a.G * src_floats * 4 + 127) & ~127;
   const int dy_bytes = (a.G * dy_floats_per_sample * 4 + 127) & ~127;
   a.dy_off = src_bytes;
   a.slot_bytes = src_bytes + dy_bytes;
   a.padded_bytes = (a.G * padded_floats * 4 + 127) & ~127;
   constexpr int stage_bytes = MODE == 0 ? TILE_BYTES : TILE_BYTES + NKB * (BLOCK_K * 128);
-  const int fixed = (MODE == 0 ? NKB * 2048 : 0) + a.padded_bytes + MAX_K * 8 + 2 * MAX_POS * 4 + (MAX_K / 8) * 20 +
-                    8 * (2 * MAX_STAGES + 2 * NACC + 2 * MAX_SLOTS) + 16 + 1024;
+  const int fixed = (MODE == 0 ? NKB * 2048 : 0) + a.padded_bytes + MAX_K * 8 + 2 * G_::MAX_POS * 4 + (MAX_K / 8) * 20 +
+                    8 * (2 * MAX_STAGES + 2 * G_::NACC + 2 * MAX_SLOTS) + 16 + 1024;
   a.slots = 2;
   a.stages = MODE == 0 ? 6 : 3;
-  while (a.stages > 2 && fixed + a.stages * stage_bytes + a.slots * a.slot_bytes > SMEM_LIMIT) --a.stages;
-  while (a.slots < 3 && fixed + a.stages * stage_bytes + (a.slots + 1) * a.slot_bytes <= SMEM_LIMIT) ++a.slots;
-  while (a.stages < (MODE == 0 ? MAX_STAGES : 4) && fixed + (a.stages + 1) * stage_bytes + a.slots * a.slot_bytes <= SMEM_LIMIT) ++a.stages;
-  const int bytes = fixed + a.stages * stage_bytes + a.slots * a.slot_bytes;
-  PG_REQUIRE(bytes <= SMEM_LIMIT, "tensor-core conv: shared-memory budget exceeded");
+  while (a.stages > 2 && fixed + a.stages * stage_bytes + a.slots * a.slot_bytes > G_::SMEM_LIMIT) --a.stages;
+  while (a.slots < 3 && fixed + a.stages * stage_bytes + (a.slots + 1) * a.slot_bytes <= G_::SMEM_LIMIT) ++a.slots;
+  while (a.stages < (MODE == 0 ? MAX_STAGES : 4) && fixed + (a.stages + 1) * stage_bytes + a.slots * a.slot_bytes <= G_::SMEM_LIMIT) ++a.stages;
+  *bytes_out = fixed + a.stages * stage_bytes + a.slots * a.slot_bytes;
+  a.tmem_cols = G_::NACC * 32;
+  if (MODE == 1) { a.tmem_cols = 32; while (a.tmem_cols < NKB * 64) a.tmem_cols *= 2; }
+  return *bytes_out <= G_::SMEM_LIMIT;
+}
+
+template <int MODE, int NKB, bool SMALL>
+int launch_geo(pg_ctx* ctx, const ConvArgs& a, int bytes) {
+  using G_ = Geo<SMALL>;
   static int attr_bytes = 0;
   if (bytes > attr_bytes) {
-    PG_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<MODE, NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    PG_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<MODE, NKB, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     attr_bytes = bytes;
   }
-  a.tmem_cols = NACC * 32;
-  if (MODE == 1) { a.tmem_cols = 32; while (a.tmem_cols < NKB * 64) a.tmem_cols *= 2; }
   const long long groups = (a.nsamples + a.G - 1) / a.G;
-  const int grid = (int)(groups < ctx->num_sms ? groups : ctx->num_sms);
-  tc_conv_kernel<MODE, NKB><<<grid, THREADS, bytes, ctx->stream>>>(a);
+  const long long ctas = (long long)ctx->num_sms * G_::CTAS_PER_SM;
+  const int grid = (int)(groups < ctas ? groups : ctas);
+  tc_conv_kernel<MODE, NKB, SMALL><<<grid, G_::THREADS, bytes, ctx->stream>>>(a);
   PG_LAUNCHED(ctx);
   return PG_OK;
+}
+
+template <int MODE, int NKB>
+int launch_nkb(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
+  static const bool want_small = getenv("PG_TCCONV_SMALL") != nullptr;     // experimental: two half-size CTAs per SM
+  int bytes = 0;
+  if (want_small) {
+    ConvArgs s = a;
+    if (plan_launch<MODE, NKB, true>(s, dy_floats_per_sample, &bytes)) return launch_geo<MODE, NKB, true>(ctx, s, bytes);
+  }
+  const bool ok = plan_launch<MODE, NKB, false>(a, dy_floats_per_sample, &bytes);
+  PG_REQUIRE(a.G > 0, "tensor-core conv: a sample (with its output gradient) does not fit a shared-memory slot");
+  PG_REQUIRE(ok, "tensor-core conv: shared-memory budget exceeded");
+  return launch_geo<MODE, NKB, false>(ctx, a, bytes);
 }
 
 template <int MODE>
