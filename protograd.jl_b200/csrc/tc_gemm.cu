@@ -212,7 +212,7 @@ template <bool A_MN, bool B_MN, int BLOCK_N, bool DBW>
 __global__ void __launch_bounds__(NUM_THREADS + (DBW ? 64 : 0), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ C,
                int M, int N, int K, Epi epi, unsigned int* __restrict__ sched) {
-  constexpr int STAGES = Cfg<BLOCK_N>::STAGES, B_STAGE_BYTES = Cfg<BLOCK_N>::B_STAGE_BYTES, STAGE_BYTES = Cfg<BLOCK_N>::STAGE_BYTES;
+  constexpr int STAGES = Cfg<BLOCK_N>::STAGES, STAGE_BYTES = Cfg<BLOCK_N>::STAGE_BYTES;
   constexpr int TMEM_COLS = Cfg<BLOCK_N>::TMEM_COLS;
   static_assert(!B_MN || BLOCK_N % 64 == 0, "MN-major B tiles are made of 64-wide TMA boxes");
   static_assert(RING >= STAGES + 4, "tile ring shorter than the producer's lead over the epilogue");
