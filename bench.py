@@ -10,8 +10,17 @@ run through the package's public API (eval_with_pullback / pb() / step) in bf16 
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
+Besides the contract keys the JSON line carries
+  parity         loss of the first step against the CPU oracle on the same inputs and, at N > 1, the all-reduced
+                 gradient of a small global batch against the single-rank full-batch gradient plus the replicas'
+                 arena checksums after one update (asserted BEFORE anything is timed);
+  roofline       the five wide tcgen05 GEMM launches of a step, event-timed one by one on REAL operands (the
+                 step's own activations / gradients / weights), against the measured burst peak;
+  other_configs  C1 / C3 / C5 (BASELINE configs[0], [2], [4]) device-timed steps with their HBM roofline (N = 1);
+  cpu_baseline   the oracle port of the same step on the host cores at the SAME 8,192-sample batch.
+
 --impl reference times the CPU oracle (numpy/OpenBLAS restatement of the reference step; Julia is
-not installed) on a bounded sample of the same workload on the host cores.
+not installed) on 8,192-sample steps of the same workload on the host cores.
 """
 import argparse
 import json
@@ -28,10 +37,15 @@ sys.path.insert(0, ROOT)
 
 D_IN, D_H, D_OUT = 784, 4096, 10
 PER_GPU_BATCH = 8192
-CPU_SAMPLE_BATCH = 1024
 SPEC = [("linear", D_IN, D_H), ("relu",), ("linear", D_H, D_H), ("relu",), ("linear", D_H, D_OUT), ("softmax",)]
 # algorithmic flop/sample: fwd + dW for all layers + dX for all but the first
 FLOP_PER_SAMPLE = 2 * (2 * (D_IN * D_H + D_H * D_H + D_H * D_OUT) + (D_H * D_H + D_H * D_OUT))
+C1_SPEC = [("linear", 784, 100), ("relu",), ("linear", 100, 10), ("softmax",)]
+C3_SPEC = [("conv", 1, 6, 5), ("relu",), ("maxpool", 2), ("conv", 6, 16, 5), ("relu",), ("maxpool", 2),
+           ("flatten",), ("linear", 256, 120), ("relu",), ("linear", 120, 84), ("relu",), ("linear", 84, 10), ("softmax",)]
+C5_SPEC = [("conv", 1, 6, 5, False), ("relu",), ("maxpool", 2), ("conv", 6, 16, 5, False), ("relu",), ("maxpool", 2),
+           ("flatten",), ("linear", 256, 10, True), ("softmax",)]
+FLOPS_OTHER = {"C1": 319_600, "C3": 1_517_040, "C5": 490_240}
 
 
 def synth(B, seed):
@@ -52,37 +66,50 @@ def init_params(seed=0):
     return ps
 
 
+def workload_config(B, world, math, dp_mode, exact_adam):
+    return {"workload": "wide MLP 784-4096-4096-10 (BASELINE configs[3]), softmax+cross-entropy, Adam(1e-3), %d samples/GPU" % B,
+            "global_batch": B * world, "parallelism": "dp%d" % world, "dp_mode": dp_mode if world > 1 else None, "math": math,
+            "adam": "float64-promoted (bit-exact)" if exact_adam else "fused float32 (normwise 1e-7 of the reference form)",
+            "l2": "working set per step (>600 MB of activations, weights, gradients, optimizer state) exceeds the 126 MB L2"}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of the reference step) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_port_throughput(steps, warmup, batch=CPU_SAMPLE_BATCH):
+def cpu_port_throughput(steps, warmup, batch=PER_GPU_BATCH, budget_s=150.0):
+    """(samples/s, s/step, timed steps actually run): `steps` is cut so the leg fits `budget_s`"""
     from oracle import protograd_oracle as O
     x, lab = synth(batch, 123)
     ts = O.TrainStep(SPEC, init_params(0), O.Adam(stepsize=1e-3), "ce")
-    for _ in range(warmup):
+    per = None
+    for _ in range(max(1, warmup)):
+        t0 = time.perf_counter()
         ts.step(x, lab)
+        per = time.perf_counter() - t0
+    steps = max(1, min(steps, int(budget_s / max(per, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps):
         ts.step(x, lab)
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps
+    return batch * steps / dt, dt / steps, steps
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 10))
-    warm = max(1, min(args.warmup, 2))
-    v, per = cpu_port_throughput(steps, warm)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    warm = max(1, min(args.warmup, 5))
+    v, per, steps = cpu_port_throughput(args.steps, warm, args.batch)
     cores = os.cpu_count()
-    sample = f"{CPU_SAMPLE_BATCH}-sample batches of the same 784-4096-4096-10 Adam step, {steps} timed steps after {warm} warm-up, numpy/OpenBLAS float32"
+    sample = (f"{args.batch}-sample steps (one GPU's shard of the workload) of the same 784-4096-4096-10 Adam step, {steps} timed steps "
+              f"after {warm} warm-up, numpy/OpenBLAS float32 oracle (CPU restatement of the reference step, not Julia: no Julia toolchain in "
+              f"this image) on all host cores; throughput is per host, independent of N")
+    cfg = workload_config(args.batch, world, args.math, args.dp_mode, args.exact_adam)
     line = {
         "impl": "reference", "metric": "train samples/sec per step", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "wide MLP 784-4096-4096-10, softmax+cross-entropy, Adam; CPU sample batch %d (GPU arm: 8192/GPU)" % CPU_SAMPLE_BATCH,
-                   "note": "CPU restatement of the reference step (not Julia: no Julia toolchain in this image)"},
+        "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -133,6 +160,54 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# algorithmic HBM bytes of one training step of a layer spec (the convention DESIGN.md §3 states): every tensor
+# of the reference's graph touches HBM once per use — inputs and activations: written once (by their producer,
+# fused with bias / ReLU), read once by the next layer, read once more in the backward pass; activation gradients:
+# written once, read once; parameters: read in forward and backward, gradient written once, plus the optimizer's
+# bytes per parameter (GD 12, Nesterov 16, Adam 28).
+# ------------------------------------------------------------------------------------------------
+def step_bytes(spec, B, opt_bytes, in_shape, isz=4):
+    shape = in_shape
+    size = [int(np.prod(shape))]       # tensor i feeds op i -> tensor i+1 (ReLU / flatten / softmax make no tensor)
+    has_grad, bwd_read = [False], [False]
+    params_t = params_f = 0
+    trainable_seen = False
+    for op in spec:
+        k = op[0]
+        if k == "linear":
+            tr = op[3] if len(op) > 3 else True
+            n = op[1] * op[2] + op[2]
+            shape = (op[2],)
+        elif k == "conv":
+            tr = op[4] if len(op) > 4 else True
+            n = op[2] * op[1] * op[3] * op[3] + op[2]
+            shape = (op[2], shape[1] - op[3] + 1, shape[2] - op[3] + 1)
+        elif k in ("maxpool", "meanpool"):
+            tr, n = False, 0
+            shape = (shape[0], shape[1] // op[1], shape[2] // op[1])
+        elif k == "flatten":
+            shape = (int(np.prod(shape)),)
+            continue
+        elif k in ("relu", "softmax"):
+            continue
+        else:
+            raise ValueError(k)
+        if tr:
+            params_t += n
+            bwd_read[-1] = True            # dW needs the layer's input
+            trainable_seen = True
+        else:
+            params_f += n
+        size.append(int(np.prod(shape)))
+        has_grad.append(trainable_seen)
+        bwd_read.append(trainable_seen)    # ReLU' mask / pool routing / next layer's dW
+    per_sample = 0
+    for i, n_el in enumerate(size):
+        per_sample += n_el * isz * ((1 if i > 0 else 0) + 1 + (1 if bwd_read[i] else 0) + (2 if has_grad[i] else 0))
+    return B * per_sample + isz * 2 * (params_t + params_f) + params_t * (4 + opt_bytes)
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -143,7 +218,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="samples per GPU")
     ap.add_argument("--math", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg and the oracle loss check")
+    ap.add_argument("--no-others", action="store_true", help="skip the C1/C3/C5 sub-lines")
     ap.add_argument("--dp-mode", default="bucket", choices=["bucket", "flat", "none"], help="gradient exchange: layer-bucketed overlapped all-reduce (default), one flat all-reduce, or none (diagnostic)")
     ap.add_argument("--sm-limit", type=int, default=0, help="size persistent grids for this many SMs (0 = all)")
     ap.add_argument("--exact-adam", action="store_true", help="Float64-promoted Adam arithmetic (bit-exact with the reference's broadcast) instead of the fused Float32 form")
@@ -166,6 +242,7 @@ def main():
     import protograd_b200 as pg
     from protograd_b200 import dp
     from protograd_b200.capi import call
+    from protograd_b200.device import f32_to_bf16
 
     ctx = pg.Context.get(local)
     stream = torch.cuda.Stream(device=local)
@@ -212,8 +289,8 @@ def main():
         _trace.call = _logged_call
         _optimizers.call = _logged_call
 
-    def train_step(x, lab):
-        out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(x), lab, global_batch=GB), model, math=args.math)
+    def train_step(x, lab, gb=GB):
+        out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(x), lab, global_batch=gb), model, math=args.math)
         if buckets is None:
             pg.step(state, pb(), shadow=use_shadow)
         elif args.dp_mode == "bucket":
@@ -273,6 +350,50 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # ---- parity, asserted before anything is timed -----------------------------------------------------------
+    parity = {}
+    if world > 1:
+        # (1) a small global batch from identical seeds: every rank draws the same global batch and takes its
+        #     shard; the bucketed all-reduce must reproduce the single-rank full-batch gradient (fp32 summation
+        #     order is the only difference) ...
+        PB = 256
+        xg, lg = synth(PB * world, 77)
+        xs, ls = xg[rank * PB:(rank + 1) * PB], lg[rank * PB:(rank + 1) * PB]
+        out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(xs), ls, global_batch=PB * world), model, math=args.math)
+        g = pb(on_ready=buckets.ready)
+        buckets.finish()
+        g_dp = g.vec().astype(np.float64)
+        out1, pb1 = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(xg), lg), model, math=args.math)
+        g_full = pb1().vec().astype(np.float64)
+        err = float(np.linalg.norm(g_dp - g_full) / np.linalg.norm(g_full))
+        t = torch.tensor([err], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity["dp_grad_vs_full_batch_rel"] = float(t.item())
+        assert parity["dp_grad_vs_full_batch_rel"] <= 1e-5, parity
+        # (2) ... and after one update from that gradient the replicas' arenas must be bit-identical
+        out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(xs), ls, global_batch=PB * world), model, math=args.math)
+        g = pb(on_ready=buckets.ready)
+        buckets.finish_and_step(state, g, shadow=use_shadow)
+        cs = torch.tensor([dp.arena_checksum(model)], dtype=torch.float64, device=f"cuda:{local}")
+        allcs = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        sums = [float(c.item()) for c in allcs]
+        parity["replica_checksums_identical"] = bool(all(s == sums[0] for s in sums))
+        assert parity["replica_checksums_identical"], sums
+    # first timed-size step: its loss against the CPU oracle's forward pass on the same shard (float32 oracle;
+    # bf16 operand rounding bounds the gap at 2e-3, tests/test_gpu_tc.py)
+    w_before = model.vec() if (rank == 0 and not args.no_cpu) else None
+    loss0 = float(train_step(x_d, lab_d, gb=B) if world == 1 else pg.eval_with_pullback(lambda m: pg.cross_entropy(m(x_d), lab_d), model, math=args.math)[0])
+    if w_before is not None:
+        from oracle import protograd_oracle as O
+        shapes = [p.shape for p in p0]
+        probs, _ = O.net_forward(SPEC, O.unvec(w_before, shapes), x_h, keep=True)
+        ref = float(O.cross_entropy(probs, lab_h))
+        parity["first_step_loss"] = loss0
+        parity["first_step_loss_oracle_f32"] = ref
+        parity["first_step_loss_rel"] = abs(loss0 - ref) / abs(ref)
+        assert parity["first_step_loss_rel"] <= 2e-3, parity
+
     # ---- device-resident leg (value) ----
     for _ in range(args.warmup):
         loss = train_step(x_d, lab_d)
@@ -327,26 +448,37 @@ def main():
     ms_e2e = timed(lambda: e2e_loop(e2e_steps), 1)
     e2e_value = GB * e2e_steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (tcgen05 GEMM): every GEMM launch of one step, event-timed ----
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): the five wide GEMM launches of one step, event-timed
+    #      one by one on REAL operands — U[0,1) inputs, the model's weights, ReLU activations (about half zeros,
+    #      as in the step) and dense random hidden gradients ----
     roofline, kernels = None, {}
-    if args.math == "bf16":
+    if args.math == "bf16" and rank == 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         bf = pg.BF16
-        A0 = pg.DeviceArray.empty(ctx, (B, D_IN), bf); A1 = pg.DeviceArray.empty(ctx, (B, D_H), bf); A2 = pg.DeviceArray.empty(ctx, (B, D_H), bf)
-        G1 = pg.DeviceArray.empty(ctx, (B, D_H), bf); G2 = pg.DeviceArray.empty(ctx, (B, D_H), bf)
-        W1 = pg.DeviceArray.empty(ctx, (D_IN, D_H), bf); W2 = pg.DeviceArray.empty(ctx, (D_H, D_H), bf)
+        rng = np.random.default_rng(5)
+
+        def dev_bf16(a):
+            d = pg.DeviceArray.empty(ctx, a.shape, bf, zero=False)
+            d.upload(f32_to_bf16(a))
+            return d
+        A0 = dev_bf16(x_h)
+        W1, W2 = dev_bf16(model.layers[0].W.numpy()), dev_bf16(model.layers[2].W.numpy())
+        A1 = dev_bf16(np.maximum(rng.standard_normal((B, D_H), dtype=np.float32), 0))
+        A2 = pg.DeviceArray.empty(ctx, (B, D_H), bf)
+        G1 = dev_bf16(1e-3 * rng.standard_normal((B, D_H), dtype=np.float32)); G2 = dev_bf16(1e-3 * rng.standard_normal((B, D_H), dtype=np.float32))
         dW1 = pg.DeviceArray.empty(ctx, (D_IN, D_H), np.float32); dW2 = pg.DeviceArray.empty(ctx, (D_H, D_H), np.float32)
-        bias = pg.DeviceArray.empty(ctx, (D_H,), np.float32)
+        db = pg.DeviceArray.empty(ctx, (D_H,), np.float32)
+        bias = pg.DeviceArray.from_numpy(ctx, (0.01 * rng.standard_normal(D_H)).astype(np.float32))
         gemms = [
-            ("fwd_L1", lambda: call("pg_tc_linear_fwd", ctx.h, A0.ptr, W1.ptr, bias.ptr, A1.ptr, 2, B, D_IN, D_H, 1), 2.0 * B * D_IN * D_H),
+            ("fwd_L1", lambda: call("pg_tc_linear_fwd", ctx.h, A0.ptr, W1.ptr, bias.ptr, A2.ptr, 2, B, D_IN, D_H, 1), 2.0 * B * D_IN * D_H),
             ("fwd_L2", lambda: call("pg_tc_linear_fwd", ctx.h, A1.ptr, W2.ptr, bias.ptr, A2.ptr, 2, B, D_H, D_H, 1), 2.0 * B * D_H * D_H),
-            ("dgrad_L2", lambda: call("pg_tc_linear_bwd", ctx.h, None, W2.ptr, G2.ptr, 2, None, None, G1.ptr, A1.ptr, B, D_H, D_H), 2.0 * B * D_H * D_H),
-            ("wgrad_L2", lambda: call("pg_tc_linear_bwd", ctx.h, A1.ptr, None, G2.ptr, 2, dW2.ptr, None, None, None, B, D_H, D_H), 2.0 * B * D_H * D_H),
-            ("wgrad_L1", lambda: call("pg_tc_linear_bwd", ctx.h, A0.ptr, None, G1.ptr, 2, dW1.ptr, None, None, None, B, D_IN, D_H), 2.0 * B * D_IN * D_H),
+            ("dgrad_L2", lambda: call("pg_tc_linear_bwd", ctx.h, None, W2.ptr, G2.ptr, 2, None, None, A2.ptr, A1.ptr, B, D_H, D_H), 2.0 * B * D_H * D_H),
+            ("wgrad_L2", lambda: call("pg_tc_linear_bwd", ctx.h, A1.ptr, None, G2.ptr, 2, dW2.ptr, db.ptr, None, None, B, D_H, D_H), 2.0 * B * D_H * D_H),
+            ("wgrad_L1", lambda: call("pg_tc_linear_bwd", ctx.h, A0.ptr, None, G1.ptr, 2, dW1.ptr, db.ptr, None, None, B, D_IN, D_H), 2.0 * B * D_IN * D_H),
         ]
         reps = 10
         tot_ms, tot_flop = 0.0, 0.0
@@ -371,41 +503,140 @@ def main():
         achieved = tot_flop / (tot_ms * 1e-3) / 1e12
         traffic, traffic_src = None, None
         try:  # DRAM bytes per launch from the committed ncu --set full capture of the same kernels
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["tc_gemm_kernel"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["tc_gemm_kernel"]
             if B == PER_GPU_BATCH:
                 traffic, traffic_src = tj["per_launch_bytes"], tj["source"]
         except Exception:
             pass
-        peak = peaks.get("bf16_tflops_sustained") or 1400.0
-        roofline = {"kernel": "tc_gemm_kernel (tcgen05 bf16, 5 launches/step)", "bound": "tensor", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak,
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
+        burst = peaks.get("bf16_tflops") or 1590.0
+        sustained = peaks.get("bf16_tflops_sustained") or 1400.0
+        roofline = {"kernel": "tc_gemm2_kernel (tcgen05 bf16 cta_group::2, the 5 wide GEMM launches of a step, real operands)", "bound": "tensor",
+                    "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst: each launch is timed alone; of measured)" if peaks
+                                    else "fallback 1.59 PFLOP/s burst (of fallback)"),
+                    "frac_of_sustained_peak": achieved / sustained, "sustained_peak": sustained,
                     "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": tot_ms / (reps * len(gemms)),
-                    "share_of_step": (tot_ms / reps) / (ms / args.steps)}
+                    "share_of_step": (tot_ms / reps) / (ms / args.steps),
+                    "whole_step_tflops": FLOP_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12,
+                    "whole_step_frac_of_burst": FLOP_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12 / burst}
+        del A0, A1, A2, G1, G2, W1, W2, dW1, dW2
+
+    others = None
+    if world == 1 and not args.no_others:
+        others = other_configs(pg, ctx, stream, torch)
 
     if rank == 0:
         line = {
             "metric": "train samples/sec per step", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.math == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "wide MLP 784-4096-4096-10 (BASELINE configs[3]), softmax+cross-entropy, Adam(1e-3), %d samples/GPU" % B,
-                       "global_batch": GB, "parallelism": "dp%d" % world, "dp_mode": args.dp_mode if world > 1 else None, "math": args.math, "adam": "float64-promoted (bit-exact)" if args.exact_adam else "fused float32 (normwise 1e-7 of the reference form)",
-                       "l2": "working set per step (>600 MB of activations, weights, gradients, optimizer state) exceeds the 126 MB L2"},
+            "config": workload_config(B, world, args.math, args.dp_mode, args.exact_adam),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(x_h.nbytes + lab_h.nbytes), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms, "clocks": clk, "loss_after_warmup": first_loss,
-            "tflops_per_gpu": FLOP_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12,
+            "tflops_per_gpu": FLOP_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12, "parity": parity,
         }
         if roofline:
             line["roofline"] = roofline
             line["kernels"] = kernels
+        if others:
+            line["other_configs"] = others
         if world == 1 and not args.no_cpu:
-            v, per = cpu_port_throughput(3, 1)
+            v, per, n = cpu_port_throughput(3, 1, B)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{CPU_SAMPLE_BATCH}-sample batches of the same step, 3 timed steps after 1 warm-up, numpy/OpenBLAS float32 oracle"}
+                                    "sample": f"{B}-sample batches of the same step (the GPU arm's batch), {n} timed steps after 1 warm-up, numpy/OpenBLAS float32 oracle"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE configs (N = 1): C1 MLP 784-100-10, C3 conv net, C5 frozen trunk + head
+# ------------------------------------------------------------------------------------------------
+def other_configs(pg, ctx, stream, torch):
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = (peaks.get("hbm_gbs") or 6650.0) * 1e9
+
+    def build(spec, rng):
+        layers = []
+        for op in spec:
+            k = op[0]
+            if k == "linear":
+                layers.append(pg.Linear(op[1], op[2], rng=rng))                 # xavier_uniform, src/layers.jl:6-8
+            elif k == "conv":
+                layers.append(pg.Conv(op[1], op[2], (op[3], op[3]), rng=rng))
+            elif k == "relu":
+                layers.append(pg.relu)
+            elif k == "maxpool":
+                layers.append(lambda t, s=op[1]: pg.maxpool(t, (s, s)))
+            elif k == "flatten":
+                layers.append(pg.flatten)
+            elif k == "softmax":
+                layers.append(pg.softmax)
+        return pg.Compose(*layers)
+
+    def run(name, spec, B, opt, opt_bytes, math, graph, steps=30, warmup=5):
+        rng = np.random.default_rng(3)
+        conv = spec[0][0] == "conv"
+        in_shape = (1, 28, 28) if conv else (784,)
+        x = rng.random((B,) + in_shape, dtype=np.float32)
+        lab = np.eye(10, dtype=np.float32)[rng.integers(0, 10, B)]
+        full = build(spec, rng)
+        xd, ld = pg.DeviceArray.from_numpy(ctx, x), pg.DeviceArray.from_numpy(ctx, lab)
+        if name == "C5":
+            head_idx = [i for i, l in enumerate(full.layers) if isinstance(l, pg.Linear)][-1]
+            m = full.layers[head_idx]
+
+            def objective(mm):
+                layers = list(full.layers); layers[head_idx] = mm
+                return pg.cross_entropy(pg.Compose(*layers)(xd), ld)
+        else:
+            m = full
+            objective = lambda mm: pg.cross_entropy(mm(xd), ld)
+        st = pg.init(opt, m)
+        if graph:
+            stepf = pg.GraphStep(objective, m, st, math=math)
+        else:
+            def stepf():
+                out, pb = pg.eval_with_pullback(objective, m, math=math)
+                pg.step(st, pb())
+                return out
+        for _ in range(warmup):
+            out = stepf()
+        float(out)
+        n0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(steps):
+            out = stepf()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        nbytes = step_bytes(spec, B, opt_bytes, in_shape)
+        roof_ms = nbytes / hbm * 1e3
+        return {"config": name, "batch": B, "optimizer": type(opt).__name__, "math": math, "mode": "cuda-graph replay" if graph else "eager",
+                "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "gflops": FLOPS_OTHER[name] * B / (ms * 1e-3) / 1e9,
+                "launches_per_step": (ctx.launch_count() - n0) / steps if not graph else None,
+                "roofline": {"bound": "hbm" if B >= 4096 else "latency (working set fits L2; HBM figure for scale only)",
+                             "algorithmic_bytes": nbytes, "roofline_ms": roof_ms, "frac": roof_ms / ms},
+                "loss": float(out)}
+
+    res = []
+    for args_ in (("C1", C1_SPEC, 128, pg.Adam(1e-3, fast=True), 28, "fp32", True),
+                  ("C1", C1_SPEC, 8192, pg.Adam(1e-3, fast=True), 28, "fp32", False),
+                  ("C3", C3_SPEC, 128, pg.NesterovMethod(1e-2), 16, "fp32", True),
+                  ("C3", C3_SPEC, 8192, pg.NesterovMethod(1e-2), 16, "bf16", False),
+                  ("C5", C5_SPEC, 8192, pg.GradientDescent(0.1), 12, "bf16", False)):
+        try:
+            res.append(run(*args_))
+        except Exception as e:      # a sub-line must never take the headline down
+            res.append({"config": args_[0], "batch": args_[2], "error": repr(e)[:300]})
+    return res
 
 
 if __name__ == "__main__":

@@ -132,3 +132,60 @@ def test_tc_steps_with_fused_shadow_match_plain_steps(pg):
     # bias gradients are accumulated with fp32 atomics, so two runs agree to rounding, not bit for bit
     assert np.allclose(res[0][0], res[1][0], rtol=1e-5) and rel_err(res[0][1], res[1][1]) <= 1e-5
     assert res[0][0][-1] < res[0][0][0]
+
+
+# ---- parity at the benchmarked configuration (BASELINE configs[3] per-GPU shard: B = 8192) --------------------
+
+
+def test_tc_training_step_c4_bench_batch(pg):
+    """One C4 step at the batch bench.py times (8,192 samples/GPU, bf16 mode): forward and data-gradient launches
+    of the 2-CTA kernel are multi-wave here (512 pair tiles on 74 SM pairs), which no smaller test reaches.
+    Same tolerances as the B = 512 test: 1e-4 (loss) / 1e-2 (gradients) against the bf16-format restatement."""
+    spec = [("linear", 784, 4096), ("relu",), ("linear", 4096, 4096), ("relu",), ("linear", 4096, 10), ("softmax",)]
+    rng = np.random.default_rng(10)
+    p0 = O.init_params(spec, np.float32, seed=5)
+    B = 8192
+    x = rng.random((B, 784)).astype(np.float32); lab = np.eye(10, dtype=np.float32)[rng.integers(0, 10, B)]
+    m = pg.Compose(pg.Linear(W=p0[0], b=p0[1]), pg.relu, pg.Linear(W=p0[2], b=p0[3]), pg.relu, pg.Linear(W=p0[4], b=p0[5]), pg.softmax)
+    st = pg.init(pg.Adam(stepsize=1e-3, fast=True), m)
+    out, pb = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(x), lab), m, math="bf16")
+    grad = pb()
+    g = [p.numpy() for p in grad.allparams()]
+    vb, gb = O.mlp_bf16_loss_and_grad(spec, p0, x, lab)
+    assert abs(float(out) - vb) <= 1e-4 * abs(vb), (float(out), vb)
+    errs = [rel_err(a, r) for a, r in zip(g, gb)]
+    assert max(errs) <= 1e-2, errs
+    # the fused Adam update from those gradients (fast fp32 form: <= 1e-6 normwise of the reference form)
+    pg.step(st, grad, shadow=True)
+    state = O.Adam(stepsize=1e-3).init(O.vec(p0).astype(np.float32).copy())
+    state.step(O.vec(g).astype(np.float32))
+    assert rel_err(m.vec(), state.x) <= 1e-6
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+def test_tc_gemm_tile_ring_wraps_2cta(pg, layout):
+    """1,536 pair tiles on 74 SM pairs: every pair takes > 16 tiles, so the scheduler's 16-slot tile-id ring
+    (tc_gemm.cu RING) wraps and its per-slot mbarrier phases flip."""
+    _gemm_case(pg, layout, 24576, 4096, 128)
+
+
+def test_tc_gemm_tile_ring_wraps_1cta(pg):
+    """N < 512 selects the single-CTA kernel: 2,432 tiles on 148 CTAs (> 16 each)."""
+    _gemm_case(pg, 0, 311296, 256, 64)
+
+
+def _gemm_case(pg, layout, M, N, K):
+    from protograd_b200.capi import call
+    rng = np.random.default_rng(M + N + K + layout)
+    A = _bf(pg, rng.standard_normal((M, K), dtype=np.float32)); B = _bf(pg, rng.standard_normal((K, N), dtype=np.float32))
+    ref = A @ B           # bf16 x bf16 products are exact in fp32; K <= 128 terms: fp32 summation error ~1e-7
+    a_st = np.ascontiguousarray(A.T) if layout == 2 else A
+    b_st = np.ascontiguousarray(B.T) if layout == 1 else B
+    ctx = pg.Context.get()
+    ad, bd = _dev_bf16(pg, a_st), _dev_bf16(pg, b_st)
+    cd = pg.DeviceArray.empty(ctx, (M, N), np.float32)
+    call("pg_tc_gemm", ctx.h, layout, ad.ptr, bd.ptr, cd.ptr, 0, M, N, K)
+    got = cd.numpy()
+    # blockwise (keeps host memory bounded) and exact-ish: every 128-row block must match
+    for r0 in range(0, M, 8192):
+        assert rel_err(got[r0:r0 + 8192], ref[r0:r0 + 8192]) <= 1e-5, r0
