@@ -255,7 +255,7 @@ def main():
     model = pg.Compose(pg.Linear(W=p0[0], b=p0[1]), pg.relu, pg.Linear(W=p0[2], b=p0[3]), pg.relu, pg.Linear(W=p0[4], b=p0[5]), pg.softmax)
     state = pg.init(pg.Adam(stepsize=1e-3, fast=not args.exact_adam), model)
     if world > 1:
-        dp.broadcast_parameters(model)
+        dp.broadcast_parameters(model, dp=dp.init(ctx))
     x_h, lab_h = synth(B, 1000 + rank)
     x_d, lab_d = pg.DeviceArray.from_numpy(ctx, x_h), pg.DeviceArray.from_numpy(ctx, lab_h)
     # pinned host copies for the end-to-end leg
@@ -263,65 +263,22 @@ def main():
     x_p, lab_p = pin_x.as_numpy(np.float32, x_h.shape), pin_l.as_numpy(np.float32, lab_h.shape)
     x_p[...] = x_h; lab_p[...] = lab_h
 
-    buckets = dp.GradientBuckets(pg.gradient_container(model), bucket_bytes=int(os.environ.get("PG_BUCKET_MB", "24")) << 20,
-                                 comm_sms=(int(os.environ["PG_COMM_SMS"]) if "PG_COMM_SMS" in os.environ else None),
-                                 delay_us=(float(os.environ["PG_COMM_DELAY_US"]) if "PG_COMM_DELAY_US" in os.environ else None),
-                                 overlap_update=(os.environ["PG_DP_OVERLAP_UPDATE"] == "1" if "PG_DP_OVERLAP_UPDATE" in os.environ else None)) if world > 1 else None
+    dpc = dp.init(ctx) if world > 1 else None        # the library's own NCCL communicator (csrc/dp.cu), id via torch.distributed
+    buckets = dp.GradientBuckets(pg.gradient_container(model), bucket_bytes=int(os.environ.get("PG_BUCKET_MB", "24")) << 20, dp=dpc,
+                                 overlap_update=os.environ.get("PG_DP_OVERLAP_UPDATE", "1") == "1") if world > 1 else None
     if args.sm_limit:
         ctx.set_sm_limit(args.sm_limit)
     use_shadow = args.math == "bf16"
-    timeline = [] if os.environ.get("PG_DP_TIMELINE") else None
-    timeline_leaves = []
-
-    klog = {"cur": None, "steps": []}
-    if os.environ.get("PG_DP_TIMELINE") == "2":
-        # per-call device timeline of the backward + update kernels (diagnostic): an event after every C-ABI call
-        from protograd_b200 import trace as _trace, optimizers as _optimizers
-        _orig_call = _trace.call
-
-        def _logged_call(name, *a):
-            r = _orig_call(name, *a)
-            if klog["cur"] is not None:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record(stream)
-                klog["cur"].append((name, e))
-            return r
-        _trace.call = _logged_call
-        _optimizers.call = _logged_call
-
     def train_step(x, lab, gb=GB):
         out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(x), lab, global_batch=gb), model, math=args.math)
         if buckets is None:
             pg.step(state, pb(), shadow=use_shadow)
         elif args.dp_mode == "bucket":
-            if timeline is not None:
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-                leaf_ev = {}
-                ev[0].record(stream)
-
-                def hook(i):
-                    buckets.ready(i)
-                    leaf_ev[i] = torch.cuda.Event(enable_timing=True)
-                    leaf_ev[i].record(stream)  # gradient leaf i has been produced
-                    if i == 2:
-                        ev[1].record(stream)   # parameter gradients of layers 2,3 done; their bucket was just issued
-                if os.environ.get("PG_DP_TIMELINE") == "2":
-                    klog["cur"] = []
-                g = pb(on_ready=hook)
-                ev[2].record(stream)           # end of backward compute
-                buckets.finish_and_step(state, g, shadow=use_shadow)
-                ev[3].record(stream)
-                if klog["cur"] is not None:
-                    klog["steps"].append((ev[0], klog["cur"]))
-                    klog["cur"] = None
-                timeline.append(ev)
-                timeline_leaves.append((ev[0], leaf_ev))
-            else:
-                g = pb(on_ready=buckets.ready)      # tail buckets reduce while the remaining backward GEMMs run
-                buckets.finish_and_step(state, g, shadow=use_shadow)
+            g = pb(on_ready=buckets.on_ready())     # tail buckets reduce while the remaining backward GEMMs run
+            buckets.finish_and_step(state, g, shadow=use_shadow)
         elif args.dp_mode == "flat":
             g = pb()
-            dp.allreduce_gradients(g)
+            dp.allreduce_gradients(g, dpc)
             pg.step(state, g, shadow=use_shadow)
         else:                                   # "none": no exchange (diagnostic only, replicas diverge)
             pg.step(state, pb(), shadow=use_shadow)
@@ -360,7 +317,7 @@ def main():
         xg, lg = synth(PB * world, 77)
         xs, ls = xg[rank * PB:(rank + 1) * PB], lg[rank * PB:(rank + 1) * PB]
         out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(xs), ls, global_batch=PB * world), model, math=args.math)
-        g = pb(on_ready=buckets.ready)
+        g = pb(on_ready=buckets.on_ready())
         buckets.finish()
         g_dp = g.vec().astype(np.float64)
         out1, pb1 = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(xg), lg), model, math=args.math)
@@ -372,12 +329,13 @@ def main():
         assert parity["dp_grad_vs_full_batch_rel"] <= 1e-5, parity
         # (2) ... and after one update from that gradient the replicas' arenas must be bit-identical
         out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(xs), ls, global_batch=PB * world), model, math=args.math)
-        g = pb(on_ready=buckets.ready)
+        g = pb(on_ready=buckets.on_ready())
         buckets.finish_and_step(state, g, shadow=use_shadow)
-        cs = torch.tensor([dp.arena_checksum(model)], dtype=torch.float64, device=f"cuda:{local}")
+        csum, cxor = dp.arena_checksum(model)            # (float64 sum, xor of the raw bits) of the parameter arena
+        cs = torch.tensor([int(np.float64(csum).view(np.int64)), cxor], dtype=torch.int64, device=f"cuda:{local}")
         allcs = [torch.zeros_like(cs) for _ in range(world)]
         dist.all_gather(allcs, cs)
-        sums = [float(c.item()) for c in allcs]
+        sums = [tuple(c.tolist()) for c in allcs]
         parity["replica_checksums_identical"] = bool(all(s == sums[0] for s in sums))
         assert parity["replica_checksums_identical"], sums
     # first timed-size step: its loss against the CPU oracle's forward pass on the same shard (float32 oracle;
@@ -405,22 +363,6 @@ def main():
     ms = timed(lambda: train_step(x_d, lab_d), args.steps)
     launches = ctx.launch_count() - n0
     host_ms = host_enqueue[0]
-    if timeline and rank == 0:
-        torch.cuda.synchronize()
-        tl = np.array([[e[0].elapsed_time(e[k]) for k in (1, 2, 3)] for e in timeline[-20:]])
-        print("DP timeline (ms from step start: bucket issued, backward done, step done):", tl.mean(0).round(4).tolist(), file=sys.stderr)
-        if klog["steps"]:
-            last = klog["steps"][-20:]
-            names = [n for n, _ in last[-1][1]]
-            t = np.array([[e0.elapsed_time(e) for _, e in log] for e0, log in last if len(log) == len(names)]).mean(0)
-            print("DP kernel timeline (ms from backward start, call finished):", file=sys.stderr)
-            prev = 0.0
-            for n, x in zip(names, t):
-                print(f"   {n:28s} done {x:7.4f}  (+{x - prev:6.4f})", file=sys.stderr)
-                prev = x
-        keys = sorted(timeline_leaves[-1][1], reverse=True)
-        lv = np.array([[e0.elapsed_time(le[k]) for k in keys] for e0, le in timeline_leaves[-20:]])
-        print("DP timeline leaves (ms from backward start, gradient leaf done):", dict(zip(keys, lv.mean(0).round(4).tolist())), file=sys.stderr)
     clk = clocks.stop() if rank == 0 else None
     value = GB * args.steps / (ms * 1e-3)
 

@@ -30,13 +30,20 @@ extern "C" {
 
 typedef struct pg_ctx pg_ctx;
 
-typedef enum { PG_F32 = 0, PG_F64 = 1, PG_BF16 = 2 } pg_dtype;
+typedef struct pg_plan pg_plan;
+typedef struct pg_arena pg_arena;
+typedef struct pg_dp pg_dp;
+
+typedef enum { PG_F32 = 0, PG_F64 = 1, PG_BF16 = 2, PG_F16 = 3, PG_I32 = 4 } pg_dtype;
 typedef enum { PG_ACT_NONE = 0, PG_ACT_RELU = 1 } pg_act;
 typedef enum { PG_OK = 0, PG_ERR_ARG = -1, PG_ERR_CUDA = -2, PG_ERR_UNSUPPORTED = -3, PG_ERR_NOMEM = -4 } pg_status;
 typedef enum { PG_ADD = 0, PG_SUB = 1 } pg_binop;
 /* model (op) scalar forms of src/model.jl:168-196 */
 typedef enum { PG_X_PLUS_C = 0, PG_X_MINUS_C = 1, PG_C_MINUS_X = 2, PG_X_TIMES_C = 3, PG_X_OVER_C = 4, PG_C_OVER_X = 5 } pg_scalarop;
-enum { PG_SCALAR_F64 = 1 };
+/* flags of the scalar-taking calls: PG_SCALAR_F64 / PG_SCALAR2_F64 = the first / second Julia scalar was a Float64
+ * (per-element math in Float64, one rounding on store); PG_MATH_FAST = fused all-Float32 Adam arithmetic
+ * (normwise ~1e-7 of the promoted form) instead of the bit-exact Float64-promoted one. */
+enum { PG_SCALAR_F64 = 1, PG_SCALAR2_F64 = 2, PG_MATH_FAST = 4 };
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
 const char* pg_last_error(void);
@@ -50,7 +57,6 @@ int pg_sync(pg_ctx* ctx);
 int pg_launch_count(pg_ctx* ctx, int64_t* n);    /* kernels launched through this ctx so far */
 int pg_reserve_workspace(pg_ctx* ctx, size_t bytes); /* pre-size scratch (needed before graph capture) */
 int pg_set_sm_limit(pg_ctx* ctx, int n_sms);     /* size persistent grids for n_sms SMs (0 = all, negative = all but |n|): leaves SMs to a concurrent NCCL kernel */
-int pg_delay_on(pg_ctx* ctx, void* stream, long long ns);   /* enqueue a one-thread kernel that sleeps ns (<= 1 ms) on `stream`: orders a collective behind the GEMM that becomes runnable at the same moment (protograd dp.py) */
 
 /* ---- device / pinned memory (arena storage; replaces Julia Array allocation for leaves) ---- */
 int pg_malloc(pg_ctx* ctx, size_t bytes, void** dptr);
@@ -189,6 +195,128 @@ int pg_gather_rows(pg_ctx* ctx, int dtype, const void* src, const int32_t* idx, 
 int pg_onehot(pg_ctx* ctx, int dtype, const int32_t* labels, void* out, int64_t B, int C);
 /* read a device loss scalar of type T (the step's only host sync) */
 int pg_loss_read(pg_ctx* ctx, int dtype, const void* loss_dev, double* result);
+
+
+/* training-mode dropout on padded / mixed-type tensors: logical [rows][cols] elements, row pitches in elements;
+ * in_dtype / out_dtype in {PG_F32, PG_F64, PG_BF16} (a cast, a zero-padding copy and the mask in one pass; p = 0
+ * makes it a plain cast / pad copy).  Element (r, c) draws the same number pg_dropout draws for index r*cols + c. */
+int pg_dropout_ex(pg_ctx* ctx, int in_dtype, int out_dtype, const void* x, void* y, int64_t rows, int64_t cols, int64_t in_pitch, int64_t out_pitch,
+                  double p, uint64_t seed, uint32_t stream_id, uint64_t elem_offset);
+/* pg_tc_linear_bwd_ex with a selectable data-gradient type: dx_dtype PG_BF16 (feeds another tensor-core Linear) or
+ * PG_F32 (feeds a pooling / conv / fp32 layer). */
+int pg_tc_linear_bwd2(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX, int dx_dtype,
+                      const void* relu_mask, int64_t M, int64_t K, int64_t N);
+
+/* ---- parameter arenas: all leaves of a Model in one device block in vec(m) order (src/model.jl:9-24,33) -------------
+ * Each leaf start is padded to 32 elements; padding is zero and invisible to length / flat indexing / dot.
+ * `leaf` arguments: 0-based leaf index, or -1 = the whole arena in vec(m) order (padding skipped). */
+int pg_arena_create(pg_ctx* ctx, int dtype, int n_leaves, const int64_t* leaf_sizes, pg_arena** arena);
+/* a non-owning arena handle over device memory the host already laid out with the same rule (leaf starts padded to 32 elements) */
+int pg_arena_wrap(pg_ctx* ctx, int dtype, int n_leaves, const int64_t* leaf_sizes, void* base, pg_arena** arena);
+int pg_arena_destroy(pg_arena* arena);
+/* mode 0 = similar (uninitialised -> zero-filled), 1 = zero, 2 = copy          (model.jl:49-56) */
+int pg_arena_like(pg_arena* src, int mode, pg_arena** out);
+int pg_arena_info(pg_arena* arena, int* dtype, int* n_leaves, int64_t* length, int64_t* n_padded, void** base);
+int pg_arena_leaf_ptr(pg_arena* arena, int leaf, void** dptr, int64_t* size);
+int pg_arena_upload(pg_arena* arena, int leaf, const void* host);             /* synchronising */
+int pg_arena_download(pg_arena* arena, int leaf, void* host);                 /* synchronising: vec(m), model.jl:33 */
+int pg_arena_get_scalar(pg_arena* arena, int64_t flat_index, double* value);  /* m[i], model.jl:79-88 (0-based here) */
+int pg_arena_set_scalar(pg_arena* arena, int64_t flat_index, double value);   /* m[i] = v, model.jl:90-99 */
+
+/* ---- generic Model broadcast (src/model.jl:148-164): out .= f(args...) for ANY flattened scalar function f --------
+ * `code` is a postfix program evaluated once per element on a small register stack.  Every value on the stack
+ * carries Julia's promoted type (the leaf eltype T or Float64): an op on two T values
+ * rounds to T, an op involving a Float64 value is done in Float64; the final value is rounded to T on store.
+ *   instruction word = opcode | (operand << 8)
+ *   PG_BC_ARG k      push arena operand k (type T)          PG_BC_CONST k   push consts[k] as Float64
+ *   PG_BC_CONST_T k  push consts[k] rounded to T (an Int / T-typed Julia scalar)    PG_BC_CONST_F32 k  push it as a Float32 scalar
+ *   binary: ADD SUB MUL DIV MAX MIN POW      unary: NEG SQRT ABS EXP LOG SQUARE RELU INV
+ * dtype in {PG_F16, PG_F32, PG_F64}.  n = padded arena length; padding stays zero when `zero_padding` gives the
+ * arena's leaf layout (n_leaves, leaf_sizes) — pass n_leaves = 0 if f(0,...) == 0. */
+enum { PG_BC_ARG = 1, PG_BC_CONST = 2, PG_BC_CONST_T = 3, PG_BC_CONST_F32 = 4, PG_BC_ADD = 10, PG_BC_SUB = 11, PG_BC_MUL = 12, PG_BC_DIV = 13, PG_BC_MAX = 14,
+       PG_BC_MIN = 15, PG_BC_POW = 16, PG_BC_NEG = 30, PG_BC_SQRT = 31, PG_BC_ABS = 32, PG_BC_EXP = 33, PG_BC_LOG = 34, PG_BC_SQUARE = 35,
+       PG_BC_RELU = 36, PG_BC_INV = 37 };
+int pg_vec_expr(pg_ctx* ctx, int dtype, void* out, const void* const* args, int n_args, const int32_t* code, int n_code,
+                const double* consts, int n_consts, int64_t n, int n_leaves, const int64_t* leaf_sizes);
+
+/* ---- the training-step plan: eval_with_pullback behind the ABI (src/gradient.jl:1-13, ext/ProtoGradZygoteExt.jl:6-13) ----
+ * The host language traces `f(m)` once (its layer calls record ops) and hands the recorded graph over; the plan fuses
+ * it (Linear/Conv + bias + ReLU, softmax + cross-entropy across the model/loss boundary with dZ produced in the same
+ * kernel, ReLU' into the upstream data-gradient epilogue), picks the kernel per layer (FP32/FP64 SIMT or bf16 tcgen05),
+ * owns the activation / gradient buffers and launches everything.  Sequential graphs only (every intermediate value
+ * has one consumer), which is every model `Compose` builds (src/layers.jl:63-75). */
+typedef enum { PG_MATH_FP32 = 0, PG_MATH_BF16 = 1 } pg_math_mode;
+typedef enum {
+  PG_OP_INPUT = 0,      /* a tensor the closure captured: minibatch, labels (dtype PG_F32/PG_F64, PG_BF16 pre-cast inputs, PG_I32 class indices) */
+  PG_OP_PARAM = 1,      /* a Model leaf; grad_leaf >= 0 when it belongs to the differentiated model */
+  PG_OP_LINEAR = 2,     /* in = {x, W, b}                 layers.jl:28-34 */
+  PG_OP_CONV2D = 3,     /* in = {x, w, b}                 layers.jl:59 */
+  PG_OP_RELU = 4,       /* layers.jl:81 */
+  PG_OP_MAXPOOL = 5,    /* window k                       layers.jl:93 */
+  PG_OP_MEANPOOL = 6,   /* layers.jl:99 */
+  PG_OP_RESHAPE = 7,    /* no-op on memory                layers.jl:105, examples/02_mnist_conv.jl:34 */
+  PG_OP_DROPOUT = 8,    /* probability p, training mode   layers.jl:118-132 */
+  PG_OP_SOFTMAX = 9,    /* over the last (class) axis     layers.jl:87 */
+  PG_OP_LOSS_CE = 10,   /* in = {probs, labels}           losses.jl:7-10; denom = global batch (0: this batch) */
+  PG_OP_LOSS_MSE = 11   /* in = {output, labels}          losses.jl:5;    denom = divisor (0: number of elements) */
+} pg_op_kind;
+typedef struct pg_op {
+  int32_t kind;
+  int32_t dtype;
+  int32_t in[3];        /* node indices, -1 = unused */
+  int32_t ndim;
+  int64_t shape[4];     /* C order */
+  int32_t grad_leaf;    /* PG_OP_PARAM: index of its gradient leaf in vec(m) order, -1 = frozen / captured model */
+  int32_t k;
+  double p;
+  double denom;
+} pg_op;
+/* node flags reported by pg_plan_node_flags */
+enum { PG_NODE_NEEDED = 1, PG_NODE_NEEDS_GRAD = 2, PG_NODE_TENSOR_CORE = 4, PG_NODE_FUSED_ACT = 8, PG_NODE_BF16_VALUE = 16, PG_NODE_FUSED_AWAY = 32 };
+typedef void (*pg_ready_fn)(void* user, int first_grad_leaf);
+
+/* Host-only (callable without a GPU): buffers are allocated by the first pg_plan_forward. */
+int pg_plan_create(pg_ctx* ctx, const pg_op* ops, int n_ops, int root, int math_mode, pg_plan** plan);
+int pg_plan_destroy(pg_plan* plan);
+int pg_plan_node_flags(pg_plan* plan, int node, int* flags);
+/* leaf_ptrs[i]: device pointer of INPUT / PARAM node i (ignored for other nodes).  leaf_bf16[i] (array nullable, entries
+ * nullable): a VALID bf16 copy of PARAM node i (e.g. written by the fused optimizer pass, pg_opt_* shadow_bf16); NULL lets
+ * the plan cast the leaf itself.  (rng_seed, rng_step, sample_offset) key the dropout masks (sample_offset = global index
+ * of this process's first sample, so data-parallel shards draw the full batch's masks).  *loss_dev: device scalar of
+ * the model dtype (read it with pg_loss_read; slots rotate, a handle stays valid for 64 forwards).  *generation
+ * identifies this forward: pg_plan_backward rejects any other (a stale pullback). */
+int pg_plan_forward(pg_plan* plan, const void* const* leaf_ptrs, const void* const* leaf_bf16, uint64_t rng_seed, uint64_t rng_step,
+                    int64_t sample_offset, void** loss_dev, int64_t* generation);
+/* grad_leaf_ptrs[j]: where dL/d(leaf j) is WRITTEN (vec(m) order; normally leaves of one gradient arena).
+ * on_ready(user, j) (nullable) fires once every gradient leaf >= j has been enqueued (layers finish last-to-first):
+ * the data-parallel caller starts reducing that slice of the arena while the remaining backward kernels run. */
+int pg_plan_backward(pg_plan* plan, int64_t generation, void* const* grad_leaf_ptrs, int n_grad_leaves, pg_ready_fn on_ready, void* user);
+/* device pointer / dtype of a node's value after pg_plan_forward (inference: `m(test_x)`) */
+int pg_plan_value(pg_plan* plan, int node, void** dptr, int* dtype, int64_t* pitch);
+
+/* ---- data parallelism: one process per GPU; the only exchange of the path is the sum of the
+ * flat gradient arena over ranks, followed by the identical fused update on every rank ---------------------------------
+ * The communicator is this library's own (libnccl is dlopen'ed; PG_NCCL_LIB overrides the path): rank 0 creates an id,
+ * the host distributes its 128 bytes (MPI / a file / torch.distributed's store), every rank calls pg_dp_init. */
+int pg_dp_unique_id(void* id128);
+int pg_dp_init(pg_ctx* ctx, int rank, int world, const void* id128, int max_ctas, pg_dp** dp);
+int pg_dp_destroy(pg_dp* dp);
+int pg_dp_info(pg_dp* dp, int* rank, int* world, int* nccl_version, int* p2p);
+/* in-place sum over ranks of buf[0..count) on the communicator's stream, ordered after everything enqueued on the ctx
+ * stream so far; pg_dp_wait makes the ctx stream wait for all outstanding collectives. */
+int pg_dp_allreduce(pg_dp* dp, void* buf, int64_t count, int dtype);
+int pg_dp_broadcast(pg_dp* dp, void* buf, int64_t count, int dtype, int root);
+int pg_dp_wait(pg_dp* dp);
+/* bucketed, overlapped reduction of a gradient arena during pg_plan_backward: pass pg_dp_bucket_ready / the bucket
+ * handle as on_ready / user.  A bucket is issued once >= bucket_bytes of finished leaves have accumulated. */
+int pg_dp_bucket_begin(pg_dp* dp, pg_arena* grads, int64_t bucket_bytes);
+void pg_dp_bucket_ready(void* dp, int first_grad_leaf);
+/* number of issued buckets; ranges as (start element, count) of the padded arena, in issue order (tail first) */
+int pg_dp_bucket_finish(pg_dp* dp, int* n_buckets, int64_t* starts, int64_t* counts, int max_buckets);
+int pg_dp_bucket_wait(pg_dp* dp, int bucket);   /* ctx stream waits for bucket k's reduction */
+/* the bucket policy as a pure host function (no GPU): slices issued for a sequence of on_ready leaf indices */
+int pg_dp_bucket_plan(int dtype, int n_leaves, const int64_t* leaf_sizes, int64_t bucket_bytes, const int* ready_leaves, int n_ready,
+                      int64_t* starts, int64_t* counts, int max_buckets, int* n_buckets);
 
 #ifdef __cplusplus
 }

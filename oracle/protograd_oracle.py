@@ -258,17 +258,34 @@ def init_params(spec, dtype=np.float32, seed=0):
     return ps
 
 
-def net_forward(spec, params, x, keep=False, conv_round=None):
+def _bf16_stored(spec, ai, linear_round):
+    """is activation index `ai` (acts[ai], the output of spec[ai-1]) stored in bf16 by the tensor-core Linear mode?
+    True for the output of a wide (N > 32) Linear that is not followed by a ReLU, and for the ReLU output after one."""
+    if linear_round is None or ai == 0:
+        return False
+    op = spec[ai - 1]
+    if op[0] == "linear":
+        return op[2] > 32 and not (ai < len(spec) and spec[ai][0] == "relu")
+    if op[0] == "relu" and ai >= 2 and spec[ai - 2][0] == "linear":
+        return spec[ai - 2][2] > 32
+    return False
+
+
+def net_forward(spec, params, x, keep=False, conv_round=None, linear_round=None):
     """conv_round: optional rounding applied to the operands of every conv (x, w) — `bf16_round` restates
-    the B200 path's tensor-core conv mode (bf16 operands, exact accumulation, float outputs)."""
+    the B200 path's tensor-core conv mode (bf16 operands, exact accumulation, float outputs).
+    linear_round: the same for Linear layers in the tensor-core mode: operands (x, W) rounded, products accumulated
+    exactly, the activation of a wide (N > 32) layer stored rounded (after its fused ReLU), narrow layers (the logits)
+    kept in float."""
     cr = conv_round if conv_round is not None else (lambda a: a)
+    lr = linear_round if linear_round is not None else (lambda a: a)
     acts = [x]
     pi = 0
     y = x
-    for op in spec:
+    for li, op in enumerate(spec):
         kind = op[0]
         if kind == "linear":
-            y = linear_fwd(y, params[pi], params[pi + 1]); pi += 2
+            y = linear_fwd(lr(y), lr(params[pi]), params[pi + 1]); pi += 2
         elif kind == "conv":
             y = conv2d_fwd(cr(y), cr(params[pi]), params[pi + 1]); pi += 2
         elif kind == "relu":
@@ -283,17 +300,21 @@ def net_forward(spec, params, x, keep=False, conv_round=None):
             y = softmax_fwd(y)
         else:
             raise ValueError(kind)
+        if _bf16_stored(spec, li + 1, linear_round):
+            y = lr(y)
         acts.append(y)
     return (y, acts) if keep else y
 
 
-def net_loss_and_grad(spec, params, x, label, loss="ce", global_batch=None, mse_denom=None, conv_round=None):
+def net_loss_and_grad(spec, params, x, label, loss="ce", global_batch=None, mse_denom=None, conv_round=None, linear_round=None):
     """One eval_with_pullback(f, m) + pb(): returns (loss, grads) with grads in vec(m) leaf order.
     Non-trainable leaves get a zero gradient and back-propagation stops below the first
     trainable layer (the reference computes-and-discards that dX; values are identical).
-    conv_round: see net_forward; the conv pullbacks then see rounded x, w and dy as well."""
+    conv_round / linear_round: see net_forward; the pullbacks then see rounded x, w and dy as well, and the gradient
+    of a bf16-stored activation is itself stored rounded (after the ReLU' mask)."""
     cr = conv_round if conv_round is not None else (lambda a: a)
-    out, acts = net_forward(spec, params, x, keep=True, conv_round=conv_round)
+    lr = linear_round if linear_round is not None else (lambda a: a)
+    out, acts = net_forward(spec, params, x, keep=True, conv_round=conv_round, linear_round=linear_round)
     if loss == "ce":
         val = cross_entropy(out, label, global_batch)
         d = cross_entropy_bwd(out, label, global_batch)
@@ -318,11 +339,14 @@ def net_loss_and_grad(spec, params, x, label, loss="ce", global_batch=None, mse_
         if kind == "linear":
             pi -= 2
             need_dx = pi > first_train_pi
-            dW, db, dx = linear_bwd(xin, params[pi], d, need_dx)
+            dW, _, dx = linear_bwd(lr(xin), lr(params[pi]), lr(d), need_dx)
+            db = d.reshape(-1, params[pi].shape[1]).sum(axis=0, dtype=d.dtype)   # the bias gradient sums the STORED dY (float for narrow layers)
             grads[pi], grads[pi + 1] = (dW, db) if train[pi] else (np.zeros_like(params[pi]), np.zeros_like(params[pi + 1]))
             if not need_dx:
                 break
             d = dx
+            if _bf16_stored(spec, li, linear_round) and spec[li - 1][0] == "linear":
+                d = lr(d)
         elif kind == "conv":
             pi -= 2
             need_dx = pi > first_train_pi
@@ -333,6 +357,8 @@ def net_loss_and_grad(spec, params, x, label, loss="ce", global_batch=None, mse_
             d = dx
         elif kind == "relu":
             d = relu_bwd(yout, d)
+            if _bf16_stored(spec, li + 1, linear_round):
+                d = lr(d)
         elif kind == "maxpool":
             d = maxpool2d_bwd(xin, d, (op[1], op[1]))
         elif kind == "meanpool":

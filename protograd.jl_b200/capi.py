@@ -10,7 +10,7 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libprotograd_b200.so")
 
-PG_F32, PG_F64, PG_BF16 = 0, 1, 2
+PG_F32, PG_F64, PG_BF16, PG_F16, PG_I32 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU = 0, 1
 ADD, SUB = 0, 1
 X_PLUS_C, X_MINUS_C, C_MINUS_X, X_TIMES_C, X_OVER_C, C_OVER_X = range(6)
@@ -41,7 +41,6 @@ _SIGS = {
     "pg_launch_count": [_P, POINTER(c_int64)],
     "pg_reserve_workspace": [_P, _Z],
     "pg_set_sm_limit": [_P, _I],
-    "pg_delay_on": [_P, _P, ctypes.c_longlong],
     "pg_malloc": [_P, _Z, POINTER(_P)],
     "pg_free": [_P, _P],
     "pg_memset0": [_P, _P, _Z],
@@ -102,14 +101,51 @@ _SIGS = {
     "pg_gather_rows": [_P, _I, _P, _P, _P, _L, _L],
     "pg_onehot": [_P, _I, _P, _P, _L, _I],
     "pg_loss_read": [_P, _I, _P, POINTER(c_double)],
+    "pg_dropout_ex": [_P, _I, _I, _P, _P, _L, _L, _L, _L, _D, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64],
+    "pg_tc_linear_bwd2": [_P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _L, _L, _L],
+    "pg_arena_create": [_P, _I, _I, POINTER(c_int64), POINTER(_P)],
+    "pg_arena_wrap": [_P, _I, _I, POINTER(c_int64), _P, POINTER(_P)],
+    "pg_arena_destroy": [_P],
+    "pg_arena_like": [_P, _I, POINTER(_P)],
+    "pg_arena_info": [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int64), POINTER(c_int64), POINTER(_P)],
+    "pg_arena_leaf_ptr": [_P, _I, POINTER(_P), POINTER(c_int64)],
+    "pg_arena_upload": [_P, _I, _P],
+    "pg_arena_download": [_P, _I, _P],
+    "pg_arena_get_scalar": [_P, _L, POINTER(c_double)],
+    "pg_arena_set_scalar": [_P, _L, _D],
+    "pg_vec_expr": [_P, _I, _P, POINTER(_P), _I, POINTER(c_int32), _I, POINTER(c_double), _I, _L, _I, POINTER(c_int64)],
+    "pg_plan_create": [_P, _P, _I, _I, _I, POINTER(_P)],
+    "pg_plan_destroy": [_P],
+    "pg_plan_node_flags": [_P, _I, POINTER(c_int)],
+    "pg_plan_forward": [_P, _P, _P, ctypes.c_uint64, ctypes.c_uint64, _L, POINTER(_P), POINTER(c_int64)],
+    "pg_plan_backward": [_P, _L, _P, _I, _P, _P],
+    "pg_plan_value": [_P, _I, POINTER(_P), POINTER(c_int), POINTER(c_int64)],
+    "pg_dp_unique_id": [_P],
+    "pg_dp_init": [_P, _I, _I, _P, _I, POINTER(_P)],
+    "pg_dp_destroy": [_P],
+    "pg_dp_info": [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)],
+    "pg_dp_allreduce": [_P, _P, _L, _I],
+    "pg_dp_broadcast": [_P, _P, _L, _I, _I],
+    "pg_dp_wait": [_P],
+    "pg_dp_bucket_begin": [_P, _P, _L],
+    "pg_dp_bucket_finish": [_P, POINTER(c_int), POINTER(c_int64), POINTER(c_int64), _I],
+    "pg_dp_bucket_wait": [_P, _I],
+    "pg_dp_bucket_plan": [_I, _I, POINTER(c_int64), _L, POINTER(c_int), _I, POINTER(c_int64), POINTER(c_int64), _I, POINTER(c_int)],
 }
+_VOID = {"pg_dp_bucket_ready": [_P, _I]}
 
-EXPORTS = tuple(_SIGS) + ("pg_last_error",)
+EXPORTS = tuple(_SIGS) + tuple(_VOID) + ("pg_last_error",)
 
 for _name, _args in _SIGS.items():
     _f = getattr(lib, _name)  # AttributeError here == header/library drift, which must be loud
     _f.argtypes = _args
     _f.restype = c_int
+
+
+for _name, _args in _VOID.items():
+    _f = getattr(lib, _name)
+    _f.argtypes = _args
+    _f.restype = None
 
 
 def check(rc):

@@ -10,8 +10,6 @@
 
 namespace {
 
-enum { PG_SCALAR2_F64 = 2, PG_MATH_FAST = 4 };
-
 template <typename P> struct Ar;
 template <> struct Ar<float> {
   static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
@@ -294,7 +292,9 @@ int axpy_t(pg_ctx* ctx, void* out, const void* x, double s, const void* g, int s
 extern "C" {
 
 int pg_vec_binary(pg_ctx* ctx, int dtype, int op, void* out, const void* x, const void* y, int64_t n) {
-  PG_CHECK_CTX(ctx); PG_DTYPE_FLOAT_ONLY(dtype);
+  PG_CHECK_CTX(ctx);
+  if (dtype == PG_F16) return pg_f16_vec_binary(ctx, op, out, x, y, n);
+  PG_DTYPE_FLOAT_ONLY(dtype);
   PG_REQUIRE(op == PG_ADD || op == PG_SUB, "unknown op");
   Ptrs<2> in{{x, y}}; MPtrs<1> o{{out}};
   if (dtype == PG_F32) {
@@ -306,27 +306,35 @@ int pg_vec_binary(pg_ctx* ctx, int dtype, int op, void* out, const void* x, cons
 }
 
 int pg_vec_scalar(pg_ctx* ctx, int dtype, int op, void* out, const void* x, double c, int flags, int64_t n) {
-  PG_CHECK_CTX(ctx); PG_DTYPE_FLOAT_ONLY(dtype);
+  PG_CHECK_CTX(ctx);
+  if (dtype == PG_F16) return pg_f16_vec_scalar(ctx, op, out, x, c, flags, n);
+  PG_DTYPE_FLOAT_ONLY(dtype);
   return dtype == PG_F32 ? scalar_op<float>(ctx, op, out, x, c, flags, n) : scalar_op<double>(ctx, op, out, x, c, flags, n);
 }
 
 int pg_vec_axpy(pg_ctx* ctx, int dtype, void* out, const void* x, double s, const void* g, int sign, int flags, int64_t n) {
-  PG_CHECK_CTX(ctx); PG_DTYPE_FLOAT_ONLY(dtype);
+  PG_CHECK_CTX(ctx);
+  if (dtype == PG_F16) return pg_f16_vec_axpy(ctx, out, x, s, g, sign, flags, n);
+  PG_DTYPE_FLOAT_ONLY(dtype);
   if (dtype == PG_F64) return axpy_t<double, double>(ctx, out, x, s, g, sign, n, nullptr);
   if (flags & PG_SCALAR_F64) return axpy_t<float, double>(ctx, out, x, s, g, sign, n, nullptr);
   return axpy_t<float, float>(ctx, out, x, s, g, sign, n, nullptr);
 }
 
 int pg_vec_fill(pg_ctx* ctx, int dtype, void* out, double c, int64_t n) {
-  PG_CHECK_CTX(ctx); PG_DTYPE_FLOAT_ONLY(dtype);
+  PG_CHECK_CTX(ctx);
+  if (dtype == PG_F16) return pg_f16_vec_fill(ctx, out, c, n);
+  PG_DTYPE_FLOAT_ONLY(dtype);
   Ptrs<0> in{}; MPtrs<1> o{{out}};
   if (dtype == PG_F32) return ew_launch<float, 0, 1>(ctx, FillF<float>{(float)c}, in, o, nullptr, n);
   return ew_launch<double, 0, 1>(ctx, FillF<double>{c}, in, o, nullptr, n);
 }
 
 int pg_vec_dot(pg_ctx* ctx, int dtype, const void* x, const void* y, int64_t n, double* result) {
-  PG_CHECK_CTX(ctx); PG_DTYPE_FLOAT_ONLY(dtype);
+  PG_CHECK_CTX(ctx);
   PG_REQUIRE(result != nullptr, "null result");
+  if (dtype == PG_F16) return pg_f16_vec_dot(ctx, x, y, n, result);
+  PG_DTYPE_FLOAT_ONLY(dtype);
   PG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "pointers must be 16-byte aligned");
   if (n <= 0) { *result = 0.0; return PG_OK; }
   int64_t blocks = pg_cdiv(pg_cdiv(n, 4), 256);

@@ -128,23 +128,6 @@ int pg_set_sm_limit(pg_ctx* ctx, int n) {
   ctx->num_sms = (n <= 0 || n > ctx->real_sms) ? ctx->real_sms : n;
   return PG_OK;
 }
-// One thread that sleeps for `ns` nanoseconds of %globaltimer: inserted on a side stream in front of a
-// collective so that the GEMM launched at the same stream-order point has claimed its SM pairs first.
-__global__ void delay_kernel(unsigned long long ns) {
-  unsigned long long t0, t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  do {
-    __nanosleep(500);
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  } while (t - t0 < ns);
-}
-int pg_delay_on(pg_ctx* ctx, void* stream, long long ns) {
-  PG_CHECK_CTX(ctx);
-  PG_REQUIRE(ns >= 0 && ns <= 1000000, "pg_delay_on: delay must be within [0, 1 ms]");
-  delay_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long)ns);
-  PG_LAUNCHED(ctx);
-  return PG_OK;
-}
 int pg_reserve_workspace(pg_ctx* ctx, size_t bytes) {
   PG_CHECK_CTX(ctx);
   return pg_ws_ensure(ctx, bytes);

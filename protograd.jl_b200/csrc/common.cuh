@@ -70,6 +70,13 @@ template <typename T> int pg_conv_fwd_tiled(pg_ctx* ctx, const T* x, const T* w,
 template <typename T> int pg_conv_dgrad_tiled(pg_ctx* ctx, const T* dy, const T* w, T* dx, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW);
 template <typename T> int pg_conv_wgrad_tiled(pg_ctx* ctx, const T* x, const T* dy, T* dw, T* db, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW);
 
+// Float16 arenas (arena.cu): the fixed-function algebra entry points lowered onto the expression interpreter
+int pg_f16_vec_binary(pg_ctx* ctx, int op, void* out, const void* x, const void* y, int64_t n);
+int pg_f16_vec_scalar(pg_ctx* ctx, int op, void* out, const void* x, double c, int flags, int64_t n);
+int pg_f16_vec_axpy(pg_ctx* ctx, void* out, const void* x, double s, const void* g, int sign, int flags, int64_t n);
+int pg_f16_vec_fill(pg_ctx* ctx, void* out, double c, int64_t n);
+int pg_f16_vec_dot(pg_ctx* ctx, const void* x, const void* y, int64_t n, double* result);
+
 static inline int64_t pg_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers ------------------------------------------------------------------------

@@ -466,3 +466,78 @@ extern "C" int pg_dropout(pg_ctx* ctx, int dtype, const void* x, void* y, int64_
   PG_LAUNCHED(ctx);
   return PG_OK;
 }
+
+
+// ---- dropout / cast / zero-padding copy on pitched, mixed-type tensors (pg_dropout_ex) ---------------------------
+namespace {
+
+template <typename T> __device__ __forceinline__ float ld_as_f32(const T* p, int64_t i) { return (float)p[i]; }
+template <> __device__ __forceinline__ float ld_as_f32<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+template <typename T> __device__ __forceinline__ void st_from_f32(T* p, int64_t i, float v) { p[i] = (T)v; }
+template <> __device__ __forceinline__ void st_from_f32<__nv_bfloat16>(__nv_bfloat16* p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// One thread per group of 4 consecutive LOGICAL elements (row-major over [rows][cols]); element e draws lane e & 3 of
+// Philox counter e >> 2, exactly like dropout_kernel, so a padded / bf16 tensor gets the mask its fp32 twin would.
+// Float64 tensors keep double arithmetic (TI == TO == double).
+template <typename TI, typename TO, bool DROP>
+__global__ void __launch_bounds__(256) dropout_ex_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t rows, int64_t cols, int64_t ipitch, int64_t opitch,
+                                                         float p, double scale, uint64_t seed, uint32_t stream_id, uint64_t elem_offset) {
+  const int64_t n = rows * cols;
+  const int64_t ngroups = (n + 3) / 4;
+  for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < ngroups; gidx += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t rr[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    if (DROP) {
+      const uint64_t ctr = (elem_offset + (uint64_t)gidx * 4) >> 2;
+      const uint4 r = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), stream_id, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+      rr[0] = r.x; rr[1] = r.y; rr[2] = r.z; rr[3] = r.w;
+    }
+    int64_t i = gidx * 4;
+    int64_t row = i / cols, col = i - row * cols;
+#pragma unroll
+    for (int j = 0; j < 4; ++j, ++i) {
+      if (i >= n) break;
+      bool keep = true;
+      if (DROP) keep = (float)(rr[j] >> 8) * (1.0f / 16777216.0f) > p;
+      if constexpr (sizeof(TI) == 8) {
+        const double v = (double)x[row * ipitch + col];
+        y[row * opitch + col] = (TO)(keep ? (DROP ? v * scale : v) : 0.0);
+      } else {
+        const float v = ld_as_f32<TI>(x, row * ipitch + col);
+        st_from_f32<TO>(y, row * opitch + col, keep ? (DROP ? v * (float)scale : v) : 0.0f);
+      }
+      if (++col == cols) { col = 0; ++row; }
+    }
+  }
+}
+
+template <typename TI, typename TO>
+int launch_dropout_ex(pg_ctx* ctx, const void* x, void* y, int64_t rows, int64_t cols, int64_t ip, int64_t op, double p, uint64_t seed, uint32_t stream_id, uint64_t off) {
+  const int64_t groups = (rows * cols + 3) / 4;
+  const double scale = 1.0 / (1.0 - p);
+  if (p > 0.0)
+    dropout_ex_kernel<TI, TO, true><<<grid_for(ctx, groups), 256, 0, ctx->stream>>>((const TI*)x, (TO*)y, rows, cols, ip, op, (float)p, scale, seed, stream_id, off);
+  else
+    dropout_ex_kernel<TI, TO, false><<<grid_for(ctx, groups), 256, 0, ctx->stream>>>((const TI*)x, (TO*)y, rows, cols, ip, op, 0.0f, 1.0, 0, 0, 0);
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
+}  // namespace
+
+extern "C" int pg_dropout_ex(pg_ctx* ctx, int in_dtype, int out_dtype, const void* x, void* y, int64_t rows, int64_t cols, int64_t in_pitch, int64_t out_pitch,
+                             double p, uint64_t seed, uint32_t stream_id, uint64_t elem_offset) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(x && y, "null pointer");
+  PG_REQUIRE(p >= 0.0 && p < 1.0, "dropout probability must be in [0, 1)");
+  PG_REQUIRE((elem_offset & 3) == 0, "element offset must be a multiple of 4");
+  PG_REQUIRE(in_pitch >= cols && out_pitch >= cols, "row pitch smaller than the row");
+  if (rows <= 0 || cols <= 0) return PG_OK;
+  typedef __nv_bfloat16 bf;
+  if (in_dtype == PG_F32 && out_dtype == PG_F32) return launch_dropout_ex<float, float>(ctx, x, y, rows, cols, in_pitch, out_pitch, p, seed, stream_id, elem_offset);
+  if (in_dtype == PG_F32 && out_dtype == PG_BF16) return launch_dropout_ex<float, bf>(ctx, x, y, rows, cols, in_pitch, out_pitch, p, seed, stream_id, elem_offset);
+  if (in_dtype == PG_BF16 && out_dtype == PG_BF16) return launch_dropout_ex<bf, bf>(ctx, x, y, rows, cols, in_pitch, out_pitch, p, seed, stream_id, elem_offset);
+  if (in_dtype == PG_BF16 && out_dtype == PG_F32) return launch_dropout_ex<bf, float>(ctx, x, y, rows, cols, in_pitch, out_pitch, p, seed, stream_id, elem_offset);
+  if (in_dtype == PG_F64 && out_dtype == PG_F64) return launch_dropout_ex<double, double>(ctx, x, y, rows, cols, in_pitch, out_pitch, p, seed, stream_id, elem_offset);
+  pg_set_error("pg_dropout_ex: unsupported dtype pair (%d -> %d)", in_dtype, out_dtype);
+  return PG_ERR_UNSUPPORTED;
+}

@@ -891,7 +891,8 @@ int narrow_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, void* Z
   return launch_tc<false, false, NARROW_N>(ctx, X, Wt, Z, M, N, K, K, K, epi);
 }
 
-int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* dW, void* db, void* dX, const void* mask, void* dx_colsum, int64_t M, int64_t K, int64_t N) {
+int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* dW, void* db, void* dX, const void* mask, void* dx_colsum, int64_t M, int64_t K, int64_t N,
+               int dx_f32 = 0) {
   PG_REQUIRE(K % 8 == 0 && M % 8 == 0, "narrow tensor-core layer needs K % 8 == 0 and batch % 8 == 0 (TMA 16-byte pitch)");
   const size_t dzp_bytes = align256((size_t)M * NARROW_K * 2), dzt_bytes = align256((size_t)NARROW_N * M * 2), wp_bytes = align256((size_t)K * NARROW_K * 2);
   // layout of the scratch: [W^T padded (forward)] [dZ padded] [dZ^T padded] [W padded]
@@ -939,7 +940,7 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
     pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, Wp, nullptr, K, (int)N, NARROW_K, 0);
     PG_LAUNCHED(ctx);
     if (dx_colsum) PG_CHECK_CUDA(cudaMemsetAsync(dx_colsum, 0, (size_t)K * sizeof(float), ctx->stream));
-    Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, 0, 0, (float*)dx_colsum, nullptr, 1, 1 << 30};
+    Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, dx_f32, 0, (float*)dx_colsum, nullptr, 1, 1 << 30};
     rc = launch_tc<false, false, 256>(ctx, dZp, Wp, dX, M, K, NARROW_K, NARROW_K, NARROW_K, epi);
     if (rc != PG_OK) return rc;
   }
@@ -970,16 +971,17 @@ int pg_tc_linear_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, v
   return tc_dispatch(ctx, 0, X, W, Y, M, N, K, epi);
 }
 
-int pg_tc_linear_bwd_ex(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
-                        const void* relu_mask, void* dx_colsum, int64_t M, int64_t K, int64_t N) {
+static int tc_linear_bwd_impl(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX, int dx_dtype,
+                              const void* relu_mask, void* dx_colsum, int64_t M, int64_t K, int64_t N) {
   PG_CHECK_CTX(ctx);
+  PG_REQUIRE(dx_dtype == PG_BF16 || dx_dtype == PG_F32, "dX must be bf16 or f32");
   PG_REQUIRE(dY != nullptr, "null dY");
   PG_REQUIRE(!dW || X, "dW needs X");
   PG_REQUIRE(!dX || W, "dX needs W");
   PG_REQUIRE(!dx_colsum || dX, "dx_colsum needs dX");
   if (N <= 32) {
     PG_REQUIRE(dy_dtype == PG_F32, "narrow layers (N <= 32) take f32 dY");
-    return narrow_bwd(ctx, X, W, dY, dW, db, dX, relu_mask, dx_colsum, M, K, N);
+    return narrow_bwd(ctx, X, W, dY, dW, db, dX, relu_mask, dx_colsum, M, K, N, dx_dtype == PG_F32);
   }
   PG_REQUIRE(dy_dtype == PG_BF16, "wide layers take bf16 dY");
   int rc;
@@ -999,16 +1001,26 @@ int pg_tc_linear_bwd_ex(pg_ctx* ctx, const void* X, const void* W, const void* d
   }
   if (dX) {  // dX[M][K] = dY W^T: GEMM (M'=M, N'=K, K'=N), A = dY [M][N] K-major, B = W [K][N] K-major
     if (dx_colsum) PG_CHECK_CUDA(cudaMemsetAsync(dx_colsum, 0, (size_t)K * sizeof(float), ctx->stream));
-    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, 0, 0, (float*)dx_colsum, nullptr, 1, 1 << 30};
+    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, dx_dtype == PG_F32, 0, (float*)dx_colsum, nullptr, 1, 1 << 30};
     rc = tc_dispatch(ctx, 1, dY, W, dX, M, K, N, epi);
     if (rc != PG_OK) return rc;
   }
   return PG_OK;
 }
 
+int pg_tc_linear_bwd_ex(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
+                        const void* relu_mask, void* dx_colsum, int64_t M, int64_t K, int64_t N) {
+  return tc_linear_bwd_impl(ctx, X, W, dY, dy_dtype, dW, db, dX, PG_BF16, relu_mask, dx_colsum, M, K, N);
+}
+
 int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
                      const void* relu_mask, int64_t M, int64_t K, int64_t N) {
-  return pg_tc_linear_bwd_ex(ctx, X, W, dY, dy_dtype, dW, db, dX, relu_mask, nullptr, M, K, N);
+  return tc_linear_bwd_impl(ctx, X, W, dY, dy_dtype, dW, db, dX, PG_BF16, relu_mask, nullptr, M, K, N);
+}
+
+int pg_tc_linear_bwd2(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX, int dx_dtype,
+                      const void* relu_mask, int64_t M, int64_t K, int64_t N) {
+  return tc_linear_bwd_impl(ctx, X, W, dY, dy_dtype, dW, db, dX, dx_dtype, relu_mask, nullptr, M, K, N);
 }
 
 }  // extern "C"

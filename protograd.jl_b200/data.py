@@ -75,4 +75,10 @@ def load(path, model, state=None):
                 getattr(state, name).set_vec(z["state_" + name])
         if "it" in z.files:
             state.it = int(z["it"])
+        if "pops" in z.files and hasattr(state, "advance"):
+            # Nesterov: re-advance the momentum sequence to where the checkpointed run stood
+            from .optimizers import NesterovMomentumSequence
+            state.momentum_iterator = iter(state.optimizer.momentum_sequence)
+            state._pops = 0
+            state.advance(int(z["pops"]))
     return model

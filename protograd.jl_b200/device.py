@@ -8,7 +8,8 @@ import numpy as np
 from . import capi
 from .capi import PG_BF16, PG_F32, PG_F64, call
 
-_DT = {np.dtype(np.float32): PG_F32, np.dtype(np.float64): PG_F64}
+PG_F16, PG_I32 = 3, 4
+_DT = {np.dtype(np.float32): PG_F32, np.dtype(np.float64): PG_F64, np.dtype(np.float16): PG_F16, np.dtype(np.int32): PG_I32}
 BF16 = "bf16"
 
 
@@ -17,7 +18,7 @@ def dtype_code(dt):
         return PG_BF16
     dt = np.dtype(dt)
     if dt not in _DT:
-        raise TypeError(f"unsupported leaf eltype {dt}: the B200 path supports Float32 and Float64")
+        raise TypeError(f"unsupported eltype {dt}: the B200 path supports Float16 / Float32 / Float64 arenas, bf16 activations and Int32 labels")
     return _DT[dt]
 
 
@@ -82,6 +83,7 @@ class DeviceBuffer:
 
     def __init__(self, ctx, nbytes, zero=True):
         self.ctx, self.nbytes = ctx, int(nbytes)
+        self.version = 0          # bumped by every host-visible mutation of the contents (see Model._mutated)
         self.ptr = ctx.malloc(max(self.nbytes, 16))
         weakref.finalize(self, Context.free, ctx, self.ptr)
         if zero and self.nbytes:
@@ -181,6 +183,7 @@ class DeviceArray:
         assert a.size == self.size, f"size mismatch {a.shape} vs {self.shape}"
         call("pg_upload", self.ctx.h, self.ptr, a.ctypes.data, a.nbytes)
         self.ctx.sync()  # `a` may be a temporary; pageable copies are staged anyway
+        self.buf.version += 1
         return self
 
     def numpy(self):

@@ -1,10 +1,23 @@
-"""Data-parallel glue: one process per GPU, the flat gradient arena is all-reduced
-in place (sum) with NCCL over NVLink through torch.distributed; each rank scales its loss/gradient
-by 1/B_global (cross_entropy(..., global_batch=...)) so the collective is a pure sum, and every rank
-then applies the identical fused optimizer update.  The reference has no distributed path; this is
-the only exchange step the training-step path has.
+"""Data-parallel glue: one process per GPU; each rank takes a batch shard and scales its loss /
+gradient by 1/B_global (cross_entropy(..., global_batch=...)), so the only exchange of the training-step path is a pure
+SUM of the flat gradient arena over ranks; every rank then applies the identical fused optimizer update.  The
+reference has no distributed path.
+
+The exchange runs behind the C ABI (csrc/dp.cu, pg_dp_*): the library's own NCCL communicator (dlopen'ed libnccl) on
+its own stream, ordered against the context's compute stream with events — no dependence on which stream the host
+framework considers "current".  `init()` bootstraps it from an already-initialised torch.distributed process group
+(its store carries the 128-byte NCCL id) or from explicit (rank, world, id) for any other launcher.
 """
+import ctypes
+import os
+import weakref
+
 import numpy as np
+
+from . import capi
+from .capi import call
+
+_DP = {}       # device -> DataParallel
 
 
 def world():
@@ -14,34 +27,91 @@ def world():
     return 0, 1
 
 
-def arena_tensor(model):
-    """zero-copy torch view of a model's whole (padded) arena"""
-    import torch
-    from .device import DeviceArray
+class DataParallel:
+    """handle of a pg_dp communicator (one per process / device)"""
+
+    def __init__(self, ctx, rank, world_size, unique_id, max_ctas=0):
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world_size)
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        h = ctypes.c_void_p()
+        call("pg_dp_init", ctx.h, self.rank, self.world, buf, int(max_ctas), ctypes.byref(h))
+        self.h = h
+        weakref.finalize(self, capi.lib.pg_dp_destroy, h)
+
+    @staticmethod
+    def unique_id():
+        buf = ctypes.create_string_buffer(128)
+        call("pg_dp_unique_id", buf)
+        return buf.raw
+
+    def nccl_version(self):
+        v = ctypes.c_int()
+        call("pg_dp_info", self.h, None, None, ctypes.byref(v), None)
+        return v.value
+
+    def allreduce(self, ptr, count, dtype_code):
+        call("pg_dp_allreduce", self.h, ptr, int(count), int(dtype_code))
+
+    def broadcast(self, ptr, count, dtype_code, root=0):
+        call("pg_dp_broadcast", self.h, ptr, int(count), int(dtype_code), int(root))
+
+    def wait(self):
+        call("pg_dp_wait", self.h)
+
+
+def init(ctx=None, rank=None, world_size=None, unique_id=None, max_ctas=None):
+    """create (or return) this process's communicator.  With torch.distributed initialised and no explicit arguments,
+    rank 0's NCCL id travels through the process group (broadcast_object_list)."""
+    from .device import Context
+    ctx = ctx or Context.get()
+    d = _DP.get(ctx.device)
+    if d is not None:
+        return d
+    if rank is None:
+        import torch.distributed as dist
+        rank, world_size = world()
+        ids = [DataParallel.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        unique_id = ids[0]
+    if max_ctas is None:
+        max_ctas = int(os.environ.get("PG_DP_MAX_CTAS", "0"))
+    d = _DP[ctx.device] = DataParallel(ctx, rank, world_size, unique_id, max_ctas)
+    return d
+
+
+def _arena_desc(model):
+    from .device import dtype_code
     ctx, base, total, leaves = model.arena()
-    flat = DeviceArray(leaves[0].buf, leaves[0].offset, (total,), leaves[0].dtype)
-    return torch.as_tensor(flat, device=f"cuda:{ctx.device}")
+    return ctx, base, total, dtype_code(leaves[0].dtype), leaves
 
 
-def allreduce_gradients(grad_model, async_op=False):
-    """in-place sum of the gradient arena over all ranks (no-op for a single process)"""
-    import torch.distributed as dist
-    rank, ws = world()
-    if ws == 1:
-        return None
-    return dist.all_reduce(arena_tensor(grad_model), op=dist.ReduceOp.SUM, async_op=async_op)
+def allreduce_gradients(grad_model, dp=None):
+    """in-place sum of the gradient arena over all ranks (no-op for a single process); the compute stream is ordered
+    behind the collective before this returns (asynchronously: no host sync)"""
+    dp = dp or (init() if world()[1] > 1 else None)
+    if dp is None or dp.world == 1:
+        return
+    ctx, base, total, code, _ = _arena_desc(grad_model)
+    dp.allreduce(base, total, code)
+    dp.wait()
+    grad_model._mutated()
 
 
-def broadcast_parameters(model, src=0):
-    import torch.distributed as dist
-    rank, ws = world()
-    if ws > 1:
-        dist.broadcast(arena_tensor(model), src=src)
+def broadcast_parameters(model, src=0, dp=None):
+    dp = dp or (init() if world()[1] > 1 else None)
+    if dp is None or dp.world == 1:
+        return
+    ctx, base, total, code, _ = _arena_desc(model)
+    dp.broadcast(base, total, code, src)
+    dp.wait()
+    model._mutated()
 
 
 def arena_checksum(model):
-    """float64 sum of the arena — replicas must agree bit-for-bit after identical updates"""
-    return float(arena_tensor(model).double().sum().item())
+    """(float64 sum, xor of the raw bits) of the arena — replicas must agree bit-for-bit after identical updates"""
+    v = model.vec()
+    bits = v.view(np.uint32 if v.dtype.itemsize == 4 else (np.uint64 if v.dtype.itemsize == 8 else np.uint16))
+    return float(v.astype(np.float64).sum()), int(np.bitwise_xor.reduce(bits))
 
 
 def shard_range(rank, world_size, global_batch):
@@ -62,132 +132,92 @@ def allreduce_host(flat, group=None):
     return flat
 
 
+def bucket_plan(leaf_sizes, ready_leaves, bucket_bytes=24 << 20, dtype_code=0):
+    """host-only: the (start, count) arena slices GradientBuckets reduces for a given sequence of on_ready leaf
+    indices (the library's policy, pg_dp_bucket_plan) — testable without a GPU"""
+    n = len(leaf_sizes)
+    sizes = (ctypes.c_int64 * n)(*leaf_sizes)
+    ready = (ctypes.c_int * max(len(ready_leaves), 1))(*ready_leaves)
+    starts, counts, nb = (ctypes.c_int64 * 64)(), (ctypes.c_int64 * 64)(), ctypes.c_int()
+    call("pg_dp_bucket_plan", int(dtype_code), n, sizes, int(bucket_bytes), ready, len(ready_leaves), starts, counts, 64, ctypes.byref(nb))
+    return [(starts[k], counts[k]) for k in range(nb.value)]
+
+
 class GradientBuckets:
-    """Layer-bucketed, overlapped all-reduce of the gradient arena: backward finishes
-    layers last-to-first, i.e. the arena tail first; as soon as >= bucket_bytes of finished gradient
-    leaves have accumulated their slice is all-reduced asynchronously on NCCL's stream while the
-    remaining backward GEMMs run; finish() reduces the head slice and joins everything before the
-    optimizer pass.
+    """Layer-bucketed, overlapped all-reduce of the gradient arena: backward finishes layers
+    last-to-first, i.e. the arena tail first; as soon as >= bucket_bytes of finished gradient leaves have accumulated
+    their slice is all-reduced on the communicator's stream while the remaining backward GEMMs run (the library's
+    on_ready callback pg_dp_bucket_ready does this without returning to Python); finish_and_step() reduces the head
+    slice and runs the fused optimizer pass bucket by bucket as each reduction lands.
 
         buckets = dp.GradientBuckets(gradient_container(model))
-        grad = pb(on_ready=buckets.ready); buckets.finish(); step(state, grad)
+        grad = pb(on_ready=buckets.on_ready()); buckets.finish_and_step(state, grad)
     """
 
-    def __init__(self, grad_model, bucket_bytes=24 << 20, comm_sms=None, delay_us=None, overlap_update=None):
-        # A bucket's all-reduce runs next to the remaining backward GEMMs (persistent CTA pairs with a dynamic
-        # tile scheduler, so a pair that becomes resident late just takes fewer tiles).  Knobs, all measured
-        # (DESIGN.md section 5): `comm_sms` sizes the GEMM grids for (all - comm_sms) SMs while a bucket is in
-        # flight; `delay_us` > 0 issues the collective from a side stream behind a short sleep (pg_delay_on) so
-        # the next GEMM claims its SM pairs first (no gain measured, off); `overlap_update` (below).
-        ws = world()[1]
-        if comm_sms is None:
-            # 8 ranks: NCCL's NVLS all-reduce runs 24 CTAs next to the backward GEMMs; with 24 SMs reserved the
-            # single-wave weight-gradient launch switches to 128-row single-CTA tiles (tc_gemm.cu use_2cta),
-            # which fit the SMs NCCL leaves.  Fewer ranks: short collectives, the dynamic scheduler absorbs them.
-            comm_sms = 24 if ws >= 8 else 0
-        if delay_us is None:
-            delay_us = 0
-        if overlap_update is None:
-            overlap_update = True
-        self.comm_sms = comm_sms
-        self.delay_us = delay_us
-        # True: the optimizer pass of the buckets that have landed runs while the head bucket is still being
-        # reduced.  The update is HBM-bound and starves the collective's memory traffic, so with many ranks
-        # joining everything first and updating the whole arena once can be faster (tools/dp_cta8.sh).
+    def __init__(self, grad_model, bucket_bytes=24 << 20, dp=None, comm_sms=None, overlap_update=True):
+        self.dp = dp or (init() if world()[1] > 1 else None)
+        self.enabled = self.dp is not None and self.dp.world > 1
+        ctx, base, total, code, leaves = _arena_desc(grad_model)
+        self.ctx, self.total, self.bucket_bytes = ctx, total, int(bucket_bytes)
         self.overlap_update = overlap_update
-        self.ctx = grad_model.arena()[0]
-        from .model import _pad
-        ctx, base, total, leaves = grad_model.arena()
-        self.flat = arena_tensor(grad_model)
-        self.offsets, off = [], 0
-        for p in leaves:
-            self.offsets.append(off)
-            off += _pad(p.size)
-        self.total = total
-        self.itemsize = leaves[0].dtype.itemsize
-        self.bucket_bytes = bucket_bytes
-        self.hi = total
-        self.lo_ready = total
-        self.works, self.ranges = [], []
-        self.pending = None
-        self.side = None
-        self.enabled = ws > 1
+        # SMs kept free of persistent GEMM CTAs while a bucket is in flight (0: the dynamic tile scheduler absorbs it)
+        self.comm_sms = int(os.environ.get("PG_COMM_SMS", "0")) if comm_sms is None else int(comm_sms)
+        self.grad_model = grad_model
+        sizes = (ctypes.c_int64 * len(leaves))(*[p.size for p in leaves])
+        h = ctypes.c_void_p()
+        call("pg_arena_wrap", ctx.h, code, len(leaves), sizes, base, ctypes.byref(h))
+        self.arena = h
+        weakref.finalize(self, capi.lib.pg_arena_destroy, h)
+        self._begun = False
+        self._ready_fn = ctypes.cast(capi.lib.pg_dp_bucket_ready, ctypes.c_void_p)
 
-    def _issue(self, lo, hi, event=None):
-        """all-reduce flat[lo:hi]; with `event` (recorded when the slice was complete) the collective is
-        ordered behind event + delay on a side stream instead of behind everything enqueued so far"""
-        import torch
-        import torch.distributed as dist
-        if event is None or not self.delay_us:
-            w = dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
-        else:
-            from .capi import call
-            if self.side is None:
-                self.side = torch.cuda.Stream(device=self.flat.device)
-            self.side.wait_event(event)
-            call("pg_delay_on", self.ctx.h, self.side.cuda_stream, int(self.delay_us * 1000))
-            with torch.cuda.stream(self.side):
-                w = dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
-        self.works.append(w)
-        self.ranges.append((lo, hi - lo))
+    def on_ready(self):
+        """(callback, user) pair for pb(on_ready=...): the library's own C callback, no Python in the loop"""
+        if not self.enabled:
+            return None
+        from .trace import READY_FN
+        call("pg_dp_bucket_begin", self.dp.h, self.arena, self.bucket_bytes)
+        self._begun = True
+        if self.comm_sms:
+            self.ctx.set_sm_limit(-self.comm_sms)
+        return (ctypes.cast(capi.lib.pg_dp_bucket_ready, READY_FN), self.dp.h)
 
-    def _flush_pending(self):
-        if self.pending is not None:
-            lo, hi, ev = self.pending
-            self.pending = None
-            self._issue(lo, hi, ev)
+    def _finish(self):
+        if not self._begun:
+            call("pg_dp_bucket_begin", self.dp.h, self.arena, self.bucket_bytes)
+        self._begun = False
+        n = ctypes.c_int()
+        starts, counts = (ctypes.c_int64 * 64)(), (ctypes.c_int64 * 64)()
+        call("pg_dp_bucket_finish", self.dp.h, ctypes.byref(n), starts, counts, 64)
+        return [(starts[k], counts[k]) for k in range(n.value)]
 
-    def ready(self, leaf_index):
+    def finish(self):
+        """reduce the head slice and order the compute stream behind every bucket"""
         if not self.enabled:
             return
-        import torch
-        self._flush_pending()       # the GEMMs enqueued since the bucket completed are ahead of it on the host side
-        lo = self.offsets[leaf_index]
-        assert lo <= self.lo_ready, "gradient leaves must complete last-to-first"
-        self.lo_ready = lo
-        if (self.hi - lo) * self.itemsize >= self.bucket_bytes and lo > 0:
-            if self.delay_us:
-                self.pending = (lo, self.hi, torch.cuda.current_stream().record_event())
-            else:
-                self._issue(lo, self.hi)
-            self.hi = lo
-            if self.comm_sms:
-                self.ctx.set_sm_limit(-self.comm_sms)
+        for k, _ in enumerate(self._finish()):
+            call("pg_dp_bucket_wait", self.dp.h, k)
+        if self.comm_sms:
+            self.ctx.set_sm_limit(0)
+        self.grad_model._mutated()
 
     def finish_and_step(self, state, grad, shadow=None):
-        """Join the buckets one by one and run the fused optimizer pass on each bucket's slice as soon
-        as its reduction has landed, so the last (head) bucket's all-reduce overlaps the update of the
-        others.  Single process: one whole-arena step."""
+        """Join the buckets one by one and run the fused optimizer pass on each bucket's slice as soon as its
+        reduction has landed, so the last (head) bucket's all-reduce overlaps the update of the others.
+        Single process: one whole-arena step."""
         from .optimizers import step, step_range
         if not self.enabled:
             return step(state, grad, shadow)
-        self._flush_pending()
-        if self.hi > 0:
-            self._issue(0, self.hi)
-        if not self.overlap_update:
-            for w in self.works:
-                w.wait()
-            self._reset()
-            return step(state, grad, shadow)
+        ranges = self._finish()
         r = None
-        for k, (w, (lo, cnt)) in enumerate(zip(self.works, self.ranges)):
-            w.wait()
-            r = step_range(state, grad, lo, cnt, shadow=shadow, last=(k == len(self.works) - 1))
-        self._reset()
-        return r
-
-    def _reset(self):
+        if not self.overlap_update:
+            for k in range(len(ranges)):
+                call("pg_dp_bucket_wait", self.dp.h, k)
+            r = step(state, grad, shadow)
+        else:
+            for k, (lo, cnt) in enumerate(ranges):
+                call("pg_dp_bucket_wait", self.dp.h, k)
+                r = step_range(state, grad, lo, cnt, shadow=shadow, last=(k == len(ranges) - 1))
         if self.comm_sms:
             self.ctx.set_sm_limit(0)
-        self.works, self.ranges = [], []
-        self.hi = self.total
-        self.lo_ready = self.total
-
-    def finish(self):
-        if self.enabled:
-            self._flush_pending()
-            if self.hi > 0:
-                self._issue(0, self.hi)
-            for w in self.works:
-                w.wait()          # the compute stream waits for NCCL's stream
-        self._reset()
+        return r

@@ -34,13 +34,20 @@ class Loss:
     _pinned = None      # ring of pinned slots shared by all Loss objects
     _ring, _next = 64, 0
 
-    def __init__(self, buf):
+    def __init__(self, buf, still_valid=None):
         self._buf = buf
         self._val = None
         self._pending = None
+        self._still_valid = still_valid     # () -> bool: the device slot has not been overwritten by a later step
+
+    def _check(self):
+        if self._still_valid is not None and not self._still_valid():
+            raise RuntimeError("stale Loss: the device slot of this step's loss has been reused by later steps; read it "
+                               "(float(loss) or loss.fetch_async()) within 64 steps of the step that produced it")
 
     def fetch_async(self):
         from .device import PinnedBuffer
+        self._check()
         ctx = self._buf.ctx
         if Loss._pinned is None:
             Loss._pinned = PinnedBuffer(8 * Loss._ring)
@@ -65,6 +72,7 @@ class Loss:
                 self._val = float(host.view(self._buf.dtype)[0])
                 self._pending = None
             else:
+                self._check()
                 r = ctypes.c_double()
                 call("pg_loss_read", self._buf.ctx.h, dtype_code(self._buf.dtype), self._buf.ptr, ctypes.byref(r))
                 self._val = r.value
@@ -121,15 +129,22 @@ def eval_with_pullback(f, m, backend="B200", math="fp32", sample_offset=0):
     if not isinstance(out, T.Tensor) or out.shape != ():
         raise TypeError("the objective must return a scalar loss (cross_entropy / mse)")
     plan = T.Plan.get(tr, out)
-    plan.forward(tr)
-    loss = Loss(plan.vals[out.id])
+    gen = plan.forward(tr)
+    # the loss lives in one of the plan's 64 rotating device slots: the handle stays readable for 64 later forwards
+    # of the same plan and raises (instead of returning a newer step's value) after that
+    slot = DeviceArray(T._Borrowed(plan.ctx, plan.loss_ptr), 0, (1,), out.dtype)
+    loss = Loss(slot, lambda: plan.gen - gen < 64)
+    loss._plan = plan
 
     def pullback(on_ready=None):
         """pb(): zero arguments like the reference's; `on_ready` is the data-parallel hook
-        (see dp.GradientBuckets) and may be ignored by single-GPU callers."""
+        (see dp.GradientBuckets) and may be ignored by single-GPU callers.  The pullback belongs to the forward
+        pass that created it: calling it after a later eval_with_pullback of the same objective signature raises
+        (the plan's activations are that later batch's), it never returns another batch's gradient."""
         g = gradient_container(m)
         gleaves = g.allparams()
-        plan.backward(gleaves, on_ready)
+        plan.backward(gen, gleaves, on_ready)
+        g._mutated()
         return g
 
     return loss, pullback

@@ -85,6 +85,8 @@ class GraphStep:
             self.state.it = it
         if sc is not None:
             self._scalars.upload(sc)
+        for a in self._arenas():
+            a._mutated()
 
     def _sync_scalars_to_device(self):
         s = np.zeros(8)
@@ -100,6 +102,9 @@ class GraphStep:
 
     def _one_step(self):
         out, pb = eval_with_pullback(self.f, self.model, math=self.math)
+        if out._plan.has_dropout:
+            raise NotImplementedError("GraphStep cannot replay training-mode dropout: the mask's (seed, step) key is a kernel "
+                                      "argument baked in at capture, so every replay would reuse one mask; use eager steps")
         g = pb()
         st = self.state
         ctx, code, p, pg_, n = st._arena(g)
@@ -116,7 +121,7 @@ class GraphStep:
         else:
             raise TypeError(f"unsupported optimizer state {type(st).__name__}")
         self._loss_buf = out._buf
-        from .trace import Plan
+        self.model._mutated()
         return out
 
     # ---- replay --------------------------------------------------------------------------------
@@ -124,9 +129,14 @@ class GraphStep:
         """run one training step (graph replay); returns the step's Loss handle"""
         call("pg_graph_launch", self.ctx.h, self._graph)
         self.steps += 1
+        self.model._mutated()
         if isinstance(self.state, AdamState):
             self.state.it += 1
-        return Loss(self._loss_buf)
+        elif isinstance(self.state, NesterovState):
+            self.state.advance(1)        # keep the host-side momentum iterator in step with the device sequence
+        k = self.steps
+        # every replay writes the captured loss slot: the handle is valid until the next replay
+        return Loss(self._loss_buf, lambda: self.steps == k)
 
     def __del__(self):
         try:

@@ -134,6 +134,12 @@ class Model:
             if extra:
                 call("pg_memset0", ctx.h, p.ptr + p.nbytes, extra * isz)
 
+    def _mutated(self):
+        """the arena's contents changed: invalidates anything derived from them (the bf16 parameter shadow)"""
+        leaves = self.allparams()
+        if leaves:
+            leaves[0].buf.version += 1
+
     @property
     def eltype(self):
         return self.allparams()[0].dtype
@@ -217,6 +223,7 @@ class Model:
         a = np.array([v], dtype=p.dtype)
         call("pg_upload", p.ctx.h, p.ptr + j * p.dtype.itemsize, a.ctypes.data, p.dtype.itemsize)
         p.ctx.sync()
+        self._mutated()
 
     # ---- algebra (model.jl:103-202) -------------------------------------------------------------
     def _check_same(self, other):
@@ -235,6 +242,7 @@ class Model:
         _, pb, _, _ = other.arena()
         _, po, _, _ = out.arena()
         call("pg_vec_binary", ctx.h, dtype_code(leaves[0].dtype), op, po, pa, pb, n)
+        out._mutated()
         return out
 
     def _scalar(self, c, op, out=None):
@@ -242,10 +250,20 @@ class Model:
         ctx, pa, n, leaves = self.arena()
         if not leaves:
             return out
+        if leaves[0].dtype == np.float16 and isinstance(c, np.float32):
+            # Float16 model with a Float32 scalar: the element math promotes to Float32 (interpreter kernel)
+            from .broadcast import L, _run_program, Expr
+            sym = {capi.X_PLUS_C: ("+", 0), capi.X_MINUS_C: ("-", 0), capi.C_MINUS_X: ("-", 1), capi.X_TIMES_C: ("*", 0),
+                   capi.X_OVER_C: ("/", 0), capi.C_OVER_X: ("/", 1)}[op]
+            e = Expr(sym[0], c, L(self)) if sym[1] else Expr(sym[0], L(self), c)
+            _run_program(out, e)
+            out._mutated()
+            return out
         _, po, _, oleaves = out.arena()
         call("pg_vec_scalar", ctx.h, dtype_code(leaves[0].dtype), op, po, pa, float(c), _scalar_flags(c), n)
         if op in (capi.X_PLUS_C, capi.X_MINUS_C, capi.C_MINUS_X, capi.C_OVER_X):
             out._zero_padding(oleaves)
+        out._mutated()
         return out
 
     def __add__(self, o):
@@ -289,6 +307,7 @@ class Model:
             call("pg_vec_fill", ctx.h, dtype_code(leaves[0].dtype), pa, float(c), n)
             if c != 0:
                 self._zero_padding(leaves)
+            self._mutated()
         return self
 
     def assign(self, expr):

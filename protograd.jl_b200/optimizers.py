@@ -81,6 +81,13 @@ class _State:
             p += self._range[0] * self._isz
         return p
 
+    def _updated(self, shadow):
+        """parameters changed: bump the arena version; a whole-arena step that also wrote the bf16 shadow stamps it"""
+        self.variable._mutated()
+        if shadow and self._range is None:
+            from .trace import shadow_written
+            shadow_written(self.variable)
+
 
 class GradientDescentState(_State):
     def __init__(self, opt, variable):
@@ -90,6 +97,7 @@ class GradientDescentState(_State):
         """gradient_descent.jl:15-17"""
         ctx, code, p, pg, n = self._arena(g)
         call("pg_opt_gd", ctx.h, code, p, pg, n, float(self.stepsize), _f64(self.stepsize), shadow)
+        self._updated(shadow)
         return self.variable
 
 
@@ -103,6 +111,7 @@ class HeavyBallMethodState(_State):
         ctx, code, p, pg, n = self._arena(g)
         fl = _f64(self.stepsize) | (capi.SCALAR2_F64 if _scalar_flags(self.optimizer.momentum) else 0)
         call("pg_opt_heavyball", ctx.h, code, p, self._ptr(self.step_), pg, n, float(self.stepsize), float(self.optimizer.momentum), fl, shadow)
+        self._updated(shadow)
         return self.variable
 
 
@@ -111,12 +120,23 @@ class NesterovState(_State):
         self.optimizer, self.stepsize, self.variable = opt, opt.stepsize, variable
         self.variable_prev = variable.zero()
         self.momentum_iterator = iter(opt.momentum_sequence)
+        self._pops = 0            # momenta taken from the sequence so far (checkpoints and graph replay restore it)
+
+    def pop_momentum(self):
+        self._pops += 1
+        return next(self.momentum_iterator)
+
+    def advance(self, k):
+        """skip k momenta (graph replays and checkpoint restore keep the host iterator in step with the device)"""
+        for _ in range(int(k)):
+            self.pop_momentum()
 
     def step(self, g, shadow=None):
         """nesterov_method.jl:33-39 (momentum popped from the host-side stateful iterator)"""
         ctx, code, p, pg, n = self._arena(g)
-        mu = next(self.momentum_iterator)
+        mu = self.pop_momentum()
         call("pg_opt_nesterov", ctx.h, code, p, self._ptr(self.variable_prev), pg, n, float(self.stepsize), float(mu), _f64(self.stepsize), shadow)
+        self._updated(shadow)
         return self.variable
 
 
@@ -155,6 +175,7 @@ class AdamState(_State):
         call("pg_opt_adam", ctx.h, code, p, self._ptr(self.m), self._ptr(self.v),
              self._ptr(self._m_hat) if self._m_hat is not None else None, self._ptr(self._v_hat) if self._v_hat is not None else None,
              pg, n, float(self.stepsize), float(o.beta1), float(o.beta2), float(o.epsilon), self.it, fl, shadow)
+        self._updated(shadow)
         self.it += 1
         return self.it
 
@@ -184,10 +205,11 @@ def step_range(state, gradient, start, count, shadow=None, last=True):
             state.it = it
         elif isinstance(state, NesterovState):
             if not hasattr(state, "_mu_cached"):
-                state._mu_cached = next(state.momentum_iterator)
+                state._mu_cached = state.pop_momentum()
             mu = state._mu_cached
             ctx, code, p, pg, n = state._arena(gradient)
             call("pg_opt_nesterov", ctx.h, code, p, state._ptr(state.variable_prev), pg, n, float(state.stepsize), float(mu), _f64(state.stepsize), shadow or None)
+            state.variable._mutated()
             if last:
                 del state._mu_cached
             r = state.variable
@@ -195,6 +217,10 @@ def step_range(state, gradient, start, count, shadow=None, last=True):
             r = state.step(gradient, shadow or None)
     finally:
         state._range = None
+    if shadow and last:
+        # every bucket of this step wrote its slice of the shadow: the whole copy matches the new parameters
+        from .trace import shadow_written
+        shadow_written(state.variable)
     return r
 
 

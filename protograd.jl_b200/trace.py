@@ -10,6 +10,7 @@ plan launches the C-ABI kernels.  Only single-consumer (sequential) graphs are s
 every model the reference builds with `Compose`.
 """
 import ctypes
+import weakref as _weakref
 
 import numpy as np
 
@@ -40,7 +41,8 @@ class Tensor:
 
     def __init__(self, trace, op, inputs, shape, dtype, attrs=None):
         self.trace, self.op, self.inputs = trace, op, tuple(inputs)
-        self.shape, self.dtype, self.attrs = tuple(int(s) for s in shape), np.dtype(dtype), attrs or {}
+        self.shape, self.attrs = tuple(int(s) for s in shape), attrs or {}
+        self.dtype = dtype if isinstance(dtype, str) and dtype == BF16 else np.dtype(dtype)
         n = 1
         for d in self.shape:
             n *= d
@@ -209,7 +211,13 @@ def cross_entropy(probs, label, global_batch=None):
     """src/losses.jl:7-10 (dims = class axis, agg = mean)."""
     tr = _tr(probs, label)
     probs, label = tr.lift(probs), tr.lift(label)
-    if probs.shape != label.shape:
+    int_labels = label.dtype != BF16 and np.issubdtype(label.dtype, np.integer)
+    if int_labels:
+        # integer class indices (0-based) instead of the dense one-hot matrix Flux.onehotbatch builds
+        # (examples/01_mnist_mlp.jl:17): 4 B/sample of label traffic instead of 4*C
+        if label.dtype != np.int32 or label.shape != probs.shape[:-1]:
+            raise ValueError("integer labels must be int32 with one entry per sample")
+    elif probs.shape != label.shape:
         raise ValueError("DimensionMismatch: probs and label shapes differ")
     return Tensor(tr, "cross_entropy", (probs, label), (), probs.dtype, {"global_batch": global_batch})
 
@@ -224,34 +232,65 @@ def mse(output, label, denom=None):
 
 
 # ---- plan -------------------------------------------------------------------------------------
+# The planner itself lives behind the C ABI (csrc/plan.cu: pg_plan_create / forward / backward): fusion, kernel
+# selection, buffers and launches are the library's.  This module records the graph, hands it over once per
+# signature, binds device pointers each step and owns the bf16 parameter shadow's validity.
+
+_KIND = {"input": 0, "param": 1, "linear": 2, "conv": 3, "relu": 4, "maxpool": 5, "meanpool": 6, "reshape": 7, "dropout": 8,
+         "softmax": 9, "cross_entropy": 10, "mse": 11}
+NODE_NEEDED, NODE_NEEDS_GRAD, NODE_TENSOR_CORE, NODE_FUSED_ACT, NODE_BF16_VALUE, NODE_FUSED_AWAY = 1, 2, 4, 8, 16, 32
+MATH_CODE = {"fp32": 0, "bf16": 1}
+
+
+class PgOp(ctypes.Structure):
+    """struct pg_op of include/protograd_b200.h"""
+    _fields_ = [("kind", ctypes.c_int32), ("dtype", ctypes.c_int32), ("inp", ctypes.c_int32 * 3), ("ndim", ctypes.c_int32),
+                ("shape", ctypes.c_int64 * 4), ("grad_leaf", ctypes.c_int32), ("k", ctypes.c_int32), ("p", ctypes.c_double),
+                ("denom", ctypes.c_double)]
+
+
+READY_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int)
 
 
 def _shadow_entry(ctx, buf):
+    """[buffer, bf16 shadow buffer, buffer version the shadow was written for]"""
     key = id(buf)
     ent = _SHADOWS.get(key)
     if ent is None or ent[0] is not buf:
-        ent = _SHADOWS[key] = [buf, DeviceBuffer(ctx, buf.nbytes // 2 + 16, zero=True), False]
+        ent = _SHADOWS[key] = [buf, DeviceBuffer(ctx, buf.nbytes // 2 + 16, zero=True), -1]
     return ent
 
 
 def shadow_target(model):
     """Device pointer where a fused optimizer pass may write bf16(p_new) for `model`'s arena
-    (`pg.step(state, grad, shadow=True)`).  The next bf16-mode forward then skips its own cast.
-    Opt-in: parameters must not be modified by anything else between that step and the forward."""
+    (`pg.step(state, grad, shadow=True)`): the next bf16-mode forward then skips its own cast.  The copy is
+    stamped with the arena's version AFTER that step; every other mutation of the parameters (set_vec, assign,
+    indexing, fill_, broadcast_parameters, checkpoint load, graph restore) bumps the version, so a stale copy is
+    never used — the forward re-casts instead."""
     ctx, base, total, leaves = model.arena()
     if leaves[0].dtype != np.float32:
         raise TypeError("bf16 shadows exist for Float32 models only")
     ent = _shadow_entry(ctx, leaves[0].buf)
-    ent[2] = True
     return ent[1].ptr + leaves[0].offset // 2
 
 
+def shadow_written(model):
+    """stamp the shadow as matching the arena's current contents (called by step(..., shadow=True))"""
+    ctx, base, total, leaves = model.arena()
+    ent = _shadow_entry(ctx, leaves[0].buf)
+    ent[2] = leaves[0].buf.version
+
+
 _PLANS = {}
-_SHADOWS = {}  # id(DeviceBuffer) -> (buffer ref, bf16 shadow buffer)
+_SHADOWS = {}  # id(DeviceBuffer) -> [buffer ref, bf16 shadow buffer, version]
+
+
+def _dt_str(dt):
+    return dt if dt == BF16 else np.dtype(dt).str
 
 
 def _sig(trace, root):
-    parts = [trace.math, trace.ctx.device, root.id]
+    parts = [trace.math, trace.ctx.device if trace.ctx is not None else None, root.id]
     for n in trace.nodes:
         a = n.attrs
         extra = ()
@@ -265,19 +304,12 @@ def _sig(trace, root):
             extra = (a["p"],)
         elif n.op == "cross_entropy":
             extra = (a["global_batch"],)
-        parts.append((n.op, n.shape, n.dtype.str, tuple(i.id for i in n.inputs), extra))
+        parts.append((n.op, n.shape, _dt_str(n.dtype), tuple(i.id for i in n.inputs), extra))
     return tuple(parts)
 
 
 class Plan:
-    """Fused schedule + cached buffers for one traced signature.
-
-    Gradient-buffer invariant: after the consumer of node i has run its backward step, grads[i]
-    holds dL/d(value of i).  For a relu output R (fused into its producer or standalone) whose
-    consumer is a Linear, the consumer's data-gradient epilogue applies [R > 0] itself
-    (`premasked`), so grads[R] already is the gradient w.r.t. the relu's input; otherwise the relu's
-    own backward step applies the mask.
-    """
+    """Host handle of a pg_plan (one per traced signature, cached)."""
 
     @classmethod
     def get(cls, trace, root):
@@ -293,434 +325,166 @@ class Plan:
         self.ctx, self.math, self.root_id = trace.ctx, trace.math, root.id
         nodes = trace.nodes
         n = self.n = len(nodes)
-        need = [False] * n
-        need[root.id] = True
-        for t in reversed(nodes):
-            if need[t.id]:
-                for i in t.inputs:
-                    need[i.id] = True
-        self.need = need
-        consumers = [[] for _ in range(n)]
+        ops = (PgOp * n)()
         for t in nodes:
-            if need[t.id]:
-                for i in t.inputs:
-                    consumers[i.id].append(t.id)
-        for t in nodes:
-            if not need[t.id]:
-                continue
-            if t.op not in ("input", "param") and len(consumers[t.id]) > 1:
-                raise NotImplementedError("the B200 path supports sequential graphs only: an intermediate value is used twice")
-            if t.op == "param" and t.attrs["grad_index"] is not None and len(consumers[t.id]) > 1:
-                raise NotImplementedError("weight sharing (a trainable leaf used by two layers) is not supported")
-        self.consumers = consumers
-        self.ops = [t.op for t in nodes]
-        self.inputs = [tuple(i.id for i in t.inputs) for t in nodes]
+            o = ops[t.id]
+            o.kind = _KIND[t.op]
+            o.dtype = dtype_code(t.dtype)
+            ins = [i.id for i in t.inputs] + [-1, -1, -1]
+            o.inp[0], o.inp[1], o.inp[2] = ins[0], ins[1], ins[2]
+            if len(t.shape) > 4:
+                raise NotImplementedError("tensors of rank > 4 are not on the B200 path")
+            o.ndim = len(t.shape)
+            for d, sdim in enumerate(t.shape):
+                o.shape[d] = sdim
+            o.grad_leaf = -1
+            a = t.attrs
+            if t.op == "param" and a["grad_index"] is not None:
+                o.grad_leaf = a["grad_index"]
+            if t.op in ("maxpool", "meanpool"):
+                o.k = a["k"]
+            if t.op == "dropout":
+                o.p = a["p"]
+            if t.op == "mse":
+                o.denom = float(a["denom"] or 0)
+            if t.op == "cross_entropy":
+                o.denom = float(a["global_batch"] or 0)
+        self.ops_kind = [t.op for t in nodes]
         self.shapes = [t.shape for t in nodes]
         self.dtypes = [t.dtype for t in nodes]
-        self.attrs = [dict((k, v) for k, v in t.attrs.items() if k not in ("src", "leaf")) for t in nodes]
-        ng = [False] * n
-        for t in nodes:
-            if t.op == "param":
-                ng[t.id] = t.attrs["grad_index"] is not None
-            elif t.op != "input":
-                ng[t.id] = any(ng[i.id] for i in t.inputs)
-        self.ng = ng
-        self.fused_act = {}      # linear/conv id -> relu id whose buffer it writes
-        self.fused_into = {}     # relu id -> producer id
-        self.fused_sce = {}      # cross_entropy id -> softmax id
-        for t in nodes:
-            if not need[t.id]:
-                continue
-            if t.op == "relu":
-                p = nodes[t.inputs[0].id]
-                if p.op in ("linear", "conv") and consumers[p.id] == [t.id]:
-                    self.fused_act[p.id] = t.id
-                    self.fused_into[t.id] = p.id
-            if t.op == "cross_entropy":
-                p = nodes[t.inputs[0].id]
-                if p.op == "softmax" and consumers[p.id] == [t.id] and p.id != root.id:
-                    self.fused_sce[t.id] = p.id
-        self.sce_softmax = set(self.fused_sce.values())
-        self.tc_linear, self.tc_conv = self._select_tensor_core_ops()
-        self.vals = [None] * n
-        self.grads = [None] * n
+        h = ctypes.c_void_p()
+        call("pg_plan_create", self.ctx.h if self.ctx is not None else None, ops, n, root.id, MATH_CODE[self.math], ctypes.byref(h))
+        self.h = h
+        self._finalizer = _weakref.finalize(self, capi.lib.pg_plan_destroy, h)
+        self.flags = []
+        f = ctypes.c_int()
+        for i in range(n):
+            call("pg_plan_node_flags", h, i, ctypes.byref(f))
+            self.flags.append(f.value)
+        self.need = [bool(f & NODE_NEEDED) for f in self.flags]
+        self.ng = [bool(f & NODE_NEEDS_GRAD) for f in self.flags]
+        self.tc_linear = {i for i in range(n) if self.flags[i] & NODE_TENSOR_CORE and self.ops_kind[i] == "linear"}
+        self.tc_conv = {i for i in range(n) if self.flags[i] & NODE_TENSOR_CORE and self.ops_kind[i] == "conv"}
+        # W leaves the tcgen05 GEMMs can read straight from the arena's bf16 shadow (no padding needed)
+        self.shadow_params = []
+        for i in self.tc_linear:
+            W = nodes[i].inputs[1]
+            K, N = W.shape
+            if K % 8 == 0 and (N % 8 == 0 or N <= 32):
+                self.shadow_params.append(W.id)
+        self.has_dropout = any(self.need[i] and self.ops_kind[i] == "dropout" for i in range(n))
+        self.leaf_ptrs = (ctypes.c_void_p * n)()
+        self.leaf_bf = (ctypes.c_void_p * n)()
         self.owned_inputs = {}
-        self.bf16_inputs = {}
-        self._fresh, self._cast_done = set(), set()
-        self._alloc()
+        self.gen = 0
+        self._live = []
 
-    # ---- graph helpers -------------------------------------------------------------------------
-    def _through_reshape_down(self, i):
-        """first non-reshape consumer of node i (None if none)"""
-        c = self.consumers[i][0] if self.consumers[i] else None
-        while c is not None and self.ops[c] == "reshape":
-            c = self.consumers[c][0] if self.consumers[c] else None
-        return c
-
-    def _base(self, i):
-        """follow reshape aliases up to the node that owns the storage"""
-        while self.ops[i] == "reshape":
-            i = self.inputs[i][0]
-        return i
-
-    def _premasked(self, r):
-        """consumers that apply relu' of their input themselves: Linear (dX epilogue mask) and maxpool
-        (routes the gradient only where the window max is > 0)"""
-        c = self._through_reshape_down(r)
-        return c is not None and self.ops[c] in ("linear", "maxpool")
-
-    def _select_tensor_core_ops(self):
-        """Which Linear / Conv nodes run on the tcgen05 kernels in math="bf16" mode.
-        Linear: bf16 operands, so its input must be a trace input (cast once) or the bf16 activation of
-        another tensor-core Linear, K % 8 == 0 and N % 8 == 0 (16-byte TMA pitch) or N <= 32 (padded
-        narrow path); a wide (N > 32) layer stores a bf16 activation and expects a bf16 gradient back, so
-        its consumer must be a tensor-core Linear too (otherwise the layer stays on the fp32 SIMT GEMM).
-        Conv: Float32 tensors in and out (csrc/tc_conv.cu rounds operands on the way into shared memory),
-        any position in the graph, shapes inside pg_tc_conv2d_supported."""
-        tc_lin, tc_conv = set(), set()
-        if self.math != "bf16":
-            return tc_lin, tc_conv
-        from . import capi
-        for i in range(self.n):
-            if not self.need[i]:
-                continue
-            if self.ops[i] == "conv" and self.dtypes[i] == np.float32:
-                Cout, Cin, kH, kW = self.shapes[self.inputs[i][1]]
-                H, W = self.shapes[self.inputs[i][0]][2:]
-                if capi._FN["pg_tc_conv2d_supported"](Cin, H, W, Cout, kH, kW) == 1:
-                    tc_conv.add(i)
-            if self.ops[i] != "linear" or self.dtypes[i] != np.float32:
-                continue
-            x, W, b = self.inputs[i]
-            K, N = self.shapes[W]
-            if K % 8 or (N > 32 and N % 8):
-                continue
-            src = self._base(x)
-            prod = self.fused_into.get(src, src) if self.ops[src] == "relu" else src
-            if self.ops[src] == "input" or (self.ops[prod] == "linear" and prod in tc_lin and self.shapes[prod][-1] > 32):
-                tc_lin.add(i)
-        changed = True
-        while changed:                        # demote wide layers whose consumer left the tensor-core chain
-            changed = False
-            for i in sorted(tc_lin, reverse=True):
-                if self.shapes[i][-1] <= 32:
-                    continue
-                out = self.fused_act.get(i, i)
-                c = self._through_reshape_down(out)
-                if c is not None and c not in tc_lin:
-                    tc_lin.discard(i)
-                    changed = True
-            for i in sorted(tc_lin):          # ... and layers fed by a demoted one
-                x = self.inputs[i][0]
-                src = self._base(x)
-                prod = self.fused_into.get(src, src) if self.ops[src] == "relu" else src
-                if self.ops[src] != "input" and prod not in tc_lin:
-                    tc_lin.discard(i)
-                    changed = True
-        return tc_lin, tc_conv
-
-    def _consumer_is_tc_linear(self, i):
-        c = self._through_reshape_down(i)
-        return c is not None and c in self.tc_linear
-
-    # ---- buffers -------------------------------------------------------------------------------
-    def _new(self, shape, dtype):
-        return DeviceArray.empty(self.ctx, shape, dtype, zero=True)
-
-    def _act_dtype(self, lin):
-        if lin in self.tc_linear and self.shapes[lin][-1] > 32:
-            return BF16
-        return self.dtypes[lin]
-
-    def _alloc(self):
-        ops = self.ops
-        for i in range(self.n):
-            if not self.need[i]:
-                continue
-            op = ops[i]
-            if op in ("linear", "conv"):
-                if i not in self.fused_act:
-                    self.vals[i] = self._new(self.shapes[i], self._act_dtype(i))
-            elif op == "relu":
-                src = self.fused_into.get(i)
-                self.vals[i] = self._new(self.shapes[i], self._act_dtype(src) if src is not None else self.dtypes[i])
-            elif op in ("maxpool", "meanpool", "dropout"):
-                self.vals[i] = self._new(self.shapes[i], self.dtypes[i])
-            elif op == "softmax":
-                if i not in self.sce_softmax:
-                    self.vals[i] = self._new(self.shapes[i], self.dtypes[i])
-            elif op in ("cross_entropy", "mse"):
-                self.vals[i] = self._new((1,), self.dtypes[i])
-        for i in range(self.n):
-            if not self.need[i] or not self.ng[i]:
-                continue
-            op = ops[i]
-            if op in ("input", "param", "cross_entropy", "mse", "reshape"):
-                continue
-            if op in ("linear", "conv") and i in self.fused_act:
-                continue                      # shares the relu node's gradient buffer
-            if op == "softmax" and i in self.sce_softmax:
-                continue                      # dZ goes straight to the logits' gradient buffer
-            dt = BF16 if self._consumer_is_tc_linear(i) else self.dtypes[i]
-            self.grads[i] = self._new(self.shapes[i], dt)
-
-    def _val(self, i):
-        op = self.ops[i]
-        if op == "reshape":
-            return self._val(self.inputs[i][0]).reshape(self.shapes[i])
-        if op in ("linear", "conv") and i in self.fused_act:
-            return self.vals[self.fused_act[i]]
-        return self.vals[i]
-
-    def _grad(self, i):
-        """buffer holding / receiving dL/d(node i), following reshape aliases and relu fusion"""
-        op = self.ops[i]
-        if op == "reshape":
-            return self._grad(self.inputs[i][0]).reshape(self.shapes[i])
-        if op in ("linear", "conv") and i in self.fused_act:
-            return self.grads[self.fused_act[i]]
-        return self.grads[i]
-
-    def value_of(self, t):
-        v = self._val(t.id)
-        if v is None:
-            raise RuntimeError("value was fused away; evaluate it as the root of its own trace")
-        return v
+    def act_is_bf16(self, i):
+        return bool(self.flags[i] & NODE_BF16_VALUE)
 
     def _bind(self, trace):
         ctx = self.ctx
+        live = []
         for t in trace.nodes:
             if not self.need[t.id]:
                 continue
             if t.op == "param":
-                self.vals[t.id] = t.attrs["leaf"]
+                leaf = t.attrs["leaf"]
+                self.leaf_ptrs[t.id] = leaf.ptr
+                live.append(leaf)
             elif t.op == "input":
                 src = t.attrs["src"]
                 if isinstance(src, np.ndarray):
                     buf = self.owned_inputs.get(t.id)
                     if buf is None:
-                        buf = self.owned_inputs[t.id] = self._new(t.shape, t.dtype)
+                        buf = self.owned_inputs[t.id] = DeviceArray.empty(ctx, t.shape, t.dtype)
                     a = np.ascontiguousarray(src)
                     call("pg_upload", ctx.h, buf.ptr, a.ctypes.data, buf.nbytes)
                     if not is_pinned(a):
                         ctx.sync()  # pageable source may be a temporary; pinned sources stay async
-                    self.vals[t.id] = buf
-                else:
-                    self.vals[t.id] = src
+                    src = buf
+                self.leaf_ptrs[t.id] = src.ptr
+                live.append(src)
+        self._live = live            # keep the bound arrays alive until the next forward
 
-    # ---- bf16 operand copies -------------------------------------------------------------------
-    def _shadow(self, leaf):
-        """bf16 copy of the whole buffer a leaf lives in (refreshed once per forward, unless the
-        optimizer already wrote it in its fused pass — see `shadow_target`)"""
-        ent = _shadow_entry(self.ctx, leaf.buf)
-        key = id(leaf.buf)
-        if key not in self._fresh:
-            if ent[2]:
-                ent[2] = False            # consume the optimizer-written copy (valid for one forward)
-            else:
-                call("pg_vec_cast_bf16", self.ctx.h, ent[1].ptr, leaf.buf.ptr, leaf.buf.nbytes // 4)
-            self._fresh.add(key)
-        return DeviceArray(ent[1], leaf.offset // 2, leaf.shape, BF16)
-
-    def _as_bf16(self, i):
-        v = self._val(i)
-        if v.dtype == BF16:
-            return v
-        if v.dtype != np.float32:
-            raise TypeError("bf16 tensor-core mode needs Float32 models and inputs")
-        b = self._base(i)
-        if self.ops[b] == "param":
-            return self._shadow(v)
-        buf = self.bf16_inputs.get(b)
-        if buf is None:
-            buf = self.bf16_inputs[b] = self._new((v.size,), BF16)
-        if b not in self._cast_done:
-            call("pg_vec_cast_bf16", self.ctx.h, buf.ptr, v.ptr, v.size)
-            self._cast_done.add(b)
-        return buf.reshape(v.shape)
-
-    def _dropout(self, i, src, dst):
-        rows = self.shapes[i][0] if self.shapes[i] else 1
-        per_sample = src.size // max(rows, 1)
-        stream_id = ((self._rng_step & 0xFFFFF) << 12) | (i & 0xFFF)
-        call("pg_dropout", self.ctx.h, dtype_code(self.dtypes[i]), src.ptr, dst.ptr, src.size, self.attrs[i]["p"],
-             self._rng_seed, stream_id, self._sample_offset * per_sample)
-
-    def _f(self, i):
-        """value of node i for a non-tensor-core op: must not be a bf16 activation"""
-        v = self._val(i)
-        if v.dtype == BF16:
-            raise NotImplementedError("a bf16 activation feeds a non-Linear op; use math='fp32' for this model")
-        return v
-
-    # ---- forward -------------------------------------------------------------------------------
-    def forward(self, trace):
-        self._rng_seed, self._rng_step, self._sample_offset = trace.rng_seed, trace.rng_step, trace.sample_offset
-        self._bind(trace)
-        self._fresh, self._cast_done = set(), set()
-        h = self.ctx.h
-        P = lambda a: a.ptr if a is not None else None
+    def _bind_shadows(self, trace):
         for i in range(self.n):
-            if not self.need[i]:
+            self.leaf_bf[i] = None
+        done = set()
+        for wid in self.shadow_params:
+            leaf = trace.nodes[wid].attrs["leaf"]
+            if leaf.dtype != np.float32:
                 continue
-            op = self.ops[i]
-            if op in ("input", "param", "reshape"):
-                continue
-            ins = self.inputs[i]
-            code = dtype_code(self.dtypes[i])
-            if op == "linear":
-                x, W, b = ins
-                K, N = self.shapes[W]
-                M = _prod(self.shapes[x][:-1])
-                act = ACT_RELU if i in self.fused_act else ACT_NONE
-                out = self._val(i)
-                if i in self.tc_linear:
-                    xv, Wv = self._as_bf16(x), self._as_bf16(W)
-                    call("pg_tc_linear_fwd", h, xv.ptr, Wv.ptr, self._val(b).ptr, out.ptr, PG_BF16 if out.dtype == BF16 else PG_F32, M, K, N, act)
-                else:
-                    call("pg_linear_fwd", h, code, self._val(x).ptr, self._val(W).ptr, self._val(b).ptr, out.ptr, M, K, N, act)
-            elif op == "conv":
-                x, w, b = ins
-                N_, Cin, H, W_ = self.shapes[x]
-                Cout, _, kH, kW = self.shapes[w]
-                act = ACT_RELU if i in self.fused_act else ACT_NONE
-                if i in self.tc_conv:
-                    call("pg_tc_conv2d_fwd", h, self._f(x).ptr, self._val(w).ptr, self._val(b).ptr, self._val(i).ptr, N_, Cin, H, W_, Cout, kH, kW, act)
-                else:
-                    call("pg_conv2d_fwd", h, code, self._f(x).ptr, self._val(w).ptr, self._val(b).ptr, self._val(i).ptr, N_, Cin, H, W_, Cout, kH, kW, act)
-            elif op == "relu":
-                if i in self.fused_into:
-                    continue
-                call("pg_relu_fwd", h, code, self._f(ins[0]).ptr, self.vals[i].ptr, self.vals[i].size)
-            elif op in ("maxpool", "meanpool"):
-                N_, C, H, W_ = self.shapes[ins[0]]
-                call("pg_%s2d_fwd" % op, h, code, self._f(ins[0]).ptr, self.vals[i].ptr, N_ * C, H, W_, self.attrs[i]["k"])
-            elif op == "dropout":
-                self._dropout(i, self._f(ins[0]), self.vals[i])
-            elif op == "softmax":
-                if i in self.sce_softmax:
-                    continue
-                C = self.shapes[i][-1]
-                call("pg_softmax_fwd", h, code, self._f(ins[0]).ptr, self.vals[i].ptr, self.vals[i].size // C, C)
-            elif op == "cross_entropy":
-                p, y = ins
-                C = self.shapes[p][-1]
-                B = _prod(self.shapes[p][:-1])
-                gb = self.attrs[i]["global_batch"] or B
-                if i in self.fused_sce:
-                    z = self.inputs[self.fused_sce[i]][0]
-                    dz = self._grad(z) if self.ng[z] else None
-                    call("pg_softmax_ce_fwd_bwd", h, code, self._f(z).ptr, self._f(y).ptr, None, P(dz), self.vals[i].ptr, B, C, 1.0 / gb)
-                else:
-                    dp = self._grad(p) if self.ng[p] else None
-                    call("pg_cross_entropy_fwd_bwd", h, code, self._f(p).ptr, self._f(y).ptr, P(dp), self.vals[i].ptr, B, C, 1.0 / gb)
-            elif op == "mse":
-                yh, y = ins
-                n_el = _prod(self.shapes[yh])
-                denom = self.attrs[i]["denom"] or n_el
-                dy = self._grad(yh) if self.ng[yh] else None
-                call("pg_mse_fwd_bwd", h, code, self._f(yh).ptr, self._f(y).ptr, P(dy), self.vals[i].ptr, n_el, 1.0 / denom)
-            else:
-                raise NotImplementedError(op)
+            ent = _shadow_entry(self.ctx, leaf.buf)
+            if id(leaf.buf) not in done and ent[2] != leaf.buf.version:
+                # one cast pass over the whole arena (skipped when the optimizer's fused pass already wrote it)
+                call("pg_vec_cast_bf16", self.ctx.h, ent[1].ptr, leaf.buf.ptr, leaf.buf.nbytes // 4)
+                ent[2] = leaf.buf.version
+            done.add(id(leaf.buf))
+            self.leaf_bf[wid] = ent[1].ptr + leaf.offset // 2
 
-    # ---- backward ------------------------------------------------------------------------------
-    def backward(self, grad_leaves, on_ready=None):
+    def forward(self, trace):
+        self._bind(trace)
+        if self.shadow_params:
+            self._bind_shadows(trace)
+        loss = ctypes.c_void_p()
+        gen = ctypes.c_int64()
+        call("pg_plan_forward", self.h, self.leaf_ptrs, self.leaf_bf, ctypes.c_uint64(trace.rng_seed), ctypes.c_uint64(trace.rng_step),
+             ctypes.c_int64(trace.sample_offset), ctypes.byref(loss), ctypes.byref(gen))
+        self.gen = gen.value
+        self.loss_ptr = loss.value
+        return self.gen
+
+    def backward(self, gen, grad_leaves, on_ready=None):
         """grad_leaves: DeviceArrays in vec(m) order receiving dW / db (written, not accumulated).
-        on_ready(i): called once the gradient kernels of leaves >= i have all been enqueued (layers
-        finish in reverse order), so a data-parallel caller can start reducing that bucket."""
-        h = self.ctx.h
-        P = lambda a: a.ptr if a is not None else None
-        db_done = set()    # linear nodes whose bias gradient was produced by a downstream epilogue
-        for i in range(self.n - 1, -1, -1):
-            if not self.need[i] or not self.ng[i]:
-                continue
-            op = self.ops[i]
-            if op in ("input", "param", "reshape", "cross_entropy", "mse"):
-                continue  # losses wrote their input gradient during the forward pass
-            ins = self.inputs[i]
-            code = dtype_code(self.dtypes[i])
-            if op in ("linear", "conv"):
-                x, W, b = ins
-                gy = self._grad(i)
-                r = self.fused_act.get(i)
-                if r is not None and not self._premasked(r):
-                    # consumer was not a Linear: apply relu' here so gy is the pre-activation gradient
-                    call("pg_relu_bwd", h, dtype_code(self.dtypes[r]), self.vals[r].ptr, gy.ptr, gy.ptr, gy.size)
-                gW = grad_leaves[self.attrs[W]["grad_index"]] if self.ng[W] else None
-                gb = grad_leaves[self.attrs[b]["grad_index"]] if self.ng[b] else None
-                gx = self._grad(x) if self.ng[x] else None
-                if op == "linear":
-                    K, N = self.shapes[W]
-                    M = _prod(self.shapes[x][:-1])
-                    mask = self._val(x) if (gx is not None and self.ops[self._base(x)] == "relu") else None
-                    if i in self.tc_linear:
-                        xv = self._as_bf16(x) if gW is not None else None
-                        Wv = self._as_bf16(W) if gx is not None else None
-                        gyc = PG_BF16 if gy.dtype == BF16 else PG_F32
-                        if i in db_done:
-                            gb = None                       # already produced by the downstream layer's dX epilogue
-                        # bias gradient of the layer that produced x = column sums of (masked) dX: let this
-                        # layer's data-gradient epilogue accumulate them instead of a separate pass over dX
-                        prev_db = None
-                        # (measured: a wash on C4 — the narrow data-gradient launch is epilogue-bound and pays
-                        #  +18 us for it, the wide one +6 us, vs ~25 us saved in the weight-gradient launches — so
-                        #  it stays off by default; tools/colsum_bench.py)
-                        if FUSE_PREV_DB and gx is not None and gx.dtype == BF16:
-                            xb = self._base(x)
-                            prod = self.fused_into.get(xb) if self.ops[xb] == "relu" else (xb if self.ops[xb] == "linear" else None)
-                            if prod is not None and self.ops[prod] == "linear" and (self.ops[xb] != "relu" or mask is not None):
-                                pb_ = self.inputs[prod][2]
-                                if self.ng[pb_]:
-                                    prev_db = grad_leaves[self.attrs[pb_]["grad_index"]]
-                                    db_done.add(prod)
-                        if on_ready is not None and gx is not None and (gW is not None or gb is not None):
-                            # data-parallel: parameter gradients first, so their bucket can start reducing
-                            # while this layer's data gradient (and everything upstream) still computes
-                            call("pg_tc_linear_bwd_ex", h, P(xv), None, gy.ptr, gyc, P(gW), P(gb), None, None, None, M, K, N)
-                            on_ready(min(self.attrs[j]["grad_index"] for j in (W, b) if self.ng[j]))
-                            call("pg_tc_linear_bwd_ex", h, None, P(Wv), gy.ptr, gyc, None, None, P(gx), P(mask), P(prev_db), M, K, N)
-                            continue
-                        call("pg_tc_linear_bwd_ex", h, P(xv), P(Wv), gy.ptr, gyc, P(gW), P(gb), P(gx), P(mask), P(prev_db), M, K, N)
-                    else:
-                        call("pg_linear_bwd", h, code, self._val(x).ptr, self._val(W).ptr, gy.ptr, P(gW), P(gb), P(gx), P(mask), M, K, N)
-                else:
-                    N_, Cin, H, W_ = self.shapes[x]
-                    Cout, _, kH, kW = self.shapes[W]
-                    if i in self.tc_conv and (gW is not None or gb is None):
-                        call("pg_tc_conv2d_bwd", h, self._val(x).ptr, self._val(W).ptr, gy.ptr, P(gW), P(gb), P(gx), N_, Cin, H, W_, Cout, kH, kW)
-                    else:
-                        call("pg_conv2d_bwd", h, code, self._val(x).ptr, self._val(W).ptr, gy.ptr, P(gW), P(gb), P(gx), N_, Cin, H, W_, Cout, kH, kW)
-                if on_ready is not None and (gW is not None or gb is not None):
-                    idx = [self.attrs[j]["grad_index"] for j in (W, b) if self.ng[j]]
-                    on_ready(min(idx))
-            elif op == "relu":
-                if i in self.fused_into:
-                    continue  # handled by the producer
-                x = ins[0]
-                gx = self._grad(x)
-                if self._premasked(i):
-                    call("pg_copy_d2d", h, gx.ptr, self.grads[i].ptr, self.grads[i].nbytes)
-                else:
-                    call("pg_relu_bwd", h, code, self.vals[i].ptr, self.grads[i].ptr, gx.ptr, gx.size)
-            elif op in ("maxpool", "meanpool"):
-                x = ins[0]
-                N_, C, H, W_ = self.shapes[x]
-                gx = self._grad(x)
-                if op == "maxpool":
-                    fuse_relu = 1 if self.ops[self._base(x)] == "relu" else 0
-                    call("pg_maxpool2d_relu_bwd", h, code, self._val(x).ptr, self.grads[i].ptr, gx.ptr, N_ * C, H, W_, self.attrs[i]["k"], fuse_relu)
-                else:
-                    call("pg_meanpool2d_bwd", h, code, self.grads[i].ptr, gx.ptr, N_ * C, H, W_, self.attrs[i]["k"])
-            elif op == "dropout":
-                g, gx = self.grads[i], self._grad(ins[0])
-                if g.dtype == BF16 or gx.dtype == BF16:
-                    raise NotImplementedError("training-mode dropout next to a bf16 tensor-core layer: use math='fp32'")
-                self._dropout(i, g, gx)      # same (seed, step, node, element) key -> same mask
-            elif op == "softmax":
-                if i in self.sce_softmax:
-                    continue  # dZ was written by the fused loss kernel
-                z = ins[0]
-                C = self.shapes[i][-1]
-                call("pg_softmax_bwd", h, code, self.vals[i].ptr, self.grads[i].ptr, self._grad(z).ptr, self.vals[i].size // C, C)
-            else:
-                raise NotImplementedError(op)
+        on_ready(i): called once the gradient kernels of leaves >= i have all been enqueued (layers finish in
+        reverse order), so a data-parallel caller can start reducing that slice; may also be a
+        (C function pointer, user pointer) pair such as (pg_dp_bucket_ready, dp handle)."""
+        n = len(grad_leaves)
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[g.ptr for g in grad_leaves])
+        if on_ready is None:
+            cb, user = ctypes.cast(None, READY_FN), None
+        elif isinstance(on_ready, tuple):
+            cb, user = on_ready
+        else:
+            err = []
+
+            def _cb(_user, leaf, _f=on_ready):
+                try:
+                    _f(leaf)
+                except BaseException as e:      # an exception must not cross the C frame
+                    err.append(e)
+            cb, user = READY_FN(_cb), None
+        call("pg_plan_backward", self.h, ctypes.c_int64(gen), ptrs, n, cb, user)
+        if on_ready is not None and not isinstance(on_ready, tuple) and err:
+            raise err[0]
+
+    def value_of(self, t):
+        p, dt, pitch = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int64()
+        call("pg_plan_value", self.h, t.id, ctypes.byref(p), ctypes.byref(dt), ctypes.byref(pitch))
+        shape = self.shapes[t.id]
+        last = shape[-1] if shape else 1
+        dtype = {0: np.float32, 1: np.float64, 2: BF16, 3: np.float16, 4: np.int32}[dt.value]
+        if pitch.value != last:
+            return _PitchedView(self.ctx, p.value, shape, dtype, pitch.value)
+        return DeviceArray(_Borrowed(self.ctx, p.value), 0, shape, dtype)
+
+
+class _Borrowed:
+    """non-owning stand-in for a DeviceBuffer (plan-owned storage)"""
+    version = 0
+
+    def __init__(self, ctx, ptr):
+        self.ctx, self.ptr, self.nbytes = ctx, ptr, 0
+
+
+class _PitchedView:
+    """a padded (pitched) plan buffer; numpy() strips the padding"""
+
+    def __init__(self, ctx, ptr, shape, dtype, pitch):
+        self.ctx, self.ptr, self.shape, self.dtype, self.pitch = ctx, ptr, tuple(shape), dtype, pitch
+
+    def numpy(self):
+        rows = _prod(self.shape[:-1])
+        full = DeviceArray(_Borrowed(self.ctx, self.ptr), 0, (rows, self.pitch), self.dtype).numpy()
+        return np.ascontiguousarray(full[:, :self.shape[-1]]).reshape(self.shape)

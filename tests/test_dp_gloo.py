@@ -75,63 +75,29 @@ def test_shard_range():
         dp.shard_range(0, 3, 64)
 
 
-# ---- dp.GradientBuckets (the class bench.py uses) over gloo: bucket boundaries, tail-first issue order,
-#      deferred issue, and the reduced result — with a host stand-in for the gradient arena -----------------
-class _FakeLeaf:
-    def __init__(self, size):
-        self.size, self.dtype = size, np.dtype(np.float32)
-
-
-class _FakeCtx:
-    def __init__(self):
-        self.limits = []
-
-    def set_sm_limit(self, n):
-        self.limits.append(n)
-
-
-class _FakeGradModel:
-    def __init__(self, sizes):
-        from protograd_b200.model import _pad
-        self.leaves = [_FakeLeaf(s) for s in sizes]
-        self.total = sum(_pad(s) for s in sizes)
-        self.ctx = _FakeCtx()
-
-    def arena(self):
-        return self.ctx, 0, self.total, self.leaves
-
-
+# ---- the bucket policy of the library (csrc/dp.cu, pg_dp_bucket_plan: the same rule pg_dp_bucket_ready applies on the
+#      GPU) over gloo: bucket boundaries, tail-first issue order, and the reduced result on a host arena ---------------
 def _bucket_worker(rank, world, port, q):
-    import torch
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from protograd_b200 import dp
     from protograd_b200.model import _pad
     sizes = [784 * 64, 64, 64 * 64, 64, 64 * 10, 10]           # W1 b1 W2 b2 W3 b3 in vec(m) order
-    gm = _FakeGradModel(sizes)
-    flat = torch.zeros(gm.total, dtype=torch.float32)
-    dp.arena_tensor = lambda m: flat                            # host stand-in for the device arena view
-    buckets = dp.GradientBuckets(gm, bucket_bytes=16 << 10, comm_sms=8)
     offs, o = [], 0
     for s in sizes:
         offs.append(o); o += _pad(s)
-    issued = []
-    orig = dp.GradientBuckets._issue
-
-    def spy(self, lo, hi, event=None):
-        issued.append((lo, hi))
-        return orig(self, lo, hi, event)
-    dp.GradientBuckets._issue = spy
-    for step in range(2):                                       # two steps: the bucket state must reset
+    total = o
+    # pg_plan_backward reports a layer's first leaf once its W and b gradients are enqueued, last layer first
+    ready = [4, 2, 0]
+    plan = dp.bucket_plan(sizes, ready, bucket_bytes=16 << 10)
+    for step in range(2):
         rng = np.random.default_rng(100 * step + rank)
-        issued.clear()
-        flat.zero_()
-        for i in range(len(sizes) - 1, -1, -1):                 # backward finishes leaves last-to-first
-            flat[offs[i]:offs[i] + sizes[i]] = torch.from_numpy(rng.standard_normal(sizes[i]).astype(np.float32))
-            if i % 2 == 0:                                      # a layer's W and b are ready together
-                buckets.ready(i)
-        buckets.finish()
-        q.put((rank, step, flat.numpy().copy(), list(issued), list(gm.ctx.limits)))
+        flat = np.zeros(total, dtype=np.float32)
+        for i in range(len(sizes) - 1, -1, -1):
+            flat[offs[i]:offs[i] + sizes[i]] = rng.standard_normal(sizes[i]).astype(np.float32)
+        for lo, cnt in plan:                                    # one collective per bucket, in issue order
+            dp.allreduce_host(flat[lo:lo + cnt])
+        q.put((rank, step, flat.copy(), plan))
     dist.destroy_process_group()
 
 
@@ -153,7 +119,7 @@ def test_gradient_buckets_over_gloo():
         offs.append(o); o += _pad(s)
     total = o
     for step in range(2):
-        got = {r: (f, iss, lim) for r, st, f, iss, lim in res if st == step}
+        got = {r: (f, plan) for r, st, f, plan in res if st == step}
         # expected: sum over ranks of the per-rank gradients, padding stays zero
         want = np.zeros(total, dtype=np.float32)
         for r in range(world):
@@ -163,12 +129,22 @@ def test_gradient_buckets_over_gloo():
                 part[offs[i]:offs[i] + sizes[i]] = rng.standard_normal(sizes[i]).astype(np.float32)
             want += part
         for r in range(world):
-            f, iss, lim = got[r]
+            f, plan = got[r]
             assert np.allclose(f, want, rtol=1e-6, atol=1e-6)
             # buckets: tail first, contiguous, disjoint, covering [0, total); W3+b3 (2.6 KB) is below the
-            # 16 KB threshold and rides with W2+b2; the head slice (W1, b1) is issued by finish()
-            assert iss == [(offs[2], total), (0, offs[2])]
+            # 16 KB threshold and rides with W2+b2; the head slice (W1, b1) is issued at the end
+            assert plan == [(offs[2], total - offs[2]), (0, offs[2])]
         assert got[0][0].tobytes() == got[1][0].tobytes()        # replicas bit-identical
-    # SMs were reserved while a bucket was in flight and released at the end of every step
-    lim = [l for r, st, f, iss, l in res if st == 1 and r == 0][0]
-    assert lim == [-8, 0, -8, 0]
+
+
+def test_bucket_plan_policy():
+    from protograd_b200 import dp
+    from protograd_b200.capi import PGError
+    sizes = [3_215_360 // 1, 4096, 16_781_312 // 1, 4096, 40_960, 10]      # C4's leaves (BASELINE configs[3])
+    plan = dp.bucket_plan(sizes, [4, 2, 0], bucket_bytes=24 << 20)
+    assert len(plan) == 2 and plan[0][0] + plan[0][1] == sum(plan[i][1] for i in range(2)) and plan[1][0] == 0
+    assert plan[0][1] * 4 > (24 << 20)                                       # [W2 b2 W3 b3] = 67 MB, then the head
+    one = dp.bucket_plan(sizes, [4, 2, 0], bucket_bytes=1 << 30)
+    assert one == [(0, plan[0][0] + plan[0][1])]                             # nothing reaches the threshold: one flat all-reduce
+    with pytest.raises(PGError, match="last-to-first"):
+        dp.bucket_plan(sizes, [2, 4], bucket_bytes=1 << 20)

@@ -24,9 +24,9 @@ def _models(pg, T, rng):
     return [("Linear", lin), ("Compose", comp)]
 
 
-@pytest.mark.parametrize("T", [np.float32, np.float64])
+@pytest.mark.parametrize("T", [np.float16, np.float32, np.float64])
 def test_basic_operations(pg, T):
-    """test/test_models.jl:17-128"""
+    """test/test_models.jl:17-128 — the reference runs this matrix for T in (Float16, Float32, Float64), :18"""
     rng = np.random.default_rng(0)
     for name, m in _models(pg, T, rng):
         v = m.vec()
@@ -55,7 +55,7 @@ def test_basic_operations(pg, T):
         assert type(m.similar()) is type(m)
         s = m * 1 + m * 2 + m * 3                         # sum(k*m for k=1:3) == 6*vec
         assert np.array_equal(s.vec(), T(1) * v + T(2) * v + T(3) * v)
-        assert np.allclose(((m * 1 + m * 2 + m * 4) / 3).vec(), T(7) / T(3) * v, rtol=1e-6)
+        assert np.allclose(((m * 1 + m * 2 + m * 4) / 3).vec(), T(7) / T(3) * v, rtol=max(1e-6, 4 * np.finfo(T).eps))
         assert np.array_equal(np.array(list(m), dtype=T), v)
         assert len(m) == v.size
         m[-2] = 42
@@ -64,10 +64,13 @@ def test_basic_operations(pg, T):
         v = m.vec()
         assert np.array_equal((1 - m).vec(), T(1) - v)
         assert np.array_equal((m * 0.1).vec(), (v.astype(np.float64) * 0.1).astype(T))
-        assert np.array_equal((m * np.float32(0.1)).vec(), v * T(np.float32(0.1)))
+        if T is np.float16:     # Float16 .* Float32 promotes to Float32 per element, rounded once on store
+            assert np.array_equal((m * np.float32(0.1)).vec(), (v.astype(np.float32) * np.float32(0.1)).astype(T))
+        else:
+            assert np.array_equal((m * np.float32(0.1)).vec(), v * T(np.float32(0.1)))
         assert np.array_equal(pg.ldiv(2, m).vec(), T(2) / v)
         # padding stays invisible to dot after non-zero-preserving ops
-        assert np.isclose(pg.dot(m1, m1), np.dot(m1.vec().astype(np.float64), m1.vec().astype(np.float64)), rtol=1e-6)
+        assert np.isclose(pg.dot(m1, m1), np.dot(m1.vec().astype(np.float64), m1.vec().astype(np.float64)), rtol=max(1e-6, 2 * np.finfo(T).eps))
 
 
 @pytest.mark.parametrize("T", [np.float32, np.float64])
@@ -195,3 +198,61 @@ def test_c4_size_arena_dot_and_adam(pg):
     assert np.array_equal(m.vec(), xo)
     # linearity property at full size: (m + g) - g == m up to one rounding
     assert rel_err(((m + g) - g).vec(), m.vec()) < 1e-6
+
+
+# ---- generic-f Model broadcast (src/model.jl:148-164: copyto! accepts ANY flattened f) -----------------------------
+@pytest.mark.parametrize("T", [np.float16, np.float32, np.float64])
+def test_generic_broadcast_expression_one_kernel(pg, T):
+    """Expressions outside the Appendix-C set run as ONE interpreter kernel (pg_vec_expr) with Julia's per-op
+    promotion: ops between T values round to T, ops touching a Float64 literal run in Float64, one rounding on store."""
+    from protograd_b200 import broadcast as B
+    rng = np.random.default_rng(5)
+    m = pg.Compose(pg.Linear(40, 33, dtype=T, rng=rng), pg.relu, pg.Linear(33, 7, dtype=T, rng=rng))
+    a, b, c = m.copy(), m.copy(), m.copy()
+    for x in (a, b, c):
+        x.set_vec((rng.standard_normal(len(m)) + 0.1).astype(T))
+    va, vb, vc = a.vec(), b.vec(), c.vec()
+    f8 = np.float64
+    ctx = pg.Context.get()
+    n0 = ctx.launch_count()
+    # the Adam update written as a user would in Model algebra (adam.jl:33-39 flattened into one expression)
+    out = m.similar()
+    out.assign(pg.L(a) - 0.001 * (pg.L(b) / (B.sqrt(B.abs_(pg.L(c))) + 1e-8)))
+    assert ctx.launch_count() - n0 <= 1 + len(m.allparams())          # one kernel (+ zeroing of leaf padding)
+    den = np.sqrt(np.abs(vc)).astype(f8) + 1e-8                          # sqrt in T, + eps in Float64
+    want = (va.astype(f8) - 0.001 * (vb.astype(f8) / den)).astype(T)
+    assert np.array_equal(out.vec(), want)
+    # all-T expression: every op rounds to T
+    out.assign(pg.L(a) * pg.L(b) + pg.L(c) * pg.L(c) - B.maximum(pg.L(a), pg.L(b)) / 3)
+    want = (va * vb + vc * vc - np.maximum(va, vb) / T(3)).astype(T)
+    assert np.array_equal(out.vec(), want)
+    # literal_pow, relu, unary minus, Int scalars stay in T
+    out.assign(-(pg.L(a) ** 2) + 2 * B.relu_(pg.L(b)))
+    want = (-(va * va) + T(2) * np.maximum(vb, T(0))).astype(T)
+    assert np.array_equal(out.vec(), want)
+    # exp / log are library functions: equal to rounding of the float64 value within 2 ulp of T
+    out.assign(B.log(B.exp(pg.L(a) * 0.5) + 1.0))
+    want = np.log(np.exp(va.astype(f8) * 0.5) + 1.0)
+    assert np.allclose(out.vec().astype(f8), want, rtol=4 * np.finfo(T).eps, atol=4 * np.finfo(T).eps)
+    # padding of the arena stays zero (dot sees only real elements) although f(0, ...) != 0
+    out.assign(pg.L(a) * 0 + 1.5)
+    assert np.isclose(float(pg.dot(out, out)), 2.25 * len(m), rtol=1e-3)
+    # dest .= scalar
+    out.assign(0.25)
+    assert np.array_equal(out.vec(), np.full(len(m), 0.25, dtype=T))
+
+
+def test_float16_optimizer_written_in_model_algebra(pg):
+    """a user optimizer written in Model algebra on a Float16 model (the drop-in case of SURVEY §8(f)#4)"""
+    T = np.float16
+    rng = np.random.default_rng(6)
+    m = pg.Linear(64, 16, dtype=T, rng=rng)
+    g = m.copy(); g.set_vec(rng.standard_normal(len(m)).astype(T))
+    d = m.zero()
+    v, gv, dv = m.vec(), g.vec(), d.vec()
+    for _ in range(3):                                               # heavy ball: d .= mu.*d .- s.*g ; m .+= d
+        d.assign(0.5 * pg.L(d) - 0.1 * pg.L(g))
+        m.assign(pg.L(m) + pg.L(d))
+        dv = (0.5 * dv.astype(np.float64) - 0.1 * gv.astype(np.float64)).astype(T)
+        v = v + dv
+    assert np.array_equal(d.vec(), dv) and np.array_equal(m.vec(), v)

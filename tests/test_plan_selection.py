@@ -1,23 +1,20 @@
-"""CPU-only: which layers a math="bf16" plan puts on the tcgen05 kernels (Plan._select_tensor_core_ops).
-The traced graph and the selection are pure host logic; a plan subclass skips the device allocations.
-Rules under test: a Linear runs on tensor cores when it is fed by a trace input or by
-the bf16 activation of another tensor-core Linear and K % 8 == 0 and (N % 8 == 0 or N <= 32); a wide layer
-whose consumer is not a tensor-core Linear is demoted; a Conv whenever pg_tc_conv2d_supported says so."""
+"""CPU-only: which layers a math="bf16" plan puts on the tcgen05 kernels.  The planner lives behind the C ABI
+(csrc/plan.cu); pg_plan_create and pg_plan_node_flags are host logic (no GPU: buffers are allocated by the first
+forward), so the traced graph and the selection can be checked here.
+Rules under test: in bf16 mode a Float32 Linear with batch % 8 == 0 runs on tensor cores —
+widths that are not multiples of 8 (the reference's own 100 / 120 / 84) through zero-padded operand copies, fp32
+inputs (pool outputs) through a cast; a wide (N > 32) layer stores a bf16 activation, so its consumer must be a
+tensor-core Linear too, otherwise it is demoted to the fp32 SIMT GEMM; a Conv whenever pg_tc_conv2d_supported says so."""
 import numpy as np
 
 from protograd_b200 import trace as T
-
-
-class DryPlan(T.Plan):
-    def _alloc(self):               # no device in the CPU suite
-        pass
 
 
 def leaf(*shape):
     return np.zeros(shape, dtype=np.float32)
 
 
-def mlp(widths, B=64, math="bf16", relu_between=True):
+def mlp(widths, B=64, math="bf16", relu_between=True, tail="ce"):
     ps = []
     for k, n in zip(widths[:-1], widths[1:]):
         ps += [leaf(k, n), leaf(n)]
@@ -29,14 +26,18 @@ def mlp(widths, B=64, math="bf16", relu_between=True):
         lins.append(h.id)
         if relu_between and i < len(widths) - 2:
             h = T.relu(h)
-    root = T.cross_entropy(T.softmax(h), np.zeros((B, widths[-1]), dtype=np.float32))
-    return DryPlan(tr, root), lins
+    if tail == "ce":
+        root = T.cross_entropy(T.softmax(h), np.zeros((B, widths[-1]), dtype=np.float32))
+    else:
+        root = T.mse(h, np.zeros((B, widths[-1]), dtype=np.float32))
+    return T.Plan(tr, root), lins
 
 
 def test_wide_mlp_is_all_tensor_core():
     plan, lins = mlp([784, 4096, 4096, 10])          # BASELINE configs[3]
     assert plan.tc_linear == set(lins) and not plan.tc_conv
-    assert plan._act_dtype(lins[0]) == T.BF16 and plan._act_dtype(lins[2]) == np.float32   # logits stay float
+    assert plan.act_is_bf16(lins[0]) and plan.act_is_bf16(lins[1]) and not plan.act_is_bf16(lins[2])   # logits stay float
+    assert set(plan.shadow_params) == {l - 2 for l in lins} or len(plan.shadow_params) == 3
 
 
 def test_fp32_mode_selects_nothing():
@@ -44,16 +45,27 @@ def test_fp32_mode_selects_nothing():
     assert not plan.tc_linear and not plan.tc_conv
 
 
-def test_awkward_width_stays_on_simt_and_demotes_its_producer():
-    # 784 -> 100: N = 100 is not a multiple of 8 -> SIMT; everything downstream then sees fp32 activations
+def test_reference_example_widths_run_on_tensor_cores_padded():
+    # examples/01_mnist_mlp.jl:20: hidden = 100 (not a multiple of 8): zero-padded operand copies, no arena shadow
     plan, lins = mlp([784, 100, 10])
-    assert not plan.tc_linear
-    # 784 -> 4096 -> 100 -> 10: the 4096-wide layer would store bf16 for a consumer that cannot read it
-    plan, lins = mlp([784, 4096, 100, 10])
-    assert not plan.tc_linear
-    # K not a multiple of 8
+    assert plan.tc_linear == set(lins)
+    assert plan.act_is_bf16(lins[0])
+    assert len(plan.shadow_params) == 0 or all(plan.shapes[w][1] != 100 and plan.shapes[w][0] != 100 for w in plan.shadow_params)
+    # K not a multiple of 8 either
     plan, lins = mlp([100, 4096, 10])
-    assert lins[0] not in plan.tc_linear and not plan.tc_linear
+    assert plan.tc_linear == set(lins)
+
+
+def test_ragged_batch_stays_on_simt():
+    plan, lins = mlp([784, 4096, 4096, 10], B=100)    # batch % 8 != 0: TMA pitch of the transposed operands
+    assert not plan.tc_linear
+
+
+def test_wide_layer_feeding_the_loss_directly_is_demoted():
+    # 784 -> 4096 -> 64 with an mse on the 64-wide output: the last layer would store bf16 for a consumer that
+    # cannot read it -> SIMT; the first layer then feeds an fp32 layer -> demoted as well
+    plan, lins = mlp([784, 4096, 64], tail="mse")
+    assert not plan.tc_linear
 
 
 def test_narrow_output_layer_alone_is_tensor_core():
@@ -78,15 +90,16 @@ def lenet(B=32, frozen_trunk=False):
         if W is not W3:
             h = T.relu(h)
     root = T.cross_entropy(T.softmax(h), np.zeros((B, 10), dtype=np.float32))
-    return DryPlan(tr, root), (conv1, conv2), lins
+    return T.Plan(tr, root), (conv1, conv2), lins
 
 
-def test_lenet_convs_on_tensor_cores_head_on_simt():
-    plan, convs, lins = lenet()                        # BASELINE configs[2]
+def test_lenet_convs_and_head_on_tensor_cores():
+    plan, convs, lins = lenet()                        # BASELINE configs[2] (examples/02_mnist_conv.jl:25-44)
     assert plan.tc_conv == set(convs)
-    assert not plan.tc_linear                          # the head is fed by a pooling layer (fp32 activations)
-    for i in lins + list(convs):
-        assert plan._act_dtype(i) == np.float32
+    assert plan.tc_linear == set(lins)                 # 256-120-84-10 head: pool-fed (cast), widths 120 / 84 padded
+    assert plan.act_is_bf16(lins[0]) and plan.act_is_bf16(lins[1]) and not plan.act_is_bf16(lins[2])
+    for c in convs:
+        assert not plan.act_is_bf16(c)                 # conv tensors stay Float32 in HBM
 
 
 def test_frozen_trunk_keeps_forward_on_tensor_cores():
@@ -100,4 +113,16 @@ def test_wide_conv_stays_on_simt():
     tr = T.Trace(None, trainable=[w, b], math="bf16")
     x = tr.lift(np.zeros((4, 3, 16, 16), dtype=np.float32))
     root = T.mse(T.conv(x, w, b), np.zeros((4, 32, 14, 14), dtype=np.float32))
-    assert not DryPlan(tr, root).tc_conv
+    assert not T.Plan(tr, root).tc_conv
+
+
+def test_graph_rules_are_enforced_by_the_library():
+    import pytest
+    from protograd_b200.capi import PGError
+    W, b = leaf(8, 8), leaf(8)
+    tr = T.Trace(None, trainable=[W, b], math="fp32")
+    x = tr.lift(np.zeros((4, 8), dtype=np.float32))
+    h = T.relu(T.linear(x, W, b))
+    root = T.mse(T.linear(h, W, b), np.zeros((4, 8), dtype=np.float32))       # the same trainable leaf used twice
+    with pytest.raises(PGError, match="weight sharing"):
+        T.Plan(tr, root)
