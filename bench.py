@@ -264,8 +264,11 @@ def main():
     x_p[...] = x_h; lab_p[...] = lab_h
 
     dpc = dp.init(ctx) if world > 1 else None        # the library's own NCCL communicator (csrc/dp.cu), id via torch.distributed
+    # fused=(model, state): gradient exchange + Adam update in ONE kernel per bucket over NVLink peer memory (csrc/dp.cu);
+    # falls back to ncclAllReduce buckets + the fused Adam pass when peer memory cannot be mapped (or PG_DP_FUSED=0)
     buckets = dp.GradientBuckets(pg.gradient_container(model), bucket_bytes=int(os.environ.get("PG_BUCKET_MB", "24")) << 20, dp=dpc,
-                                 overlap_update=os.environ.get("PG_DP_OVERLAP_UPDATE", "1") == "1") if world > 1 else None
+                                 overlap_update=os.environ.get("PG_DP_OVERLAP_UPDATE", "1") == "1",
+                                 fused=(model, state) if args.dp_mode == "bucket" else None) if world > 1 else None
     if args.sm_limit:
         ctx.set_sm_limit(args.sm_limit)
     use_shadow = args.math == "bf16"
@@ -317,7 +320,7 @@ def main():
         xg, lg = synth(PB * world, 77)
         xs, ls = xg[rank * PB:(rank + 1) * PB], lg[rank * PB:(rank + 1) * PB]
         out, pb = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(xs), ls, global_batch=PB * world), model, math=args.math)
-        g = pb(on_ready=buckets.on_ready())
+        g = pb(on_ready=buckets.on_ready(reduce_only=True))
         buckets.finish()
         g_dp = g.vec().astype(np.float64)
         out1, pb1 = pg.eval_with_pullback(lambda m: pg.cross_entropy(m(xg), lg), model, math=args.math)

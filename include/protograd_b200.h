@@ -314,6 +314,17 @@ void pg_dp_bucket_ready(void* dp, int first_grad_leaf);
 /* number of issued buckets; ranges as (start element, count) of the padded arena, in issue order (tail first) */
 int pg_dp_bucket_finish(pg_dp* dp, int* n_buckets, int64_t* starts, int64_t* counts, int max_buckets);
 int pg_dp_bucket_wait(pg_dp* dp, int bucket);   /* ctx stream waits for bucket k's reduction */
+/* Fused gradient exchange + optimizer update over NVLink peer memory (CUDA IPC; csrc/dp.cu): each rank owns 1/world of
+ * every bucket; ONE kernel per bucket reads that slice of the gradient arena from all peers (P2P loads, summed in rank
+ * order), applies the optimizer to the slice (touching 1/world of the optimizer state) and stores the new fp32 parameters
+ * and their bf16 copy into every replica (P2P stores).  It replaces ncclAllReduce + the full-arena pg_opt_* pass of a
+ * data-parallel step.  shadow2: bf16 [2][n_padded] double buffer (nullable): the step in flight reads one half, the
+ * kernels write the other.  PG_ERR_UNSUPPORTED (peer memory cannot be mapped) leaves the all-reduce path in use. */
+int pg_dp_p2p_enable(pg_dp* dp, pg_arena* params, pg_arena* grads, void* shadow2);
+/* the optimizer the NEXT bucketed backward applies: kind 0 = Adam (m, v: state arenas; `it` before the increment; flags as
+ * pg_opt_adam), 2 = GradientDescent, -1 = off (buckets are plain all-reduces again) */
+int pg_dp_p2p_set_optimizer(pg_dp* dp, int kind, void* m, void* v, double stepsize, double beta1, double beta2, double epsilon, int64_t it, int flags);
+int pg_dp_p2p_shadow_half(pg_dp* dp, int* half);
 /* the bucket policy as a pure host function (no GPU): slices issued for a sequence of on_ready leaf indices */
 int pg_dp_bucket_plan(int dtype, int n_leaves, const int64_t* leaf_sizes, int64_t bucket_bytes, const int* ready_leaves, int n_ready,
                       int64_t* starts, int64_t* counts, int max_buckets, int* n_buckets);

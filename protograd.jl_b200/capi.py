@@ -130,6 +130,9 @@ _SIGS = {
     "pg_dp_bucket_begin": [_P, _P, _L],
     "pg_dp_bucket_finish": [_P, POINTER(c_int), POINTER(c_int64), POINTER(c_int64), _I],
     "pg_dp_bucket_wait": [_P, _I],
+    "pg_dp_p2p_enable": [_P, _P, _P, _P],
+    "pg_dp_p2p_set_optimizer": [_P, _I, _P, _P, _D, _D, _D, _D, _L, _I],
+    "pg_dp_p2p_shadow_half": [_P, POINTER(c_int)],
     "pg_dp_bucket_plan": [_I, _I, POINTER(c_int64), _L, POINTER(c_int), _I, POINTER(c_int64), POINTER(c_int64), _I, POINTER(c_int)],
 }
 _VOID = {"pg_dp_bucket_ready": [_P, _I]}

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "optim.cuh"
 
 // from arena.cu
 void* pg_arena_base(pg_arena* a);
@@ -47,6 +48,7 @@ struct Nccl {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 Nccl g_nccl;
@@ -68,7 +70,7 @@ int nccl_load() {
 #define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name)
   SYM(GetVersion, "ncclGetVersion"); SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank");
   SYM(CommInitRankConfig, "ncclCommInitRankConfig"); SYM(CommDestroy, "ncclCommDestroy"); SYM(AllReduce, "ncclAllReduce");
-  SYM(Broadcast, "ncclBroadcast"); SYM(GetErrorString, "ncclGetErrorString");
+  SYM(Broadcast, "ncclBroadcast"); SYM(GetErrorString, "ncclGetErrorString"); SYM(AllGather, "ncclAllGather");
 #undef SYM
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Broadcast || !g_nccl.CommDestroy) {
     pg_set_error("libnccl is missing a required symbol");
@@ -98,6 +100,135 @@ int nccl_type(int dtype) {
   return -1;
 }
 
+
+// ================================================================================================================
+// Fused gradient exchange + optimizer update over NVLink peer memory.
+//
+// ncclAllReduce + a full-arena Adam pass moves every gradient byte across NVLink twice (reduce-scatter + all-gather),
+// runs ~24 CTAs with their own shared memory next to the backward GEMMs and then streams 28 B/param of optimizer
+// state through HBM on every rank.  Here each rank OWNS 1/world of every bucket: one kernel
+//   1. waits until every peer has finished producing the bucket (epoch flags written into this rank's memory),
+//   2. reads its slice of the gradient arena from all peers (P2P loads: each gradient byte crosses NVLink once), sums in
+//      rank order (deterministic, identical on every replica by construction),
+//   3. applies the optimizer to its slice — optimizer state is touched for 1/world of the arena only,
+//   4. stores the new fp32 parameters and their bf16 shadow into EVERY replica (P2P stores; the shadow goes to the half
+//      of a double buffer that the step in flight does not read, so a peer's backward GEMMs are never raced),
+//   5. signals completion to every peer and waits for theirs, so kernel completion means "my replica is up to date".
+// The kernel uses no shared memory and few registers: it co-resides with the persistent GEMM CTAs instead of
+// taking SMs away from them.
+// ================================================================================================================
+constexpr int MAXR = 8, SLOTS = 16;
+
+struct P2PArgs {
+  const float* grad[MAXR];
+  float* param[MAXR];
+  __nv_bfloat16* shadow[MAXR];
+  unsigned int* flags[MAXR];
+  float* m; float* v;
+  unsigned int* block_counter;
+  int rank, world, slot;
+  unsigned int epoch;
+  long long lo, hi;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_sys_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_epoch(const unsigned int* p, unsigned int epoch) {
+  if ((int)(ld_acquire_sys(p) - epoch) >= 0) return;
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(p) - epoch) < 0) {
+    __nanosleep(200);
+    if (clock64() - t0 > 6000000000ll) __trap();       // ~3 s: a peer died; fail loudly instead of hanging the GPU
+  }
+}
+
+// F: per-element update functor, f(p, m, v, g) -> writes p, m, v (GD ignores m, v)
+// Launched as clusters of two CTAs: a pair occupies one whole TPC, so the co-running 2-CTA GEMM kernels (which need both
+// SMs of a TPC) lose whole pairs, never half of one.
+template <typename F, bool STATE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512) p2p_update_kernel(P2PArgs a, F f) {
+  const int W = a.world, R = a.rank;
+  unsigned int* mine = a.flags[R];
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();                           // this rank's gradient kernels precede in stream order
+      for (int p = 0; p < W; ++p) st_release_sys(a.flags[p] + R * SLOTS + 2 * a.slot, a.epoch);
+    }
+    for (int p = 0; p < W; ++p) wait_epoch(mine + p * SLOTS + 2 * a.slot, a.epoch);
+  }
+  __syncthreads();
+  const long long len = a.hi - a.lo;
+  long long chunk = (len + W - 1) / W;
+  chunk = (chunk + 3) / 4 * 4;
+  const long long c0 = a.lo + (long long)R * chunk;
+  long long c1 = c0 + chunk;
+  if (c1 > a.hi) c1 = a.hi;
+  const long long nvec = c1 > c0 ? (c1 - c0) / 4 : 0;   // lo, hi and chunk are multiples of 4
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = c0 + 4 * i;
+    float4 g = ld_sys_f4(a.grad[0] + e);
+    for (int p = 1; p < W; ++p) {
+      const float4 t = ld_sys_f4(a.grad[p] + e);
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    float4 pv = *reinterpret_cast<const float4*>(a.param[R] + e);
+    float4 mv = make_float4(0, 0, 0, 0), vv = mv;
+    if (STATE) { mv = *reinterpret_cast<const float4*>(a.m + e); vv = *reinterpret_cast<const float4*>(a.v + e); }
+    f(pv.x, mv.x, vv.x, g.x); f(pv.y, mv.y, vv.y, g.y); f(pv.z, mv.z, vv.z, g.z); f(pv.w, mv.w, vv.w, g.w);
+    if (STATE) { *reinterpret_cast<float4*>(a.m + e) = mv; *reinterpret_cast<float4*>(a.v + e) = vv; }
+    __nv_bfloat162 pk[2];
+    pk[0] = __floats2bfloat162_rn(pv.x, pv.y); pk[1] = __floats2bfloat162_rn(pv.z, pv.w);
+    const uint2 sh = *reinterpret_cast<uint2*>(pk);
+    for (int p = 0; p < W; ++p) {
+      *reinterpret_cast<float4*>(a.param[p] + e) = pv;
+      if (a.shadow[p] != nullptr) *reinterpret_cast<uint2*>(a.shadow[p] + e) = sh;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(a.block_counter, 1u) == gridDim.x - 1) {
+      *a.block_counter = 0u;
+      __threadfence_system();
+      for (int p = 0; p < W; ++p) st_release_sys(a.flags[p] + R * SLOTS + 2 * a.slot + 1, a.epoch);
+      for (int p = 0; p < W; ++p) wait_epoch(mine + p * SLOTS + 2 * a.slot + 1, a.epoch);
+    }
+  }
+}
+
+struct P2PAdamFast {           // AdamFastF of optim.cuh on scalars
+  float s, b1, omb1, b2, omb2, rc1, rc2, eps;
+  __device__ __forceinline__ void operator()(float& p, float& m, float& v, float g) const {
+    m = fmaf(b1, m, omb1 * g);
+    v = fmaf(b2, v, omb2 * g * g);
+    p = p - s * __fdividef(m * rc1, sqrtf(v * rc2) + eps);
+  }
+};
+struct P2PAdamExact {          // AdamF<float, double>: Float64-promoted per-element math (bit-exact with the reference's broadcast)
+  double s, b1, omb1, b2, omb2, c1, c2, eps;
+  __device__ __forceinline__ void operator()(float& p, float& m, float& v, float g) const {
+    const float in[4] = {p, m, v, g};
+    float out[5];
+    AdamF<float, double>{s, b1, omb1, b2, omb2, c1, c2, eps, nullptr}(in, out);
+    p = out[0]; m = out[1]; v = out[2];
+  }
+};
+struct P2PGd {
+  double s; int f64;
+  __device__ __forceinline__ void operator()(float& p, float&, float&, float g) const {
+    p = f64 ? (float)__dsub_rn((double)p, __dmul_rn(s, (double)g)) : __fsub_rn(p, __fmul_rn((float)s, g));
+  }
+};
+
 struct Bucket { int64_t start, count; cudaEvent_t done; };
 
 }  // namespace
@@ -116,6 +247,22 @@ struct pg_dp {
   std::vector<Bucket> buckets;
   std::vector<cudaEvent_t> event_pool;
   int error = PG_OK;                        // first error raised inside the on_ready callback
+  // ---- fused exchange + update over NVLink peer memory (pg_dp_p2p_*) ----
+  bool p2p = false;
+  void* peer_grad[8] = {nullptr};           // every rank's gradient arena, mapped here (own = local pointer)
+  void* peer_param[8] = {nullptr};
+  void* peer_shadow[8] = {nullptr};         // bf16 [2][n_padded] (nullable)
+  void* peer_flags[8] = {nullptr};
+  void* opened[32] = {nullptr}; int n_opened = 0;
+  void* flags_local = nullptr;              // [8 ranks][16 slots] epochs written by the peers
+  unsigned int* block_counter = nullptr;
+  int64_t p2p_padded = 0;
+  unsigned int epoch = 0;
+  int shadow_half = 0;                      // the half the CURRENT parameters' bf16 copy lives in
+  // optimizer of the step in flight (set by pg_dp_p2p_set_adam before pg_plan_backward)
+  struct { int kind = -1; void* m = nullptr; void* v = nullptr; double s = 0, b1 = 0, b2 = 0, eps = 0; int64_t it = 1; int flags = 0; } opt;
+  int p2p_blocks = 16, p2p_blocks_last = 96;
+  bool fused_step = false;
 };
 
 namespace {
@@ -126,13 +273,57 @@ int order_after_ctx(pg_dp* dp) {
   return PG_OK;
 }
 
+int launch_p2p(pg_dp* dp, int64_t lo, int64_t hi, int slot, bool last) {
+  P2PArgs a;
+  memset(&a, 0, sizeof(a));
+  const bool use_shadow = dp->peer_shadow[dp->rank] != nullptr;
+  for (int p = 0; p < dp->world; ++p) {
+    a.grad[p] = (const float*)dp->peer_grad[p];
+    a.param[p] = (float*)dp->peer_param[p];
+    // bf16 copies of the NEW parameters go to the half the step in flight does not read
+    a.shadow[p] = use_shadow ? (__nv_bfloat16*)dp->peer_shadow[p] + (size_t)(dp->shadow_half ^ 1) * dp->p2p_padded : nullptr;
+    a.flags[p] = (unsigned int*)dp->peer_flags[p];
+  }
+  a.m = (float*)dp->opt.m; a.v = (float*)dp->opt.v;
+  a.block_counter = dp->block_counter;
+  a.rank = dp->rank; a.world = dp->world; a.slot = slot; a.epoch = dp->epoch;
+  a.lo = lo; a.hi = hi;
+  const double s = dp->opt.s, b1 = dp->opt.b1, b2 = dp->opt.b2;
+  // buckets that overlap the remaining backward GEMMs run on a few TPCs; the last one has the GPU to itself
+  int grid = last ? dp->p2p_blocks_last : dp->p2p_blocks;
+  grid = (grid + 1) / 2 * 2;
+  if (dp->opt.kind == 0) {
+    const double c1 = 1.0 - pow(b1, (double)dp->opt.it), c2 = 1.0 - pow(b2, (double)dp->opt.it);
+    if (dp->opt.flags & PG_MATH_FAST) {
+      P2PAdamFast f{(float)s, (float)b1, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)(1.0 / c1), (float)(1.0 / c2), (float)dp->opt.eps};
+      p2p_update_kernel<P2PAdamFast, true><<<grid, 512, 0, dp->stream>>>(a, f);
+    } else {
+      P2PAdamExact f{s, b1, 1.0 - b1, b2, 1.0 - b2, c1, c2, dp->opt.eps};
+      p2p_update_kernel<P2PAdamExact, true><<<grid, 512, 0, dp->stream>>>(a, f);
+    }
+  } else {
+    P2PGd f{s, (dp->opt.flags & PG_SCALAR_F64) ? 1 : 0};
+    p2p_update_kernel<P2PGd, false><<<grid, 512, 0, dp->stream>>>(a, f);
+  }
+  dp->ctx->launches++;
+  PG_CHECK_CUDA(cudaGetLastError());
+  return PG_OK;
+}
+
 int issue_bucket(pg_dp* dp, int64_t lo, int64_t hi) {
   const int dt = pg_arena_dtype(dp->grads);
   const size_t es = dt == PG_F64 ? 8 : dt == PG_F16 ? 2 : 4;
   int rc = order_after_ctx(dp);
   if (rc != PG_OK) return rc;
   char* p = (char*)pg_arena_base(dp->grads) + (size_t)lo * es;
-  PG_CHECK_NCCL(g_nccl.AllReduce(p, p, (size_t)(hi - lo), nccl_type(dt), ncclSum, dp->comm, dp->stream));
+  if (dp->p2p && dp->opt.kind >= 0) {
+    PG_REQUIRE(dp->buckets.size() < SLOTS / 2, "too many buckets for the fused exchange (8)");
+    PG_REQUIRE(pg_arena_base(dp->grads) == dp->peer_grad[dp->rank], "fused exchange: not the gradient arena that was registered");
+    rc = launch_p2p(dp, lo, hi, (int)dp->buckets.size(), lo == 0);
+    if (rc != PG_OK) return rc;
+  } else {
+    PG_CHECK_NCCL(g_nccl.AllReduce(p, p, (size_t)(hi - lo), nccl_type(dt), ncclSum, dp->comm, dp->stream));
+  }
   Bucket b{lo, hi - lo, nullptr};
   const size_t k = dp->buckets.size();
   if (k >= dp->event_pool.size()) {
@@ -201,6 +392,9 @@ int pg_dp_destroy(pg_dp* dp) {
   cudaSetDevice(dp->ctx->device);
   if (dp->stream) cudaStreamSynchronize(dp->stream);
   if (dp->comm) g_nccl.CommDestroy(dp->comm);
+  for (int k = 0; k < dp->n_opened; ++k) cudaIpcCloseMemHandle(dp->opened[k]);
+  if (dp->flags_local) cudaFree(dp->flags_local);
+  if (dp->block_counter) cudaFree(dp->block_counter);
   for (cudaEvent_t e : dp->event_pool) cudaEventDestroy(e);
   if (dp->ready) cudaEventDestroy(dp->ready);
   if (dp->done) cudaEventDestroy(dp->done);
@@ -214,7 +408,7 @@ int pg_dp_info(pg_dp* dp, int* rank, int* world, int* nccl_version, int* p2p) {
   if (rank) *rank = dp->rank;
   if (world) *world = dp->world;
   if (nccl_version) *nccl_version = dp->version;
-  if (p2p) *p2p = 0;
+  if (p2p) *p2p = dp->p2p ? 1 : 0;
   return PG_OK;
 }
 
@@ -249,6 +443,105 @@ int pg_dp_wait(pg_dp* dp) {
   return PG_OK;
 }
 
+
+// ---- fused exchange + update over peer memory: setup -------------------------------------------------------------
+static int ipc_export(void* ptr, cudaIpcMemHandle_t* h, int64_t* offset) {
+  // the handle names the whole allocation: find its base to learn the offset of `ptr` inside it
+  typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+  static GetRange get_range = nullptr;
+  if (!get_range) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    PG_CHECK_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+    get_range = (GetRange)fn;
+  }
+  unsigned long long base = 0; size_t size = 0;
+  if (!get_range || get_range(&base, &size, (unsigned long long)ptr) != 0) { pg_set_error("cuMemGetAddressRange failed"); return PG_ERR_CUDA; }
+  PG_CHECK_CUDA(cudaIpcGetMemHandle(h, (void*)base));
+  *offset = (int64_t)((unsigned long long)ptr - base);
+  return PG_OK;
+}
+
+int pg_dp_p2p_enable(pg_dp* dp, pg_arena* params, pg_arena* grads, void* shadow2) {
+  PG_REQUIRE(dp != nullptr && params != nullptr && grads != nullptr, "null pointer");
+  PG_REQUIRE(dp->world <= MAXR, "the fused exchange supports up to 8 ranks (one NVSwitch domain)");
+  PG_REQUIRE(pg_arena_dtype(params) == PG_F32 && pg_arena_dtype(grads) == PG_F32, "the fused exchange needs Float32 arenas");
+  PG_REQUIRE(pg_arena_padded(params) == pg_arena_padded(grads), "parameter and gradient arenas differ in layout");
+  PG_REQUIRE(g_nccl.AllGather != nullptr, "libnccl has no ncclAllGather");
+  if (dp->p2p) return PG_OK;
+  PG_CHECK_CUDA(cudaSetDevice(dp->ctx->device));
+  const int W = dp->world, R = dp->rank;
+  dp->p2p_padded = pg_arena_padded(params);
+  // flag block: peers write their epochs here
+  PG_CHECK_CUDA(cudaMalloc(&dp->flags_local, MAXR * SLOTS * sizeof(unsigned int)));
+  PG_CHECK_CUDA(cudaMemset(dp->flags_local, 0, MAXR * SLOTS * sizeof(unsigned int)));
+  PG_CHECK_CUDA(cudaMalloc((void**)&dp->block_counter, sizeof(unsigned int)));
+  PG_CHECK_CUDA(cudaMemset(dp->block_counter, 0, sizeof(unsigned int)));
+  struct Rec { cudaIpcMemHandle_t h[4]; int64_t off[4]; int has_shadow; int pad; };
+  Rec mine;
+  memset(&mine, 0, sizeof(mine));
+  void* ptrs[4] = {pg_arena_base(grads), pg_arena_base(params), shadow2, dp->flags_local};
+  mine.has_shadow = shadow2 != nullptr;
+  for (int k = 0; k < 4; ++k) {
+    if (!ptrs[k]) continue;
+    int rc = ipc_export(ptrs[k], &mine.h[k], &mine.off[k]);
+    if (rc != PG_OK) return rc;
+  }
+  // exchange the records through the communicator itself
+  Rec* dev = nullptr;
+  PG_CHECK_CUDA(cudaMalloc((void**)&dev, sizeof(Rec) * (W + 1)));
+  PG_CHECK_CUDA(cudaMemcpy(dev + W, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
+  PG_CHECK_NCCL(g_nccl.AllGather(dev + W, dev, sizeof(Rec), 0 /* ncclInt8 */, dp->comm, dp->stream));
+  PG_CHECK_CUDA(cudaStreamSynchronize(dp->stream));
+  std::vector<Rec> all(W);
+  PG_CHECK_CUDA(cudaMemcpy(all.data(), dev, sizeof(Rec) * W, cudaMemcpyDeviceToHost));
+  PG_CHECK_CUDA(cudaFree(dev));
+  void** tables[4] = {dp->peer_grad, dp->peer_param, dp->peer_shadow, dp->peer_flags};
+  for (int p = 0; p < W; ++p) {
+    PG_REQUIRE(all[p].has_shadow == mine.has_shadow, "ranks disagree about the bf16 shadow");
+    for (int k = 0; k < 4; ++k) {
+      if (!ptrs[k]) { tables[k][p] = nullptr; continue; }
+      if (p == R) { tables[k][p] = ptrs[k]; continue; }
+      void* base = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&base, all[p].h[k], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        pg_set_error("cudaIpcOpenMemHandle(rank %d, buffer %d) failed: %s — peer memory is not available; the NCCL all-reduce path stays in use", p, k, cudaGetErrorString(e));
+        cudaGetLastError();
+        return PG_ERR_UNSUPPORTED;
+      }
+      dp->opened[dp->n_opened++] = base;
+      tables[k][p] = (char*)base + all[p].off[k];
+    }
+  }
+  const char* nb = getenv("PG_DP_P2P_BLOCKS");
+  if (nb && atoi(nb) > 0) dp->p2p_blocks = atoi(nb);
+  nb = getenv("PG_DP_P2P_BLOCKS_LAST");
+  if (nb && atoi(nb) > 0) dp->p2p_blocks_last = atoi(nb);
+  dp->p2p = true;
+  return PG_OK;
+}
+
+/* optimizer of the step whose backward pass comes next: kind 0 = Adam (adam.jl:32-41; `it` before the increment; flags
+ * PG_MATH_FAST / PG_SCALAR_F64 as in pg_opt_adam; m, v = this rank's state arenas, of which only its own slices are
+ * touched), kind 2 = GradientDescent (gradient_descent.jl:15-17).  kind -1 switches back to plain all-reduce buckets. */
+int pg_dp_p2p_set_optimizer(pg_dp* dp, int kind, void* m, void* v, double stepsize, double beta1, double beta2, double epsilon, int64_t it, int flags) {
+  PG_REQUIRE(dp != nullptr, "null dp handle");
+  PG_REQUIRE(kind == -1 || dp->p2p, "pg_dp_p2p_enable first");
+  PG_REQUIRE(kind == -1 || kind == 0 || kind == 2, "kind: 0 Adam, 2 GradientDescent, -1 off");
+  PG_REQUIRE(kind != 0 || (m != nullptr && v != nullptr && it >= 1), "Adam needs its state arenas and it >= 1");
+  dp->opt.kind = kind; dp->opt.m = m; dp->opt.v = v; dp->opt.s = stepsize; dp->opt.b1 = beta1; dp->opt.b2 = beta2; dp->opt.eps = epsilon;
+  dp->opt.it = it; dp->opt.flags = flags;
+  return PG_OK;
+}
+
+/* after pg_dp_bucket_finish + waits of a fused step: which half of the shadow double buffer now holds the bf16 copy of
+ * the (new) parameters */
+int pg_dp_p2p_shadow_half(pg_dp* dp, int* half) {
+  PG_REQUIRE(dp != nullptr && half != nullptr, "null pointer");
+  *half = dp->shadow_half;
+  return PG_OK;
+}
+
 int pg_dp_bucket_begin(pg_dp* dp, pg_arena* grads, int64_t bucket_bytes) {
   PG_REQUIRE(dp != nullptr && grads != nullptr, "null pointer");
   dp->grads = grads;
@@ -256,6 +549,8 @@ int pg_dp_bucket_begin(pg_dp* dp, pg_arena* grads, int64_t bucket_bytes) {
   dp->hi = dp->lo_ready = pg_arena_padded(grads);
   dp->buckets.clear();
   dp->error = PG_OK;
+  dp->fused_step = dp->p2p && dp->opt.kind >= 0;
+  if (dp->fused_step) dp->epoch += 1;
   return PG_OK;
 }
 
@@ -282,6 +577,10 @@ int pg_dp_bucket_finish(pg_dp* dp, int* n_buckets, int64_t* starts, int64_t* cou
     int rc = issue_bucket(dp, 0, dp->hi);
     if (rc != PG_OK) return rc;
     dp->hi = 0;
+  }
+  if (dp->fused_step) {                 // the fused kernels wrote the other half of the shadow double buffer
+    if (dp->peer_shadow[dp->rank] != nullptr) dp->shadow_half ^= 1;
+    dp->fused_step = false;
   }
   const int n = (int)dp->buckets.size();
   if (n_buckets) *n_buckets = n;

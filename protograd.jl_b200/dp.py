@@ -154,7 +154,7 @@ class GradientBuckets:
         grad = pb(on_ready=buckets.on_ready()); buckets.finish_and_step(state, grad)
     """
 
-    def __init__(self, grad_model, bucket_bytes=24 << 20, dp=None, comm_sms=None, overlap_update=True):
+    def __init__(self, grad_model, bucket_bytes=24 << 20, dp=None, comm_sms=None, overlap_update=True, fused=None):
         self.dp = dp or (init() if world()[1] > 1 else None)
         self.enabled = self.dp is not None and self.dp.world > 1
         ctx, base, total, code, leaves = _arena_desc(grad_model)
@@ -169,13 +169,69 @@ class GradientBuckets:
         self.arena = h
         weakref.finalize(self, capi.lib.pg_arena_destroy, h)
         self._begun = False
-        self._ready_fn = ctypes.cast(capi.lib.pg_dp_bucket_ready, ctypes.c_void_p)
+        self.fused = False
+        if fused is not None and self.enabled and os.environ.get("PG_DP_FUSED", "1") != "0":
+            self._enable_fused(*fused)
 
-    def on_ready(self):
-        """(callback, user) pair for pb(on_ready=...): the library's own C callback, no Python in the loop"""
+    def _enable_fused(self, model, state):
+        """Fused exchange + update over NVLink peer memory (pg_dp_p2p_*): each rank owns 1/world of every bucket, reads
+        that slice of the gradient from all peers, applies the optimizer to it and writes the new parameters (and their
+        bf16 copy) into every replica — instead of ncclAllReduce + a full-arena update.  Needs Float32 arenas, Adam or
+        GradientDescent; anything else (or a box without peer access) keeps the all-reduce path."""
+        import sys
+        from .optimizers import AdamState, GradientDescentState
+        from .trace import _shadow_entry
+        if not isinstance(state, (AdamState, GradientDescentState)) or state.variable is not model:
+            return
+        ctx, base, total, code, leaves = _arena_desc(model)
+        if leaves[0].dtype != np.float32 or leaves[0].offset != 0:
+            return
+        if isinstance(state, AdamState) and (state._m_hat is not None):
+            return                               # keep_hats=True materialises m_hat / v_hat every step: use the plain pass
+        sizes = (ctypes.c_int64 * len(leaves))(*[p.size for p in leaves])
+        h = ctypes.c_void_p()
+        call("pg_arena_wrap", ctx.h, code, len(leaves), sizes, base, ctypes.byref(h))
+        self.param_arena = h
+        weakref.finalize(self, capi.lib.pg_arena_destroy, h)
+        ent = _shadow_entry(ctx, leaves[0].buf, halves=2)
+        assert ent.half_bytes == total * 2 or ent.half_bytes >= total * 2
+        self._shadow = ent
+        try:
+            # the double buffer's halves must be `total` bf16 elements apart (csrc/dp.cu indexes [2][n_padded])
+            if ent.half_bytes != total * 2:
+                raise capi.PGError("shadow half size %d != arena %d bytes" % (ent.half_bytes, total * 2))
+            call("pg_dp_p2p_enable", self.dp.h, self.param_arena, self.arena, ent.store.ptr)
+        except capi.PGError as e:
+            if self.dp.rank == 0:
+                print(f"[protograd_b200.dp] fused peer-memory exchange unavailable ({e}); using ncclAllReduce buckets", file=sys.stderr)
+            return
+        self.fused, self._state, self._model = True, state, model
+
+    def _set_optimizer(self):
+        from .optimizers import AdamState, _f64
+        st = self._state
+        if isinstance(st, AdamState):
+            o = st.optimizer
+            fl = _f64(st.stepsize) | (capi.MATH_FAST if o.fast else 0)
+            call("pg_dp_p2p_set_optimizer", self.dp.h, 0, st.m.arena()[1], st.v.arena()[1], float(st.stepsize), float(o.beta1), float(o.beta2),
+                 float(o.epsilon), int(st.it), fl)
+        else:
+            call("pg_dp_p2p_set_optimizer", self.dp.h, 2, None, None, float(st.stepsize), 0.0, 0.0, 0.0, 1, _f64(st.stepsize))
+
+    def on_ready(self, reduce_only=False):
+        """(callback, user) pair for pb(on_ready=...): the library's own C callback, no Python in the loop.
+        reduce_only=True: plain all-reduce buckets for this backward even when the fused exchange is enabled."""
         if not self.enabled:
             return None
+        if reduce_only and self.fused:
+            call("pg_dp_p2p_set_optimizer", self.dp.h, -1, None, None, 0.0, 0.0, 0.0, 0.0, 1, 0)
+            call("pg_dp_bucket_begin", self.dp.h, self.arena, self.bucket_bytes)
+            self._begun = "reduce"
+            from .trace import READY_FN
+            return (ctypes.cast(capi.lib.pg_dp_bucket_ready, READY_FN), self.dp.h)
         from .trace import READY_FN
+        if self.fused:
+            self._set_optimizer()
         call("pg_dp_bucket_begin", self.dp.h, self.arena, self.bucket_bytes)
         self._begun = True
         if self.comm_sms:
@@ -192,9 +248,11 @@ class GradientBuckets:
         return [(starts[k], counts[k]) for k in range(n.value)]
 
     def finish(self):
-        """reduce the head slice and order the compute stream behind every bucket"""
+        """reduce the head slice and order the compute stream behind every bucket (plain all-reduce buckets only)"""
         if not self.enabled:
             return
+        if self.fused and self._begun is True:
+            raise RuntimeError("this step's buckets apply the fused update: call finish_and_step")
         for k, _ in enumerate(self._finish()):
             call("pg_dp_bucket_wait", self.dp.h, k)
         if self.comm_sms:
@@ -208,6 +266,24 @@ class GradientBuckets:
         from .optimizers import step, step_range
         if not self.enabled:
             return step(state, grad, shadow)
+        if self.fused:
+            if state is not self._state:
+                raise ValueError("the fused exchange was set up for another optimizer state")
+            if not self._begun:
+                raise RuntimeError("fused data-parallel step: pass buckets.on_ready() to the pullback of this step")
+            for k, _ in enumerate(self._finish()):
+                call("pg_dp_bucket_wait", self.dp.h, k)
+            # the kernels applied the update and wrote the bf16 copy of the new parameters into the other half
+            self._model._mutated()
+            ent = self._shadow
+            half = ctypes.c_int()
+            call("pg_dp_p2p_shadow_half", self.dp.h, ctypes.byref(half))
+            ent.half = half.value
+            ent.version = ent.buf.version
+            if hasattr(state, "it"):
+                state.it += 1
+                return state.it
+            return state.variable
         ranges = self._finish()
         r = None
         if not self.overlap_update:

@@ -252,12 +252,26 @@ class PgOp(ctypes.Structure):
 READY_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int)
 
 
-def _shadow_entry(ctx, buf):
-    """[buffer, bf16 shadow buffer, buffer version the shadow was written for]"""
+class Shadow:
+    """bf16 copy of a parameter buffer: `store` holds `halves` copies (2 = the double buffer the fused data-parallel
+    exchange writes into, csrc/dp.cu); `version` is the buffer version the CURRENT half was written for."""
+
+    def __init__(self, ctx, buf, halves=1):
+        self.buf, self.halves = buf, halves
+        self.half_bytes = (buf.nbytes // 2 + 15) // 16 * 16
+        self.store = DeviceBuffer(ctx, self.half_bytes * halves + 16, zero=True)
+        self.version, self.half = -1, 0
+
+    @property
+    def ptr(self):
+        return self.store.ptr + self.half * self.half_bytes
+
+
+def _shadow_entry(ctx, buf, halves=1):
     key = id(buf)
     ent = _SHADOWS.get(key)
-    if ent is None or ent[0] is not buf:
-        ent = _SHADOWS[key] = [buf, DeviceBuffer(ctx, buf.nbytes // 2 + 16, zero=True), -1]
+    if ent is None or ent.buf is not buf or ent.halves < halves:
+        ent = _SHADOWS[key] = Shadow(ctx, buf, halves)
     return ent
 
 
@@ -271,18 +285,18 @@ def shadow_target(model):
     if leaves[0].dtype != np.float32:
         raise TypeError("bf16 shadows exist for Float32 models only")
     ent = _shadow_entry(ctx, leaves[0].buf)
-    return ent[1].ptr + leaves[0].offset // 2
+    return ent.ptr + leaves[0].offset // 2
 
 
 def shadow_written(model):
     """stamp the shadow as matching the arena's current contents (called by step(..., shadow=True))"""
     ctx, base, total, leaves = model.arena()
     ent = _shadow_entry(ctx, leaves[0].buf)
-    ent[2] = leaves[0].buf.version
+    ent.version = leaves[0].buf.version
 
 
 _PLANS = {}
-_SHADOWS = {}  # id(DeviceBuffer) -> [buffer ref, bf16 shadow buffer, version]
+_SHADOWS = {}  # id(DeviceBuffer) -> Shadow
 
 
 def _dt_str(dt):
@@ -416,12 +430,12 @@ class Plan:
             if leaf.dtype != np.float32:
                 continue
             ent = _shadow_entry(self.ctx, leaf.buf)
-            if id(leaf.buf) not in done and ent[2] != leaf.buf.version:
+            if id(leaf.buf) not in done and ent.version != leaf.buf.version:
                 # one cast pass over the whole arena (skipped when the optimizer's fused pass already wrote it)
-                call("pg_vec_cast_bf16", self.ctx.h, ent[1].ptr, leaf.buf.ptr, leaf.buf.nbytes // 4)
-                ent[2] = leaf.buf.version
+                call("pg_vec_cast_bf16", self.ctx.h, ent.ptr, leaf.buf.ptr, leaf.buf.nbytes // 4)
+                ent.version = leaf.buf.version
             done.add(id(leaf.buf))
-            self.leaf_bf[wid] = ent[1].ptr + leaf.offset // 2
+            self.leaf_bf[wid] = ent.ptr + leaf.offset // 2
 
     def forward(self, trace):
         self._bind(trace)

@@ -23,7 +23,8 @@ class AbiStep:
         # ---- arenas: parameters, gradient, Adam m / v ----
         sizes = (ctypes.c_int64 * len(params))(*[p.size for p in params])
         self.params = self._arena_create(sizes, len(params))
-        call("pg_arena_upload", self.params, -1, np.concatenate([np.ascontiguousarray(p, dtype=dtype).ravel() for p in params]).ctypes.data)
+        flat = np.concatenate([np.ascontiguousarray(p, dtype=dtype).ravel() for p in params])     # (kept alive across the call)
+        call("pg_arena_upload", self.params, -1, flat.ctypes.data)
         self.grads, self.m, self.v = (self._arena_like(self.params, 1) for _ in range(3))
         self.n_leaves = len(params)
         self.length = sum(p.size for p in params)

@@ -82,10 +82,11 @@ def test_tc_conv_envelope(pg):
 
 @pytest.mark.parametrize("spec_name,B", [("C3_SPEC", 8), ("C3_SPEC", 200), ("C5_SPEC", 64)])
 def test_conv_net_step_bf16_mode(pg, spec_name, B):
-    """LeNet-shaped nets (BASELINE configs[2] / [4]) with math="bf16": the convs run on the tensor-core
-    kernels, the small Linear head stays on the fp32 SIMT GEMM (fed by a pooling layer).  Loss and every
-    gradient leaf vs the float64 oracle with bf16-rounded conv operands: <= 2e-4 normwise (a ReLU gate may
-    flip where fp32 and float64 accumulation disagree about the sign of a pre-activation)."""
+    """LeNet-shaped nets (BASELINE configs[2] / [4]) with math="bf16": the convs run on the tensor-core conv
+    kernels and the Linear head on the tcgen05 GEMM (pool-fed: cast in, fp32 data gradient out; widths 120 / 84
+    zero-padded).  Loss and every gradient leaf vs the float64 oracle with bf16-rounded conv AND Linear operands
+    (and bf16-stored wide activations): loss <= 2e-4, gradients <= 2e-2 normwise (a ReLU gate may flip where fp32
+    and float64 accumulation disagree about the sign of a pre-activation; measured ~1e-3)."""
     from tests.golden import make_golden as MG
     from tests.helpers import build_model, leaves_numpy
     spec = getattr(MG, spec_name)
@@ -97,13 +98,13 @@ def test_conv_net_step_bf16_mode(pg, spec_name, B):
     out, pb = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(xd), ld), m, math="bf16")
     g = pb()
     p64 = [p.astype(np.float64) for p in params]
-    loss, grads = O.net_loss_and_grad(spec, p64, x.astype(np.float64), lab.astype(np.float64), conv_round=O.bf16_round)
+    loss, grads = O.net_loss_and_grad(spec, p64, x.astype(np.float64), lab.astype(np.float64), conv_round=O.bf16_round, linear_round=O.bf16_round)
     assert abs(float(out) - loss) <= 2e-4 * abs(loss)
     got = leaves_numpy(g)
     train = O.spec_trainable(spec)
     for i, (a, b) in enumerate(zip(got, grads)):
         if train[i]:
-            assert rel_err(a, b) <= 2e-4, (i, rel_err(a, b))
+            assert rel_err(a, b) <= 2e-2, (i, rel_err(a, b))
     # the plan really used the tensor-core conv kernels
     from protograd_b200 import trace as T
     plans = [p for p in T._PLANS.values() if p.math == "bf16" and p.tc_conv]
