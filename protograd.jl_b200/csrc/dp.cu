@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "optim.cuh"
+#include "tc_ptx.cuh"
 
 // from arena.cu
 void* pg_arena_base(pg_arena* a);
@@ -154,7 +155,10 @@ __device__ __forceinline__ void wait_epoch(const unsigned int* p, unsigned int e
 // F: per-element update functor, f(p, m, v, g) -> writes p, m, v (GD ignores m, v)
 // Launched as clusters of two CTAs: a pair occupies one whole TPC, so the co-running 2-CTA GEMM kernels (which need both
 // SMs of a TPC) lose whole pairs, never half of one.
-template <typename F, bool STATE>
+// NVLink reads are latency-bound (a few microseconds per round trip): every thread keeps U float4 loads per peer in
+// flight — all loads of an iteration are issued before the first one is consumed (WMAX = 2 / 4 / 8 peers: U = 4 / 2 / 2,
+// i.e. 64-224 remote bytes per thread, 0.5-1.8 MB per 16-CTA launch; register budget 128 at 512 threads).
+template <typename F, bool STATE, int WMAX, int U>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512) p2p_update_kernel(P2PArgs a, F f) {
   const int W = a.world, R = a.rank;
   unsigned int* mine = a.flags[R];
@@ -173,24 +177,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512) p2p_update_kern
   long long c1 = c0 + chunk;
   if (c1 > a.hi) c1 = a.hi;
   const long long nvec = c1 > c0 ? (c1 - c0) / 4 : 0;   // lo, hi and chunk are multiples of 4
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const long long e = c0 + 4 * i;
-    float4 g = ld_sys_f4(a.grad[0] + e);
-    for (int p = 1; p < W; ++p) {
-      const float4 t = ld_sys_f4(a.grad[p] + e);
-      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * U) {
+    float4 pv[U], mv[U], vv[U], g[U][WMAX];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        const long long e = c0 + 4 * i;
+        pv[u] = *reinterpret_cast<const float4*>(a.param[R] + e);
+        if (STATE) { mv[u] = *reinterpret_cast<const float4*>(a.m + e); vv[u] = *reinterpret_cast<const float4*>(a.v + e); }
+      }
     }
-    float4 pv = *reinterpret_cast<const float4*>(a.param[R] + e);
-    float4 mv = make_float4(0, 0, 0, 0), vv = mv;
-    if (STATE) { mv = *reinterpret_cast<const float4*>(a.m + e); vv = *reinterpret_cast<const float4*>(a.v + e); }
-    f(pv.x, mv.x, vv.x, g.x); f(pv.y, mv.y, vv.y, g.y); f(pv.z, mv.z, vv.z, g.z); f(pv.w, mv.w, vv.w, g.w);
-    if (STATE) { *reinterpret_cast<float4*>(a.m + e) = mv; *reinterpret_cast<float4*>(a.v + e) = vv; }
-    __nv_bfloat162 pk[2];
-    pk[0] = __floats2bfloat162_rn(pv.x, pv.y); pk[1] = __floats2bfloat162_rn(pv.z, pv.w);
-    const uint2 sh = *reinterpret_cast<uint2*>(pk);
-    for (int p = 0; p < W; ++p) {
-      *reinterpret_cast<float4*>(a.param[p] + e) = pv;
-      if (a.shadow[p] != nullptr) *reinterpret_cast<uint2*>(a.shadow[p] + e) = sh;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        const long long e = c0 + 4 * i;
+#pragma unroll
+        for (int p = 0; p < WMAX; ++p)
+          if (p < W) g[u][p] = ld_sys_f4(a.grad[p] + e);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= nvec) continue;
+      const long long e = c0 + 4 * i;
+      float4 s = g[u][0];
+#pragma unroll
+      for (int p = 1; p < WMAX; ++p)
+        if (p < W) { s.x += g[u][p].x; s.y += g[u][p].y; s.z += g[u][p].z; s.w += g[u][p].w; }      // rank order: deterministic
+      float4 P = pv[u], Mv = make_float4(0, 0, 0, 0), Vv = Mv;
+      if (STATE) { Mv = mv[u]; Vv = vv[u]; }
+      f(P.x, Mv.x, Vv.x, s.x); f(P.y, Mv.y, Vv.y, s.y); f(P.z, Mv.z, Vv.z, s.z); f(P.w, Mv.w, Vv.w, s.w);
+      if (STATE) { *reinterpret_cast<float4*>(a.m + e) = Mv; *reinterpret_cast<float4*>(a.v + e) = Vv; }
+      __nv_bfloat162 pk[2];
+      pk[0] = __floats2bfloat162_rn(P.x, P.y); pk[1] = __floats2bfloat162_rn(P.z, P.w);
+      const uint2 sh = *reinterpret_cast<uint2*>(pk);
+#pragma unroll
+      for (int p = 0; p < WMAX; ++p) {
+        if (p < W) {
+          *reinterpret_cast<float4*>(a.param[p] + e) = P;
+          if (a.shadow[p] != nullptr) *reinterpret_cast<uint2*>(a.shadow[p] + e) = sh;
+        }
+      }
     }
   }
   __syncthreads();
@@ -203,6 +234,124 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512) p2p_update_kern
       for (int p = 0; p < W; ++p) wait_epoch(mine + p * SLOTS + 2 * a.slot + 1, a.epoch);
     }
   }
+}
+
+template <typename F, bool STATE>
+void launch_p2p_kernel(int world, int grid, cudaStream_t st, const P2PArgs& a, const F& f) {
+  if (world <= 2) p2p_update_kernel<F, STATE, 2, 4><<<grid, 512, 0, st>>>(a, f);
+  else if (world <= 4) p2p_update_kernel<F, STATE, 4, 2><<<grid, 512, 0, st>>>(a, f);
+  else p2p_update_kernel<F, STATE, 8, 2><<<grid, 512, 0, st>>>(a, f);
+}
+
+// ---- TMA (bulk-copy) variant: memory-level parallelism from shared memory instead of registers -----------------------
+// One elected thread streams tiles of every operand — the W peer gradient slices over NVLink, the local parameter and
+// optimizer-state slices from HBM — into a ring of shared-memory stages with cp.async.bulk (completion on an mbarrier);
+// the 512 threads of the CTA consume a stage (one float4 each), write the results with plain (posted) stores and hand
+// the stage back.  ~170-200 KB in flight per CTA, so a few CTAs saturate NVLink where a register-resident loop is
+// latency-bound.
+constexpr int P2P_TILE = 2048;                      // floats per stream per stage (8 KB); 512 threads x float4
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <typename F, bool STATE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512) p2p_update_tma_kernel(P2PArgs a, F f, int stages) {
+  extern __shared__ __align__(128) uint8_t p2p_smem[];
+  const int W = a.world, R = a.rank;
+  const int NS = W + (STATE ? 3 : 1);               // streams per stage: W gradients, p, (m, v)
+  const uint32_t stage_bytes = (uint32_t)NS * P2P_TILE * 4;
+  const uint32_t smem0 = smem_u32(p2p_smem);
+  const uint32_t bar0 = smem0 + (uint32_t)stages * stage_bytes;      // full[stages]
+  unsigned int* mine = a.flags[R];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(bar0 + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      for (int p = 0; p < W; ++p) st_release_sys(a.flags[p] + R * SLOTS + 2 * a.slot, a.epoch);
+    }
+    for (int p = 0; p < W; ++p) wait_epoch(mine + p * SLOTS + 2 * a.slot, a.epoch);
+  }
+  __syncthreads();
+  const long long len = a.hi - a.lo;
+  long long chunk = (len + W - 1) / W;
+  chunk = (chunk + 3) / 4 * 4;
+  const long long c0 = a.lo + (long long)R * chunk;
+  long long c1 = c0 + chunk;
+  if (c1 > a.hi) c1 = a.hi;
+  const long long n_el = c1 > c0 ? c1 - c0 : 0;
+  const long long n_tiles = (n_el + P2P_TILE - 1) / P2P_TILE;
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto issue = [&](long long k) {                    // elected thread: load this CTA's k-th tile into stage k % stages
+    const int s = (int)(k % stages);
+    const long long e = c0 + (blockIdx.x + k * gridDim.x) * P2P_TILE;
+    const long long rem = c1 - e;
+    const uint32_t bytes = (uint32_t)((rem < P2P_TILE ? rem : P2P_TILE) * 4);
+    const uint32_t bar = bar0 + 8u * s, dst = smem0 + (uint32_t)s * stage_bytes;
+    mbar_expect_tx(bar, bytes * NS);
+    for (int p = 0; p < W; ++p) bulk_load(dst + (uint32_t)p * P2P_TILE * 4, a.grad[p] + e, bytes, bar);
+    bulk_load(dst + (uint32_t)W * P2P_TILE * 4, a.param[R] + e, bytes, bar);
+    if (STATE) {
+      bulk_load(dst + (uint32_t)(W + 1) * P2P_TILE * 4, a.m + e, bytes, bar);
+      bulk_load(dst + (uint32_t)(W + 2) * P2P_TILE * 4, a.v + e, bytes, bar);
+    }
+  };
+  if (threadIdx.x == 0)
+    for (long long k = 0; k < my_tiles && k < stages; ++k) issue(k);
+  for (long long k = 0; k < my_tiles; ++k) {
+    const int s = (int)(k % stages);
+    mbar_wait(bar0 + 8u * s, (uint32_t)((k / stages) & 1));
+    const long long e = c0 + (blockIdx.x + k * gridDim.x) * P2P_TILE + 4 * (long long)threadIdx.x;
+    if (e < c1) {
+      const float4* st = reinterpret_cast<const float4*>(p2p_smem + (size_t)s * stage_bytes) + threadIdx.x;
+      float4 g = st[0];
+      for (int p = 1; p < W; ++p) {                  // rank order: deterministic, identical on every replica
+        const float4 t = st[p * (P2P_TILE / 4)];
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+      float4 P = st[W * (P2P_TILE / 4)], Mv = make_float4(0, 0, 0, 0), Vv = Mv;
+      if (STATE) { Mv = st[(W + 1) * (P2P_TILE / 4)]; Vv = st[(W + 2) * (P2P_TILE / 4)]; }
+      f(P.x, Mv.x, Vv.x, g.x); f(P.y, Mv.y, Vv.y, g.y); f(P.z, Mv.z, Vv.z, g.z); f(P.w, Mv.w, Vv.w, g.w);
+      if (STATE) { *reinterpret_cast<float4*>(a.m + e) = Mv; *reinterpret_cast<float4*>(a.v + e) = Vv; }
+      __nv_bfloat162 pk[2];
+      pk[0] = __floats2bfloat162_rn(P.x, P.y); pk[1] = __floats2bfloat162_rn(P.z, P.w);
+      const uint2 sh = *reinterpret_cast<uint2*>(pk);
+      for (int p = 0; p < W; ++p) {
+        *reinterpret_cast<float4*>(a.param[p] + e) = P;
+        if (a.shadow[p] != nullptr) *reinterpret_cast<uint2*>(a.shadow[p] + e) = sh;
+      }
+    }
+    __syncthreads();                                 // every thread has read stage s: it can be refilled
+    if (threadIdx.x == 0 && k + stages < my_tiles) issue(k + stages);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(a.block_counter, 1u) == gridDim.x - 1) {
+      *a.block_counter = 0u;
+      __threadfence_system();
+      for (int p = 0; p < W; ++p) st_release_sys(a.flags[p] + R * SLOTS + 2 * a.slot + 1, a.epoch);
+      for (int p = 0; p < W; ++p) wait_epoch(mine + p * SLOTS + 2 * a.slot + 1, a.epoch);
+    }
+  }
+}
+
+template <typename F, bool STATE>
+int launch_p2p_tma(int world, int grid, cudaStream_t st, const P2PArgs& a, const F& f) {
+  const int NS = world + (STATE ? 3 : 1);
+  const int stage_bytes = NS * P2P_TILE * 4;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  const int smem = stages * stage_bytes + 8 * stages + 64;
+  static bool attr_set = false;                      // (per instantiation)
+  if (!attr_set) {
+    PG_CHECK_CUDA(cudaFuncSetAttribute(p2p_update_tma_kernel<F, STATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    attr_set = true;
+  }
+  p2p_update_tma_kernel<F, STATE><<<grid, 512, smem, st>>>(a, f, stages);
+  return PG_OK;
 }
 
 struct P2PAdamFast {           // AdamFastF of optim.cuh on scalars
@@ -263,6 +412,7 @@ struct pg_dp {
   struct { int kind = -1; void* m = nullptr; void* v = nullptr; double s = 0, b1 = 0, b2 = 0, eps = 0; int64_t it = 1; int flags = 0; } opt;
   int p2p_blocks = 16, p2p_blocks_last = 96;
   bool fused_step = false;
+  bool p2p_tma = true;                      // PG_DP_P2P_TMA=0: register-pipelined loads instead of cp.async.bulk
 };
 
 namespace {
@@ -296,14 +446,17 @@ int launch_p2p(pg_dp* dp, int64_t lo, int64_t hi, int slot, bool last) {
     const double c1 = 1.0 - pow(b1, (double)dp->opt.it), c2 = 1.0 - pow(b2, (double)dp->opt.it);
     if (dp->opt.flags & PG_MATH_FAST) {
       P2PAdamFast f{(float)s, (float)b1, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)(1.0 / c1), (float)(1.0 / c2), (float)dp->opt.eps};
-      p2p_update_kernel<P2PAdamFast, true><<<grid, 512, 0, dp->stream>>>(a, f);
+      if (dp->p2p_tma) { int rc = launch_p2p_tma<P2PAdamFast, true>(dp->world, grid, dp->stream, a, f); if (rc != PG_OK) return rc; }
+      else launch_p2p_kernel<P2PAdamFast, true>(dp->world, grid, dp->stream, a, f);
     } else {
       P2PAdamExact f{s, b1, 1.0 - b1, b2, 1.0 - b2, c1, c2, dp->opt.eps};
-      p2p_update_kernel<P2PAdamExact, true><<<grid, 512, 0, dp->stream>>>(a, f);
+      if (dp->p2p_tma) { int rc = launch_p2p_tma<P2PAdamExact, true>(dp->world, grid, dp->stream, a, f); if (rc != PG_OK) return rc; }
+      else launch_p2p_kernel<P2PAdamExact, true>(dp->world, grid, dp->stream, a, f);
     }
   } else {
     P2PGd f{s, (dp->opt.flags & PG_SCALAR_F64) ? 1 : 0};
-    p2p_update_kernel<P2PGd, false><<<grid, 512, 0, dp->stream>>>(a, f);
+    if (dp->p2p_tma) { int rc = launch_p2p_tma<P2PGd, false>(dp->world, grid, dp->stream, a, f); if (rc != PG_OK) return rc; }
+    else launch_p2p_kernel<P2PGd, false>(dp->world, grid, dp->stream, a, f);
   }
   dp->ctx->launches++;
   PG_CHECK_CUDA(cudaGetLastError());
@@ -515,6 +668,8 @@ int pg_dp_p2p_enable(pg_dp* dp, pg_arena* params, pg_arena* grads, void* shadow2
   }
   const char* nb = getenv("PG_DP_P2P_BLOCKS");
   if (nb && atoi(nb) > 0) dp->p2p_blocks = atoi(nb);
+  nb = getenv("PG_DP_P2P_TMA");
+  if (nb && nb[0] == '0') dp->p2p_tma = false;
   nb = getenv("PG_DP_P2P_BLOCKS_LAST");
   if (nb && atoi(nb) > 0) dp->p2p_blocks_last = atoi(nb);
   dp->p2p = true;
