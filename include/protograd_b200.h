@@ -325,6 +325,10 @@ int pg_dp_p2p_enable(pg_dp* dp, pg_arena* params, pg_arena* grads, void* shadow2
  * pg_opt_adam), 2 = GradientDescent, -1 = off (buckets are plain all-reduces again) */
 int pg_dp_p2p_set_optimizer(pg_dp* dp, int kind, void* m, void* v, double stepsize, double beta1, double beta2, double epsilon, int64_t it, int flags);
 int pg_dp_p2p_shadow_half(pg_dp* dp, int* half);
+/* tuning knobs of the fused exchange: "p2p_blocks" (CTAs of a bucket that overlaps the backward pass), "p2p_blocks_last" (CTAs of
+ * the final bucket), "reserve_sms" (SMs the persistent GEMM grids leave free while a bucket is in flight), "p2p_tma" (1: bulk-copy
+ * pipeline, 0: register-resident loads), "timing", "debug" */
+int pg_dp_set_option(pg_dp* dp, const char* name, int value);
 /* the bucket policy as a pure host function (no GPU): slices issued for a sequence of on_ready leaf indices */
 int pg_dp_bucket_plan(int dtype, int n_leaves, const int64_t* leaf_sizes, int64_t bucket_bytes, const int* ready_leaves, int n_ready,
                       int64_t* starts, int64_t* counts, int max_buckets, int* n_buckets);

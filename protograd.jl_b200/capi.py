@@ -133,6 +133,7 @@ _SIGS = {
     "pg_dp_p2p_enable": [_P, _P, _P, _P],
     "pg_dp_p2p_set_optimizer": [_P, _I, _P, _P, _D, _D, _D, _D, _L, _I],
     "pg_dp_p2p_shadow_half": [_P, POINTER(c_int)],
+    "pg_dp_set_option": [_P, c_char_p, _I],
     "pg_dp_bucket_plan": [_I, _I, POINTER(c_int64), _L, POINTER(c_int), _I, POINTER(c_int64), POINTER(c_int64), _I, POINTER(c_int)],
 }
 _VOID = {"pg_dp_bucket_ready": [_P, _I]}

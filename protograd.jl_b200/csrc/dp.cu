@@ -130,6 +130,7 @@ struct P2PArgs {
   int rank, world, slot;
   unsigned int epoch;
   long long lo, hi;
+  int debug;                   // diagnostics (PG_DP_P2P_DEBUG): 1 skip remote fp32 stores, 2 skip remote bf16 stores, 4 skip local state stores
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -148,7 +149,7 @@ __device__ __forceinline__ void wait_epoch(const unsigned int* p, unsigned int e
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys(p) - epoch) < 0) {
     __nanosleep(200);
-    if (clock64() - t0 > 6000000000ll) __trap();       // ~3 s: a peer died; fail loudly instead of hanging the GPU
+    if (clock64() - t0 > 240000000000ll) __trap();     // ~2 min: a peer died (ranks may legitimately be seconds apart on the host side); fail loudly instead of hanging forever
   }
 }
 
@@ -172,7 +173,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512) p2p_update_kern
   __syncthreads();
   const long long len = a.hi - a.lo;
   long long chunk = (len + W - 1) / W;
-  chunk = (chunk + 3) / 4 * 4;
+  chunk = (chunk + 7) / 8 * 8;          // bf16 slices stay 16-byte aligned
   const long long c0 = a.lo + (long long)R * chunk;
   long long c1 = c0 + chunk;
   if (c1 > a.hi) c1 = a.hi;
@@ -254,14 +255,24 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <typename F, bool STATE>
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+// Results leave the same way they came: every thread writes its float4 (and its bf16 x 4) into an output slot in shared
+// memory, and the elected thread sends the slot to every replica with cp.async.bulk stores (posted through the async
+// proxy: deep queues, nothing for the SM's load/store units to wait on) — local optimizer state likewise.
+template <typename F, bool STATE, int TILE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512) p2p_update_tma_kernel(P2PArgs a, F f, int stages) {
   extern __shared__ __align__(128) uint8_t p2p_smem[];
   const int W = a.world, R = a.rank;
-  const int NS = W + (STATE ? 3 : 1);               // streams per stage: W gradients, p, (m, v)
-  const uint32_t stage_bytes = (uint32_t)NS * P2P_TILE * 4;
+  const int NS = W + (STATE ? 3 : 1);               // input streams per stage: W gradients, p, (m, v)
+  constexpr int OUT_BYTES = TILE * 4 + TILE * 2 + (STATE ? 2 * TILE * 4 : 0);     // p fp32, p bf16, (m, v)
+  const uint32_t stage_bytes = (uint32_t)NS * TILE * 4;
   const uint32_t smem0 = smem_u32(p2p_smem);
-  const uint32_t bar0 = smem0 + (uint32_t)stages * stage_bytes;      // full[stages]
+  const uint32_t out0 = smem0 + (uint32_t)stages * stage_bytes;      // two output slots
+  const uint32_t bar0 = out0 + 2u * OUT_BYTES;                       // full[stages]
+  uint8_t* out_gen = p2p_smem + (size_t)stages * stage_bytes;
   unsigned int* mine = a.flags[R];
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) mbar_init(bar0 + 8u * s, 1);
@@ -275,56 +286,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512) p2p_update_tma_
   __syncthreads();
   const long long len = a.hi - a.lo;
   long long chunk = (len + W - 1) / W;
-  chunk = (chunk + 3) / 4 * 4;
+  chunk = (chunk + 7) / 8 * 8;          // bf16 slices stay 16-byte aligned
   const long long c0 = a.lo + (long long)R * chunk;
   long long c1 = c0 + chunk;
   if (c1 > a.hi) c1 = a.hi;
   const long long n_el = c1 > c0 ? c1 - c0 : 0;
-  const long long n_tiles = (n_el + P2P_TILE - 1) / P2P_TILE;
-  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const long long n_tiles = (n_el + TILE - 1) / TILE;
   const long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto tile_start = [&](long long k) { return c0 + (blockIdx.x + k * gridDim.x) * TILE; };
+  auto tile_elems = [&](long long k) { const long long rem = c1 - tile_start(k); return (uint32_t)(rem < TILE ? rem : TILE); };
   auto issue = [&](long long k) {                    // elected thread: load this CTA's k-th tile into stage k % stages
     const int s = (int)(k % stages);
-    const long long e = c0 + (blockIdx.x + k * gridDim.x) * P2P_TILE;
-    const long long rem = c1 - e;
-    const uint32_t bytes = (uint32_t)((rem < P2P_TILE ? rem : P2P_TILE) * 4);
+    const long long e = tile_start(k);
+    const uint32_t bytes = tile_elems(k) * 4;
     const uint32_t bar = bar0 + 8u * s, dst = smem0 + (uint32_t)s * stage_bytes;
     mbar_expect_tx(bar, bytes * NS);
-    for (int p = 0; p < W; ++p) bulk_load(dst + (uint32_t)p * P2P_TILE * 4, a.grad[p] + e, bytes, bar);
-    bulk_load(dst + (uint32_t)W * P2P_TILE * 4, a.param[R] + e, bytes, bar);
+    for (int p = 0; p < W; ++p) bulk_load(dst + (uint32_t)p * TILE * 4, a.grad[p] + e, bytes, bar);
+    bulk_load(dst + (uint32_t)W * TILE * 4, a.param[R] + e, bytes, bar);
     if (STATE) {
-      bulk_load(dst + (uint32_t)(W + 1) * P2P_TILE * 4, a.m + e, bytes, bar);
-      bulk_load(dst + (uint32_t)(W + 2) * P2P_TILE * 4, a.v + e, bytes, bar);
+      bulk_load(dst + (uint32_t)(W + 1) * TILE * 4, a.m + e, bytes, bar);
+      bulk_load(dst + (uint32_t)(W + 2) * TILE * 4, a.v + e, bytes, bar);
     }
   };
   if (threadIdx.x == 0)
     for (long long k = 0; k < my_tiles && k < stages; ++k) issue(k);
   for (long long k = 0; k < my_tiles; ++k) {
-    const int s = (int)(k % stages);
+    const int s = (int)(k % stages), o = (int)(k & 1);
+    // the bulk stores that last used output slot `o` (tile k-2) must have finished READING it
+    if (threadIdx.x == 0 && k >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
     mbar_wait(bar0 + 8u * s, (uint32_t)((k / stages) & 1));
-    const long long e = c0 + (blockIdx.x + k * gridDim.x) * P2P_TILE + 4 * (long long)threadIdx.x;
-    if (e < c1) {
+    const uint32_t nel = tile_elems(k);
+    uint8_t* ob = out_gen + (size_t)o * OUT_BYTES;
+    if (4u * threadIdx.x < nel) {
       const float4* st = reinterpret_cast<const float4*>(p2p_smem + (size_t)s * stage_bytes) + threadIdx.x;
       float4 g = st[0];
       for (int p = 1; p < W; ++p) {                  // rank order: deterministic, identical on every replica
-        const float4 t = st[p * (P2P_TILE / 4)];
+        const float4 t = st[p * (TILE / 4)];
         g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
       }
-      float4 P = st[W * (P2P_TILE / 4)], Mv = make_float4(0, 0, 0, 0), Vv = Mv;
-      if (STATE) { Mv = st[(W + 1) * (P2P_TILE / 4)]; Vv = st[(W + 2) * (P2P_TILE / 4)]; }
+      float4 P = st[W * (TILE / 4)], Mv = make_float4(0, 0, 0, 0), Vv = Mv;
+      if (STATE) { Mv = st[(W + 1) * (TILE / 4)]; Vv = st[(W + 2) * (TILE / 4)]; }
       f(P.x, Mv.x, Vv.x, g.x); f(P.y, Mv.y, Vv.y, g.y); f(P.z, Mv.z, Vv.z, g.z); f(P.w, Mv.w, Vv.w, g.w);
-      if (STATE) { *reinterpret_cast<float4*>(a.m + e) = Mv; *reinterpret_cast<float4*>(a.v + e) = Vv; }
+      reinterpret_cast<float4*>(ob)[threadIdx.x] = P;
       __nv_bfloat162 pk[2];
       pk[0] = __floats2bfloat162_rn(P.x, P.y); pk[1] = __floats2bfloat162_rn(P.z, P.w);
-      const uint2 sh = *reinterpret_cast<uint2*>(pk);
-      for (int p = 0; p < W; ++p) {
-        *reinterpret_cast<float4*>(a.param[p] + e) = P;
-        if (a.shadow[p] != nullptr) *reinterpret_cast<uint2*>(a.shadow[p] + e) = sh;
+      reinterpret_cast<uint2*>(ob + TILE * 4)[threadIdx.x] = *reinterpret_cast<uint2*>(pk);
+      if (STATE) {
+        reinterpret_cast<float4*>(ob + TILE * 6)[threadIdx.x] = Mv;
+        reinterpret_cast<float4*>(ob + TILE * 10)[threadIdx.x] = Vv;
       }
     }
-    __syncthreads();                                 // every thread has read stage s: it can be refilled
-    if (threadIdx.x == 0 && k + stages < my_tiles) issue(k + stages);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk stores
+    __syncthreads();                                 // stage s fully consumed, output slot o fully written
+    if (threadIdx.x == 0) {
+      const long long e = tile_start(k);
+      const uint32_t so = out0 + (uint32_t)o * OUT_BYTES;
+      for (int p = 0; p < W; ++p) {
+        if (p == R || !(a.debug & 1)) bulk_store(a.param[p] + e, so, nel * 4);
+        if (a.shadow[p] != nullptr && (p == R || !(a.debug & 2))) bulk_store(a.shadow[p] + e, so + TILE * 4, nel * 2);
+      }
+      if (STATE && !(a.debug & 4)) { bulk_store(a.m + e, so + TILE * 6, nel * 4); bulk_store(a.v + e, so + TILE * 10, nel * 4); }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (k + stages < my_tiles) issue(k + stages);
+    }
   }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every store of this CTA has completed
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
@@ -337,21 +364,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512) p2p_update_tma_
   }
 }
 
-template <typename F, bool STATE>
-int launch_p2p_tma(int world, int grid, cudaStream_t st, const P2PArgs& a, const F& f) {
+template <typename F, bool STATE, int TILE>
+int launch_p2p_tma_t(int world, int grid, cudaStream_t st, const P2PArgs& a, const F& f) {
   const int NS = world + (STATE ? 3 : 1);
-  const int stage_bytes = NS * P2P_TILE * 4;
-  int stages = (200 * 1024) / stage_bytes;
+  const int stage_bytes = NS * TILE * 4;
+  const int out_bytes = 2 * (TILE * 4 + TILE * 2 + (STATE ? 2 * TILE * 4 : 0));
+  int stages = (212 * 1024 - out_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
-  const int smem = stages * stage_bytes + 8 * stages + 64;
+  const int smem = stages * stage_bytes + out_bytes + 8 * stages + 64;
   static bool attr_set = false;                      // (per instantiation)
   if (!attr_set) {
-    PG_CHECK_CUDA(cudaFuncSetAttribute(p2p_update_tma_kernel<F, STATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    PG_CHECK_CUDA(cudaFuncSetAttribute(p2p_update_tma_kernel<F, STATE, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr_set = true;
   }
-  p2p_update_tma_kernel<F, STATE><<<grid, 512, smem, st>>>(a, f, stages);
+  p2p_update_tma_kernel<F, STATE, TILE><<<grid, 512, smem, st>>>(a, f, stages);
   return PG_OK;
+}
+template <typename F, bool STATE>
+int launch_p2p_tma(int world, int grid, cudaStream_t st, const P2PArgs& a, const F& f) {
+  // 8 ranks: 11 input streams per stage; 4 KB tiles keep three stages in flight inside 227 KB
+  if (world > 4) return launch_p2p_tma_t<F, STATE, 1024>(world, grid, st, a, f);
+  return launch_p2p_tma_t<F, STATE, 2048>(world, grid, st, a, f);
 }
 
 struct P2PAdamFast {           // AdamFastF of optim.cuh on scalars
@@ -412,7 +446,9 @@ struct pg_dp {
   struct { int kind = -1; void* m = nullptr; void* v = nullptr; double s = 0, b1 = 0, b2 = 0, eps = 0; int64_t it = 1; int flags = 0; } opt;
   int p2p_blocks = 16, p2p_blocks_last = 96;
   bool fused_step = false;
-  bool p2p_tma = true;                      // PG_DP_P2P_TMA=0: register-pipelined loads instead of cp.async.bulk
+  cudaEvent_t tev[16] = {nullptr}; double tsum[8] = {0}; long tcount[8] = {0}; int debug = 0; int timing = 0;
+  int reserve_sms = 16;                     // SMs the persistent GEMM grids leave free while a fused bucket is in flight
+  bool p2p_tma = false;                     // PG_DP_P2P_TMA=1: cp.async.bulk pipeline instead of register-resident loads (measured slower per CTA)
 };
 
 namespace {
@@ -437,7 +473,17 @@ int launch_p2p(pg_dp* dp, int64_t lo, int64_t hi, int slot, bool last) {
   a.m = (float*)dp->opt.m; a.v = (float*)dp->opt.v;
   a.block_counter = dp->block_counter;
   a.rank = dp->rank; a.world = dp->world; a.slot = slot; a.epoch = dp->epoch;
-  a.lo = lo; a.hi = hi;
+  a.lo = lo; a.hi = hi; a.debug = dp->debug;
+  if (dp->timing && slot < 8) {
+    for (int k = 0; k < 2; ++k)
+      if (!dp->tev[2 * slot + k]) PG_CHECK_CUDA(cudaEventCreate(&dp->tev[2 * slot + k]));
+    if (dp->tcount[slot] >= 0 && cudaEventQuery(dp->tev[2 * slot + 1]) == cudaSuccess && dp->epoch > 1) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, dp->tev[2 * slot], dp->tev[2 * slot + 1]) == cudaSuccess) { dp->tsum[slot] += ms; dp->tcount[slot]++; }
+    }
+    cudaGetLastError();
+    PG_CHECK_CUDA(cudaEventRecord(dp->tev[2 * slot], dp->stream));
+  }
   const double s = dp->opt.s, b1 = dp->opt.b1, b2 = dp->opt.b2;
   // buckets that overlap the remaining backward GEMMs run on a few TPCs; the last one has the GPU to itself
   int grid = last ? dp->p2p_blocks_last : dp->p2p_blocks;
@@ -460,6 +506,7 @@ int launch_p2p(pg_dp* dp, int64_t lo, int64_t hi, int slot, bool last) {
   }
   dp->ctx->launches++;
   PG_CHECK_CUDA(cudaGetLastError());
+  if (dp->timing && slot < 8) PG_CHECK_CUDA(cudaEventRecord(dp->tev[2 * slot + 1], dp->stream));
   return PG_OK;
 }
 
@@ -474,6 +521,10 @@ int issue_bucket(pg_dp* dp, int64_t lo, int64_t hi) {
     PG_REQUIRE(pg_arena_base(dp->grads) == dp->peer_grad[dp->rank], "fused exchange: not the gradient arena that was registered");
     rc = launch_p2p(dp, lo, hi, (int)dp->buckets.size(), lo == 0);
     if (rc != PG_OK) return rc;
+    // The backward kernels enqueued from here on run next to this bucket's kernel: their persistent grids (one CTA per
+    // SM, all of its shared memory) leave `reserve_sms` SMs — whole TPCs — free, so the exchange starts at once instead of
+    // waiting for a GEMM CTA to retire.  Restored by pg_dp_bucket_finish.
+    if (lo > 0 && dp->reserve_sms > 0) dp->ctx->num_sms = dp->ctx->real_sms - dp->reserve_sms;
   } else {
     PG_CHECK_NCCL(g_nccl.AllReduce(p, p, (size_t)(hi - lo), nccl_type(dt), ncclSum, dp->comm, dp->stream));
   }
@@ -543,6 +594,9 @@ int pg_dp_init(pg_ctx* ctx, int rank, int world, const void* id128, int max_ctas
 int pg_dp_destroy(pg_dp* dp) {
   if (!dp) return PG_OK;
   cudaSetDevice(dp->ctx->device);
+  if (dp->timing && dp->rank == 0)
+    for (int k = 0; k < 8; ++k)
+      if (dp->tcount[k] > 0) fprintf(stderr, "[pg_dp] fused exchange kernel, bucket %d: %.1f us average over %ld launches (includes waiting for the peers)\n", k, 1e3 * dp->tsum[k] / dp->tcount[k], dp->tcount[k]);
   if (dp->stream) cudaStreamSynchronize(dp->stream);
   if (dp->comm) g_nccl.CommDestroy(dp->comm);
   for (int k = 0; k < dp->n_opened; ++k) cudaIpcCloseMemHandle(dp->opened[k]);
@@ -666,8 +720,17 @@ int pg_dp_p2p_enable(pg_dp* dp, pg_arena* params, pg_arena* grads, void* shadow2
       tables[k][p] = (char*)base + all[p].off[k];
     }
   }
+  // measured at 2 ranks: the kernel moves ~76 GB/s per CTA; 2 ranks own half the arena each, so
+  // they need more CTAs than 8 ranks (an eighth each) to finish inside the remaining backward GEMMs
+  dp->p2p_blocks = dp->reserve_sms = W <= 2 ? 32 : 24;
   const char* nb = getenv("PG_DP_P2P_BLOCKS");
   if (nb && atoi(nb) > 0) dp->p2p_blocks = atoi(nb);
+  nb = getenv("PG_DP_P2P_DEBUG");
+  if (nb) dp->debug = atoi(nb);
+  nb = getenv("PG_DP_P2P_TIMING");
+  if (nb && nb[0] == '1') dp->timing = 1;
+  nb = getenv("PG_DP_RESERVE_SMS");
+  if (nb) dp->reserve_sms = atoi(nb);
   nb = getenv("PG_DP_P2P_TMA");
   if (nb && nb[0] == '0') dp->p2p_tma = false;
   nb = getenv("PG_DP_P2P_BLOCKS_LAST");
@@ -686,6 +749,18 @@ int pg_dp_p2p_set_optimizer(pg_dp* dp, int kind, void* m, void* v, double stepsi
   PG_REQUIRE(kind != 0 || (m != nullptr && v != nullptr && it >= 1), "Adam needs its state arenas and it >= 1");
   dp->opt.kind = kind; dp->opt.m = m; dp->opt.v = v; dp->opt.s = stepsize; dp->opt.b1 = beta1; dp->opt.b2 = beta2; dp->opt.eps = epsilon;
   dp->opt.it = it; dp->opt.flags = flags;
+  return PG_OK;
+}
+
+int pg_dp_set_option(pg_dp* dp, const char* name, int value) {
+  PG_REQUIRE(dp != nullptr && name != nullptr, "null pointer");
+  if (!strcmp(name, "p2p_blocks")) dp->p2p_blocks = value;
+  else if (!strcmp(name, "p2p_blocks_last")) dp->p2p_blocks_last = value;
+  else if (!strcmp(name, "p2p_tma")) dp->p2p_tma = value != 0;
+  else if (!strcmp(name, "reserve_sms")) dp->reserve_sms = value;
+  else if (!strcmp(name, "debug")) dp->debug = value;
+  else if (!strcmp(name, "timing")) dp->timing = value;
+  else { pg_set_error("pg_dp_set_option: unknown option %s", name); return PG_ERR_ARG; }
   return PG_OK;
 }
 
@@ -733,6 +808,7 @@ int pg_dp_bucket_finish(pg_dp* dp, int* n_buckets, int64_t* starts, int64_t* cou
     if (rc != PG_OK) return rc;
     dp->hi = 0;
   }
+  dp->ctx->num_sms = dp->ctx->real_sms;
   if (dp->fused_step) {                 // the fused kernels wrote the other half of the shadow double buffer
     if (dp->peer_shadow[dp->rank] != nullptr) dp->shadow_half ^= 1;
     dp->fused_step = false;
