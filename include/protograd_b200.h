@@ -158,6 +158,16 @@ int pg_tc_conv2d_fwd(pg_ctx* ctx, const void* x, const void* w, const void* b, v
                      int64_t N, int Cin, int H, int W, int Cout, int kH, int kW, int act);
 int pg_tc_conv2d_bwd(pg_ctx* ctx, const void* x, const void* w, const void* dy, void* dw, void* db, void* dx,
                      int64_t N, int Cin, int H, int W, int Cout, int kH, int kW);
+/* Conv + bias + ReLU + 2x2 max-pool in ONE kernel each way (csrc/conv_fused.cu; examples/02_mnist_conv.jl:27-33 chains exactly
+ * these three): Float32 NCHW, fp32 math.  y_pool [N][Cout][H'/2][W'/2]; argmax (nullable for inference) one byte per pooled
+ * element: which of the window's four positions won (W fastest, first maximum).  The un-pooled conv output never touches HBM.
+ * The backward rebuilds the conv-output gradient from (dy_pool, argmax, y_pool > 0) in shared memory; dw / db are summed
+ * from per-CTA partials in a fixed order (no floating-point atomics).  Envelope: pg_conv2d_relu_pool2_supported == 1. */
+int pg_conv2d_relu_pool2_supported(int Cin, int H, int W, int Cout, int kH, int kW);
+int pg_conv2d_relu_pool2_fwd(pg_ctx* ctx, const void* x, const void* w, const void* b, void* y_pool, void* argmax,
+                             int64_t N, int Cin, int H, int W, int Cout, int kH, int kW);
+int pg_conv2d_relu_pool2_bwd(pg_ctx* ctx, const void* x, const void* w, const void* y_pool, const void* argmax, const void* dy_pool,
+                             void* dw, void* db, void* dx, int64_t N, int Cin, int H, int W, int Cout, int kH, int kW);
 int pg_maxpool2d_fwd(pg_ctx* ctx, int dtype, const void* x, void* y, int64_t NC, int H, int W, int k);
 int pg_maxpool2d_bwd(pg_ctx* ctx, int dtype, const void* x, const void* dy, void* dx, int64_t NC, int H, int W, int k);
 /* same, fused with relu' of the pool input (x = a ReLU output): dx is the gradient w.r.t. the pre-activation */
@@ -272,7 +282,8 @@ typedef struct pg_op {
   double denom;
 } pg_op;
 /* node flags reported by pg_plan_node_flags */
-enum { PG_NODE_NEEDED = 1, PG_NODE_NEEDS_GRAD = 2, PG_NODE_TENSOR_CORE = 4, PG_NODE_FUSED_ACT = 8, PG_NODE_BF16_VALUE = 16, PG_NODE_FUSED_AWAY = 32 };
+enum { PG_NODE_NEEDED = 1, PG_NODE_NEEDS_GRAD = 2, PG_NODE_TENSOR_CORE = 4, PG_NODE_FUSED_ACT = 8, PG_NODE_BF16_VALUE = 16, PG_NODE_FUSED_AWAY = 32,
+       PG_NODE_FUSED_POOL = 64 /* a Conv whose ReLU and 2x2 max-pool run inside its kernel (pg_conv2d_relu_pool2_*) */ };
 typedef void (*pg_ready_fn)(void* user, int first_grad_leaf);
 
 /* Host-only (callable without a GPU): buffers are allocated by the first pg_plan_forward. */

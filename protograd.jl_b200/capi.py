@@ -83,6 +83,9 @@ _SIGS = {
     "pg_tc_conv2d_supported": [_I, _I, _I, _I, _I, _I],
     "pg_tc_conv2d_fwd": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I],
     "pg_tc_conv2d_bwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I],
+    "pg_conv2d_relu_pool2_supported": [_I, _I, _I, _I, _I, _I],
+    "pg_conv2d_relu_pool2_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I],
+    "pg_conv2d_relu_pool2_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I],
     "pg_maxpool2d_fwd": [_P, _I, _P, _P, _L, _I, _I, _I],
     "pg_maxpool2d_bwd": [_P, _I, _P, _P, _P, _L, _I, _I, _I],
     "pg_maxpool2d_relu_bwd": [_P, _I, _P, _P, _P, _L, _I, _I, _I, _I],

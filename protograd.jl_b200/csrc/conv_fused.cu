@@ -391,12 +391,17 @@ int run_bwd(pg_ctx* ctx, const float* x, const float* w, const float* y, const u
 }
 
 // the compiled geometries (Cin, Cout, K, H, W): LeNet on 28x28 (examples/02_mnist_conv.jl) and on 32x32 inputs
-#define DISPATCH(CALL)                                                              \
-  if (Cin == 1 && Cout == 6 && kH == 5 && H == 28 && W == 28) return CALL(Geo<1, 6, 5, 28, 28>);   \
-  if (Cin == 6 && Cout == 16 && kH == 5 && H == 12 && W == 12) return CALL(Geo<6, 16, 5, 12, 12>);  \
-  if (Cin == 1 && Cout == 6 && kH == 5 && H == 32 && W == 32) return CALL(Geo<1, 6, 5, 32, 32>);   \
-  if (Cin == 3 && Cout == 6 && kH == 5 && H == 32 && W == 32) return CALL(Geo<3, 6, 5, 32, 32>);   \
-  if (Cin == 6 && Cout == 16 && kH == 5 && H == 14 && W == 14) return CALL(Geo<6, 16, 5, 14, 14>);
+typedef Geo<1, 6, 5, 28, 28> G_1_6_28;
+typedef Geo<6, 16, 5, 12, 12> G_6_16_12;
+typedef Geo<1, 6, 5, 32, 32> G_1_6_32;
+typedef Geo<3, 6, 5, 32, 32> G_3_6_32;
+typedef Geo<6, 16, 5, 14, 14> G_6_16_14;
+#define DISPATCH(CALL)                                                                    \
+  if (Cin == 1 && Cout == 6 && kH == 5 && H == 28 && W == 28) return CALL(G_1_6_28);      \
+  if (Cin == 6 && Cout == 16 && kH == 5 && H == 12 && W == 12) return CALL(G_6_16_12);    \
+  if (Cin == 1 && Cout == 6 && kH == 5 && H == 32 && W == 32) return CALL(G_1_6_32);      \
+  if (Cin == 3 && Cout == 6 && kH == 5 && H == 32 && W == 32) return CALL(G_3_6_32);      \
+  if (Cin == 6 && Cout == 16 && kH == 5 && H == 14 && W == 14) return CALL(G_6_16_14);
 
 }  // namespace
 

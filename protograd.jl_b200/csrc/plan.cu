@@ -58,6 +58,8 @@ struct pg_plan {
   std::vector<char> need, ng, sce_softmax, tc_lin, tc_conv;
   std::vector<std::vector<int>> consumers;
   std::vector<int> fused_act, fused_into, fused_sce;
+  std::vector<int> fused_pool, pool_of;      // conv id -> the 2x2 max-pool fused into it (conv_fused.cu), and the inverse
+  std::vector<void*> amax;                    // per fused pool node: winner byte per pooled element
   std::vector<Buf> vals, grads;
   std::vector<int> vdt;                 // value dtype per node
   std::vector<int64_t> vpitch;          // last-axis pitch of the value
@@ -160,6 +162,21 @@ int analyse(pg_plan& P) {
       if (P.is(p, PG_OP_SOFTMAX) && P.consumers[p].size() == 1 && p != P.root) { P.fused_sce[i] = p; P.sce_softmax[p] = 1; }
     }
   }
+  // Conv + ReLU + 2x2 max-pool chains (examples/02_mnist_conv.jl:27-33) run as one fused kernel each way when the
+  // geometry is compiled in (Float32, any math mode: the kernel computes in fp32)
+  P.fused_pool.assign(n, -1); P.pool_of.assign(n, -1);
+  for (int i = 0; i < n; ++i) {
+    if (!P.need[i] || !P.is(i, PG_OP_CONV2D) || ops[i].dtype != PG_F32 || P.fused_act[i] < 0) continue;
+    const int r = P.fused_act[i];
+    if (P.consumers[r].size() != 1 || r == P.root) continue;
+    const int q = P.consumers[r][0];
+    if (!P.is(q, PG_OP_MAXPOOL) || ops[q].k != 2) continue;
+    const pg_op& w = ops[ops[i].in[1]];
+    const pg_op& x = ops[ops[i].in[0]];
+    if (x.dtype != PG_F32 || x.ndim != 4) continue;
+    if (pg_conv2d_relu_pool2_supported((int)w.shape[1], (int)x.shape[2], (int)x.shape[3], (int)w.shape[0], (int)w.shape[2], (int)w.shape[3]) != 1) continue;
+    P.fused_pool[i] = q; P.pool_of[q] = i;
+  }
   P.dtype = ops[P.root].dtype;
   return PG_OK;
 }
@@ -179,7 +196,7 @@ void select_tensor_core(pg_plan& P) {
     if (P.is(i, PG_OP_CONV2D)) {
       const pg_op& w = P.ops[P.ops[i].in[1]];
       const pg_op& x = P.ops[P.ops[i].in[0]];
-      if (x.dtype == PG_F32 && pg_tc_conv2d_supported((int)w.shape[1], (int)x.shape[2], (int)x.shape[3], (int)w.shape[0], (int)w.shape[2], (int)w.shape[3]) == 1)
+      if (P.fused_pool[i] < 0 && x.dtype == PG_F32 && pg_tc_conv2d_supported((int)w.shape[1], (int)x.shape[2], (int)x.shape[3], (int)w.shape[0], (int)w.shape[2], (int)w.shape[3]) == 1)
         P.tc_conv[i] = 1;
     }
     if (!P.is(i, PG_OP_LINEAR)) continue;
@@ -275,7 +292,8 @@ int allocate(pg_plan& P) {
     const int k = P.ops[i].kind;
     bool own = false;
     if (k == PG_OP_LINEAR || k == PG_OP_CONV2D) own = P.fused_act[i] < 0;
-    else if (k == PG_OP_RELU || k == PG_OP_MAXPOOL || k == PG_OP_MEANPOOL || k == PG_OP_DROPOUT) own = true;
+    else if (k == PG_OP_RELU) own = !(P.fused_into[i] >= 0 && P.fused_pool[P.fused_into[i]] >= 0);   // never materialised when the pool is fused in
+    else if (k == PG_OP_MAXPOOL || k == PG_OP_MEANPOOL || k == PG_OP_DROPOUT) own = true;
     else if (k == PG_OP_SOFTMAX) own = !P.sce_softmax[i];
     if (own) {
       rc = new_buf(P, i, P.vdt[i], P.vpitch[i], &P.vals[i]);
@@ -288,7 +306,14 @@ int allocate(pg_plan& P) {
     if (k == PG_OP_INPUT || k == PG_OP_PARAM || k == PG_OP_LOSS_CE || k == PG_OP_LOSS_MSE || k == PG_OP_RESHAPE) continue;
     if ((k == PG_OP_LINEAR || k == PG_OP_CONV2D) && P.fused_act[i] >= 0) continue;   // shares the relu node's gradient buffer
     if (k == PG_OP_SOFTMAX && P.sce_softmax[i]) continue;                              // dZ goes straight to the logits' gradient
+    if (k == PG_OP_RELU && P.fused_into[i] >= 0 && P.fused_pool[P.fused_into[i]] >= 0) continue;   // the fused backward starts from the pooled gradient
     rc = new_buf(P, i, P.vdt[i], P.vpitch[i], &P.grads[i]);
+    if (rc != PG_OK) return rc;
+  }
+  P.amax.assign(n, nullptr);
+  for (int i = 0; i < n; ++i) {
+    if (!P.need[i] || P.pool_of[i] < 0 || !P.ng[P.pool_of[i]]) continue;
+    rc = dalloc(P, (size_t)P.size[i], &P.amax[i]);
     if (rc != PG_OK) return rc;
   }
   for (int i = 0; i < n; ++i) {
@@ -405,8 +430,15 @@ int forward(pg_plan& P) {
         const int x = o.in[0], w = o.in[1], b = o.in[2];
         const pg_op& xs = P.ops[x]; const pg_op& ws = P.ops[w];
         const int act = P.fused_act[i] >= 0 ? PG_ACT_RELU : PG_ACT_NONE;
-        Buf xv = val(P, x), out = val(P, i);
+        Buf xv = val(P, x);
         RC(need_float(xv));
+        if (P.fused_pool[i] >= 0) {
+          const int q = P.fused_pool[i];
+          RC(pg_conv2d_relu_pool2_fwd(ctx, xv.p, P.leaf[w], P.leaf[b], P.vals[q].p, P.amax[q], xs.shape[0], (int)xs.shape[1], (int)xs.shape[2], (int)xs.shape[3],
+                                      (int)ws.shape[0], (int)ws.shape[2], (int)ws.shape[3]));
+          break;
+        }
+        Buf out = val(P, i);
         if (P.tc_conv[i])
           RC(pg_tc_conv2d_fwd(ctx, xv.p, P.leaf[w], P.leaf[b], out.p, xs.shape[0], (int)xs.shape[1], (int)xs.shape[2], (int)xs.shape[3], (int)ws.shape[0], (int)ws.shape[2], (int)ws.shape[3], act));
         else
@@ -421,6 +453,7 @@ int forward(pg_plan& P) {
         break;
       }
       case PG_OP_MAXPOOL: case PG_OP_MEANPOOL: {
+        if (P.pool_of[i] >= 0) break;              // produced by the fused conv kernel
         const pg_op& xs = P.ops[o.in[0]];
         Buf xv = val(P, o.in[0]);
         RC(need_float(xv));
@@ -491,6 +524,22 @@ int backward(pg_plan& P, void* const* gleaf, int n_leaves, pg_ready_fn on_ready,
         break;                       // losses wrote their input gradient during the forward pass
       case PG_OP_LINEAR: case PG_OP_CONV2D: {
         const int x = o.in[0], W = o.in[1], b = o.in[2];
+        if (o.kind == PG_OP_CONV2D && P.fused_pool[i] >= 0) {
+          // pooled gradient -> (max-pool routing, ReLU', conv pullbacks) in one pass
+          const int q = P.fused_pool[i];
+          const pg_op& xs = P.ops[x]; const pg_op& ws = P.ops[W];
+          void* gW = leaf_of(W); void* gb = leaf_of(b);
+          if (P.ng[W] && !gW) return P.fail(PG_ERR_ARG, "missing gradient leaf pointer");
+          Buf gxb = P.ng[x] ? grad(P, x) : Buf();
+          if (gxb.p) RC(need_float(gxb));
+          RC(pg_conv2d_relu_pool2_bwd(ctx, val(P, x).p, P.leaf[W], P.vals[q].p, P.amax[q], P.grads[q].p, gW, gb, gxb.p, xs.shape[0], (int)xs.shape[1],
+                                      (int)xs.shape[2], (int)xs.shape[3], (int)ws.shape[0], (int)ws.shape[2], (int)ws.shape[3]));
+          int first_leaf = 1 << 30;
+          if (gW) first_leaf = std::min(first_leaf, P.ops[W].grad_leaf);
+          if (gb) first_leaf = std::min(first_leaf, P.ops[b].grad_leaf);
+          if (on_ready && first_leaf != (1 << 30)) on_ready(user, first_leaf);
+          break;
+        }
         Buf gy = grad(P, i);
         const int r = P.fused_act[i];
         if (r >= 0 && !P.premasked(r)) {   // the consumer does not apply relu' itself: gy becomes the pre-activation gradient here
@@ -562,6 +611,7 @@ int backward(pg_plan& P, void* const* gleaf, int n_leaves, pg_ready_fn on_ready,
         break;
       }
       case PG_OP_MAXPOOL: case PG_OP_MEANPOOL: {
+        if (P.pool_of[i] >= 0) break;              // handled by the fused conv backward
         const int x = o.in[0];
         const pg_op& xs = P.ops[x];
         Buf gx = grad(P, x);
@@ -625,6 +675,7 @@ int pg_plan_node_flags(pg_plan* P, int node, int* flags) {
   if (P->ng[node]) f |= PG_NODE_NEEDS_GRAD;
   if (P->tc_lin[node] || P->tc_conv[node]) f |= PG_NODE_TENSOR_CORE;
   if (P->fused_act[node] >= 0) f |= PG_NODE_FUSED_ACT;
+  if (P->fused_pool[node] >= 0) f |= PG_NODE_FUSED_POOL;
   if (P->need[node] && P->vdt[node] == PG_BF16 && !P->is(node, PG_OP_INPUT)) f |= PG_NODE_BF16_VALUE;
   if ((P->is(node, PG_OP_SOFTMAX) && P->sce_softmax[node]) || ((P->is(node, PG_OP_LINEAR) || P->is(node, PG_OP_CONV2D)) && P->fused_act[node] >= 0))
     f |= PG_NODE_FUSED_AWAY;

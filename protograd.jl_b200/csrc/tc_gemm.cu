@@ -48,7 +48,7 @@ struct Epi {
   int narrow;                   // 1: N not a multiple of 8 -> scalar guarded loads/stores (f32 out only)
   float* colsum;                // data-gradient launches: also accumulate column sums of the (masked, bf16-rounded) output
                                 // = the bias gradient of the layer that produced the masking activation (nullable, pre-zeroed)
-  float* db;                    // weight-gradient launches: fused bias gradient db[n] = sum_k B[k][n] (nullable)
+  float* db;                    // weight-gradient launches: fused bias gradient, as partials db[m_blk][n] = sum over this m-block's share of the k-blocks of B[k][n] (nullable)
   int splits;                   // split-K: work item = (tile, split); split s writes its fp32 partial to C + s*M*N
   int kb_per_split;
 };
@@ -373,7 +373,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (n0 + col0 + j < N) atomicAdd(epi.db + n0 + col0 + j, acc4[j]);
+          if (n0 + col0 + j < N) epi.db[(size_t)m_blk * N + n0 + col0 + j] = acc4[j];     // one partial per (m-block, column): summed in a fixed order afterwards
           acc4[j] = 0.f;
         }
     }
@@ -650,7 +650,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int cbase = n0 + (int)rank * 128 + col0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (cbase + j < N) atomicAdd(epi.db + cbase + j, acc4[j]);
+        if (cbase + j < N) epi.db[(size_t)m_blk * N + cbase + j] = acc4[j];
         acc4[j] = 0.f;
       }
     }
@@ -988,12 +988,23 @@ static int tc_linear_bwd_impl(pg_ctx* ctx, const void* X, const void* W, const v
   if (dW) {  // dW[K][N] = X^T dY: GEMM (M'=K, N'=N, K'=M), A = X stored [M][K] (MN-major), B = dY stored [M][N] (MN-major)
     // db = column sums of dY ride along when enough m-blocks share the work: reducer warps sum the dY
     // tiles already staged in shared memory (no extra pass over dY)
-    const bool fuse_db = db != nullptr && (use_2cta(ctx, K, N) && getenv("PG_DBW_1CTA") == nullptr ? pg_cdiv(K, 256) >= 4 : pg_cdiv(K, BLOCK_M) >= 4);
-    if (fuse_db) PG_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), ctx->stream));
-    Epi epi{nullptr, nullptr, 0, 1, 0, nullptr, fuse_db ? (float*)db : nullptr, 1, 1 << 30};
+    const bool two = use_2cta(ctx, K, N) && getenv("PG_DBW_1CTA") == nullptr;
+    const int64_t m_blocks = two ? pg_cdiv(K, 256) : pg_cdiv(K, BLOCK_M);
+    const bool fuse_db = db != nullptr && m_blocks >= 4;
+    float* db_part = nullptr;
+    if (fuse_db) {      // per-(m-block, column) partial sums in scratch; summed in a fixed order below: no floating-point atomics
+      rc = pg_ws_ensure(ctx, (size_t)m_blocks * N * sizeof(float));
+      if (rc != PG_OK) return rc;
+      db_part = (float*)ctx->ws;
+    }
+    Epi epi{nullptr, nullptr, 0, 1, 0, nullptr, db_part, 1, 1 << 30};
     rc = tc_dispatch(ctx, 2, X, dY, dW, K, N, M, epi);
     if (rc != PG_OK) return rc;
-    if (fuse_db) db = nullptr;
+    if (fuse_db) {
+      reduce_f32_kernel<<<(unsigned)pg_cdiv(N, 256), 256, 0, ctx->stream>>>(db_part, (float*)db, N, (int)m_blocks);
+      PG_LAUNCHED(ctx);
+      db = nullptr;
+    }
   }
   if (db) {
     rc = pg_colsum_launch(ctx, PG_BF16, dY, db, M, N);

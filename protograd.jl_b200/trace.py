@@ -238,7 +238,7 @@ def mse(output, label, denom=None):
 
 _KIND = {"input": 0, "param": 1, "linear": 2, "conv": 3, "relu": 4, "maxpool": 5, "meanpool": 6, "reshape": 7, "dropout": 8,
          "softmax": 9, "cross_entropy": 10, "mse": 11}
-NODE_NEEDED, NODE_NEEDS_GRAD, NODE_TENSOR_CORE, NODE_FUSED_ACT, NODE_BF16_VALUE, NODE_FUSED_AWAY = 1, 2, 4, 8, 16, 32
+NODE_NEEDED, NODE_NEEDS_GRAD, NODE_TENSOR_CORE, NODE_FUSED_ACT, NODE_BF16_VALUE, NODE_FUSED_AWAY, NODE_FUSED_POOL = 1, 2, 4, 8, 16, 32, 64
 MATH_CODE = {"fp32": 0, "bf16": 1}
 
 
@@ -379,6 +379,7 @@ class Plan:
         self.ng = [bool(f & NODE_NEEDS_GRAD) for f in self.flags]
         self.tc_linear = {i for i in range(n) if self.flags[i] & NODE_TENSOR_CORE and self.ops_kind[i] == "linear"}
         self.tc_conv = {i for i in range(n) if self.flags[i] & NODE_TENSOR_CORE and self.ops_kind[i] == "conv"}
+        self.fused_conv = {i for i in range(n) if self.flags[i] & NODE_FUSED_POOL}     # conv + relu + maxpool(2) in one kernel
         # W leaves the tcgen05 GEMMs can read straight from the arena's bf16 shadow (no padding needed)
         self.shadow_params = []
         for i in self.tc_linear:

@@ -107,5 +107,5 @@ def test_conv_net_step_bf16_mode(pg, spec_name, B):
             assert rel_err(a, b) <= 2e-2, (i, rel_err(a, b))
     # the plan really used the tensor-core conv kernels
     from protograd_b200 import trace as T
-    plans = [p for p in T._PLANS.values() if p.math == "bf16" and p.tc_conv]
-    assert plans, "no plan selected the tensor-core conv path"
+    plans = [p for p in T._PLANS.values() if p.math == "bf16" and (p.tc_conv or p.fused_conv)]
+    assert plans, "no plan selected the tensor-core / fused conv path"

@@ -129,8 +129,9 @@ def test_tc_steps_with_fused_shadow_match_plain_steps(pg):
             pg.step(st, pb(), shadow=use_shadow)
             losses.append(float(out))
         res.append((losses, m.vec()))
-    # bias gradients are accumulated with fp32 atomics, so two runs agree to rounding, not bit for bit
-    assert np.allclose(res[0][0], res[1][0], rtol=1e-5) and rel_err(res[0][1], res[1][1]) <= 1e-5
+    # no floating-point atomics on the path (bias gradients are per-m-block partials summed in a fixed order; tiles are
+    # handed out dynamically but each tile's arithmetic is fixed): the two runs agree BIT for bit
+    assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1])
     assert res[0][0][-1] < res[0][0][0]
 
 

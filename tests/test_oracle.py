@@ -323,3 +323,25 @@ def test_conv_operand_rounding_option():
     y_plain = O.conv2d_fwd(O.bf16_round(x), O.bf16_round(params[0]), params[1])
     y_opt = O.net_forward(spec[:1], params[:2], x, conv_round=O.bf16_round)
     assert np.array_equal(y_plain, y_opt)
+
+
+def test_xavier_uniform_scale_and_bounds_host_and_oracle():
+    """src/layers.jl:6-11: sqrt(T(6)/(fan_in+fan_out)) * (2*rand(T, dims...) .- 1): uniform on (-s, s), mean 0, variance s^2/3,
+    eltype T; Linear / Conv constructors use fan_in/fan_out as layers.jl:20-24,43-57 (biases zero).  Checked for the host
+    mirror's initialiser (protograd_b200.layers.xavier_uniform, which the device constructors call) and the oracle's."""
+    from protograd_b200.layers import xavier_uniform as xu_host
+    for xu in (O.xavier_uniform, xu_host):
+        for T in (np.float32, np.float64, np.float16):
+            rng = np.random.default_rng(0)
+            fan_in, fan_out = 784, 100
+            a = xu(rng, T, (fan_in, fan_out), fan_in, fan_out)
+            s = np.sqrt(6.0 / (fan_in + fan_out))
+            assert a.dtype == T and a.shape == (fan_in, fan_out)
+            assert np.abs(a).max() <= s * (1 + 1e-3) and np.abs(a).max() >= 0.99 * s
+            assert abs(float(a.astype(np.float64).mean())) < 3 * s / np.sqrt(3 * a.size) * 1.5
+            assert abs(float(a.astype(np.float64).var()) / (s * s / 3) - 1) < 0.02
+    # conv fan-in / fan-out: k*k*Cin and k*k*Cout (layers.jl:44-45)
+    w = O.xavier_uniform(np.random.default_rng(1), np.float32, (16, 6, 5, 5), 25 * 6, 25 * 16)
+    assert np.abs(w).max() <= np.sqrt(6.0 / (150 + 400)) * (1 + 1e-6)
+    ps = O.init_params([("conv", 6, 16, 5), ("linear", 256, 120)], np.float32, seed=0)
+    assert ps[0].shape == (16, 6, 5, 5) and not ps[1].any() and ps[2].shape == (256, 120) and not ps[3].any()

@@ -73,15 +73,16 @@ def test_narrow_output_layer_alone_is_tensor_core():
     assert plan.tc_linear == set(lins)
 
 
-def lenet(B=32, frozen_trunk=False):
+def lenet(B=32, frozen_trunk=False, pool=None):
+    pool = pool or T.maxpool
     w1, b1, w2, b2 = leaf(6, 1, 5, 5), leaf(6), leaf(16, 6, 5, 5), leaf(16)
     W1, c1, W2, c2, W3, c3 = leaf(256, 120), leaf(120), leaf(120, 84), leaf(84), leaf(84, 10), leaf(10)
     train = [W1, c1, W2, c2, W3, c3] if frozen_trunk else [w1, b1, w2, b2, W1, c1, W2, c2, W3, c3]
     tr = T.Trace(None, trainable=train, math="bf16")
     x = tr.lift(np.zeros((B, 1, 28, 28), dtype=np.float32))
-    h = T.maxpool(T.relu(T.conv(x, w1, b1)), 2)
+    h = pool(T.relu(T.conv(x, w1, b1)), 2)
     conv1 = h.inputs[0].inputs[0].id
-    h = T.maxpool(T.relu(T.conv(h, w2, b2)), 2)
+    h = pool(T.relu(T.conv(h, w2, b2)), 2)
     conv2 = h.inputs[0].inputs[0].id
     h = T.flatten(h)
     lins = []
@@ -93,19 +94,26 @@ def lenet(B=32, frozen_trunk=False):
     return T.Plan(tr, root), (conv1, conv2), lins
 
 
-def test_lenet_convs_and_head_on_tensor_cores():
+def test_lenet_fused_conv_pool_trunk_and_tensor_core_head():
     plan, convs, lins = lenet()                        # BASELINE configs[2] (examples/02_mnist_conv.jl:25-44)
-    assert plan.tc_conv == set(convs)
+    # conv + relu + maxpool(2) chains of the compiled geometries run as ONE bandwidth-shaped kernel each way
+    # (csrc/conv_fused.cu): these layers are HBM-bound, not tensor-bound
+    assert plan.fused_conv == set(convs) and not plan.tc_conv
     assert plan.tc_linear == set(lins)                 # 256-120-84-10 head: pool-fed (cast), widths 120 / 84 padded
     assert plan.act_is_bf16(lins[0]) and plan.act_is_bf16(lins[1]) and not plan.act_is_bf16(lins[2])
     for c in convs:
         assert not plan.act_is_bf16(c)                 # conv tensors stay Float32 in HBM
 
 
-def test_frozen_trunk_keeps_forward_on_tensor_cores():
+def test_frozen_trunk_keeps_the_fused_forward():
     plan, convs, lins = lenet(frozen_trunk=True)       # BASELINE configs[4]: no conv gradients needed
-    assert plan.tc_conv == set(convs)
+    assert plan.fused_conv == set(convs)
     assert not any(plan.ng[c] for c in convs)
+
+
+def test_conv_without_the_maxpool_pattern_uses_the_tensor_core_conv():
+    plan, convs, lins = lenet(pool=T.meanpool)         # mean-pool: no fused kernel -> tcgen05 implicit GEMM in bf16 mode
+    assert plan.tc_conv == set(convs) and not plan.fused_conv
 
 
 def test_wide_conv_stays_on_simt():

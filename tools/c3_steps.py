@@ -42,27 +42,4 @@ for _ in range(steps):
 e1.record(stream); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(f"C3 B={B} math={math}: {ms:.4f} ms/step = {B / ms / 1e3:.2f} M samples/s   loss {float(out):.5f}")
-# per-call breakdown of one step
-from protograd_b200 import trace as T, optimizers as OPT
-log = []
-orig = T.call
-
-
-def logged(name, *a):
-    r = orig(name, *a)
-    e = torch.cuda.Event(enable_timing=True); e.record(stream); log.append((name, e))
-    return r
-
-
-T.call = logged; OPT.call = logged
-acc = {}
-for rep in range(10):
-    log.clear()
-    torch.cuda._sleep(2_000_000)     # keep the GPU busy ~1 ms so the host runs ahead and the per-call intervals hold no launch gaps
-    s = torch.cuda.Event(enable_timing=True); s.record(stream)
-    step(); torch.cuda.synchronize()
-    prev = s
-    for k, (name, e) in enumerate(log):
-        acc.setdefault((k, name), []).append(prev.elapsed_time(e)); prev = e
-for (k, name), v in acc.items():
-    print(f"  {k:2d} {name:28s} {np.mean(v) * 1e3:8.1f} us")
+# (per-kernel breakdown: the planner launches from inside the library now — use the ncu launch list, tools/r2_profile.sh)
