@@ -553,12 +553,9 @@ int launch_geo(pg_ctx* ctx, const ConvArgs& a, int bytes) {
 
 template <int MODE, int NKB>
 int launch_nkb(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
-  static const bool want_small = getenv("PG_TCCONV_SMALL") != nullptr;     // experimental: two half-size CTAs per SM
+  // (the half-size two-CTAs-per-SM geometry of round 1 was measured in round 2 — conv1 forward 138 -> 113 us, conv2
+  //  backward 346 -> 435 us at C3 B = 8192, profiles/r2_tc_conv_small.md — and is no longer instantiated)
   int bytes = 0;
-  if (want_small) {
-    ConvArgs s = a;
-    if (plan_launch<MODE, NKB, true>(s, dy_floats_per_sample, &bytes)) return launch_geo<MODE, NKB, true>(ctx, s, bytes);
-  }
   const bool ok = plan_launch<MODE, NKB, false>(a, dy_floats_per_sample, &bytes);
   PG_REQUIRE(a.G > 0, "tensor-core conv: a sample (with its output gradient) does not fit a shared-memory slot");
   PG_REQUIRE(ok, "tensor-core conv: shared-memory budget exceeded");

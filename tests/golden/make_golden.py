@@ -49,7 +49,10 @@ def biased_params(spec, T, seed):
 def _train_case(spec, B, opt_name, opt_kw, steps, seed, T=np.float32):
     x, lab = class_data(spec, B, T, seed)
     p0 = biased_params(spec, T, seed)
-    out = {}
+    # raw inputs and initial leaves (C order; Julia reads them with reversed dims): julia/parity.jl rebuilds the exact case
+    out = {"x": x, "label": lab}
+    for i, p in enumerate(p0):
+        out[f"p0_{i}"] = p
     v, g = O.net_loss_and_grad(spec, p0, x, lab, "ce")
     v64, g64 = O.net_loss_and_grad(spec, [p.astype(np.float64) for p in p0], x.astype(np.float64), lab.astype(np.float64), "ce")
     out["loss"] = np.array(v); out["loss_f64"] = np.array(v64)

@@ -94,8 +94,9 @@ def test_c1_hidden_100_on_tensor_cores(pg):
 
 
 def test_c3_lenet_fully_on_tensor_cores(pg):
-    """examples/02_mnist_conv.jl:25-44: conv trunk on the tcgen05 implicit-GEMM kernels AND the 256-120-84-10 head on
-    the tcgen05 GEMM (pool-fed: fp32 -> bf16 cast in, fp32 data gradient out; widths 120 / 84 padded)."""
+    """examples/02_mnist_conv.jl:25-44: conv + relu + maxpool chains on the fused bandwidth-shaped kernels (fp32 math) AND
+    the 256-120-84-10 head on the tcgen05 GEMM (pool-fed: fp32 -> bf16 cast in, fp32 data gradient out; widths 120 / 84
+    padded)."""
     spec = MG.C3_SPEC
     B = 64
     x, lab = MG.class_data(spec, B, np.float32, 4)
@@ -103,9 +104,9 @@ def test_c3_lenet_fully_on_tensor_cores(pg):
     m = build_model(pg, spec, p0)
     out, pb = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(x), lab), m, math="bf16")
     plan = out._plan
-    assert len(plan.tc_conv) == 2 and len(plan.tc_linear) == 3
+    assert len(plan.fused_conv) == 2 and not plan.tc_conv and len(plan.tc_linear) == 3
     g = [p.numpy() for p in pb().allparams()]
-    v, gr = O.net_loss_and_grad(spec, _f64(p0), x.astype(np.float64), lab.astype(np.float64), conv_round=O.bf16_round, linear_round=O.bf16_round)
+    v, gr = O.net_loss_and_grad(spec, _f64(p0), x.astype(np.float64), lab.astype(np.float64), linear_round=O.bf16_round)
     assert abs(float(out) - v) <= 1e-4 * abs(v)
     errs = [rel_err(a, r) for a, r in zip(g, gr)]
     assert max(errs) <= 2e-2, errs
