@@ -117,48 +117,28 @@ __global__ void __launch_bounds__(FwdCfg<G>::THREADS) conv_relu_pool_fwd_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// backward, shared: rebuild the conv-output gradient of one sample in shared memory from the pooled gradient
-//   dyt[i][j][co] (channel-last, for the weight gradient)   or   dyp[co][i + K-1][j + K-1] zero-bordered (data gradient)
-// ---------------------------------------------------------------------------------------------------------------
-template <typename G, bool CHANNEL_LAST>
-__device__ __forceinline__ void expand_dy(float* dst, const float* __restrict__ gy, const float* __restrict__ y, const uint8_t* __restrict__ amax,
-                                          int64_t n, int tid, int nthreads) {
-  constexpr int K = G::K, PH = G::HO + 2 * (K - 1), PW = G::WO + 2 * (K - 1);
-  constexpr int TOTAL = CHANNEL_LAST ? G::HO * G::WO * G::COUTP : G::COUT * PH * PW;
-  for (int i = tid; i < TOTAL; i += nthreads) dst[i] = 0.0f;
-  __syncwarp();
-  // (caller synchronises between the zero fill and the scatter when several warps share the tile)
-  (void)gy; (void)y; (void)amax; (void)n;
-}
-template <typename G, bool CHANNEL_LAST>
-__device__ __forceinline__ void scatter_dy(float* dst, const float* __restrict__ gy, const float* __restrict__ y, const uint8_t* __restrict__ amax,
-                                           int64_t n, int tid, int nthreads) {
-  constexpr int K = G::K, PH = G::HO + 2 * (K - 1), PW = G::WO + 2 * (K - 1);
-  for (int e = tid; e < G::YS; e += nthreads) {
-    const int win = e % G::WIN, co = e / G::WIN;
-    const int64_t o = n * G::YS + e;
-    const float d = y[o] > 0.0f ? gy[o] : 0.0f;                  // relu'(0) = 0
-    const int k = amax[o];
-    const int i = 2 * (win / G::WP) + (k >> 1), j = 2 * (win % G::WP) + (k & 1);
-    if (CHANNEL_LAST) dst[(i * G::WO + j) * G::COUTP + co] = d;
-    else dst[(co * PH + i + K - 1) * PW + j + K - 1] = d;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // weight + bias gradient: thread (ci, u, i) holds input row x[ci][i+u][:] in registers and accumulates
 // acc[v][co] += x[i+u][j+v] * dy[i][j][co] while j slides along the row; summed over samples in registers, over the
 // HO row-threads in shared memory at the end, written as one partial per CTA.
+// dy is never materialised: per (j, 4 channels) it is selected on the fly from the pooled gradient (already masked by
+// relu') and the winner bytes, staged channel-last in shared memory: gm[window][co], am[window][co].
+// Latency: the NEXT sample's global data (input tile, pooled gradient / value / winner) is prefetched into registers
+// while the current one is consumed, and the shared-memory tiles are double-buffered: one __syncthreads per sample.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename G>
 struct WgCfg {
   static constexpr int TPS = G::CIN * G::K * G::HO;            // threads per sample slot
   static constexpr int SLOTS = (256 / TPS) > 0 ? (256 / TPS) : 1;
   static constexpr int THREADS = ((SLOTS * TPS + 31) / 32) * 32;
-  static constexpr int DYT = G::HO * G::WO * G::COUTP;
   static constexpr int NW = G::COUT * G::CIN * G::K * G::K;    // filter elements
+  static constexpr int GROW = G::WP * G::COUTP + 4;            // padded window-row pitch (floats): rows land in different banks
+  static constexpr int GM = G::HP * GROW;                      // masked pooled gradient, channel-last
+  static constexpr int AM = (G::HP * G::WP * G::COUTP + 3) / 4;   // winner bytes, channel-last (as 32-bit words)
+  static constexpr int XV = (G::XS / 4 + TPS - 1) / TPS;       // float4 of the input tile per thread
+  static constexpr int SV = (G::YS + TPS - 1) / TPS;           // pooled elements per thread
+  static constexpr int BUF = G::XS + GM + AM;                  // one sample's tiles (floats)
   static constexpr int RED = SLOTS * TPS * G::K * G::COUTP;    // final cross-thread reduction buffer (floats)
-  static constexpr int STAGE = SLOTS * (G::XS + DYT);
+  static constexpr int STAGE = SLOTS * 2 * BUF;
   static constexpr int SMEM_FLOATS = STAGE > RED ? STAGE : RED;
 };
 
@@ -172,8 +152,7 @@ __global__ void __launch_bounds__(WgCfg<G>::THREADS) conv_relu_pool_wgrad_kernel
   const int slot = threadIdx.x / C::TPS, t = threadIdx.x % C::TPS;
   const bool worker = threadIdx.x < C::SLOTS * C::TPS;
   const int i = t % HO, u = (t / HO) % K, ci = t / (HO * K);
-  float* xs = smem + slot * (G::XS + C::DYT);
-  float* dyt = xs + G::XS;
+  float* base = smem + slot * 2 * C::BUF;
   float acc[K][COUTP];
   float dbacc[COUTP];
 #pragma unroll
@@ -182,28 +161,74 @@ __global__ void __launch_bounds__(WgCfg<G>::THREADS) conv_relu_pool_wgrad_kernel
     for (int c = 0; c < COUTP; ++c) acc[v][c] = 0.0f;
 #pragma unroll
   for (int c = 0; c < COUTP; ++c) dbacc[c] = 0.0f;
-  for (int64_t n0 = (int64_t)blockIdx.x * C::SLOTS; n0 < N; n0 += (int64_t)gridDim.x * C::SLOTS) {
-    __syncthreads();
-    const int64_t n = n0 + slot;
-    const bool live = worker && n < N;
-    if (live) {
-      const float4* src = reinterpret_cast<const float4*>(x + n * G::XS);
-      for (int k = t; k < G::XS / 4; k += C::TPS) reinterpret_cast<float4*>(xs)[k] = src[k];
-      for (int k = t; k < C::DYT; k += C::TPS) dyt[k] = 0.0f;
+  // ---- register prefetch of one sample ----
+  float4 xr[C::XV];
+  float gr[C::SV];
+  uint8_t ar[C::SV];
+  auto prefetch = [&](int64_t n) {
+    const float4* src = reinterpret_cast<const float4*>(x + n * G::XS);
+#pragma unroll
+    for (int k = 0; k < C::XV; ++k) {
+      const int e = t + k * C::TPS;
+      xr[k] = e < G::XS / 4 ? __ldg(src + e) : make_float4(0, 0, 0, 0);
     }
-    __syncthreads();
-    if (live) scatter_dy<G, true>(dyt, gy, y, amax, n, t, C::TPS);
-    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < C::SV; ++k) {
+      const int e = t + k * C::TPS;
+      if (e < G::YS) {
+        const int64_t o = n * G::YS + e;
+        gr[k] = __ldg(y + o) > 0.0f ? __ldg(gy + o) : 0.0f;     // relu'(0) = 0
+        ar[k] = __ldg(amax + o);
+      }
+    }
+  };
+  auto stash = [&](float* buf) {                                // registers -> this sample's shared-memory tiles
+#pragma unroll
+    for (int k = 0; k < C::XV; ++k) {
+      const int e = t + k * C::TPS;
+      if (e < G::XS / 4) reinterpret_cast<float4*>(buf)[e] = xr[k];
+    }
+    float* gm = buf + G::XS;
+    uint8_t* am = reinterpret_cast<uint8_t*>(gm + C::GM);
+#pragma unroll
+    for (int k = 0; k < C::SV; ++k) {
+      const int e = t + k * C::TPS;
+      if (e < G::YS) {
+        const int win = e % G::WIN, co = e / G::WIN;
+        gm[(win / G::WP) * C::GROW + (win % G::WP) * COUTP + co] = gr[k];
+        am[win * COUTP + co] = ar[k];
+      }
+    }
+  };
+  int64_t n = (int64_t)blockIdx.x * C::SLOTS + slot;
+  const int64_t stride = (int64_t)gridDim.x * C::SLOTS;
+  if (worker && n < N) prefetch(n);
+  int it = 0;
+  for (int64_t n0 = (int64_t)blockIdx.x * C::SLOTS; n0 < N; n0 += stride, n += stride, ++it) {
+    float* buf = base + (it & 1) * C::BUF;
+    const bool live = worker && n < N;
+    if (live) stash(buf);
+    __syncthreads();                                             // (the other buffer is still being read by slower warps: double buffering)
+    if (live && n + stride < N) prefetch(n + stride);
     if (!live) continue;
     float row[G::W];
 #pragma unroll
-    for (int c = 0; c < G::W; ++c) row[c] = xs[(ci * G::H + i + u) * G::W + c];
-    const float4* dv = reinterpret_cast<const float4*>(dyt + i * WO * COUTP);
+    for (int c = 0; c < G::W; ++c) row[c] = buf[(ci * G::H + i + u) * G::W + c];
+    const float* gm = buf + G::XS + (i >> 1) * C::GROW;
+    const uint32_t* am = reinterpret_cast<const uint32_t*>(buf + G::XS + C::GM) + (i >> 1) * G::WP * (COUTP / 4);
+    const uint32_t krow = (uint32_t)(i & 1) << 1;
 #pragma unroll
     for (int j = 0; j < WO; ++j) {
+      const uint32_t kpos = krow | (uint32_t)(j & 1);            // which window position (i, j) is
 #pragma unroll
       for (int c4 = 0; c4 < COUTP / 4; ++c4) {
-        const float4 d = dv[j * (COUTP / 4) + c4];
+        const float4 g4 = *reinterpret_cast<const float4*>(gm + (j >> 1) * COUTP + 4 * c4);
+        const uint32_t a4 = am[(j >> 1) * (COUTP / 4) + c4];
+        float4 d;
+        d.x = ((a4 & 0xffu) == kpos) ? g4.x : 0.0f;
+        d.y = (((a4 >> 8) & 0xffu) == kpos) ? g4.y : 0.0f;
+        d.z = (((a4 >> 16) & 0xffu) == kpos) ? g4.z : 0.0f;
+        d.w = ((a4 >> 24) == kpos) ? g4.w : 0.0f;
 #pragma unroll
         for (int v = 0; v < K; ++v) {
           acc[v][4 * c4 + 0] = fmaf(row[j + v], d.x, acc[v][4 * c4 + 0]);
@@ -249,30 +274,43 @@ __global__ void __launch_bounds__(WgCfg<G>::THREADS) conv_relu_pool_wgrad_kernel
   }
 }
 
+// sum of the per-CTA partials in a fixed order: one warp per output element (lane-strided partial sums, then a fixed
+// shuffle tree) — deterministic
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
                                                            int nw, int nb, int nparts) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (e >= nw + nb) return;
   float s = 0.0f;
-  for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * (nw + nb) + e];
-  if (e < nw) { if (dw != nullptr) dw[e] = s; }
-  else if (db != nullptr) db[e - nw] = s;
+  for (int p = lane; p < nparts; p += 32) s += partial[(int64_t)p * (nw + nb) + e];
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (e < nw) { if (dw != nullptr) dw[e] = s; }
+    else if (db != nullptr) db[e - nw] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// data gradient: dx[ci][p][q] = sum_{co,a,b} dyp[co][p+a][q+b] * w[co][ci][a][b]  (dyp zero-bordered by K-1; the double
-// flip of a full correlation with the flipped kernel is the original kernel).  One thread = a 2x2 block of outputs,
-// all input channels.
+// data gradient: dx[ci][p][q] = sum_{co,a,b} dyp[co][p+a][q+b] * w[co][ci][a][b]  (dyp = conv-output gradient zero-bordered
+// by K-1; the double flip of a full correlation with the flipped kernel is the original kernel).  One thread = a 2x2
+// block of outputs at even (p, q), all input channels.  With K - 1 even, the (K+1) x (K+1) patch of dyp such a thread
+// needs is exactly (K+1)/2 x (K+1)/2 WHOLE pooling windows, each holding one non-zero: the patch is built in registers
+// from the pooled gradient (masked by relu') and the winner byte, staged channel-first with a zero border of windows —
+// the conv-output gradient is never materialised.  Next sample prefetched into registers, tiles double-buffered.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename G>
 struct DgCfg {
+  static_assert(G::H % 2 == 0 && G::W % 2 == 0 && (G::K - 1) % 2 == 0, "even input and odd filter");
   static constexpr int TPS = (G::H / 2) * (G::W / 2);
   static constexpr int SLOTS = (256 / TPS) > 0 ? (256 / TPS) : 1;
   static constexpr int THREADS = ((SLOTS * TPS + 31) / 32) * 32;
-  static constexpr int PH = G::HO + 2 * (G::K - 1), PW = G::WO + 2 * (G::K - 1);
-  static constexpr int DYP = G::COUT * PH * PW;
-  static constexpr int SMEM_FLOATS = SLOTS * DYP + G::COUT * G::K * G::K * G::CINP;
-  static_assert(G::H % 2 == 0 && G::W % 2 == 0, "input must be even");
+  static constexpr int BW = (G::K - 1) / 2;                     // border, in windows
+  static constexpr int NWIN = (G::K + 1) / 2;                   // windows per patch side
+  static constexpr int PHW = G::HP + 2 * BW, PWW = G::WP + 2 * BW;
+  static constexpr int GZ = G::COUT * PHW * PWW;                // bordered pooled gradient (floats)
+  static constexpr int AZ = (GZ + 3) / 4;                       // bordered winner bytes (as words)
+  static constexpr int SV = (G::YS + TPS - 1) / TPS;
+  static constexpr int BUF = GZ + AZ;
+  static constexpr int SMEM_FLOATS = SLOTS * 2 * BUF + G::COUT * G::K * G::K * G::CINP;
 };
 
 template <typename G>
@@ -280,40 +318,79 @@ __global__ void __launch_bounds__(DgCfg<G>::THREADS) conv_relu_pool_dgrad_kernel
                                                                                  const uint8_t* __restrict__ amax, const float* __restrict__ gy,
                                                                                  float* __restrict__ dx, int64_t N) {
   using C = DgCfg<G>;
-  constexpr int K = G::K, CIN = G::CIN, CINP = G::CINP, COUT = G::COUT;
+  constexpr int K = G::K, CIN = G::CIN, CINP = G::CINP, COUT = G::COUT, NWIN = C::NWIN;
   extern __shared__ __align__(16) float smem[];
-  float* ws = smem + C::SLOTS * C::DYP;                          // [co][a][b][CINP]
+  float* ws = smem + C::SLOTS * 2 * C::BUF;                      // [co][a][b][CINP]
   for (int i = threadIdx.x; i < COUT * K * K * CINP; i += blockDim.x) {
     const int ci = i % CINP, t = i / CINP, bq = t % K, a = (t / K) % K, co = t / (K * K);
     ws[i] = ci < CIN ? w[((co * CIN + ci) * K + a) * K + bq] : 0.0f;
   }
+  for (int i = threadIdx.x; i < C::SLOTS * 2 * C::BUF; i += blockDim.x) smem[i] = 0.0f;     // borders stay zero for the whole kernel
+  __syncthreads();
   const int slot = threadIdx.x / C::TPS, t = threadIdx.x % C::TPS;
   const bool worker = threadIdx.x < C::SLOTS * C::TPS;
   const int p0 = 2 * (t / (G::W / 2)), q0 = 2 * (t % (G::W / 2));
-  float* dyp = smem + slot * C::DYP;
-  for (int64_t n0 = (int64_t)blockIdx.x * C::SLOTS; n0 < N; n0 += (int64_t)gridDim.x * C::SLOTS) {
-    __syncthreads();
-    const int64_t n = n0 + slot;
+  float* base = smem + slot * 2 * C::BUF;
+  float gr[C::SV];
+  uint8_t ar[C::SV];
+  auto prefetch = [&](int64_t n) {
+#pragma unroll
+    for (int k = 0; k < C::SV; ++k) {
+      const int e = t + k * C::TPS;
+      if (e < G::YS) {
+        const int64_t o = n * G::YS + e;
+        gr[k] = __ldg(y + o) > 0.0f ? __ldg(gy + o) : 0.0f;     // relu'(0) = 0
+        ar[k] = __ldg(amax + o);
+      }
+    }
+  };
+  auto stash = [&](float* buf) {
+    uint8_t* az = reinterpret_cast<uint8_t*>(buf + C::GZ);
+#pragma unroll
+    for (int k = 0; k < C::SV; ++k) {
+      const int e = t + k * C::TPS;
+      if (e < G::YS) {
+        const int win = e % G::WIN, co = e / G::WIN;
+        const int idx = (co * C::PHW + win / G::WP + C::BW) * C::PWW + win % G::WP + C::BW;
+        buf[idx] = gr[k];
+        az[idx] = ar[k];
+      }
+    }
+  };
+  int64_t n = (int64_t)blockIdx.x * C::SLOTS + slot;
+  const int64_t stride = (int64_t)gridDim.x * C::SLOTS;
+  if (worker && n < N) prefetch(n);
+  int it = 0;
+  for (int64_t n0 = (int64_t)blockIdx.x * C::SLOTS; n0 < N; n0 += stride, n += stride, ++it) {
+    float* buf = base + (it & 1) * C::BUF;
     const bool live = worker && n < N;
-    if (live)
-      for (int k = t; k < C::DYP; k += C::TPS) dyp[k] = 0.0f;
+    if (live) stash(buf);
     __syncthreads();
-    if (live) scatter_dy<G, false>(dyp, gy, y, amax, n, t, C::TPS);
-    __syncthreads();
+    if (live && n + stride < N) prefetch(n + stride);
     if (!live) continue;
     float acc[4][CINP];
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
       for (int c = 0; c < CINP; ++c) acc[p][c] = 0.0f;
+    const uint8_t* az = reinterpret_cast<const uint8_t*>(buf + C::GZ);
+    // patch rows p0 .. p0+K of the bordered gradient = conv rows p0-(K-1) .. p0+1 = windows p0/2 - BW .. p0/2 - BW + NWIN-1,
+    // i.e. bordered window rows p0/2 .. p0/2 + NWIN-1
 #pragma unroll 1
     for (int co = 0; co < COUT; ++co) {
       float patch[K + 1][K + 1];
-      const float* src = dyp + (co * C::PH + p0) * C::PW + q0;
+      const int wb = (co * C::PHW + (p0 >> 1)) * C::PWW + (q0 >> 1);
 #pragma unroll
-      for (int r = 0; r <= K; ++r)
+      for (int wr = 0; wr < NWIN; ++wr)
 #pragma unroll
-        for (int c = 0; c <= K; ++c) patch[r][c] = src[r * C::PW + c];
+        for (int wc = 0; wc < NWIN; ++wc) {
+          const float g = buf[wb + wr * C::PWW + wc];
+          const int a = az[wb + wr * C::PWW + wc];
+          patch[2 * wr][2 * wc] = a == 0 ? g : 0.0f;
+          patch[2 * wr][2 * wc + 1] = a == 1 ? g : 0.0f;
+          patch[2 * wr + 1][2 * wc] = a == 2 ? g : 0.0f;
+          patch[2 * wr + 1][2 * wc + 1] = a == 3 ? g : 0.0f;
+        }
       const float4* wv = reinterpret_cast<const float4*>(ws + co * K * K * CINP);
 #pragma unroll
       for (int a = 0; a < K; ++a)
@@ -373,7 +450,7 @@ int run_bwd(pg_ctx* ctx, const float* x, const float* w, const float* y, const u
     if (rc != PG_OK) return rc;
     conv_relu_pool_wgrad_kernel<G><<<(unsigned)blocks, C::THREADS, smem, ctx->stream>>>(x, y, amax, gy, (float*)ctx->ws, N);
     PG_LAUNCHED(ctx);
-    sum_partials_kernel<<<(unsigned)pg_cdiv(nw + nb, 256), 256, 0, ctx->stream>>>((const float*)ctx->ws, dw, db, nw, nb, (int)blocks);
+    sum_partials_kernel<<<(unsigned)pg_cdiv((int64_t)(nw + nb) * 32, 256), 256, 0, ctx->stream>>>((const float*)ctx->ws, dw, db, nw, nb, (int)blocks);
     PG_LAUNCHED(ctx);
   }
   if (dx != nullptr) {

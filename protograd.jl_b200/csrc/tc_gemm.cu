@@ -997,9 +997,31 @@ static int tc_linear_bwd_impl(pg_ctx* ctx, const void* X, const void* W, const v
       if (rc != PG_OK) return rc;
       db_part = (float*)ctx->ws;
     }
-    Epi epi{nullptr, nullptr, 0, 1, 0, nullptr, db_part, 1, 1 << 30};
-    rc = tc_dispatch(ctx, 2, X, dY, dW, K, N, M, epi);
+    // few output tiles but a deep reduction (K' = batch): the small layers of the example nets (256x120, 120x84 at 8,192
+    // samples were ONE or TWO CTAs walking 128 k-blocks: 73 / 55 us).  Split the batch over the idle SMs, fp32 partials,
+    // summed in a fixed order.
+    const int64_t tiles = m_blocks * pg_cdiv(N, 256), num_kb = pg_cdiv(M, BLOCK_K);
+    int splits = 1, kb_per = 1 << 30;
+    if (!two && !fuse_db && tiles * 2 <= ctx->num_sms && num_kb >= 8) {
+      splits = (int)(ctx->num_sms / tiles);
+      if (splits > 32) splits = 32;
+      if (splits > num_kb / 2) splits = (int)(num_kb / 2);
+      kb_per = (int)pg_cdiv(num_kb, splits);
+      splits = (int)pg_cdiv(num_kb, kb_per);
+    }
+    void* target = dW;
+    if (splits > 1) {
+      rc = pg_ws_ensure(ctx, (size_t)splits * K * N * sizeof(float));
+      if (rc != PG_OK) return rc;
+      target = ctx->ws;
+    }
+    Epi epi{nullptr, nullptr, 0, 1, 0, nullptr, db_part, splits, kb_per};
+    rc = tc_dispatch(ctx, 2, X, dY, target, K, N, M, epi);
     if (rc != PG_OK) return rc;
+    if (splits > 1) {
+      reduce_f32_kernel<<<(unsigned)pg_cdiv(K * N, 256), 256, 0, ctx->stream>>>((const float*)ctx->ws, (float*)dW, K * N, splits);
+      PG_LAUNCHED(ctx);
+    }
     if (fuse_db) {
       reduce_f32_kernel<<<(unsigned)pg_cdiv(N, 256), 256, 0, ctx->stream>>>(db_part, (float*)db, N, (int)m_blocks);
       PG_LAUNCHED(ctx);
