@@ -409,8 +409,9 @@ int forward(pg_plan& P) {
         if (P.tc_lin[i]) {
           Lin& L = P.lin[i];
           const void* xp = xv.p;
-          if (L.xbf) {            // fp32 (or unpadded) source: cast + zero-pad into the staging operand
-            RC(pg_dropout_ex(ctx, xv.dtype, PG_BF16, xv.p, L.xbf, M, K, xv.pitch, L.Kp, 0.0, 0, 0, 0));
+          if (L.xbf) {            // fp32 (or unpadded) source: cast (+ zero-pad) into the staging operand
+            if (xv.dtype == PG_F32 && xv.pitch == K && L.Kp == K) RC(pg_vec_cast_bf16(ctx, L.xbf, xv.p, M * K));     // 128-bit vectorised
+            else RC(pg_dropout_ex(ctx, xv.dtype, PG_BF16, xv.p, L.xbf, M, K, xv.pitch, L.Kp, 0.0, 0, 0, 0));
             xp = L.xbf;
           }
           const void* wp;

@@ -18,6 +18,8 @@
 // Layers with N <= 32 (the 10-class logits layer) are HBM-bound; they reuse the kernel with a 32-wide
 // N tile on small zero-padded operand copies (see "Narrow layers" below).
 #include <cuda.h>
+
+#include <algorithm>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -155,7 +157,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       if (col + j < N) {
-        float o = v[j] + (epi.bias != nullptr ? epi.bias[col + j] : 0.0f);
+        float o = v[j] + ((epi.bias != nullptr && split == 0) ? epi.bias[col + j] : 0.0f);     // split-K: the bias rides with split 0
         if (epi.relu) o = fmaxf(o, 0.0f);
         op[col + j] = o;
       }
@@ -887,8 +889,92 @@ int narrow_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, void* Z
   int64_t total = K * NARROW_N;
   pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, nullptr, Wt, K, (int)N, 0, NARROW_N);
   PG_LAUNCHED(ctx);
-  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, 1, 1, nullptr, nullptr, 1, 1 << 30};
-  return launch_tc<false, false, NARROW_N>(ctx, X, Wt, Z, M, N, K, K, K, epi);
+  // M / 128 tiles of a 10-wide layer keep only a fraction of the SMs streaming the activations (64 CTAs at C4: 26 us for a
+  // 10 us pass): split K over the idle SMs, fp32 partials summed in a fixed order (no activation: the logits layer)
+  const int64_t tiles = pg_cdiv(M, BLOCK_M), num_kb = pg_cdiv(K, BLOCK_K);
+  int splits = 1, kb_per = 1 << 30;
+  if (act != PG_ACT_RELU && tiles * 2 <= ctx->num_sms && num_kb >= 16) {
+    splits = (int)(ctx->num_sms / tiles);
+    if (splits > 4) splits = 4;
+    kb_per = (int)pg_cdiv(num_kb, splits);
+    splits = (int)pg_cdiv(num_kb, kb_per);
+  }
+  void* target = Z;
+  if (splits > 1) {
+    rc = pg_ws_ensure(ctx, (size_t)splits * M * N * sizeof(float));
+    if (rc != PG_OK) return rc;
+    target = ctx->ws;
+  }
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, 1, 1, nullptr, nullptr, splits, kb_per};
+  rc = launch_tc<false, false, NARROW_N>(ctx, X, Wt, target, M, N, K, K, K, epi);
+  if (rc != PG_OK) return rc;
+  if (splits > 1) {
+    reduce_f32_kernel<<<(unsigned)pg_cdiv(M * N, 256), 256, 0, ctx->stream>>>((const float*)ctx->ws, (float*)Z, M * N, splits);
+    PG_LAUNCHED(ctx);
+  }
+  return PG_OK;
+}
+
+
+// Data gradient of a narrow layer (N <= 16 even: the 10-class logits layer), bandwidth-shaped instead of a K' = 64 padded
+// GEMM: dX[m][k] = [mask[m][k] > 0] * sum_n dZ[m][n] W[k][n].  The launch is one pass over the ReLU mask (read) and dX
+// (write), 134 MB at C4; the GEMM form took 2.6x the HBM time because its single k-block per tile leaves the mask loads
+// exposed.  One thread: 8 consecutive k (one 16-byte store / mask load) x ROWS rows, W[k..k+8][0..N) held in registers.
+template <int N, int ROWS>
+__global__ void __launch_bounds__(256) narrow_dgrad_kernel(const float* __restrict__ dZ, const __nv_bfloat16* __restrict__ W,
+                                                           const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dX, int M, int K) {
+  const int kt = blockIdx.x * blockDim.x + threadIdx.x;          // which group of 8 k
+  if (kt * 8 >= K) return;
+  const int k8 = kt * 8;
+  float w[8][N];
+  {
+    const uint4* wp = reinterpret_cast<const uint4*>(W + (size_t)k8 * N);    // 8 rows of N bf16: 16 N bytes, contiguous
+    __nv_bfloat16 tmp[8 * N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) reinterpret_cast<uint4*>(tmp)[i] = __ldg(wp + i);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int n = 0; n < N; ++n) w[k][n] = __bfloat162float(tmp[k * N + n]);
+  }
+  for (int m0 = blockIdx.y * ROWS; m0 < M; m0 += gridDim.y * ROWS) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int m = m0 + r;
+      if (m >= M) break;
+      float dz[N];
+      const float2* zp = reinterpret_cast<const float2*>(dZ + (size_t)m * N);
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i) { const float2 t = __ldg(zp + i); dz[2 * i] = t.x; dz[2 * i + 1] = t.y; }
+      // the tensor-core path multiplies bf16(dZ): keep the same operand rounding
+#pragma unroll
+      for (int n = 0; n < N; ++n) dz[n] = __bfloat162float(__float2bfloat16_rn(dz[n]));
+      uint4 mk = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+      if (mask != nullptr) mk = __ldg(reinterpret_cast<const uint4*>(mask + (size_t)m * K + k8));
+      const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk);
+      __nv_bfloat162 pk[4];
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int n = 0; n < N; ++n) { a0 = fmaf(dz[n], w[k][n], a0); a1 = fmaf(dz[n], w[k + 1][n], a1); }
+        a0 = __bfloat162float(me[k]) > 0.0f ? a0 : 0.0f;
+        a1 = __bfloat162float(me[k + 1]) > 0.0f ? a1 : 0.0f;
+        pk[k / 2] = __floats2bfloat162_rn(a0, a1);
+      }
+      *reinterpret_cast<uint4*>(dX + (size_t)m * K + k8) = *reinterpret_cast<uint4*>(pk);
+    }
+  }
+}
+
+template <int N>
+int launch_narrow_dgrad(pg_ctx* ctx, const void* dZ, const void* W, const void* mask, void* dX, int64_t M, int64_t K) {
+  constexpr int ROWS = 4;
+  dim3 grid((unsigned)pg_cdiv(K / 8, 256), (unsigned)std::min<int64_t>(pg_cdiv(M, ROWS), (int64_t)ctx->num_sms * 16 / std::max<int64_t>(1, pg_cdiv(K / 8, 256))));
+  if (grid.y < 1) grid.y = 1;
+  narrow_dgrad_kernel<N, ROWS><<<grid, 256, 0, ctx->stream>>>((const float*)dZ, (const __nv_bfloat16*)W, (const __nv_bfloat16*)mask, (__nv_bfloat16*)dX, (int)M, (int)K);
+  PG_LAUNCHED(ctx);
+  return PG_OK;
 }
 
 int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* dW, void* db, void* dX, const void* mask, void* dx_colsum, int64_t M, int64_t K, int64_t N,
@@ -903,10 +989,13 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
   __nv_bfloat16* dZp = (__nv_bfloat16*)base;                               // [M][64]
   __nv_bfloat16* dZt = (__nv_bfloat16*)(base + dzp_bytes);                 // [32][M]
   __nv_bfloat16* Wp = (__nv_bfloat16*)(base + dzp_bytes + dzt_bytes);      // [K][64]
-  {
+  // the bandwidth-shaped data-gradient kernel covers even N <= 16 with bf16 output and no fused column sums
+  const bool simt_dx = dX != nullptr && !dx_f32 && dx_colsum == nullptr && N % 2 == 0 && N <= 16 && getenv("PG_NARROW_DGRAD_GEMM") == nullptr;
+  const bool gemm_dx = dX != nullptr && !simt_dx;
+  if (dW || gemm_dx) {
     int64_t total = M * NARROW_K;
-    pad_copy_kernel<float><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const float*)dZ, dX ? dZp : nullptr, dW ? dZt : nullptr, M, (int)N,
-                                                                                   dX ? NARROW_K : 0, dW ? NARROW_N : 0);
+    pad_copy_kernel<float><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const float*)dZ, gemm_dx ? dZp : nullptr, dW ? dZt : nullptr, M, (int)N,
+                                                                                   gemm_dx ? NARROW_K : 0, dW ? NARROW_N : 0);
     PG_LAUNCHED(ctx);
   }
   if (dW) {  // dW[K][N] f32 = X^T dZ : M' = K, N' = N (tile 32), K' = batch
@@ -935,7 +1024,19 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
     rc = pg_colsum_launch(ctx, PG_F32, dZ, db, M, N);
     if (rc != PG_OK) return rc;
   }
-  if (dX) {  // dX[M][K] bf16 = dZ W^T : M' = M, N' = K, K' = 64 (zero padded beyond N)
+  if (simt_dx) {
+    switch (N) {
+      case 2: return launch_narrow_dgrad<2>(ctx, dZ, W, mask, dX, M, K);
+      case 4: return launch_narrow_dgrad<4>(ctx, dZ, W, mask, dX, M, K);
+      case 6: return launch_narrow_dgrad<6>(ctx, dZ, W, mask, dX, M, K);
+      case 8: return launch_narrow_dgrad<8>(ctx, dZ, W, mask, dX, M, K);
+      case 10: return launch_narrow_dgrad<10>(ctx, dZ, W, mask, dX, M, K);
+      case 12: return launch_narrow_dgrad<12>(ctx, dZ, W, mask, dX, M, K);
+      case 14: return launch_narrow_dgrad<14>(ctx, dZ, W, mask, dX, M, K);
+      default: return launch_narrow_dgrad<16>(ctx, dZ, W, mask, dX, M, K);
+    }
+  }
+  if (gemm_dx) {  // dX[M][K] bf16 = dZ W^T : M' = M, N' = K, K' = 64 (zero padded beyond N)
     int64_t total = K * NARROW_K;
     pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, Wp, nullptr, K, (int)N, NARROW_K, 0);
     PG_LAUNCHED(ctx);
