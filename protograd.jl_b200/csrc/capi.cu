@@ -108,7 +108,7 @@ int pg_set_stream(pg_ctx* ctx, void* s) {
   return PG_OK;
 }
 int pg_get_stream(pg_ctx* ctx, void** s) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
   *s = (void*)ctx->stream;
   return PG_OK;
 }
@@ -118,7 +118,7 @@ int pg_sync(pg_ctx* ctx) {
   return PG_OK;
 }
 int pg_launch_count(pg_ctx* ctx, int64_t* n) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
   *n = ctx->launches;
   return PG_OK;
 }
@@ -134,34 +134,38 @@ int pg_reserve_workspace(pg_ctx* ctx, size_t bytes) {
 }
 
 int pg_malloc(pg_ctx* ctx, size_t bytes, void** dptr) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
   PG_REQUIRE(dptr != nullptr, "null out pointer");
   PG_CHECK_CUDA(cudaSetDevice(ctx->device));
   PG_CHECK_CUDA(cudaMalloc(dptr, bytes ? bytes : 16));
   return PG_OK;
 }
 int pg_free(pg_ctx* ctx, void* dptr) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
   if (dptr) PG_CHECK_CUDA(cudaFree(dptr));
   return PG_OK;
 }
 int pg_memset0(pg_ctx* ctx, void* dptr, size_t bytes) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
+  if (pg_deferred_overlaps(ctx, dptr, bytes)) pg_flush_deferred(ctx);
   PG_CHECK_CUDA(cudaMemsetAsync(dptr, 0, bytes, ctx->stream));
   return PG_OK;
 }
 int pg_copy_d2d(pg_ctx* ctx, void* dst, const void* src, size_t bytes) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
+  if (pg_deferred_overlaps(ctx, dst, bytes) || pg_deferred_overlaps(ctx, src, bytes)) pg_flush_deferred(ctx);
   PG_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return PG_OK;
 }
 int pg_upload(pg_ctx* ctx, void* dst, const void* src, size_t bytes) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
+  if (pg_deferred_overlaps(ctx, dst, bytes)) pg_flush_deferred(ctx);
   PG_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return PG_OK;
 }
 int pg_download_async(pg_ctx* ctx, void* dst, const void* src, size_t bytes) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
+  if (pg_deferred_overlaps(ctx, src, bytes)) pg_flush_deferred(ctx);
   PG_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return PG_OK;
 }
@@ -184,7 +188,7 @@ int pg_host_free(void* p) {
 static cudaStream_t pick_stream(pg_ctx* ctx, int which) { return which == 1 ? ctx->copy_stream : ctx->stream; }
 
 int pg_event_create(pg_ctx* ctx, void** event) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
   PG_REQUIRE(event != nullptr, "null out pointer");
   cudaEvent_t e;
   PG_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -192,27 +196,28 @@ int pg_event_create(pg_ctx* ctx, void** event) {
   return PG_OK;
 }
 int pg_event_destroy(pg_ctx* ctx, void* event) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
   if (event) PG_CHECK_CUDA(cudaEventDestroy((cudaEvent_t)event));
   return PG_OK;
 }
 int pg_event_record(pg_ctx* ctx, void* event, int which_stream) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
   PG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)event, pick_stream(ctx, which_stream)));
   return PG_OK;
 }
 int pg_stream_wait_event(pg_ctx* ctx, int which_stream, void* event) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
   PG_CHECK_CUDA(cudaStreamWaitEvent(pick_stream(ctx, which_stream), (cudaEvent_t)event, 0));
   return PG_OK;
 }
 int pg_event_sync(pg_ctx* ctx, void* event) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
   PG_CHECK_CUDA(cudaEventSynchronize((cudaEvent_t)event));
   return PG_OK;
 }
 int pg_upload_on(pg_ctx* ctx, int which_stream, void* dst, const void* src, size_t bytes) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
+  if (pg_deferred_overlaps(ctx, dst, bytes)) pg_flush_deferred(ctx);
   PG_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pick_stream(ctx, which_stream)));
   return PG_OK;
 }
@@ -248,7 +253,8 @@ int pg_graph_destroy(pg_ctx* ctx, void* graph_exec) {
 }
 
 int pg_loss_read(pg_ctx* ctx, int dtype, const void* loss_dev, double* result) {
-  PG_CHECK_CTX(ctx);
+  PG_CHECK_CTX_NF(ctx);
+  if (pg_deferred_overlaps(ctx, loss_dev, 8)) pg_flush_deferred(ctx);
   PG_REQUIRE(result != nullptr && loss_dev != nullptr, "null pointer");
   size_t sz = dtype == PG_F64 ? 8 : 4;
   PG_CHECK_CUDA(cudaMemcpyAsync(ctx->result_host, loss_dev, sz, cudaMemcpyDeviceToHost, ctx->stream));

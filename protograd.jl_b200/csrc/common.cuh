@@ -30,7 +30,26 @@ struct pg_ctx {
   bool capturing = false;
   // driver entry point for TMA descriptor encoding (resolved lazily, no libcuda link dependency)
   void* encode_tiled = nullptr;
+  // A deferred stream dependency (data-parallel exchange, dp.cu): the tail bucket's fused exchange + update may still be
+  // running when the next step's forward starts; the compute stream only has to wait for it before the first kernel
+  // that reads parameters in [deferred_lo, deferred_hi).  Every API call that launches work flushes the wait
+  // (PG_CHECK_CTX) unless the planner holds it (deferred_hold) while it runs the layers in front of that point.
+  cudaEvent_t deferred_event = nullptr;
+  const char* deferred_lo = nullptr;
+  const char* deferred_hi = nullptr;
+  bool deferred_armed = false, deferred_hold = false;
 };
+
+// make the compute stream wait for the deferred event now
+static inline void pg_flush_deferred(pg_ctx* ctx) {
+  if (ctx->deferred_armed) {
+    cudaStreamWaitEvent(ctx->stream, ctx->deferred_event, 0);
+    ctx->deferred_armed = false;
+  }
+}
+static inline bool pg_deferred_overlaps(const pg_ctx* ctx, const void* p, size_t bytes) {
+  return ctx->deferred_armed && p != nullptr && (const char*)p < ctx->deferred_hi && (const char*)p + bytes > ctx->deferred_lo;
+}
 
 void pg_set_error(const char* fmt, ...);
 
@@ -51,7 +70,14 @@ void pg_set_error(const char* fmt, ...);
     }                                                             \
   } while (0)
 
-#define PG_CHECK_CTX(ctx) PG_REQUIRE((ctx) != nullptr, "null context")
+// entry-point prologue: also orders the compute stream behind a deferred exchange (see pg_ctx::deferred_*)
+#define PG_CHECK_CTX(ctx)                                                      \
+  do {                                                                         \
+    PG_REQUIRE((ctx) != nullptr, "null context");                              \
+    if ((ctx)->deferred_armed && !(ctx)->deferred_hold) pg_flush_deferred(ctx); \
+  } while (0)
+// plumbing calls that touch no model memory (events, copies of other buffers): no flush
+#define PG_CHECK_CTX_NF(ctx) PG_REQUIRE((ctx) != nullptr, "null context")
 
 // call after every kernel launch
 #define PG_LAUNCHED(ctx)                         \

@@ -19,6 +19,10 @@
 // Float32 only; geometries are compile-time (see DISPATCH at the bottom); everything else uses conv_tiled.cu.
 #include "common.cuh"
 
+#ifndef PG_WGRAD_MINB
+#define PG_WGRAD_MINB 1
+#endif
+
 namespace {
 
 template <int CIN_, int COUT_, int K_, int H_, int W_>
@@ -140,10 +144,11 @@ struct WgCfg {
   static constexpr int RED = SLOTS * TPS * G::K * G::COUTP;    // final cross-thread reduction buffer (floats)
   static constexpr int STAGE = SLOTS * 2 * BUF;
   static constexpr int SMEM_FLOATS = STAGE > RED ? STAGE : RED;
+  static constexpr int MINB = PG_WGRAD_MINB;                   // CTAs per SM the register budget is sized for
 };
 
 template <typename G>
-__global__ void __launch_bounds__(WgCfg<G>::THREADS) conv_relu_pool_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ y,
+__global__ void __launch_bounds__(WgCfg<G>::THREADS, WgCfg<G>::MINB) conv_relu_pool_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                                                  const uint8_t* __restrict__ amax, const float* __restrict__ gy,
                                                                                  float* __restrict__ partial, int64_t N) {
   using C = WgCfg<G>;

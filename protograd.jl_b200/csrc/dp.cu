@@ -130,6 +130,7 @@ struct P2PArgs {
   int rank, world, slot;
   unsigned int epoch;
   long long lo, hi;
+  unsigned long long* phase_ns; // diagnostics (timing): per slot, accumulated ns of [wait for peers, own slice, wait for completion] + launch count
   int debug;                   // diagnostics (PG_DP_P2P_DEBUG): 1 skip remote fp32 stores, 2 skip remote bf16 stores, 4 skip local state stores
 };
 
@@ -143,6 +144,11 @@ __device__ __forceinline__ float4 ld_sys_f4(const float* p) {
   float4 v;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ void wait_epoch(const unsigned int* p, unsigned int epoch) {
   if ((int)(ld_acquire_sys(p) - epoch) >= 0) return;
@@ -163,12 +169,15 @@ template <typename F, bool STATE, int WMAX, int U>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512) p2p_update_kernel(P2PArgs a, F f) {
   const int W = a.world, R = a.rank;
   unsigned int* mine = a.flags[R];
+  unsigned long long t0 = 0, t1 = 0;
   if (threadIdx.x == 0) {
+    if (a.phase_ns != nullptr && blockIdx.x == 0) t0 = globaltimer_ns();
     if (blockIdx.x == 0) {
       __threadfence_system();                           // this rank's gradient kernels precede in stream order
       for (int p = 0; p < W; ++p) st_release_sys(a.flags[p] + R * SLOTS + 2 * a.slot, a.epoch);
     }
     for (int p = 0; p < W; ++p) wait_epoch(mine + p * SLOTS + 2 * a.slot, a.epoch);
+    if (a.phase_ns != nullptr && blockIdx.x == 0) t1 = globaltimer_ns();
   }
   __syncthreads();
   const long long len = a.hi - a.lo;
@@ -228,11 +237,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512) p2p_update_kern
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
+    unsigned long long t2 = 0;
+    if (a.phase_ns != nullptr && blockIdx.x == 0) {     // (block 0's own share done; the last block closes the kernel)
+      t2 = globaltimer_ns();
+      a.phase_ns[4 * a.slot + 0] += t1 - t0;
+      a.phase_ns[4 * a.slot + 1] += t2 - t1;
+      a.phase_ns[4 * a.slot + 3] += 1;
+    }
     if (atomicAdd(a.block_counter, 1u) == gridDim.x - 1) {
       *a.block_counter = 0u;
       __threadfence_system();
+      const unsigned long long t3 = a.phase_ns != nullptr ? globaltimer_ns() : 0;
       for (int p = 0; p < W; ++p) st_release_sys(a.flags[p] + R * SLOTS + 2 * a.slot + 1, a.epoch);
       for (int p = 0; p < W; ++p) wait_epoch(mine + p * SLOTS + 2 * a.slot + 1, a.epoch);
+      if (a.phase_ns != nullptr) atomicAdd(a.phase_ns + 4 * a.slot + 2, globaltimer_ns() - t3);
     }
   }
 }
@@ -421,6 +439,7 @@ struct pg_dp {
   int rank = 0, world = 1, version = 0;
   ncclComm_t comm = nullptr;
   cudaStream_t stream = nullptr;            // collectives run here
+  cudaStream_t stream2 = nullptr;           // the final (head) bucket of a fused step: runs next to the tail bucket's kernel, not behind it
   cudaEvent_t ready = nullptr;              // ctx stream -> comm stream
   cudaEvent_t done = nullptr;               // comm stream -> ctx stream (pg_dp_wait)
   bool outstanding = false;
@@ -446,20 +465,23 @@ struct pg_dp {
   struct { int kind = -1; void* m = nullptr; void* v = nullptr; double s = 0, b1 = 0, b2 = 0, eps = 0; int64_t it = 1; int flags = 0; } opt;
   int p2p_blocks = 16, p2p_blocks_last = 96;
   bool fused_step = false;
+  unsigned long long* phase_ns = nullptr;   // device, [8 slots][4]
   cudaEvent_t tev[16] = {nullptr}; double tsum[8] = {0}; long tcount[8] = {0}; int debug = 0; int timing = 0;
   int reserve_sms = 16;                     // SMs the persistent GEMM grids leave free while a fused bucket is in flight
+  bool overlap_next = true;                 // PG_DP_OVERLAP_NEXT=0: every bucket is waited for before the step returns
+  bool was_fused = false;                   // the buckets of the last pg_dp_bucket_finish were fused exchange kernels
   bool p2p_tma = false;                     // PG_DP_P2P_TMA=1: cp.async.bulk pipeline instead of register-resident loads (measured slower per CTA)
 };
 
 namespace {
 
-int order_after_ctx(pg_dp* dp) {
+int order_after_ctx(pg_dp* dp, cudaStream_t st = nullptr) {
   PG_CHECK_CUDA(cudaEventRecord(dp->ready, dp->ctx->stream));
-  PG_CHECK_CUDA(cudaStreamWaitEvent(dp->stream, dp->ready, 0));
+  PG_CHECK_CUDA(cudaStreamWaitEvent(st ? st : dp->stream, dp->ready, 0));
   return PG_OK;
 }
 
-int launch_p2p(pg_dp* dp, int64_t lo, int64_t hi, int slot, bool last) {
+int launch_p2p(pg_dp* dp, int64_t lo, int64_t hi, int slot, bool last, cudaStream_t st) {
   P2PArgs a;
   memset(&a, 0, sizeof(a));
   const bool use_shadow = dp->peer_shadow[dp->rank] != nullptr;
@@ -471,9 +493,11 @@ int launch_p2p(pg_dp* dp, int64_t lo, int64_t hi, int slot, bool last) {
     a.flags[p] = (unsigned int*)dp->peer_flags[p];
   }
   a.m = (float*)dp->opt.m; a.v = (float*)dp->opt.v;
-  a.block_counter = dp->block_counter;
+  a.block_counter = dp->block_counter + slot;
   a.rank = dp->rank; a.world = dp->world; a.slot = slot; a.epoch = dp->epoch;
   a.lo = lo; a.hi = hi; a.debug = dp->debug;
+  if (dp->timing && !dp->phase_ns) { PG_CHECK_CUDA(cudaMalloc((void**)&dp->phase_ns, 32 * sizeof(unsigned long long))); PG_CHECK_CUDA(cudaMemset(dp->phase_ns, 0, 32 * sizeof(unsigned long long))); }
+  a.phase_ns = dp->timing ? dp->phase_ns : nullptr;
   if (dp->timing && slot < 8) {
     for (int k = 0; k < 2; ++k)
       if (!dp->tev[2 * slot + k]) PG_CHECK_CUDA(cudaEventCreate(&dp->tev[2 * slot + k]));
@@ -482,7 +506,7 @@ int launch_p2p(pg_dp* dp, int64_t lo, int64_t hi, int slot, bool last) {
       if (cudaEventElapsedTime(&ms, dp->tev[2 * slot], dp->tev[2 * slot + 1]) == cudaSuccess) { dp->tsum[slot] += ms; dp->tcount[slot]++; }
     }
     cudaGetLastError();
-    PG_CHECK_CUDA(cudaEventRecord(dp->tev[2 * slot], dp->stream));
+    PG_CHECK_CUDA(cudaEventRecord(dp->tev[2 * slot], st));
   }
   const double s = dp->opt.s, b1 = dp->opt.b1, b2 = dp->opt.b2;
   // buckets that overlap the remaining backward GEMMs run on a few TPCs; the last one has the GPU to itself
@@ -492,34 +516,38 @@ int launch_p2p(pg_dp* dp, int64_t lo, int64_t hi, int slot, bool last) {
     const double c1 = 1.0 - pow(b1, (double)dp->opt.it), c2 = 1.0 - pow(b2, (double)dp->opt.it);
     if (dp->opt.flags & PG_MATH_FAST) {
       P2PAdamFast f{(float)s, (float)b1, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)(1.0 / c1), (float)(1.0 / c2), (float)dp->opt.eps};
-      if (dp->p2p_tma) { int rc = launch_p2p_tma<P2PAdamFast, true>(dp->world, grid, dp->stream, a, f); if (rc != PG_OK) return rc; }
-      else launch_p2p_kernel<P2PAdamFast, true>(dp->world, grid, dp->stream, a, f);
+      if (dp->p2p_tma) { int rc = launch_p2p_tma<P2PAdamFast, true>(dp->world, grid, st, a, f); if (rc != PG_OK) return rc; }
+      else launch_p2p_kernel<P2PAdamFast, true>(dp->world, grid, st, a, f);
     } else {
       P2PAdamExact f{s, b1, 1.0 - b1, b2, 1.0 - b2, c1, c2, dp->opt.eps};
-      if (dp->p2p_tma) { int rc = launch_p2p_tma<P2PAdamExact, true>(dp->world, grid, dp->stream, a, f); if (rc != PG_OK) return rc; }
-      else launch_p2p_kernel<P2PAdamExact, true>(dp->world, grid, dp->stream, a, f);
+      if (dp->p2p_tma) { int rc = launch_p2p_tma<P2PAdamExact, true>(dp->world, grid, st, a, f); if (rc != PG_OK) return rc; }
+      else launch_p2p_kernel<P2PAdamExact, true>(dp->world, grid, st, a, f);
     }
   } else {
     P2PGd f{s, (dp->opt.flags & PG_SCALAR_F64) ? 1 : 0};
-    if (dp->p2p_tma) { int rc = launch_p2p_tma<P2PGd, false>(dp->world, grid, dp->stream, a, f); if (rc != PG_OK) return rc; }
-    else launch_p2p_kernel<P2PGd, false>(dp->world, grid, dp->stream, a, f);
+    if (dp->p2p_tma) { int rc = launch_p2p_tma<P2PGd, false>(dp->world, grid, st, a, f); if (rc != PG_OK) return rc; }
+    else launch_p2p_kernel<P2PGd, false>(dp->world, grid, st, a, f);
   }
   dp->ctx->launches++;
   PG_CHECK_CUDA(cudaGetLastError());
-  if (dp->timing && slot < 8) PG_CHECK_CUDA(cudaEventRecord(dp->tev[2 * slot + 1], dp->stream));
+  if (dp->timing && slot < 8) PG_CHECK_CUDA(cudaEventRecord(dp->tev[2 * slot + 1], st));
   return PG_OK;
 }
 
 int issue_bucket(pg_dp* dp, int64_t lo, int64_t hi) {
   const int dt = pg_arena_dtype(dp->grads);
   const size_t es = dt == PG_F64 ? 8 : dt == PG_F16 ? 2 : 4;
-  int rc = order_after_ctx(dp);
+  const bool fused = dp->p2p && dp->opt.kind >= 0;
+  // the final (head) bucket of a fused step gets its own stream: it runs NEXT TO the tail bucket's kernel instead of
+  // behind it, and the next step's first layers only wait for it (the tail bucket's wait is deferred, see below)
+  cudaStream_t st = (fused && lo == 0 && !dp->buckets.empty() && dp->overlap_next) ? dp->stream2 : dp->stream;
+  int rc = order_after_ctx(dp, st);
   if (rc != PG_OK) return rc;
   char* p = (char*)pg_arena_base(dp->grads) + (size_t)lo * es;
-  if (dp->p2p && dp->opt.kind >= 0) {
+  if (fused) {
     PG_REQUIRE(dp->buckets.size() < SLOTS / 2, "too many buckets for the fused exchange (8)");
     PG_REQUIRE(pg_arena_base(dp->grads) == dp->peer_grad[dp->rank], "fused exchange: not the gradient arena that was registered");
-    rc = launch_p2p(dp, lo, hi, (int)dp->buckets.size(), lo == 0);
+    rc = launch_p2p(dp, lo, hi, (int)dp->buckets.size(), lo == 0, st);
     if (rc != PG_OK) return rc;
     // The backward kernels enqueued from here on run next to this bucket's kernel: their persistent grids (one CTA per
     // SM, all of its shared memory) leave `reserve_sms` SMs — whole TPCs — free, so the exchange starts at once instead of
@@ -536,7 +564,7 @@ int issue_bucket(pg_dp* dp, int64_t lo, int64_t hi) {
     dp->event_pool.push_back(e);
   }
   b.done = dp->event_pool[k];
-  PG_CHECK_CUDA(cudaEventRecord(b.done, dp->stream));
+  PG_CHECK_CUDA(cudaEventRecord(b.done, st));
   dp->buckets.push_back(b);
   return PG_OK;
 }
@@ -585,6 +613,7 @@ int pg_dp_init(pg_ctx* ctx, int rank, int world, const void* id128, int max_ctas
     return PG_ERR_CUDA;
   }
   PG_CHECK_CUDA(cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking));
+  PG_CHECK_CUDA(cudaStreamCreateWithFlags(&dp->stream2, cudaStreamNonBlocking));
   PG_CHECK_CUDA(cudaEventCreateWithFlags(&dp->ready, cudaEventDisableTiming));
   PG_CHECK_CUDA(cudaEventCreateWithFlags(&dp->done, cudaEventDisableTiming));
   *out = dp;
@@ -597,6 +626,14 @@ int pg_dp_destroy(pg_dp* dp) {
   if (dp->timing && dp->rank == 0)
     for (int k = 0; k < 8; ++k)
       if (dp->tcount[k] > 0) fprintf(stderr, "[pg_dp] fused exchange kernel, bucket %d: %.1f us average over %ld launches (includes waiting for the peers)\n", k, 1e3 * dp->tsum[k] / dp->tcount[k], dp->tcount[k]);
+  if (dp->timing && dp->phase_ns && dp->rank == 0) {
+    unsigned long long h[32];
+    if (cudaMemcpy(h, dp->phase_ns, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+      for (int k = 0; k < 8; ++k)
+        if (h[4 * k + 3] > 0)
+          fprintf(stderr, "[pg_dp]   bucket %d phases (rank 0, us, mean of %llu): wait for every peer's gradients %.1f | own slice (CTA 0) %.1f | wait for every peer's stores %.1f\n",
+                  k, h[4 * k + 3], 1e-3 * h[4 * k] / h[4 * k + 3], 1e-3 * h[4 * k + 1] / h[4 * k + 3], 1e-3 * h[4 * k + 2] / h[4 * k + 3]);
+  }
   if (dp->stream) cudaStreamSynchronize(dp->stream);
   if (dp->comm) g_nccl.CommDestroy(dp->comm);
   for (int k = 0; k < dp->n_opened; ++k) cudaIpcCloseMemHandle(dp->opened[k]);
@@ -606,6 +643,7 @@ int pg_dp_destroy(pg_dp* dp) {
   if (dp->ready) cudaEventDestroy(dp->ready);
   if (dp->done) cudaEventDestroy(dp->done);
   if (dp->stream) cudaStreamDestroy(dp->stream);
+  if (dp->stream2) { cudaStreamSynchronize(dp->stream2); cudaStreamDestroy(dp->stream2); }
   delete dp;
   return PG_OK;
 }
@@ -643,6 +681,7 @@ int pg_dp_broadcast(pg_dp* dp, void* buf, int64_t count, int dtype, int root) {
 
 int pg_dp_wait(pg_dp* dp) {
   PG_REQUIRE(dp != nullptr, "null dp handle");
+  pg_flush_deferred(dp->ctx);                 // (also a deferred bucket wait of the last fused step)
   if (!dp->outstanding) return PG_OK;
   PG_CHECK_CUDA(cudaEventRecord(dp->done, dp->stream));
   PG_CHECK_CUDA(cudaStreamWaitEvent(dp->ctx->stream, dp->done, 0));
@@ -682,8 +721,8 @@ int pg_dp_p2p_enable(pg_dp* dp, pg_arena* params, pg_arena* grads, void* shadow2
   // flag block: peers write their epochs here
   PG_CHECK_CUDA(cudaMalloc(&dp->flags_local, MAXR * SLOTS * sizeof(unsigned int)));
   PG_CHECK_CUDA(cudaMemset(dp->flags_local, 0, MAXR * SLOTS * sizeof(unsigned int)));
-  PG_CHECK_CUDA(cudaMalloc((void**)&dp->block_counter, sizeof(unsigned int)));
-  PG_CHECK_CUDA(cudaMemset(dp->block_counter, 0, sizeof(unsigned int)));
+  PG_CHECK_CUDA(cudaMalloc((void**)&dp->block_counter, SLOTS * sizeof(unsigned int)));       // one per bucket slot: two buckets' kernels may overlap
+  PG_CHECK_CUDA(cudaMemset(dp->block_counter, 0, SLOTS * sizeof(unsigned int)));
   struct Rec { cudaIpcMemHandle_t h[4]; int64_t off[4]; int has_shadow; int pad; };
   Rec mine;
   memset(&mine, 0, sizeof(mine));
@@ -729,6 +768,8 @@ int pg_dp_p2p_enable(pg_dp* dp, pg_arena* params, pg_arena* grads, void* shadow2
   if (nb) dp->debug = atoi(nb);
   nb = getenv("PG_DP_P2P_TIMING");
   if (nb && nb[0] == '1') dp->timing = 1;
+  nb = getenv("PG_DP_OVERLAP_NEXT");
+  if (nb && nb[0] == '0') dp->overlap_next = false;
   nb = getenv("PG_DP_RESERVE_SMS");
   if (nb) dp->reserve_sms = atoi(nb);
   nb = getenv("PG_DP_P2P_TMA");
@@ -758,6 +799,7 @@ int pg_dp_set_option(pg_dp* dp, const char* name, int value) {
   else if (!strcmp(name, "p2p_blocks_last")) dp->p2p_blocks_last = value;
   else if (!strcmp(name, "p2p_tma")) dp->p2p_tma = value != 0;
   else if (!strcmp(name, "reserve_sms")) dp->reserve_sms = value;
+  else if (!strcmp(name, "overlap_next")) dp->overlap_next = value != 0;
   else if (!strcmp(name, "debug")) dp->debug = value;
   else if (!strcmp(name, "timing")) dp->timing = value;
   else { pg_set_error("pg_dp_set_option: unknown option %s", name); return PG_ERR_ARG; }
@@ -809,6 +851,7 @@ int pg_dp_bucket_finish(pg_dp* dp, int* n_buckets, int64_t* starts, int64_t* cou
     dp->hi = 0;
   }
   dp->ctx->num_sms = dp->ctx->real_sms;
+  dp->was_fused = dp->fused_step;
   if (dp->fused_step) {                 // the fused kernels wrote the other half of the shadow double buffer
     if (dp->peer_shadow[dp->rank] != nullptr) dp->shadow_half ^= 1;
     dp->fused_step = false;
@@ -853,7 +896,20 @@ int pg_dp_bucket_plan(int dtype, int n_leaves, const int64_t* leaf_sizes, int64_
 
 int pg_dp_bucket_wait(pg_dp* dp, int k) {
   PG_REQUIRE(dp != nullptr && k >= 0 && k < (int)dp->buckets.size(), "bucket index out of range");
-  PG_CHECK_CUDA(cudaStreamWaitEvent(dp->ctx->stream, dp->buckets[k].done, 0));
+  pg_ctx* ctx = dp->ctx;
+  // Fused step with several buckets: the FIRST (tail) bucket holds the parameters of the later layers.  Its wait is
+  // deferred: the compute stream picks it up in front of the first kernel that touches those parameters (pg_plan_forward)
+  // — or at the next API call that launches anything else — so the next step's first layers overlap the rest of the exchange.
+  if (dp->was_fused && dp->overlap_next && k == 0 && dp->buckets.size() > 1 && !ctx->capturing && dp->p2p_padded > 0) {
+    if (ctx->deferred_armed) pg_flush_deferred(ctx);
+    const char* base = (const char*)dp->peer_param[dp->rank];
+    ctx->deferred_event = dp->buckets[0].done;
+    ctx->deferred_lo = base + (size_t)dp->buckets[0].start * 4;
+    ctx->deferred_hi = base + (size_t)(dp->buckets[0].start + dp->buckets[0].count) * 4;
+    ctx->deferred_armed = true;
+    return PG_OK;
+  }
+  PG_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, dp->buckets[k].done, 0));
   return PG_OK;
 }
 

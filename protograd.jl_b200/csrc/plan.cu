@@ -389,13 +389,33 @@ int run_dropout(pg_plan& P, int i, const Buf& src, const Buf& dst) {
                        P.rng_seed, stream_of(P, i), (uint64_t)(P.sample_offset * per_sample));
 }
 
+int forward_nodes(pg_plan& P);
+
+// A data-parallel exchange of the previous step may still be updating the parameters of the LATER layers (pg_ctx::
+// deferred_*): the layers in front of the first one that reads them run meanwhile; the wait is inserted right there.
 int forward(pg_plan& P) {
+  pg_ctx* ctx = P.ctx;
+  ctx->deferred_hold = ctx->deferred_armed && !ctx->capturing;
+  const int rc = forward_nodes(P);
+  ctx->deferred_hold = false;
+  return rc;
+}
+
+int forward_nodes(pg_plan& P) {
   pg_ctx* ctx = P.ctx;
   const int n = P.n;
   void* loss_slot = (char*)P.loss_ring + (size_t)(P.gen % LOSS_RING) * 16;
   for (int i = 0; i < n; ++i) {
     if (!P.need[i]) continue;
     const pg_op& o = P.ops[i];
+    if (ctx->deferred_armed && (o.kind == PG_OP_LINEAR || o.kind == PG_OP_CONV2D)) {
+      const int W = o.in[1], b = o.in[2];
+      if (pg_deferred_overlaps(ctx, P.leaf[W], (size_t)P.size[W] * dsize(P.ops[W].dtype)) ||
+          pg_deferred_overlaps(ctx, P.leaf[b], (size_t)P.size[b] * dsize(P.ops[b].dtype))) {
+        pg_flush_deferred(ctx);
+        ctx->deferred_hold = false;
+      }
+    }
     switch (o.kind) {
       case PG_OP_INPUT: case PG_OP_PARAM:
         if (P.leaf[i] == nullptr) return P.fail(PG_ERR_ARG, "a needed input / parameter node has no device pointer");

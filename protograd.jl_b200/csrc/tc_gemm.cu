@@ -118,8 +118,12 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) 
 }
 
 // One 32-column chunk of one accumulator row: bias / ReLU / ReLU' mask / store (shared by both kernels).
+// bias_lane: this lane's share of the chunk's bias, bias[col + lane], prefetched BEFORE the accumulator wait (the chunk's 32
+// values are then distributed by shuffles: no global-load latency between tcgen05.ld and the stores); has_bias_lane = 0 keeps
+// the direct loads (narrow kernels).
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Epi& epi, void* __restrict__ C, int M, int N,
-                                               int row, int col, int split, const uint4* mk4) {
+                                               int row, int col, int split, const uint4* mk4, float bias_lane = 0.0f, int has_bias_lane = 0) {
+
   if (epi.colsum != nullptr) {
     // column sums of this warp's 32 x 32 block (rows = lanes): butterfly transpose-reduce, 31 shuffles;
     // afterwards lane l holds the sum of column l.  Values are masked and bf16-rounded exactly like the
@@ -147,10 +151,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
     }
     if (col + lane < N) atomicAdd(epi.colsum + col + lane, t[0]);
   }
-  if (!(row < M && col < N)) return;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (has_bias_lane) {       // all 32 lanes take part: before the early exit
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
+  }
+  if (!(row < M && col < N)) return;
   if (epi.narrow) {
     // N is not a multiple of 8 (e.g. 10 logits): scalar, fully guarded fp32 path
     float* op = reinterpret_cast<float*>(C) + (size_t)split * M * N + (size_t)row * N;
@@ -164,7 +172,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
     }
     return;
   }
-  if (epi.bias != nullptr) {
+  if (!has_bias_lane && epi.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       if (col + j < N) {
@@ -402,6 +410,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int j = 0; j < COLS_PER_WARP / 8; ++j)
           mk[j] = (row < M && n0 + c_begin + 8 * j < N) ? __ldg(reinterpret_cast<const uint4*>(mp) + j) : make_uint4(0, 0, 0, 0);
       }
+      // bias of this warp's columns, one value per lane and chunk, also fetched before the wait
+      float bl[COLS_PER_WARP / 32];
+      const int use_bl = (epi.bias != nullptr && !epi.narrow && active) ? 1 : 0;
+#pragma unroll
+      for (int ci = 0; ci < COLS_PER_WARP / 32; ++ci) {
+        const int cc = n0 + c_begin + ci * 32 + lane;
+        bl[ci] = (use_bl && cc < N && split == 0) ? __ldg(epi.bias + cc) : 0.0f;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
@@ -412,7 +428,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         tmem_ld_wait();
-        epilogue_chunk(r, epi, C, M, N, row, n0 + c, split, &mk[ci * 4]);
+        epilogue_chunk(r, epi, C, M, N, row, n0 + c, split, &mk[ci * 4], bl[ci], use_bl);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -675,6 +691,13 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int j = 0; j < COLS_PER_WARP / 8; ++j)
           mk[j] = (row < M && n0 + c_begin + 8 * j < N) ? __ldg(reinterpret_cast<const uint4*>(mp) + j) : make_uint4(0, 0, 0, 0);
       }
+      float bl[COLS_PER_WARP / 32];
+      const int use_bl = epi.bias != nullptr ? 1 : 0;
+#pragma unroll
+      for (int ci = 0; ci < COLS_PER_WARP / 32; ++ci) {
+        const int cc = n0 + c_begin + ci * 32 + lane;
+        bl[ci] = (use_bl && cc < N) ? __ldg(epi.bias + cc) : 0.0f;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -684,7 +707,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         tmem_ld_wait();
-        epilogue_chunk(r, epi, C, M, N, row, n0 + c, 0, &mk[ci * 4]);
+        epilogue_chunk(r, epi, C, M, N, row, n0 + c, 0, &mk[ci * 4], bl[ci], use_bl);
       }
       tcgen05_fence_before();
       __syncwarp();
