@@ -83,6 +83,101 @@ gemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C,
   }
 }
 
+
+// ---- larger register tile for Float32: 128 x 128 x 16 per CTA, 8 x 8 per thread, 128-bit shared-memory operand loads,
+// the next k-tile prefetched into registers while the current one is consumed (double-buffered shared memory: one
+// __syncthreads per k-tile).  16 FMA per shared-memory load instead of 2 -> FMA-bound instead of LDS-bound.  Same
+// arguments and epilogues as gemm_kernel; used when the output is at least one tile in each direction (FP32-SIMT mode of the
+// wide layers; the 64 x 64 kernel keeps the small and Float64 shapes).
+constexpr int TM = 128, TN = 128, TK = 16, TPAD = 4;
+
+__global__ void __launch_bounds__(256)
+gemm128_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, float* __restrict__ part,
+               int64_t M, int64_t N, int64_t K, int64_t sam, int64_t sak, int64_t sbk, int64_t sbn, int64_t ldc,
+               int epi, const float* __restrict__ bias, const float* __restrict__ mask, int64_t k_per_split) {
+  __shared__ __align__(16) float As[2][TK][TM + TPAD];
+  __shared__ __align__(16) float Bs[2][TK][TN + TPAD];
+  const int t = threadIdx.x;
+  const int tx = t & 15, ty = t >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * TM, n0 = (int64_t)blockIdx.x * TN;
+  const int64_t kb = (int64_t)blockIdx.z * k_per_split;
+  const int64_t ke = (kb + k_per_split < K) ? kb + k_per_split : K;
+  const bool a_kcontig = (sak == 1), b_ncontig = (sbn == 1);
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  float ra[8], rb[8];
+  auto gload = [&](int64_t k0) {              // this thread's 8 + 8 elements of the k-tile starting at k0
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int mm, kk;
+      if (a_kcontig) { kk = t & 15; mm = (t >> 4) + 16 * i; } else { mm = t & 127; kk = (t >> 7) + 2 * i; }
+      const int64_t gm = m0 + mm, gk = k0 + kk;
+      ra[i] = (gm < M && gk < ke) ? __ldg(A + gm * sam + gk * sak) : 0.0f;
+      int nn, k2;
+      if (b_ncontig) { nn = t & 127; k2 = (t >> 7) + 2 * i; } else { k2 = t & 15; nn = (t >> 4) + 16 * i; }
+      const int64_t gn = n0 + nn, gk2 = k0 + k2;
+      rb[i] = (gn < N && gk2 < ke) ? __ldg(B + gk2 * sbk + gn * sbn) : 0.0f;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int mm, kk;
+      if (a_kcontig) { kk = t & 15; mm = (t >> 4) + 16 * i; } else { mm = t & 127; kk = (t >> 7) + 2 * i; }
+      As[buf][kk][mm] = ra[i];
+      int nn, k2;
+      if (b_ncontig) { nn = t & 127; k2 = (t >> 7) + 2 * i; } else { k2 = t & 15; nn = (t >> 4) + 16 * i; }
+      Bs[buf][k2][nn] = rb[i];
+    }
+  };
+  int buf = 0;
+  if (kb < ke) { gload(kb); sstore(0); }
+  __syncthreads();
+  for (int64_t k0 = kb; k0 < ke; k0 += TK) {
+    const bool more = k0 + TK < ke;
+    if (more) gload(k0 + TK);                 // global latency hidden behind this tile's FMAs
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4 + 64]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4 + 64]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) sstore(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  const bool split = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t gm = m0 + ty * 4 + (i & 3) + (i >> 2) * 64;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t gn = n0 + tx * 4 + (j & 3) + (j >> 2) * 64;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (split) { part[((int64_t)blockIdx.z * M + gm) * N + gn] = v; continue; }
+      if (epi == EPI_BIAS || epi == EPI_BIAS_RELU) {
+        if (bias) v += bias[gn];
+        if (epi == EPI_BIAS_RELU) v = v < 0.0f ? 0.0f : v;
+      } else if (epi == EPI_MASK) {
+        v = mask[gm * ldc + gn] > 0.0f ? v : 0.0f;
+      }
+      C[gm * ldc + gn] = v;
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const T* __restrict__ part, T* __restrict__ C, int64_t MN, int splits) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,20 +249,23 @@ template <typename T>
 int gemm_launch(pg_ctx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, int64_t sam, int64_t sak, int64_t sbk,
                 int64_t sbn, int64_t ldc, int epi, const T* bias, const T* mask, bool allow_split) {
   if (M <= 0 || N <= 0) return PG_OK;
-  int64_t gx = pg_cdiv(N, BN), gy = pg_cdiv(M, BM);
+  // Float32 with at least a 96 x 96 output: the 128 x 128 register-tiled kernel
+  const bool big = std::is_same<T, float>::value && M >= 96 && N >= 96;
+  const int bm = big ? TM : BM, bn = big ? TN : BN, bk = big ? TK : BK;
+  int64_t gx = pg_cdiv(N, bn), gy = pg_cdiv(M, bm);
   PG_REQUIRE(gy <= 65535, "M too large for the SIMT GEMM grid");
   int splits = 1;
   if (allow_split && epi == EPI_NONE && ldc == N) {
     int64_t tiles = gx * gy;
     int64_t want = pg_cdiv(2 * (int64_t)ctx->num_sms, tiles);
-    int64_t maxs = pg_cdiv(K, 8 * BK);
+    int64_t maxs = pg_cdiv(K, 8 * bk);
     splits = (int)(want < maxs ? want : maxs);
     if (splits < 1) splits = 1;
     if (splits > 256) splits = 256;
   }
-  int64_t kps = pg_cdiv(pg_cdiv(K, splits), BK) * BK;
+  int64_t kps = pg_cdiv(pg_cdiv(K, splits), bk) * bk;
   splits = (int)pg_cdiv(K, kps);
-  if (K <= 0) { splits = 1; kps = BK; }
+  if (K <= 0) { splits = 1; kps = bk; }
   T* part = nullptr;
   if (splits > 1) {
     int rc = pg_ws_ensure(ctx, (size_t)splits * M * N * sizeof(T));
@@ -175,7 +273,12 @@ int gemm_launch(pg_ctx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N,
     part = (T*)ctx->ws;
   }
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)splits);
-  gemm_kernel<T><<<grid, 256, 0, ctx->stream>>>(A, B, C, part, M, N, K, sam, sak, sbk, sbn, ldc, epi, bias, mask, kps);
+  if constexpr (std::is_same<T, float>::value) {
+    if (big) gemm128_kernel<<<grid, 256, 0, ctx->stream>>>(A, B, C, part, M, N, K, sam, sak, sbk, sbn, ldc, epi, bias, mask, kps);
+    else gemm_kernel<T><<<grid, 256, 0, ctx->stream>>>(A, B, C, part, M, N, K, sam, sak, sbk, sbn, ldc, epi, bias, mask, kps);
+  } else {
+    gemm_kernel<T><<<grid, 256, 0, ctx->stream>>>(A, B, C, part, M, N, K, sam, sak, sbk, sbn, ldc, epi, bias, mask, kps);
+  }
   PG_LAUNCHED(ctx);
   if (splits > 1) {
     int64_t MN = M * N;

@@ -1013,7 +1013,8 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
   __nv_bfloat16* dZt = (__nv_bfloat16*)(base + dzp_bytes);                 // [32][M]
   __nv_bfloat16* Wp = (__nv_bfloat16*)(base + dzp_bytes + dzt_bytes);      // [K][64]
   // the bandwidth-shaped data-gradient kernel covers even N <= 16 with bf16 output and no fused column sums
-  const bool simt_dx = dX != nullptr && !dx_f32 && dx_colsum == nullptr && N % 2 == 0 && N <= 16 && getenv("PG_NARROW_DGRAD_GEMM") == nullptr;
+  static const bool narrow_gemm_dx = getenv("PG_NARROW_DGRAD_GEMM") != nullptr;      // A/B switch, read once
+  const bool simt_dx = dX != nullptr && !dx_f32 && dx_colsum == nullptr && N % 2 == 0 && N <= 16 && !narrow_gemm_dx;
   const bool gemm_dx = dX != nullptr && !simt_dx;
   if (dW || gemm_dx) {
     int64_t total = M * NARROW_K;
@@ -1112,7 +1113,8 @@ static int tc_linear_bwd_impl(pg_ctx* ctx, const void* X, const void* W, const v
   if (dW) {  // dW[K][N] = X^T dY: GEMM (M'=K, N'=N, K'=M), A = X stored [M][K] (MN-major), B = dY stored [M][N] (MN-major)
     // db = column sums of dY ride along when enough m-blocks share the work: reducer warps sum the dY
     // tiles already staged in shared memory (no extra pass over dY)
-    const bool two = use_2cta(ctx, K, N) && getenv("PG_DBW_1CTA") == nullptr;
+    static const bool dbw_1cta_env = getenv("PG_DBW_1CTA") != nullptr;              // A/B switch, read once
+    const bool two = use_2cta(ctx, K, N) && !dbw_1cta_env;
     const int64_t m_blocks = two ? pg_cdiv(K, 256) : pg_cdiv(K, BLOCK_M);
     const bool fuse_db = db != nullptr && m_blocks >= 4;
     float* db_part = nullptr;
