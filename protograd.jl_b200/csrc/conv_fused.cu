@@ -124,8 +124,9 @@ __global__ void __launch_bounds__(FwdCfg<G>::THREADS) conv_relu_pool_fwd_kernel(
 // weight + bias gradient: thread (ci, u, i) holds input row x[ci][i+u][:] in registers and accumulates
 // acc[v][co] += x[i+u][j+v] * dy[i][j][co] while j slides along the row; summed over samples in registers, over the
 // HO row-threads in shared memory at the end, written as one partial per CTA.
-// dy is never materialised: per (j, 4 channels) it is selected on the fly from the pooled gradient (already masked by
-// relu') and the winner bytes, staged channel-last in shared memory: gm[window][co], am[window][co].
+// The conv-output gradient exists only as a shared-memory tile dy[i][j][co]: every pooled element (held in a register by
+// the thread that prefetched it) writes its whole 2x2 window — the winner position gets the relu'-masked pooled gradient,
+// the other three get zero — so the tile is complete without a zero-fill pass or a second phase.
 // Latency: the NEXT sample's global data (input tile, pooled gradient / value / winner) is prefetched into registers
 // while the current one is consumed, and the shared-memory tiles are double-buffered: one __syncthreads per sample.
 // ---------------------------------------------------------------------------------------------------------------
@@ -135,12 +136,11 @@ struct WgCfg {
   static constexpr int SLOTS = (256 / TPS) > 0 ? (256 / TPS) : 1;
   static constexpr int THREADS = ((SLOTS * TPS + 31) / 32) * 32;
   static constexpr int NW = G::COUT * G::CIN * G::K * G::K;    // filter elements
-  static constexpr int GROW = G::WP * G::COUTP + 4;            // padded window-row pitch (floats): rows land in different banks
-  static constexpr int GM = G::HP * GROW;                      // masked pooled gradient, channel-last
-  static constexpr int AM = (G::HP * G::WP * G::COUTP + 3) / 4;   // winner bytes, channel-last (as 32-bit words)
+  static constexpr int DROW = G::WO * G::COUTP + 4;            // padded row pitch of the conv-output gradient tile dy[i][j][co] (floats): rows land in different banks
+  static constexpr int DY = G::HO * DROW;
   static constexpr int XV = (G::XS / 4 + TPS - 1) / TPS;       // float4 of the input tile per thread
   static constexpr int SV = (G::YS + TPS - 1) / TPS;           // pooled elements per thread
-  static constexpr int BUF = G::XS + GM + AM;                  // one sample's tiles (floats)
+  static constexpr int BUF = G::XS + DY;                       // one sample's tiles (floats)
   static constexpr int RED = SLOTS * TPS * G::K * G::COUTP;    // final cross-thread reduction buffer (floats)
   static constexpr int STAGE = SLOTS * 2 * BUF;
   static constexpr int SMEM_FLOATS = STAGE > RED ? STAGE : RED;
@@ -193,15 +193,19 @@ __global__ void __launch_bounds__(WgCfg<G>::THREADS, WgCfg<G>::MINB) conv_relu_p
       const int e = t + k * C::TPS;
       if (e < G::XS / 4) reinterpret_cast<float4*>(buf)[e] = xr[k];
     }
-    float* gm = buf + G::XS;
-    uint8_t* am = reinterpret_cast<uint8_t*>(gm + C::GM);
+    float* dy = buf + G::XS;
 #pragma unroll
     for (int k = 0; k < C::SV; ++k) {
       const int e = t + k * C::TPS;
       if (e < G::YS) {
         const int win = e % G::WIN, co = e / G::WIN;
-        gm[(win / G::WP) * C::GROW + (win % G::WP) * COUTP + co] = gr[k];
-        am[win * COUTP + co] = ar[k];
+        float* d = dy + (2 * (win / G::WP)) * C::DROW + (2 * (win % G::WP)) * COUTP + co;
+        const int a = ar[k];
+        const float g = gr[k];
+        d[0] = a == 0 ? g : 0.0f;
+        d[COUTP] = a == 1 ? g : 0.0f;
+        d[C::DROW] = a == 2 ? g : 0.0f;
+        d[C::DROW + COUTP] = a == 3 ? g : 0.0f;
       }
     }
   };
@@ -219,21 +223,12 @@ __global__ void __launch_bounds__(WgCfg<G>::THREADS, WgCfg<G>::MINB) conv_relu_p
     float row[G::W];
 #pragma unroll
     for (int c = 0; c < G::W; ++c) row[c] = buf[(ci * G::H + i + u) * G::W + c];
-    const float* gm = buf + G::XS + (i >> 1) * C::GROW;
-    const uint32_t* am = reinterpret_cast<const uint32_t*>(buf + G::XS + C::GM) + (i >> 1) * G::WP * (COUTP / 4);
-    const uint32_t krow = (uint32_t)(i & 1) << 1;
+    const float4* dv = reinterpret_cast<const float4*>(buf + G::XS + i * C::DROW);
 #pragma unroll
     for (int j = 0; j < WO; ++j) {
-      const uint32_t kpos = krow | (uint32_t)(j & 1);            // which window position (i, j) is
 #pragma unroll
       for (int c4 = 0; c4 < COUTP / 4; ++c4) {
-        const float4 g4 = *reinterpret_cast<const float4*>(gm + (j >> 1) * COUTP + 4 * c4);
-        const uint32_t a4 = am[(j >> 1) * (COUTP / 4) + c4];
-        float4 d;
-        d.x = ((a4 & 0xffu) == kpos) ? g4.x : 0.0f;
-        d.y = (((a4 >> 8) & 0xffu) == kpos) ? g4.y : 0.0f;
-        d.z = (((a4 >> 16) & 0xffu) == kpos) ? g4.z : 0.0f;
-        d.w = ((a4 >> 24) == kpos) ? g4.w : 0.0f;
+        const float4 d = dv[j * (COUTP / 4) + c4];
 #pragma unroll
         for (int v = 0; v < K; ++v) {
           acc[v][4 * c4 + 0] = fmaf(row[j + v], d.x, acc[v][4 * c4 + 0]);
@@ -241,8 +236,17 @@ __global__ void __launch_bounds__(WgCfg<G>::THREADS, WgCfg<G>::MINB) conv_relu_p
           acc[v][4 * c4 + 2] = fmaf(row[j + v], d.z, acc[v][4 * c4 + 2]);
           acc[v][4 * c4 + 3] = fmaf(row[j + v], d.w, acc[v][4 * c4 + 3]);
         }
-        if (ci == 0 && u == 0) { dbacc[4 * c4] += d.x; dbacc[4 * c4 + 1] += d.y; dbacc[4 * c4 + 2] += d.z; dbacc[4 * c4 + 3] += d.w; }
       }
+      asm volatile("" ::: "memory");     // keep the (fully unrolled) tile loads next to their FMAs: hoisting all of them costs > 128 registers
+    }
+    if (ci == 0 && u == 0) {            // bias gradient: row i of the tile, by the HO threads of (ci = 0, u = 0) only
+#pragma unroll
+      for (int j = 0; j < WO; ++j)
+#pragma unroll
+        for (int c4 = 0; c4 < COUTP / 4; ++c4) {
+          const float4 d = dv[j * (COUTP / 4) + c4];
+          dbacc[4 * c4] += d.x; dbacc[4 * c4 + 1] += d.y; dbacc[4 * c4 + 2] += d.z; dbacc[4 * c4 + 3] += d.w;
+        }
     }
   }
   // ---- reduce over the HO row-threads and the sample slots (fixed order), one partial per CTA ----

@@ -249,8 +249,9 @@ template <typename T>
 int gemm_launch(pg_ctx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, int64_t sam, int64_t sak, int64_t sbk,
                 int64_t sbn, int64_t ldc, int epi, const T* bias, const T* mask, bool allow_split) {
   if (M <= 0 || N <= 0) return PG_OK;
-  // Float32 with at least a 96 x 96 output: the 128 x 128 register-tiled kernel
-  const bool big = std::is_same<T, float>::value && M >= 96 && N >= 96;
+  // Float32 outputs with at least one 128 x 128 tile per SM: the register-tiled kernel (smaller problems fill the GPU
+  // better with 64 x 64 tiles: measured C1 at B = 8192, N = 100: 0.247 ms/step with 64-tiles, 0.323 with 128-tiles)
+  const bool big = std::is_same<T, float>::value && pg_cdiv(M, TM) * pg_cdiv(N, TN) >= ctx->num_sms;
   const int bm = big ? TM : BM, bn = big ? TN : BN, bk = big ? TK : BK;
   int64_t gx = pg_cdiv(N, bn), gy = pg_cdiv(M, bm);
   PG_REQUIRE(gy <= 65535, "M too large for the SIMT GEMM grid");
