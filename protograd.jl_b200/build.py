@@ -63,5 +63,24 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
+def build_trace_lib():
+    """Debug variant (tools/tc_trace.py): tc_gemm.cu compiled with -DPG_TC_TRACE (per-tile clock stamps of the pair kernel's
+    roles), everything else from the regular objects -> libprotograd_b200_trace.so; loaded with PG_LIB_PATH=<that file>."""
+    build_lib()
+    obj = os.path.join(OBJ, "tc_gemm_trace.o")
+    r = subprocess.run([NVCC] + FLAGS + ["-DPG_TC_TRACE", "-c", os.path.join(CSRC, "tc_gemm.cu"), "-o", obj], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stdout + r.stderr)
+    objs = [os.path.join(OBJ, f) for f in sorted(os.listdir(OBJ)) if f.endswith(".o") and f not in ("tc_gemm.o", "tc_gemm_trace.o")] + [obj]
+    out = os.path.join(HERE, "libprotograd_b200_trace.so")
+    r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stdout + r.stderr)
+    return out
+
+
 if __name__ == "__main__":
+    if "--trace" in sys.argv:
+        print(build_trace_lib())
+        sys.exit(0)
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

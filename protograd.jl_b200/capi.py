@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libprotograd_b200.so")
+LIB_PATH = os.environ.get("PG_LIB_PATH") or os.path.join(HERE, "libprotograd_b200.so")   # PG_LIB_PATH: a debug build of the same library
 
 PG_F32, PG_F64, PG_BF16, PG_F16, PG_I32 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU = 0, 1

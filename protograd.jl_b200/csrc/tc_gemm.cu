@@ -57,6 +57,19 @@ struct Epi {
 
 #include "tc_ptx.cuh"
 
+// Debug build only (-DPG_TC_TRACE, tools/tc_trace.py): per-tile clock64 stamps of the first pair's roles
+#ifdef PG_TC_TRACE
+constexpr int TRACE_TILES = 8;
+constexpr int TRACE_BYTES = 3 * TRACE_TILES * 4 * 8;
+__device__ long long g_tc_trace[3][TRACE_TILES][4];   // [role: 0 producer, 1 MMA issuer, 2 epilogue warp][tile #][event]
+// stamps go to shared memory (behind the tile ring) and are copied out when the kernel ends: no global traffic while it runs
+#define TC_TRACE(role, n, ev) do { if (blockIdx.x == 0 && (n) < TRACE_TILES) \
+    reinterpret_cast<volatile long long*>(smem_aligned + BAR_OFF + 512)[((role) * TRACE_TILES + (n)) * 4 + (ev)] = clock64(); } while (0)
+#else
+constexpr int TRACE_BYTES = 0;
+#define TC_TRACE(role, n, ev) do { } while (0)
+#endif
+
 // ---- dynamic tile scheduler ----------------------------------------------------------------------
 // Work items are handed out by an atomic counter instead of the static `work += gridDim.x` stride, so
 // a CTA (pair) that becomes resident late — its SM was busy with a concurrent kernel, e.g. an NCCL
@@ -94,6 +107,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   while (!mbar_try_wait_cluster(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) __trap();
   }
+}
+// The scheduler's fetch as raw PTX: the CUDA atomicAdd() is compiled into a warp-aggregated sequence whose SHFL consumes the
+// result at once — the ~1k-cycle round trip then sits at the top of every tile instead of behind the tile's loads.
+__device__ __forceinline__ unsigned int sched_fetch(unsigned int* counter) {
+  unsigned int v;
+  asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(counter) : "memory");
+  return v;
 }
 struct TileFeed {            // consumer side of the ring (any thread of any role)
   uint32_t base;             // RING barriers (8 B each), then RING ids (4 B each)
@@ -228,7 +248,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   static_assert(RING >= STAGES + 4, "tile ring shorter than the producer's lead over the epilogue");
   // the scheduler thread's first fetch is in flight while the barriers / TMEM are set up
   unsigned int first_work = 0;
-  if (threadIdx.x == 0) first_work = atomicAdd(sched, 1u);
+  if (threadIdx.x == 0) first_work = sched_fetch(sched);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -286,7 +306,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int work = (int)first_work;
       publish(work);
       while (work < num_work) {
-        const int next_work = (int)atomicAdd(sched, 1u);   // consumed after this tile's loads have been issued
+        const int next_work = (int)sched_fetch(sched);   // consumed after this tile's loads have been issued
         const int tile = work % num_tiles, split = work / num_tiles;
         const int kb0 = split * epi.kb_per_split, kb1 = min(num_kb, kb0 + epi.kb_per_split);
         int m0, n0;
@@ -459,7 +479,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 constexpr int STAGES2 = 6;
 constexpr int B2_STAGE_BYTES = 128 * BLOCK_K * 2;
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;      // 32 KB per CTA
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + 256;
+constexpr int OUT_BOX_BYTES = 128 * 128;                           // staged epilogue: one 128-row x 128-byte TMA box per column half
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 2 * OUT_BOX_BYTES + 1024 + 256 + 256 + TRACE_BYTES;
 constexpr int GROUP_M2 = 8;                                        // rasterisation group, in 256-row blocks
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -489,6 +510,21 @@ __device__ __forceinline__ void tcgen05_commit_2sm(uint32_t bar) {   // arrive o
                ::"r"(bar), "h"((uint16_t)3)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -506,26 +542,36 @@ __host__ __device__ constexpr uint32_t make_idesc2(bool a_mn, bool b_mn) {   // 
 // DBW (weight-gradient launches): one extra reducer warp per CTA sums the CTA's half of the staged dY
 // tiles (see the 1-CTA kernel).  The peer CTA cannot wait on the leader's full barrier, so the leader's
 // MMA thread forwards every "stage landed" to the peer's ready[] barrier with a remote arrive.
-template <bool A_MN, bool B_MN, bool DBW>
+//
+// STAGED epilogue (default).  The mainloop keeps the SM's shared-memory pipe saturated (64 B/clk of tensor-core operand reads +
+// 64 B/clk of TMA writes = its 128 B/clk): a direct epilogue — every lane storing 16 B of its own output row, 32 lines per
+// store instruction — costs one L1 wavefront per 16 B and was measured (tools/tc_trace.py) to halve the MMA rate while it
+// runs.  Here each group of four epilogue warps converts a 128-row x 128-byte box (64 bf16 / 32 fp32 columns) into a
+// SWIZZLE_128B staging buffer (conflict-free 16-byte shared stores: 4 wavefronts per instruction) and one thread hands it to
+// the TMA store unit: whole-line writes, 1/4 of the wavefronts.  The data gradient's ReLU' mask tile arrives the same way (a
+// TMA load into the staging box it will be overwritten in).
+template <bool A_MN, bool B_MN, bool DBW, bool STAGED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS + (DBW ? 32 : 0), 1)
-tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ C,
-                int M, int N, int K, Epi epi, unsigned int* __restrict__ sched) {
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_c,
+                const __grid_constant__ CUtensorMap map_mask, void* __restrict__ C, int M, int N, int K, Epi epi, unsigned int* __restrict__ sched) {
   constexpr int BN = 256;
   static_assert(RING >= STAGES2 + 4, "tile ring shorter than the producer's lead over the epilogue");
   const uint32_t rank = cluster_ctarank();
   // the leader's scheduler thread fetches the pair's first tile while the barriers / TMEM are set up
   unsigned int first_tile = 0;
-  if (threadIdx.x == 0 && rank == 0) first_tile = atomicAdd(sched, 1u);
+  if (threadIdx.x == 0 && rank == 0) first_tile = sched_fetch(sched);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + STAGES2 * STAGE2_BYTES;
+  constexpr int BAR_OFF = STAGES2 * STAGE2_BYTES + 2 * OUT_BOX_BYTES;
+  const uint32_t bar_base = smem_base + BAR_OFF;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES2 + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + 2 + a); };
   auto ready_bar = [&](int s) { return bar_base + 8u * (2 * STAGES2 + 4 + s); };     // peer CTA: "stage s has landed"
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_aligned + STAGES2 * STAGE2_BYTES + 8 * (3 * STAGES2 + 4));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_aligned + BAR_OFF + 8 * (3 * STAGES2 + 4));
+  auto mask_bar = [&](int h) { return bar_base + 8u * (3 * STAGES2 + 5 + h); };      // staged epilogue: "mask box of half h has landed"
   const uint32_t ring_base = bar_base + 256;             // tile ring (same offset in both CTAs): RING barriers + RING ids
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -541,13 +587,17 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     n0 = (r / gm) * BN;
   };
 
+#ifdef PG_TC_TRACE
+  if (threadIdx.x < 3 * TRACE_TILES * 4) reinterpret_cast<volatile long long*>(smem_aligned + BAR_OFF + 512)[threadIdx.x] = 0;
+#endif
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), DBW ? 2 : 1); mbar_init(ready_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); mbar_init(mask_bar(a), 1); }
     for (int i = 0; i < RING; ++i) mbar_init(ring_base + 8u * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (STAGED) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
   }
   if (warp == 1) {  // one warp of EACH CTA, same warp id, same smem slot
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512) : "memory");
@@ -568,21 +618,28 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const uint32_t id_addr = ring_base + 8u * RING + 4u * slot, bar = ring_base + 8u * slot;
         st_shared_u32(id_addr, (uint32_t)id);
         mbar_arrive(bar);
-        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(map_to_rank(id_addr, 1)), "r"((uint32_t)id) : "memory");
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_rank(bar, 1)) : "memory");
+        // peer's copy: an asynchronous DSMEM store that completes 4 tx-bytes on the peer's slot barrier, armed by a relaxed remote
+        // arrive — the hardware orders data before completion, so no release fence (MEMBAR.ALL.GPU, ~1.5k cycles of producer
+        // stall per tile, tools/tc_trace.py) and the peer's waits need no cluster-scope acquire (CCTL.IVALL)
+        const uint32_t rbar = map_to_rank(bar, 1);
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(map_to_rank(id_addr, 1)), "r"((uint32_t)id), "r"(rbar) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], 4;" ::"r"(rbar) : "memory");
         if (++slot == RING) slot = 0;
       };
-      TileFeed feed(ring_base, true);                    // peer: reads what the leader published
+      TileFeed feed(ring_base, false);                   // peer: reads what the leader published (st.async + complete_tx)
       int tile;
       if (rank == 0) { tile = (int)first_tile; publish(tile); } else { tile = feed.next(); }
+      [[maybe_unused]] int tn = 0;
       while (tile < num_tiles) {
         int next_tile = 0;
-        if (rank == 0) next_tile = (int)atomicAdd(sched, 1u);   // consumed after this tile's loads have been issued
+        if (rank == 0) next_tile = (int)sched_fetch(sched);   // consumed after this tile's loads have been issued
         int m0, n0;
         tile_coords(tile, m0, n0);
         const int my_m0 = m0 + (int)rank * 128, my_n0 = n0 + (int)rank * 128;
+        TC_TRACE(0, tn, 0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
+          if (kb == 0) TC_TRACE(0, tn, 1);
           const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
           const uint32_t lbar = map_to_rank(full_bar(stage), 0);
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE2_BYTES);
@@ -601,7 +658,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
+        TC_TRACE(0, tn, 2);
         if (rank == 0) { publish(next_tile); tile = next_tile; } else { tile = feed.next(); }
+        TC_TRACE(0, tn, 3);
+        ++tn;
       }
       // every pair fetches exactly one terminal id; the last one to do so re-arms the counters
       if (rank == 0 && atomicAdd(sched + 1, 1u) == (unsigned)num_clusters - 1) { sched[0] = 0; sched[1] = 0; }
@@ -613,12 +673,16 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       TileFeed feed(ring_base, false);
-      for (int tile = feed.next(); tile < num_tiles; tile = feed.next()) {
+      [[maybe_unused]] int tn = 0;
+      for (int tile = feed.next(); tile < num_tiles; tile = feed.next(), ++tn) {
+        TC_TRACE(1, tn, 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
         tcgen05_fence_after();
+        TC_TRACE(1, tn, 1);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);             // both CTAs' bytes have landed
+          if (kb == 0) TC_TRACE(1, tn, 2);
           if (DBW) mbar_arrive_cluster(map_to_rank(ready_bar(stage), 1));   // tell the peer's reducer warp
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
@@ -632,6 +696,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (kb == num_kb - 1) tcgen05_commit_2sm(tfull_bar(acc));
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
+        TC_TRACE(1, tn, 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -643,7 +708,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int chunk = (col0 & 63) >> 3;
     float acc4[4] = {0.f, 0.f, 0.f, 0.f};
     int stage = 0; uint32_t phase = 0;
-    TileFeed feed(ring_base, rank != 0);
+    TileFeed feed(ring_base, false);
     for (int tile = feed.next(); tile < num_tiles; tile = feed.next()) {
       int m0, n0;
       tile_coords(tile, m0, n0);
@@ -674,14 +739,120 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else {
     // ===== epilogue warps (both CTAs): own 128 rows x 256 columns from the local TMEM =====
+    if constexpr (STAGED) {
+      const int q = warp & 3;
+      const int half = (warp - 2) >> 2;                  // warps 2-5: columns [0, 128) of the tile, warps 6-9: [128, 256)
+      const bool elected = ((warp - 2) & 3) == 0 && lane == 0;
+      const int rr = q * 32 + lane;                      // row inside the CTA's 128 (= TMEM lane)
+      const uint32_t box = smem_base + STAGES2 * STAGE2_BYTES + half * OUT_BOX_BYTES;
+      const uint32_t my_row = box + (uint32_t)rr * 128u;
+      const uint32_t sw = (uint32_t)(rr & 7);
+      const int bar_free = 1 + 2 * half, bar_written = 2 + 2 * half;
+      const bool f32 = epi.out_f32 != 0, has_mask = epi.mask != nullptr;
+      const int cols_per_round = f32 ? 32 : 64, rounds = f32 ? 4 : 2;
+      uint32_t mphase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      TileFeed feed(ring_base, false);
+      [[maybe_unused]] int tn = 0;
+      for (int tile = feed.next(); tile < num_tiles; tile = feed.next(), ++tn) {
+        int m0, n0;
+        tile_coords(tile, m0, n0);
+        if (threadIdx.x == 64) TC_TRACE(2, tn, 0);
+        const int row0 = m0 + (int)rank * 128;
+        const int c_begin = half * 128;
+        if (has_mask && elected && n0 + c_begin < N) {   // round 0's mask box; the previous tile's last store has long been read
+          tma_store_wait_read();
+          mbar_expect_tx(mask_bar(half), OUT_BOX_BYTES);
+          tma_load_2d(box, &map_mask, mask_bar(half), n0 + c_begin, row0);
+        }
+        float bl[4];
+        const int use_bl = epi.bias != nullptr ? 1 : 0;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int cc = n0 + c_begin + ci * 32 + lane;
+          bl[ci] = (use_bl && cc < N) ? __ldg(epi.bias + cc) : 0.0f;
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        if (threadIdx.x == 64) TC_TRACE(2, tn, 1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c_begin;
+        for (int rd = 0; rd < rounds; ++rd) {
+          const int c0 = rd * cols_per_round;            // column offset inside the half
+          const bool live = n0 + c_begin + c0 < N;       // warp-uniform (and uniform over the half's four warps)
+          uint32_t r[2][32];
+          tmem_ld32(taddr + c0, r[0]);
+          if (!f32) tmem_ld32(taddr + c0 + 32, r[1]);
+          tmem_ld_wait();
+          if (rd == rounds - 1) {                        // the accumulator is in registers: hand it back to the MMA issuer
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(map_to_rank(tempty_bar(acc), 0));
+          }
+          if (elected) tma_store_wait_read();            // the previous box has left the staging buffer
+          named_bar_sync(bar_free, 128);
+          if (has_mask && live) { mbar_wait(mask_bar(half), mphase); mphase ^= 1; }
+          if (f32) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              st_shared_v4(my_row + ((((uint32_t)u) ^ sw) << 4), r[0][4 * u], r[0][4 * u + 1], r[0][4 * u + 2], r[0][4 * u + 3]);
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[ch][j]);
+              if (use_bl) {
+                const float b = (rd == 0) ? bl[ch] : bl[2 + ch];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, b, j);
+              }
+              if (epi.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t addr = my_row + ((((uint32_t)(4 * ch + u)) ^ sw) << 4);
+                if (has_mask) {
+                  const uint4 mk = ld_shared_v4(addr);
+                  const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[8 * u + e] = (__bfloat162float(me[e]) > 0.0f) ? v[8 * u + e] : 0.0f;
+                }
+                __nv_bfloat162 pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pk[e] = __floats2bfloat162_rn(v[8 * u + 2 * e], v[8 * u + 2 * e + 1]);
+                const uint32_t* pw = reinterpret_cast<const uint32_t*>(pk);
+                st_shared_v4(addr, pw[0], pw[1], pw[2], pw[3]);
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(bar_written, 128);
+          if (elected && live) {
+            tma_store_2d(&map_c, box, n0 + c_begin + c0, row0);
+            if (has_mask && rd + 1 < rounds && n0 + c_begin + c0 + cols_per_round < N) {
+              tma_store_wait_read();
+              mbar_expect_tx(mask_bar(half), OUT_BOX_BYTES);
+              tma_load_2d(box, &map_mask, mask_bar(half), n0 + c_begin + c0 + cols_per_round, row0);
+            }
+          }
+        }
+        if (threadIdx.x == 64) TC_TRACE(2, tn, 2);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (elected) tma_store_wait_read();                // the staging buffer must outlive the last store's read
+    } else {
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int COLS_PER_WARP = BN / 2;
     int acc = 0; uint32_t acc_phase = 0;
-    TileFeed feed(ring_base, rank != 0);
-    for (int tile = feed.next(); tile < num_tiles; tile = feed.next()) {
+    TileFeed feed(ring_base, false);
+    [[maybe_unused]] int tn = 0;
+    for (int tile = feed.next(); tile < num_tiles; tile = feed.next(), ++tn) {
       int m0, n0;
       tile_coords(tile, m0, n0);
+      if (threadIdx.x == 64) TC_TRACE(2, tn, 0);
       const int row = m0 + (int)rank * 128 + q * 32 + lane;
       const int c_begin = half * COLS_PER_WARP;
       uint4 mk[COLS_PER_WARP / 8];
@@ -700,6 +871,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
+      if (threadIdx.x == 64) TC_TRACE(2, tn, 1);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll
       for (int ci = 0; ci < COLS_PER_WARP / 32; ++ci) {
@@ -711,8 +883,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       tcgen05_fence_before();
       __syncwarp();
+      if (threadIdx.x == 64) TC_TRACE(2, tn, 2);
       if (lane == 0) mbar_arrive_cluster(map_to_rank(tempty_bar(acc), 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
     }
   }
 
@@ -723,6 +897,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+#ifdef PG_TC_TRACE
+  if (blockIdx.x == 0 && threadIdx.x < 3 * TRACE_TILES * 4)
+    (&g_tc_trace[0][0][0])[threadIdx.x] = reinterpret_cast<volatile long long*>(smem_aligned + BAR_OFF + 512)[threadIdx.x];
+#endif
 }
 
 // ---- TMA descriptor encoding (driver entry point resolved at run time: no libcuda link) ------------
@@ -745,16 +923,16 @@ int get_encoder(pg_ctx* ctx, EncodeTiledFn* fn) {
   return PG_OK;
 }
 
-// row-major bf16 matrix [rows][cols] with row pitch `ld` elements; box = {box_cols (<= 64), box_rows}
-int make_map(pg_ctx* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+// row-major bf16 (or fp32: f32 = true) matrix [rows][cols] with row pitch `ld` elements; box = {box_cols (<= 128 bytes), box_rows}
+int make_map(pg_ctx* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, bool f32 = false) {
   EncodeTiledFn enc;
   int rc = get_encoder(ctx, &enc);
   if (rc != PG_OK) return rc;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     pg_set_error("cuTensorMapEncodeTiled failed (%d) for [%lld][%lld] box {%d,%d}", (int)r, (long long)rows, (long long)cols, box_cols, box_rows);
@@ -787,15 +965,24 @@ int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int
   return PG_OK;
 }
 
-template <bool A_MN, bool B_MN, bool DBW = false>
-int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, const Epi& epi) {
-  CUtensorMap ma, mb;
+template <bool A_MN, bool B_MN, bool DBW, bool STAGED>
+int launch_tc2_impl(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, const Epi& epi) {
+  CUtensorMap ma, mb, mc, mm;
   int rc;
   rc = A_MN ? make_map(ctx, &ma, A, K, M, lda, 64, BLOCK_K) : make_map(ctx, &ma, A, M, K, lda, BLOCK_K, 128);
   if (rc != PG_OK) return rc;
   rc = B_MN ? make_map(ctx, &mb, B, K, N, ldb, 64, BLOCK_K) : make_map(ctx, &mb, B, N, K, ldb, BLOCK_K, 128);
   if (rc != PG_OK) return rc;
-  auto kern = tc_gemm2_kernel<A_MN, B_MN, DBW>;
+  if (STAGED) {     // output (and ReLU' mask) boxes of the staged epilogue: 128 rows x 128 bytes
+    rc = epi.out_f32 ? make_map(ctx, &mc, C, M, N, N, 32, 128, true) : make_map(ctx, &mc, C, M, N, N, 64, 128);
+    if (rc != PG_OK) return rc;
+    mm = mc;
+    if (epi.mask != nullptr) rc = make_map(ctx, &mm, epi.mask, M, N, N, 64, 128);
+    if (rc != PG_OK) return rc;
+  } else {
+    mc = ma; mm = ma;
+  }
+  auto kern = tc_gemm2_kernel<A_MN, B_MN, DBW, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
     PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -803,9 +990,19 @@ int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, in
   }
   int64_t tiles = pg_cdiv(M, 256) * pg_cdiv(N, 256);
   int clusters = (int)(tiles < ctx->num_sms / 2 ? tiles : ctx->num_sms / 2);
-  kern<<<2 * clusters, NUM_THREADS + (DBW ? 32 : 0), SMEM2_BYTES, ctx->stream>>>(ma, mb, C, (int)M, (int)N, (int)K, epi, ctx->counters + SCHED_SLOT);
+  kern<<<2 * clusters, NUM_THREADS + (DBW ? 32 : 0), SMEM2_BYTES, ctx->stream>>>(ma, mb, mc, mm, C, (int)M, (int)N, (int)K, epi, ctx->counters + SCHED_SLOT);
   PG_LAUNCHED(ctx);
   return PG_OK;
+}
+
+template <bool A_MN, bool B_MN, bool DBW = false>
+int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, const Epi& epi) {
+  // the staged (TMA-store) epilogue covers bf16 outputs with bias / ReLU / ReLU' mask and plain fp32 outputs; the rest (fused
+  // column sums, fp32 outputs with an elementwise epilogue) keeps the direct one.  PG_TC_DIRECT_EPI=1: A/B switch.
+  static const bool direct = getenv("PG_TC_DIRECT_EPI") != nullptr;
+  const bool staged = !direct && epi.colsum == nullptr && !(epi.out_f32 && (epi.bias != nullptr || epi.relu || epi.mask != nullptr));
+  return staged ? launch_tc2_impl<A_MN, B_MN, DBW, true>(ctx, A, B, C, M, N, K, lda, ldb, epi)
+                : launch_tc2_impl<A_MN, B_MN, DBW, false>(ctx, A, B, C, M, N, K, lda, ldb, epi);
 }
 
 // The pair kernel needs both SMs of a TPC.  A concurrent kernel (NCCL's all-reduce CTAs during the data-
@@ -1075,6 +1272,12 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
 }  // namespace
 
 extern "C" {
+
+#ifdef PG_TC_TRACE
+int pg_debug_tc_trace(long long* host_out) {     // debug build only: copies g_tc_trace (3 x 512 x 4 clock64 stamps)
+  return cudaMemcpyFromSymbol(host_out, g_tc_trace, sizeof(g_tc_trace)) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+}
+#endif
 
 int pg_tc_gemm(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, int c_dtype, int64_t M, int64_t N, int64_t K) {
   PG_CHECK_CTX(ctx);
