@@ -1138,61 +1138,146 @@ int narrow_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, void* Z
 
 // Data gradient of a narrow layer (N <= 16 even: the 10-class logits layer), bandwidth-shaped instead of a K' = 64 padded
 // GEMM: dX[m][k] = [mask[m][k] > 0] * sum_n dZ[m][n] W[k][n].  The launch is one pass over the ReLU mask (read) and dX
-// (write), 134 MB at C4; the GEMM form took 2.6x the HBM time because its single k-block per tile leaves the mask loads
-// exposed.  One thread: 8 consecutive k (one 16-byte store / mask load) x ROWS rows, W[k..k+8][0..N) held in registers.
-template <int N, int ROWS>
-__global__ void __launch_bounds__(256) narrow_dgrad_kernel(const float* __restrict__ dZ, const __nv_bfloat16* __restrict__ W,
-                                                           const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dX, int M, int K) {
-  const int kt = blockIdx.x * blockDim.x + threadIdx.x;          // which group of 8 k
-  if (kt * 8 >= K) return;
-  const int k8 = kt * 8;
-  float w[8][N];
-  {
+// (write), 134 MB at C4 = 20.5 us at the measured HBM rate; the GEMM form leaves the mask loads exposed (one k-block per tile).
+// One thread: 8 consecutive k (one 16-byte mask load / store per row), W[k..k+8][0..N) in registers as fp32 PAIRS so the
+// products run as packed FFMA2 (fma.rn.f32x2: two k per instruction, half the issue slots — the kernel is issue-bound
+// otherwise: 10 FMA per output element); a block owns a contiguous range of rows, stages its rows of bf16-rounded dZ once in
+// shared memory (as duplicated pairs, read as broadcasts) and keeps R mask loads per thread in flight (rolling prefetch).
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+
+// Mask rows arrive through a 3-stage shared-memory ring of bulk copies (cp.async.bulk, 16 rows x up to 4 KB per stage): the
+// bytes in flight (2 x 64 KB per SM while the third stage is consumed) live in shared memory, not in registers — 8 warps with
+// register-resident loads kept only ~32 KB per SM in flight and ran at 2.2 TB/s.
+constexpr int ND_ROWS = 16, ND_STAGES = 3, ND_THREADS = 256, ND_SEG = ND_THREADS * 16;      // 4 KB of a mask row per block
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int N, bool HAS_MASK>
+__global__ void __launch_bounds__(ND_THREADS, 1) narrow_dgrad_kernel(const float* __restrict__ dZ, const __nv_bfloat16* __restrict__ W,
+                                                                     const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dX, int M, int K,
+                                                                     int rows_per_block) {
+  extern __shared__ __align__(128) uint8_t nd_smem[];
+  // layout: [ND_STAGES][ND_ROWS][ND_SEG] mask ring | full barriers | dz2[rows][N] pairs
+  uint8_t* ring = nd_smem;
+  const uint32_t ring_u32 = smem_u32(ring);
+  const uint32_t bar0 = ring_u32 + (HAS_MASK ? ND_STAGES * ND_ROWS * ND_SEG : 0);
+  unsigned long long* dz2 = reinterpret_cast<unsigned long long*>(nd_smem + (HAS_MASK ? ND_STAGES * ND_ROWS * ND_SEG : 0) + 64);
+  const int m_begin = blockIdx.y * rows_per_block;
+  const int m_end = min(M, m_begin + rows_per_block);
+  if (m_begin >= m_end) return;
+  const int rows = m_end - m_begin;
+  const int kbase = blockIdx.x * (ND_THREADS * 8);                // first k of this block's column segment
+  const uint32_t seg_bytes = (uint32_t)min(ND_THREADS * 8, K - kbase) * 2u;
+  const int num_chunks = (rows + ND_ROWS - 1) / ND_ROWS;
+  auto issue = [&](int chunk) {                                   // thread 0: one bulk copy per row of the chunk
+    const int st = chunk % ND_STAGES;
+    const int r0 = chunk * ND_ROWS, nr = min(ND_ROWS, rows - r0);
+    const uint32_t bar = bar0 + 8u * st;
+    mbar_expect_tx(bar, (uint32_t)nr * seg_bytes);
+    for (int r = 0; r < nr; ++r)
+      bulk_load_1d(ring_u32 + (uint32_t)((st * ND_ROWS + r) * ND_SEG), mask + (size_t)(m_begin + r0 + r) * K + kbase, seg_bytes, bar);
+  };
+  if (HAS_MASK && threadIdx.x == 0) {
+    for (int st = 0; st < ND_STAGES; ++st) mbar_init(bar0 + 8u * st, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int c = 0; c < ND_STAGES && c < num_chunks; ++c) issue(c);
+  }
+  for (int i = threadIdx.x; i < rows * N; i += ND_THREADS) {
+    const float z = __bfloat162float(__float2bfloat16_rn(__ldg(dZ + (size_t)m_begin * N + i)));
+    dz2[i] = pack_f32x2(z, z);
+  }
+  const int k8 = kbase + threadIdx.x * 8;
+  const bool active = k8 < K;
+  unsigned long long w2[4][N];                                    // w2[p][n] = (W[k8 + 2p][n], W[k8 + 2p + 1][n])
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int n = 0; n < N; ++n) w2[p][n] = 0ull;
+  if (active) {
     const uint4* wp = reinterpret_cast<const uint4*>(W + (size_t)k8 * N);    // 8 rows of N bf16: 16 N bytes, contiguous
     __nv_bfloat16 tmp[8 * N];
 #pragma unroll
     for (int i = 0; i < N; ++i) reinterpret_cast<uint4*>(tmp)[i] = __ldg(wp + i);
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int n = 0; n < N; ++n) w[k][n] = __bfloat162float(tmp[k * N + n]);
+      for (int n = 0; n < N; ++n) w2[p][n] = pack_f32x2(__bfloat162float(tmp[(2 * p) * N + n]), __bfloat162float(tmp[(2 * p + 1) * N + n]));
   }
-  for (int m0 = blockIdx.y * ROWS; m0 < M; m0 += gridDim.y * ROWS) {
+  __syncthreads();                                                // dz2 staged, barriers initialised
+  uint4* op = reinterpret_cast<uint4*>(dX + (size_t)m_begin * K + k8);
+  const size_t pitch = (size_t)(K >> 3);
+  for (int chunk = 0; chunk < num_chunks; ++chunk) {
+    const int st = chunk % ND_STAGES;
+    if (HAS_MASK) mbar_wait(bar0 + 8u * st, (uint32_t)(chunk / ND_STAGES) & 1u);
+    const int r0 = chunk * ND_ROWS, nr = min(ND_ROWS, rows - r0);
+    if (active) {
+#pragma unroll 4
+      for (int r = 0; r < nr; ++r) {
+        uint4 cur = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        if (HAS_MASK) cur = *reinterpret_cast<const uint4*>(ring + (size_t)(st * ND_ROWS + r) * ND_SEG + threadIdx.x * 16);
+        unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+        const ulonglong2* zr = reinterpret_cast<const ulonglong2*>(dz2 + (size_t)(r0 + r) * N);
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      const int m = m0 + r;
-      if (m >= M) break;
-      float dz[N];
-      const float2* zp = reinterpret_cast<const float2*>(dZ + (size_t)m * N);
+        for (int n = 0; n < N; n += 2) {
+          const ulonglong2 z = zr[n >> 1];
 #pragma unroll
-      for (int i = 0; i < N / 2; ++i) { const float2 t = __ldg(zp + i); dz[2 * i] = t.x; dz[2 * i + 1] = t.y; }
-      // the tensor-core path multiplies bf16(dZ): keep the same operand rounding
+          for (int p = 0; p < 4; ++p) acc[p] = ffma2(z.x, w2[p][n], acc[p]);
 #pragma unroll
-      for (int n = 0; n < N; ++n) dz[n] = __bfloat162float(__float2bfloat16_rn(dz[n]));
-      uint4 mk = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
-      if (mask != nullptr) mk = __ldg(reinterpret_cast<const uint4*>(mask + (size_t)m * K + k8));
-      const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk);
-      __nv_bfloat162 pk[4];
+          for (int p = 0; p < 4; ++p) acc[p] = ffma2(z.y, w2[p][n + 1], acc[p]);
+        }
+        const uint32_t mw[4] = {cur.x, cur.y, cur.z, cur.w};
+        uint32_t out[4];
 #pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-        for (int n = 0; n < N; ++n) { a0 = fmaf(dz[n], w[k][n], a0); a1 = fmaf(dz[n], w[k + 1][n], a1); }
-        a0 = __bfloat162float(me[k]) > 0.0f ? a0 : 0.0f;
-        a1 = __bfloat162float(me[k + 1]) > 0.0f ? a1 : 0.0f;
-        pk[k / 2] = __floats2bfloat162_rn(a0, a1);
+        for (int p = 0; p < 4; ++p) {
+          float a0 = __uint_as_float((uint32_t)acc[p]), a1 = __uint_as_float((uint32_t)(acc[p] >> 32));
+          a0 = __uint_as_float(mw[p] << 16) > 0.0f ? a0 : 0.0f;                  // bf16 -> fp32 is a 16-bit shift
+          a1 = __uint_as_float(mw[p] & 0xffff0000u) > 0.0f ? a1 : 0.0f;
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(a0, a1);
+          out[p] = *reinterpret_cast<const uint32_t*>(&pk);
+        }
+        op[(size_t)(r0 + r) * pitch] = make_uint4(out[0], out[1], out[2], out[3]);
       }
-      *reinterpret_cast<uint4*>(dX + (size_t)m * K + k8) = *reinterpret_cast<uint4*>(pk);
+    }
+    if (HAS_MASK) {
+      __syncthreads();                                            // everyone has read the stage: refill it
+      if (threadIdx.x == 0 && chunk + ND_STAGES < num_chunks) issue(chunk + ND_STAGES);
     }
   }
 }
 
 template <int N>
 int launch_narrow_dgrad(pg_ctx* ctx, const void* dZ, const void* W, const void* mask, void* dX, int64_t M, int64_t K) {
-  constexpr int ROWS = 4;
-  dim3 grid((unsigned)pg_cdiv(K / 8, 256), (unsigned)std::min<int64_t>(pg_cdiv(M, ROWS), (int64_t)ctx->num_sms * 16 / std::max<int64_t>(1, pg_cdiv(K / 8, 256))));
-  if (grid.y < 1) grid.y = 1;
-  narrow_dgrad_kernel<N, ROWS><<<grid, 256, 0, ctx->stream>>>((const float*)dZ, (const __nv_bfloat16*)W, (const __nv_bfloat16*)mask, (__nv_bfloat16*)dX, (int)M, (int)K);
+  const int64_t gx = pg_cdiv(K, ND_THREADS * 8);
+  int64_t gy = std::max<int64_t>(1, ctx->num_sms / gx);         // one block per SM: each amortises its W registers over M / gy rows
+  int64_t rows_per_block = pg_cdiv(M, gy);
+  rows_per_block = std::min<int64_t>(rows_per_block, 256);       // shared-memory bound of the staged dZ rows (256 x N pairs x 8 B <= 32 KB)
+  gy = pg_cdiv(M, rows_per_block);
+  PG_REQUIRE(gy <= 65535, "narrow data gradient: batch too large");
+  const bool has_mask = mask != nullptr;
+  const size_t smem = (has_mask ? (size_t)ND_STAGES * ND_ROWS * ND_SEG : 0) + 64 + (size_t)rows_per_block * N * sizeof(unsigned long long);
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int max_smem = ND_STAGES * ND_ROWS * ND_SEG + 64 + 256 * N * (int)sizeof(unsigned long long);
+    PG_CHECK_CUDA(cudaFuncSetAttribute(narrow_dgrad_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PG_CHECK_CUDA(cudaFuncSetAttribute(narrow_dgrad_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr_set = true;
+  }
+  const dim3 grid((unsigned)gx, (unsigned)gy);
+  if (has_mask)
+    narrow_dgrad_kernel<N, true><<<grid, ND_THREADS, smem, ctx->stream>>>((const float*)dZ, (const __nv_bfloat16*)W, (const __nv_bfloat16*)mask,
+                                                                          (__nv_bfloat16*)dX, (int)M, (int)K, (int)rows_per_block);
+  else
+    narrow_dgrad_kernel<N, false><<<grid, ND_THREADS, smem, ctx->stream>>>((const float*)dZ, (const __nv_bfloat16*)W, nullptr,
+                                                                           (__nv_bfloat16*)dX, (int)M, (int)K, (int)rows_per_block);
   PG_LAUNCHED(ctx);
   return PG_OK;
 }
@@ -1263,7 +1348,7 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
     PG_LAUNCHED(ctx);
     if (dx_colsum) PG_CHECK_CUDA(cudaMemsetAsync(dx_colsum, 0, (size_t)K * sizeof(float), ctx->stream));
     Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, dx_f32, 0, (float*)dx_colsum, nullptr, 1, 1 << 30};
-    rc = launch_tc<false, false, 256>(ctx, dZp, Wp, dX, M, K, NARROW_K, NARROW_K, NARROW_K, epi);
+    rc = tc_dispatch(ctx, 1, dZp, Wp, dX, M, K, NARROW_K, epi);      // pair kernel + staged epilogue when the output is wide enough
     if (rc != PG_OK) return rc;
   }
   return PG_OK;

@@ -45,6 +45,17 @@ gemms = [
     ("wgrad_L2", lambda: call("pg_tc_linear_bwd", ctx.h, A1.ptr, None, G2.ptr, 2, dW2.ptr, db.ptr, None, None, B, D_H, D_H), 2.0 * B * D_H * D_H),
     ("wgrad_L1", lambda: call("pg_tc_linear_bwd", ctx.h, A0.ptr, None, G1.ptr, 2, dW1.ptr, db.ptr, None, None, B, D_IN, D_H), 2.0 * B * D_IN * D_H),
 ]
+# the narrow (4096 -> 10) layer: forward (fp32 logits) and the whole backward (dW, db, dX masked by the hidden activation)
+W3 = dev_bf16((0.02 * rng.standard_normal((D_H, 10))).astype(np.float32))
+b3 = pg.DeviceArray.from_numpy(ctx, np.zeros(10, np.float32))
+Z = pg.DeviceArray.empty(ctx, (B, 10), np.float32)
+dZ = pg.DeviceArray.from_numpy(ctx, (1e-4 * rng.standard_normal((B, 10))).astype(np.float32))
+dW3 = pg.DeviceArray.empty(ctx, (D_H, 10), np.float32); db3 = pg.DeviceArray.empty(ctx, (10,), np.float32)
+gemms += [
+    ("narrow_fwd", lambda: call("pg_tc_linear_fwd", ctx.h, A1.ptr, W3.ptr, b3.ptr, Z.ptr, 0, B, D_H, 10, 0), 2.0 * B * D_H * 10),
+    ("narrow_bwd", lambda: call("pg_tc_linear_bwd", ctx.h, A1.ptr, W3.ptr, dZ.ptr, 0, dW3.ptr, db3.ptr, A2.ptr, A1.ptr, B, D_H, 10), 4.0 * B * D_H * 10),
+    ("narrow_dx", lambda: call("pg_tc_linear_bwd", ctx.h, None, W3.ptr, dZ.ptr, 0, None, None, A2.ptr, A1.ptr, B, D_H, 10), 2.0 * B * D_H * 10),
+]
 for _, fn, _ in gemms:
     fn(); fn()
 torch.cuda.synchronize()
@@ -59,5 +70,6 @@ tot = {}
 for name, flop, a, b in evs:
     t = tot.setdefault(name, [0.0, flop])
     t[0] += a.elapsed_time(b) / reps
-sum_ms = sum(t[0] for t in tot.values()); sum_fl = sum(t[1] for t in tot.values())
+wide = {n: t for n, t in tot.items() if not n.startswith("narrow")}
+sum_ms = sum(t[0] for t in wide.values()); sum_fl = sum(t[1] for t in wide.values())
 print("  ".join(f"{n} {t[0]*1e3:.1f} us {t[1]/t[0]/1e9:.0f} TF" for n, t in tot.items()), f" | total {sum_ms*1e3:.1f} us {sum_fl/sum_ms/1e9:.0f} TFLOP/s")
