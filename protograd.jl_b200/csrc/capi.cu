@@ -63,8 +63,8 @@ int pg_init(int device, pg_ctx** out) {
   PG_CHECK_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   PG_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  PG_CHECK_CUDA(cudaMalloc((void**)&c->counters, 64 * sizeof(unsigned int)));
-  PG_CHECK_CUDA(cudaMemset(c->counters, 0, 64 * sizeof(unsigned int)));
+  PG_CHECK_CUDA(cudaMalloc((void**)&c->counters, 256 * sizeof(unsigned int)));
+  PG_CHECK_CUDA(cudaMemset(c->counters, 0, 256 * sizeof(unsigned int)));
   PG_CHECK_CUDA(cudaMalloc((void**)&c->result_slot, 16 * sizeof(double)));
   PG_CHECK_CUDA(cudaMallocHost((void**)&c->result_host, 16 * sizeof(double)));
   *out = c;

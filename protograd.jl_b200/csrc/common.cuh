@@ -23,7 +23,7 @@ struct pg_ctx {
   // padded bf16 operand copies of narrow (N <= 32) tensor-core layers
   void* aux = nullptr;
   size_t aux_bytes = 0;
-  // small persistent scratch: [0..63] counters (zeroed), [64..] result slots
+  // small persistent scratch (256 words, zeroed): [0..63] reduction / tile-scheduler counters, [64..255] K-split tail flags of the pair GEMM
   unsigned int* counters = nullptr;
   double* result_slot = nullptr;     // device
   double* result_host = nullptr;     // pinned

@@ -53,6 +53,13 @@ struct Epi {
   float* db;                    // weight-gradient launches: fused bias gradient, as partials db[m_blk][n] = sum over this m-block's share of the k-blocks of B[k][n] (nullable)
   int splits;                   // split-K: work item = (tile, split); split s writes its fp32 partial to C + s*M*N
   int kb_per_split;
+  // pair kernel, plain fp32 outputs (weight gradients): the last `tail` tiles (the partial last wave) are split into two K
+  // halves so that the wave costs half a tile (256 tiles on 74 pairs: 3.5 instead of 4 tile times).  The second half's
+  // partial goes to tail_ws (tail x 256 x 256 fp32) and is added by the first half's epilogue; tail_flags (tail x 4, zero
+  // between launches) order the two.  db then holds two partial rows per m-block.
+  int tail;
+  float* tail_ws;
+  unsigned int* tail_flags;
 };
 
 #include "tc_ptx.cuh"
@@ -586,6 +593,14 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     m0 = (g * GROUP_M2 + r % gm) * 256;
     n0 = (r / gm) * BN;
   };
+  // work items: [0, split_first) whole tiles; [split_first, num_tiles) SECOND K half of the tail tiles (partials, fetched
+  // first so that they never wait); [num_tiles, num_items) FIRST K half of the tail tiles (+ the partial, final store)
+  const int num_items = num_tiles + epi.tail, split_first = num_tiles - epi.tail, kb_half = num_kb >> 1;
+  auto decode = [&](int item, int& tile, int& kb0, int& kb1, int& part) {
+    if (item < split_first) { tile = item; kb0 = 0; kb1 = num_kb; part = -1; }
+    else if (item < num_tiles) { tile = item; kb0 = kb_half; kb1 = num_kb; part = 1; }
+    else { tile = item - epi.tail; kb0 = 0; kb1 = kb_half; part = 0; }
+  };
 
 #ifdef PG_TC_TRACE
   if (threadIdx.x < 3 * TRACE_TILES * 4) reinterpret_cast<volatile long long*>(smem_aligned + BAR_OFF + 512)[threadIdx.x] = 0;
@@ -627,19 +642,20 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (++slot == RING) slot = 0;
       };
       TileFeed feed(ring_base, false);                   // peer: reads what the leader published (st.async + complete_tx)
-      int tile;
-      if (rank == 0) { tile = (int)first_tile; publish(tile); } else { tile = feed.next(); }
+      int item;
+      if (rank == 0) { item = (int)first_tile; publish(item); } else { item = feed.next(); }
       [[maybe_unused]] int tn = 0;
-      while (tile < num_tiles) {
+      while (item < num_items) {
         int next_tile = 0;
         if (rank == 0) next_tile = (int)sched_fetch(sched);   // consumed after this tile's loads have been issued
-        int m0, n0;
+        int tile, kb0, kb1, part, m0, n0;
+        decode(item, tile, kb0, kb1, part);
         tile_coords(tile, m0, n0);
         const int my_m0 = m0 + (int)rank * 128, my_n0 = n0 + (int)rank * 128;
         TC_TRACE(0, tn, 0);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          if (kb == 0) TC_TRACE(0, tn, 1);
+          if (kb == kb0) TC_TRACE(0, tn, 1);
           const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
           const uint32_t lbar = map_to_rank(full_bar(stage), 0);
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE2_BYTES);
@@ -659,7 +675,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
         TC_TRACE(0, tn, 2);
-        if (rank == 0) { publish(next_tile); tile = next_tile; } else { tile = feed.next(); }
+        if (rank == 0) { publish(next_tile); item = next_tile; } else { item = feed.next(); }
         TC_TRACE(0, tn, 3);
         ++tn;
       }
@@ -674,15 +690,17 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int acc = 0; uint32_t acc_phase = 0;
       TileFeed feed(ring_base, false);
       [[maybe_unused]] int tn = 0;
-      for (int tile = feed.next(); tile < num_tiles; tile = feed.next(), ++tn) {
+      for (int item = feed.next(); item < num_items; item = feed.next(), ++tn) {
+        int tile, kb0, kb1, part;
+        decode(item, tile, kb0, kb1, part);
         TC_TRACE(1, tn, 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
         tcgen05_fence_after();
         TC_TRACE(1, tn, 1);
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);             // both CTAs' bytes have landed
-          if (kb == 0) TC_TRACE(1, tn, 2);
+          if (kb == kb0) TC_TRACE(1, tn, 2);
           if (DBW) mbar_arrive_cluster(map_to_rank(ready_bar(stage), 1));   // tell the peer's reducer warp
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
@@ -690,10 +708,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t ad = A_MN ? make_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
             const uint64_t bd = B_MN ? make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            umma_bf16_2sm(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0);
           }
           tcgen05_commit_2sm(empty_bar(stage));          // frees the slot in both CTAs
-          if (kb == num_kb - 1) tcgen05_commit_2sm(tfull_bar(acc));
+          if (kb == kb1 - 1) tcgen05_commit_2sm(tfull_bar(acc));
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
         TC_TRACE(1, tn, 3);
@@ -709,11 +727,13 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     float acc4[4] = {0.f, 0.f, 0.f, 0.f};
     int stage = 0; uint32_t phase = 0;
     TileFeed feed(ring_base, false);
-    for (int tile = feed.next(); tile < num_tiles; tile = feed.next()) {
-      int m0, n0;
+    const int db_rows = epi.tail > 0 ? 2 : 1;            // partial rows per m-block: [whole tile or first K half][second K half]
+    for (int item = feed.next(); item < num_items; item = feed.next()) {
+      int tile, kb0, kb1, part, m0, n0;
+      decode(item, tile, kb0, kb1, part);
       tile_coords(tile, m0, n0);
       const int m_blk = m0 / 256;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(rank == 0 ? full_bar(stage) : ready_bar(stage), phase);
         if (kb % num_m == m_blk) {
           const uint8_t* sb = smem_aligned + stage * STAGE2_BYTES + A_STAGE_BYTES + box_off;
@@ -733,7 +753,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int cbase = n0 + (int)rank * 128 + col0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (cbase + j < N) epi.db[(size_t)m_blk * N + cbase + j] = acc4[j];
+        if (cbase + j < N) {
+          epi.db[(size_t)(m_blk * db_rows + (part == 1 ? 1 : 0)) * N + cbase + j] = acc4[j];
+          if (db_rows == 2 && part < 0) epi.db[(size_t)(m_blk * 2 + 1) * N + cbase + j] = 0.0f;
+        }
         acc4[j] = 0.f;
       }
     }
@@ -754,16 +777,35 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int acc = 0; uint32_t acc_phase = 0;
       TileFeed feed(ring_base, false);
       [[maybe_unused]] int tn = 0;
-      for (int tile = feed.next(); tile < num_tiles; tile = feed.next(), ++tn) {
-        int m0, n0;
+      for (int item = feed.next(); item < num_items; item = feed.next(), ++tn) {
+        int tile, kb0, kb1, part, m0, n0;
+        decode(item, tile, kb0, kb1, part);
         tile_coords(tile, m0, n0);
         if (threadIdx.x == 64) TC_TRACE(2, tn, 0);
         const int row0 = m0 + (int)rank * 128;
         const int c_begin = half * 128;
-        if (has_mask && elected && n0 + c_begin < N) {   // round 0's mask box; the previous tile's last store has long been read
+        // K-split tail tiles (fp32 outputs only): part 1 stores its partial into the tail workspace (map_mask describes it: a
+        // [tail * 256][256] fp32 matrix), part 0 loads that partial like a mask box and adds it before the final store
+        const int ws_row0 = (tile - split_first) * 256 + (int)rank * 128;
+        unsigned int* flag = epi.tail_flags + ((tile - split_first) * 2 + (int)rank) * 2 + half;
+        const bool has_in = has_mask || part == 0;
+        const int in_c = part == 0 ? c_begin : n0 + c_begin, in_r = part == 0 ? ws_row0 : row0;
+        const int out_c = part == 1 ? c_begin : n0 + c_begin, out_r = part == 1 ? ws_row0 : row0;
+        const CUtensorMap* out_map = part == 1 ? &map_mask : &map_c;
+        if (has_in && elected && n0 + c_begin < N) {     // round 0's mask / partial box; the previous tile's last store has long been read
+          if (part == 0) {                               // the quadrant's partial must have landed (its writer was scheduled earlier)
+            unsigned int f;
+            const long long t0 = clock64();
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory");
+              if (f == 0u && clock64() - t0 > 4000000000ll) __trap();          // bounded like the mbarrier waits
+            } while (f == 0u);
+            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(0u) : "memory");     // re-armed for the next launch
+          }
           tma_store_wait_read();
           mbar_expect_tx(mask_bar(half), OUT_BOX_BYTES);
-          tma_load_2d(box, &map_mask, mask_bar(half), n0 + c_begin, row0);
+          tma_load_2d(box, &map_mask, mask_bar(half), in_c, in_r);
         }
         float bl[4];
         const int use_bl = epi.bias != nullptr ? 1 : 0;
@@ -790,11 +832,20 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
           if (elected) tma_store_wait_read();            // the previous box has left the staging buffer
           named_bar_sync(bar_free, 128);
-          if (has_mask && live) { mbar_wait(mask_bar(half), mphase); mphase ^= 1; }
+          if (has_in && live) { mbar_wait(mask_bar(half), mphase); mphase ^= 1; }
           if (f32) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-              st_shared_v4(my_row + ((((uint32_t)u) ^ sw) << 4), r[0][4 * u], r[0][4 * u + 1], r[0][4 * u + 2], r[0][4 * u + 3]);
+            for (int u = 0; u < 8; ++u) {
+              const uint32_t addr = my_row + ((((uint32_t)u) ^ sw) << 4);
+              if (part == 0) {                           // + the second K half's partial
+                const uint4 pv = ld_shared_v4(addr);
+                r[0][4 * u] = __float_as_uint(__uint_as_float(r[0][4 * u]) + __uint_as_float(pv.x));
+                r[0][4 * u + 1] = __float_as_uint(__uint_as_float(r[0][4 * u + 1]) + __uint_as_float(pv.y));
+                r[0][4 * u + 2] = __float_as_uint(__uint_as_float(r[0][4 * u + 2]) + __uint_as_float(pv.z));
+                r[0][4 * u + 3] = __float_as_uint(__uint_as_float(r[0][4 * u + 3]) + __uint_as_float(pv.w));
+              }
+              st_shared_v4(addr, r[0][4 * u], r[0][4 * u + 1], r[0][4 * u + 2], r[0][4 * u + 3]);
+            }
           } else {
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
@@ -830,13 +881,18 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           fence_proxy_async_smem();
           named_bar_sync(bar_written, 128);
           if (elected && live) {
-            tma_store_2d(&map_c, box, n0 + c_begin + c0, row0);
-            if (has_mask && rd + 1 < rounds && n0 + c_begin + c0 + cols_per_round < N) {
+            tma_store_2d(out_map, box, out_c + c0, out_r);
+            if (has_in && rd + 1 < rounds && n0 + c_begin + c0 + cols_per_round < N) {
               tma_store_wait_read();
               mbar_expect_tx(mask_bar(half), OUT_BOX_BYTES);
-              tma_load_2d(box, &map_mask, mask_bar(half), n0 + c_begin + c0 + cols_per_round, row0);
+              tma_load_2d(box, &map_mask, mask_bar(half), in_c + c0 + cols_per_round, in_r);
             }
           }
+        }
+        if (part == 1 && elected) {                      // the quadrant's partial is complete and visible: release its reader
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
         }
         if (threadIdx.x == 64) TC_TRACE(2, tn, 2);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -965,6 +1021,17 @@ int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int
   return PG_OK;
 }
 
+constexpr int TAIL_FLAG_SLOT = 64;     // pg_ctx::counters[64 ..]: tail_flags (4 per split tile, <= 37 tiles)
+
+// how many tiles of the last (partial) wave of an M x N pair-kernel launch are worth splitting in two K halves
+int tail_split_tiles(const pg_ctx* ctx, int64_t M, int64_t N, int64_t K) {
+  static const bool off = getenv("PG_TC_NO_TAIL_SPLIT") != nullptr;      // A/B switch
+  const int64_t tiles = pg_cdiv(M, 256) * pg_cdiv(N, 256), pairs = ctx->num_sms / 2;
+  if (off || tiles <= pairs || pg_cdiv(K, BLOCK_K) < 16) return 0;
+  const int64_t rem = tiles % pairs;
+  return (rem > 0 && 2 * rem <= pairs) ? (int)rem : 0;
+}
+
 template <bool A_MN, bool B_MN, bool DBW, bool STAGED>
 int launch_tc2_impl(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, const Epi& epi) {
   CUtensorMap ma, mb, mc, mm;
@@ -978,17 +1045,20 @@ int launch_tc2_impl(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t 
     if (rc != PG_OK) return rc;
     mm = mc;
     if (epi.mask != nullptr) rc = make_map(ctx, &mm, epi.mask, M, N, N, 64, 128);
+    else if (epi.tail > 0) rc = make_map(ctx, &mm, epi.tail_ws, (int64_t)epi.tail * 256, 256, 256, 32, 128, true);
     if (rc != PG_OK) return rc;
   } else {
+    PG_REQUIRE(epi.tail == 0, "tail split needs the staged epilogue");
     mc = ma; mm = ma;
   }
+  PG_REQUIRE(epi.tail == 0 || (epi.out_f32 && epi.mask == nullptr && epi.bias == nullptr && !epi.relu), "tail split: plain fp32 outputs only");
   auto kern = tc_gemm2_kernel<A_MN, B_MN, DBW, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
     PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     attr_set = true;
   }
-  int64_t tiles = pg_cdiv(M, 256) * pg_cdiv(N, 256);
+  int64_t tiles = pg_cdiv(M, 256) * pg_cdiv(N, 256) + epi.tail;
   int clusters = (int)(tiles < ctx->num_sms / 2 ? tiles : ctx->num_sms / 2);
   kern<<<2 * clusters, NUM_THREADS + (DBW ? 32 : 0), SMEM2_BYTES, ctx->stream>>>(ma, mb, mc, mm, C, (int)M, (int)N, (int)K, epi, ctx->counters + SCHED_SLOT);
   PG_LAUNCHED(ctx);
@@ -1405,11 +1475,18 @@ static int tc_linear_bwd_impl(pg_ctx* ctx, const void* X, const void* W, const v
     const bool two = use_2cta(ctx, K, N) && !dbw_1cta_env;
     const int64_t m_blocks = two ? pg_cdiv(K, 256) : pg_cdiv(K, BLOCK_M);
     const bool fuse_db = db != nullptr && m_blocks >= 4;
+    // the partial last wave of the pair kernel is split in two K halves (Epi::tail); scratch: [db partials][tail partial tiles]
+    static const bool direct_epi = getenv("PG_TC_DIRECT_EPI") != nullptr;
+    const int tail = (two && !direct_epi) ? tail_split_tiles(ctx, K, N, M) : 0;
+    const int db_rows = tail > 0 ? 2 : 1;
+    const size_t db_bytes = fuse_db ? (((size_t)m_blocks * db_rows * N * sizeof(float) + 1023) & ~(size_t)1023) : 0;
     float* db_part = nullptr;
-    if (fuse_db) {      // per-(m-block, column) partial sums in scratch; summed in a fixed order below: no floating-point atomics
-      rc = pg_ws_ensure(ctx, (size_t)m_blocks * N * sizeof(float));
+    float* tail_ws = nullptr;
+    if (fuse_db || tail > 0) {      // per-(m-block, column) partial sums in scratch; summed in a fixed order below: no floating-point atomics
+      rc = pg_ws_ensure(ctx, db_bytes + (size_t)tail * 256 * 256 * sizeof(float));
       if (rc != PG_OK) return rc;
-      db_part = (float*)ctx->ws;
+      if (fuse_db) db_part = (float*)ctx->ws;
+      tail_ws = (float*)((char*)ctx->ws + db_bytes);
     }
     // few output tiles but a deep reduction (K' = batch): the small layers of the example nets (256x120, 120x84 at 8,192
     // samples were ONE or TWO CTAs walking 128 k-blocks: 73 / 55 us).  Split the batch over the idle SMs, fp32 partials,
@@ -1429,7 +1506,7 @@ static int tc_linear_bwd_impl(pg_ctx* ctx, const void* X, const void* W, const v
       if (rc != PG_OK) return rc;
       target = ctx->ws;
     }
-    Epi epi{nullptr, nullptr, 0, 1, 0, nullptr, db_part, splits, kb_per};
+    Epi epi{nullptr, nullptr, 0, 1, 0, nullptr, db_part, splits, kb_per, tail, tail_ws, ctx->counters + TAIL_FLAG_SLOT};
     rc = tc_dispatch(ctx, 2, X, dY, target, K, N, M, epi);
     if (rc != PG_OK) return rc;
     if (splits > 1) {
@@ -1437,7 +1514,7 @@ static int tc_linear_bwd_impl(pg_ctx* ctx, const void* X, const void* W, const v
       PG_LAUNCHED(ctx);
     }
     if (fuse_db) {
-      reduce_f32_kernel<<<(unsigned)pg_cdiv(N, 256), 256, 0, ctx->stream>>>(db_part, (float*)db, N, (int)m_blocks);
+      reduce_f32_kernel<<<(unsigned)pg_cdiv(N, 256), 256, 0, ctx->stream>>>(db_part, (float*)db, N, (int)m_blocks * db_rows);
       PG_LAUNCHED(ctx);
       db = nullptr;
     }
