@@ -1352,6 +1352,49 @@ int launch_narrow_dgrad(pg_ctx* ctx, const void* dZ, const void* W, const void* 
   return PG_OK;
 }
 
+// One pass over dZ [M][N] (f32, N <= 32) for the narrow layer's backward: dZt [32][M] bf16 (zero rows beyond N: the K-major B
+// operand of the weight-gradient GEMM) and db[n] = sum_m dZ[m][n] — per-block partials, summed in block order by the block that
+// finishes last (deterministic).  Replaces three launches (pad copy, column sum, partial reduce) of ~5 us latency each.
+constexpr int PREP_COUNTER_SLOT = 4;
+__global__ void __launch_bounds__(256) narrow_prep_kernel(const float* __restrict__ dZ, __nv_bfloat16* __restrict__ dZt, float* __restrict__ db,
+                                                          float* __restrict__ part, unsigned int* __restrict__ ticket, int64_t M, int N) {
+  __shared__ float wsum[8][32];
+  __shared__ bool last;
+  const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float my = 0.0f;                                  // lane n ends up with the warp's sum of column n
+  for (int n = 0; n < NARROW_N; ++n) {
+    float v = (n < N && m < M) ? __ldg(dZ + m * N + n) : 0.0f;
+    if (m < M) dZt[(int64_t)n * M + m] = __float2bfloat16_rn(v);
+    if (db != nullptr && n < N) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == n) my = v;
+    }
+  }
+  if (db == nullptr) return;
+  wsum[warp][lane] = my;
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += wsum[w][threadIdx.x];
+    part[(int64_t)blockIdx.x * N + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < N) {
+    float s = 0.0f;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(part + (int64_t)b * N + threadIdx.x);
+    db[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) *ticket = 0;               // re-armed for the next launch
+}
+
 int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* dW, void* db, void* dX, const void* mask, void* dx_colsum, int64_t M, int64_t K, int64_t N,
                int dx_f32 = 0) {
   PG_REQUIRE(K % 8 == 0 && M % 8 == 0, "narrow tensor-core layer needs K % 8 == 0 and batch % 8 == 0 (TMA 16-byte pitch)");
@@ -1368,7 +1411,17 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
   static const bool narrow_gemm_dx = getenv("PG_NARROW_DGRAD_GEMM") != nullptr;      // A/B switch, read once
   const bool simt_dx = dX != nullptr && !dx_f32 && dx_colsum == nullptr && N % 2 == 0 && N <= 16 && !narrow_gemm_dx;
   const bool gemm_dx = dX != nullptr && !simt_dx;
-  if (dW || gemm_dx) {
+  bool db_done = false;
+  if (dW && !gemm_dx) {       // one pass over dZ: transposed bf16 operand copy + (deterministic) bias gradient
+    const unsigned blocks = (unsigned)pg_cdiv(M, 256);
+    if (db) {
+      rc = pg_ws_ensure(ctx, (size_t)blocks * N * sizeof(float));
+      if (rc != PG_OK) return rc;
+    }
+    narrow_prep_kernel<<<blocks, 256, 0, ctx->stream>>>((const float*)dZ, dZt, (float*)db, (float*)ctx->ws, ctx->counters + PREP_COUNTER_SLOT, M, (int)N);
+    PG_LAUNCHED(ctx);
+    db_done = db != nullptr;
+  } else if (dW || gemm_dx) {
     int64_t total = M * NARROW_K;
     pad_copy_kernel<float><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const float*)dZ, gemm_dx ? dZp : nullptr, dW ? dZt : nullptr, M, (int)N,
                                                                                    gemm_dx ? NARROW_K : 0, dW ? NARROW_N : 0);
@@ -1396,7 +1449,7 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
       PG_LAUNCHED(ctx);
     }
   }
-  if (db) {
+  if (db && !db_done) {
     rc = pg_colsum_launch(ctx, PG_F32, dZ, db, M, N);
     if (rc != PG_OK) return rc;
   }
