@@ -50,7 +50,9 @@ def test_tc_gemm_layouts(pg, layout, M, N, K):
     assert rel_err(cd.numpy(), ref) <= 1e-5
 
 
-@pytest.mark.parametrize("M,K,N,act", [(256, 784, 512, 1), (1024, 512, 4096, 1), (200, 264, 72, 0), (512, 4096, 10, 0), (64, 128, 32, 0)])
+# (1000, 776, 520): pair kernel with the staged TMA-store epilogue on ragged tiles — partial row blocks, a last column box of 8
+# valid columns, the ReLU' mask box clipped the same way
+@pytest.mark.parametrize("M,K,N,act", [(256, 784, 512, 1), (1024, 512, 4096, 1), (200, 264, 72, 0), (512, 4096, 10, 0), (64, 128, 32, 0), (1000, 776, 520, 1)])
 def test_tc_linear_fwd_bwd(pg, M, K, N, act):
     """pg_tc_linear_fwd/bwd (wide: tcgen05; N <= 32: skinny) vs float64 on bf16-rounded operands."""
     from protograd_b200.capi import call
@@ -161,6 +163,31 @@ def test_tc_training_step_c4_bench_batch(pg):
     state = O.Adam(stepsize=1e-3).init(O.vec(p0).astype(np.float32).copy())
     state.step(O.vec(g).astype(np.float32))
     assert rel_err(m.vec(), state.x) <= 1e-6
+
+
+def test_tc_wgrad_tail_k_split(pg):
+    """Weight gradient with 9 x 9 = 81 pair tiles on 74 SM pairs: the 7 tiles of the partial last wave are split into two K
+    halves (17 k-blocks: 8 + 9, the last one ragged), the second half's partial travels through the scratch tile + flag and
+    the fused bias gradient keeps two partial rows per m-block.  Must match float64 and be bit-identical run to run."""
+    from protograd_b200.capi import call
+    B, K, N = 1032, 2296, 2304
+    rng = np.random.default_rng(7)
+    X = _bf(pg, np.maximum(rng.standard_normal((B, K), dtype=np.float32), 0)); dY = _bf(pg, rng.standard_normal((B, N), dtype=np.float32))
+    ctx = pg.Context.get()
+    Xd, dYd = _dev_bf16(pg, X), _dev_bf16(pg, dY)
+    outs = []
+    for _ in range(2):
+        dWd, dbd = pg.DeviceArray.empty(ctx, (K, N), np.float32), pg.DeviceArray.empty(ctx, (N,), np.float32)
+        call("pg_tc_linear_bwd", ctx.h, Xd.ptr, None, dYd.ptr, 2, dWd.ptr, dbd.ptr, None, None, B, K, N)
+        outs.append((dWd.numpy(), dbd.numpy()))
+    dW = X.astype(np.float64).T @ dY.astype(np.float64)
+    assert rel_err(outs[0][0], dW) <= 1e-5
+    assert rel_err(outs[0][1], dY.astype(np.float64).sum(0)) <= 1e-5
+    # every 256 x 256 tile separately: a wrong or missing partial of one tail tile would hide in the global norm
+    for r0 in range(0, K, 256):
+        for c0 in range(0, N, 256):
+            assert rel_err(outs[0][0][r0:r0 + 256, c0:c0 + 256], dW[r0:r0 + 256, c0:c0 + 256]) <= 1e-5, (r0, c0)
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
 
 
 @pytest.mark.parametrize("layout", [0, 1, 2])
