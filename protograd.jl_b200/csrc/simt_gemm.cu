@@ -187,6 +187,24 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const T* __restrict_
   C[i] = s;
 }
 
+// same, with the GEMM's epilogue (bias / ReLU / ReLU' mask) and a pitched output: split-K forward and data-gradient launches
+template <typename T>
+__global__ void __launch_bounds__(256) splitk_reduce_epi_kernel(const T* __restrict__ part, T* __restrict__ C, int64_t M, int64_t N, int64_t ldc, int splits,
+                                                                int epi, const T* __restrict__ bias, const T* __restrict__ mask) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const int64_t gm = i / N, gn = i - gm * N;
+  T v = T(0);
+  for (int z = 0; z < splits; ++z) v += part[(int64_t)z * M * N + i];
+  if (epi == EPI_BIAS || epi == EPI_BIAS_RELU) {
+    if (bias) v += bias[gn];
+    if (epi == EPI_BIAS_RELU) v = v < T(0) ? T(0) : v;
+  } else if (epi == EPI_MASK) {
+    v = mask[gm * ldc + gn] > T(0) ? v : T(0);
+  }
+  C[gm * ldc + gn] = v;
+}
+
 template <typename TO, typename TI> __device__ __forceinline__ TO cvt(TI v) {
   if constexpr (std::is_same<TI, __nv_bfloat16>::value) return (TO)__bfloat162float(v);
   else return (TO)v;
@@ -256,13 +274,21 @@ int gemm_launch(pg_ctx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N,
   int64_t gx = pg_cdiv(N, bn), gy = pg_cdiv(M, bm);
   PG_REQUIRE(gy <= 65535, "M too large for the SIMT GEMM grid");
   int splits = 1;
+  const int64_t tiles = gx * gy;
   if (allow_split && epi == EPI_NONE && ldc == N) {
-    int64_t tiles = gx * gy;
     int64_t want = pg_cdiv(2 * (int64_t)ctx->num_sms, tiles);
     int64_t maxs = pg_cdiv(K, 8 * bk);
     splits = (int)(want < maxs ? want : maxs);
     if (splits < 1) splits = 1;
     if (splits > 256) splits = 256;
+  } else if (tiles * 8 <= ctx->num_sms && K >= 32 * bk) {
+    // a handful of tiles with a deep reduction (forward / data gradient at small batch: 128 x 100 x 784 is 4 CTAs walking 49
+    // k-tiles): split K over idle SMs, 4 k-tiles per split at least; the reducer applies the epilogue.  Shorter reductions
+    // (K < 512) do not pay for the second launch (measured on the conv net's 256-120-84-10 head at batch 128)
+    int64_t want = ctx->num_sms / tiles, maxs = K / (4 * bk);
+    splits = (int)(want < maxs ? want : maxs);
+    if (splits < 1) splits = 1;
+    if (splits > 32) splits = 32;
   }
   int64_t kps = pg_cdiv(pg_cdiv(K, splits), bk) * bk;
   splits = (int)pg_cdiv(K, kps);
@@ -283,7 +309,8 @@ int gemm_launch(pg_ctx* ctx, const T* A, const T* B, T* C, int64_t M, int64_t N,
   PG_LAUNCHED(ctx);
   if (splits > 1) {
     int64_t MN = M * N;
-    splitk_reduce_kernel<T><<<(unsigned)pg_cdiv(MN, 256), 256, 0, ctx->stream>>>(part, C, MN, splits);
+    if (epi == EPI_NONE && ldc == N) splitk_reduce_kernel<T><<<(unsigned)pg_cdiv(MN, 256), 256, 0, ctx->stream>>>(part, C, MN, splits);
+    else splitk_reduce_epi_kernel<T><<<(unsigned)pg_cdiv(MN, 256), 256, 0, ctx->stream>>>(part, C, M, N, ldc, splits, epi, bias, mask);
     PG_LAUNCHED(ctx);
   }
   return PG_OK;
