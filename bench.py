@@ -557,7 +557,9 @@ def other_configs(pg, ctx, stream, torch):
             m = full
             objective = lambda mm: pg.cross_entropy(mm(xd), ld)
         st = pg.init(opt, m)
-        if graph:
+        if graph == "mega":
+            stepf = pg.MegaStep(objective, m, st)           # forward + loss + backward + update in ONE cooperative launch
+        elif graph:
             stepf = pg.GraphStep(objective, m, st, math=math)
         else:
             def stepf():
@@ -578,7 +580,8 @@ def other_configs(pg, ctx, stream, torch):
         ms = e0.elapsed_time(e1) / steps
         nbytes = step_bytes(spec, B, opt_bytes, in_shape)
         roof_ms = nbytes / hbm * 1e3
-        return {"config": name, "batch": B, "optimizer": type(opt).__name__, "math": math, "mode": "cuda-graph replay" if graph else "eager",
+        return {"config": name, "batch": B, "optimizer": type(opt).__name__, "math": math,
+                "mode": "one cooperative launch (MegaStep, csrc/mlp_step.cu)" if graph == "mega" else "cuda-graph replay" if graph else "eager",
                 "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "gflops": FLOPS_OTHER[name] * B / (ms * 1e-3) / 1e9,
                 "launches_per_step": (ctx.launch_count() - n0) / steps if not graph else None,
                 "roofline": {"bound": "hbm" if B >= 4096 else "latency (working set fits L2; HBM figure for scale only)",
@@ -586,7 +589,8 @@ def other_configs(pg, ctx, stream, torch):
                 "loss": float(out)}
 
     res = []
-    for args_ in (("C1", C1_SPEC, 128, pg.Adam(1e-3, fast=True), 28, "fp32", True),
+    for args_ in (("C1", C1_SPEC, 128, pg.Adam(1e-3, fast=True), 28, "fp32", "mega"),
+                  ("C1", C1_SPEC, 128, pg.Adam(1e-3, fast=True), 28, "fp32", True),
                   ("C1", C1_SPEC, 8192, pg.Adam(1e-3, fast=True), 28, "fp32", False),
                   ("C1", C1_SPEC, 8192, pg.Adam(1e-3, fast=True), 28, "bf16", False),
                   ("C3", C3_SPEC, 128, pg.NesterovMethod(1e-2), 16, "fp32", True),

@@ -286,6 +286,32 @@ enum { PG_NODE_NEEDED = 1, PG_NODE_NEEDS_GRAD = 2, PG_NODE_TENSOR_CORE = 4, PG_N
        PG_NODE_FUSED_POOL = 64 /* a Conv whose ReLU and 2x2 max-pool run inside its kernel (pg_conv2d_relu_pool2_*) */ };
 typedef void (*pg_ready_fn)(void* user, int first_grad_leaf);
 
+/* ---- one training step of a small MLP in ONE cooperative launch (csrc/mlp_step.cu) -------------------------------------
+ * Linear -> ReLU -> ... -> Linear -> softmax -> cross_entropy (the model of /root/reference/examples/01_mnist_mlp.jl:19-29
+ * without dropout; forward src/layers.jl:28-34,81,87, loss src/losses.jl:7-10, pullbacks as pg_linear_bwd /
+ * pg_softmax_ce_fwd_bwd) followed by the optimizer update over the parameter arena (gradient_descent.jl:15-17 or
+ * adam.jl:32-41, same arithmetic and flags as pg_opt_gd / pg_opt_adam).  Float32; widths and batch <= 1536; gradients are
+ * written to gW / gb (they stay readable), the loss to loss_out.  Replaces the eval_with_pullback -> pb() -> step! call
+ * sequence for models where 13 dependent launches cost more than the arithmetic. */
+typedef struct pg_mlp_desc {
+  int32_t n_layers;          /* Linear layers, 2..4 */
+  int32_t opt;               /* 0: no update, 1: GradientDescent, 2: Adam */
+  int64_t batch;
+  int64_t dims[5];           /* dims[0] = input width, dims[l+1] = output width of layer l */
+  const void* x;             /* [batch][dims[0]] f32 */
+  const void* labels;        /* [batch][dims[n_layers]] f32 (one-hot or soft) */
+  void* W[4]; void* b[4];    /* W[l]: [dims[l]][dims[l+1]] (Julia's W[out,in] bytes), b[l]: [dims[l+1]] */
+  void* gW[4]; void* gb[4];  /* gradients, same shapes */
+  void* loss_out;            /* f32 device scalar */
+  double loss_scale;         /* 1 / (global) batch */
+  void* arena_p; void* arena_g; void* arena_m; void* arena_v; void* arena_m_hat; void* arena_v_hat;  /* m_hat, v_hat nullable */
+  int64_t arena_n;           /* padded arena length (elements) */
+  double stepsize, beta1, beta2, eps;
+  int64_t it;                /* Adam iteration counter of THIS step (starts at 1, adam.jl:28) */
+  int32_t flags;             /* PG_SCALAR_F64 | PG_MATH_FAST, as pg_opt_adam */
+} pg_mlp_desc;
+int pg_mlp_step(pg_ctx* ctx, const pg_mlp_desc* desc);
+
 /* Host-only (callable without a GPU): buffers are allocated by the first pg_plan_forward. */
 int pg_plan_create(pg_ctx* ctx, const pg_op* ops, int n_ops, int root, int math_mode, pg_plan** plan);
 int pg_plan_destroy(pg_plan* plan);

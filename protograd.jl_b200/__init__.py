@@ -29,7 +29,7 @@ from .layers import (Compose, Conv, Dropout, Linear, MaxPool, MeanPool, ReLU, Re
                      maxpool, meanpool, relu, reshape, softmax, xavier_uniform)
 from .model import Model, allparams, dot, ldiv, overlap, vec  # noqa: E402
 from .pipeline import Prefetcher  # noqa: E402
-from .graph import GraphStep  # noqa: E402
+from .graph import GraphStep, MegaStep  # noqa: E402
 from .data import DeviceDataset, load, save  # noqa: E402
 from .optimizers import Adam, GradientDescent, HeavyBallMethod, NesterovMethod, NesterovMomentumSequence, init, step  # noqa: E402
 from .trace import cross_entropy, mse, seed  # noqa: E402

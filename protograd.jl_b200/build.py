@@ -64,14 +64,18 @@ def build_lib(force=False, verbose=False):
 
 
 def build_trace_lib():
-    """Debug variant (tools/tc_trace.py): tc_gemm.cu compiled with -DPG_TC_TRACE (per-tile clock stamps of the pair kernel's
-    roles), everything else from the regular objects -> libprotograd_b200_trace.so; loaded with PG_LIB_PATH=<that file>."""
+    """Debug variant (tools/tc_trace.py): tc_gemm.cu and mlp_step.cu compiled with -DPG_TC_TRACE (per-tile clock stamps of the pair
+    kernel's roles, phase stamps of the one-launch MLP step), everything else from the regular objects -> libprotograd_b200_trace.so; loaded with PG_LIB_PATH=<that file>."""
     build_lib()
-    obj = os.path.join(OBJ, "tc_gemm_trace.o")
-    r = subprocess.run([NVCC] + FLAGS + ["-DPG_TC_TRACE", "-c", os.path.join(CSRC, "tc_gemm.cu"), "-o", obj], capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(r.stdout + r.stderr)
-    objs = [os.path.join(OBJ, f) for f in sorted(os.listdir(OBJ)) if f.endswith(".o") and f not in ("tc_gemm.o", "tc_gemm_trace.o")] + [obj]
+    traced = []
+    for name in ("tc_gemm", "mlp_step"):
+        obj = os.path.join(OBJ, name + "_trace.o")
+        r = subprocess.run([NVCC] + FLAGS + ["-DPG_TC_TRACE", "-c", os.path.join(CSRC, name + ".cu"), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stdout + r.stderr)
+        traced.append(obj)
+    skip = ("tc_gemm.o", "mlp_step.o", "tc_gemm_trace.o", "mlp_step_trace.o")
+    objs = [os.path.join(OBJ, f) for f in sorted(os.listdir(OBJ)) if f.endswith(".o") and f not in skip] + traced
     out = os.path.join(HERE, "libprotograd_b200_trace.so")
     r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs, capture_output=True, text=True)
     if r.returncode != 0:

@@ -21,6 +21,15 @@ class PGError(RuntimeError):
     pass
 
 
+class MlpDesc(ctypes.Structure):
+    """struct pg_mlp_desc of include/protograd_b200.h"""
+    _fields_ = [("n_layers", c_int32), ("opt", c_int32), ("batch", c_int64), ("dims", c_int64 * 5), ("x", c_void_p), ("labels", c_void_p),
+                ("W", c_void_p * 4), ("b", c_void_p * 4), ("gW", c_void_p * 4), ("gb", c_void_p * 4), ("loss_out", c_void_p),
+                ("loss_scale", c_double), ("arena_p", c_void_p), ("arena_g", c_void_p), ("arena_m", c_void_p), ("arena_v", c_void_p),
+                ("arena_m_hat", c_void_p), ("arena_v_hat", c_void_p), ("arena_n", c_int64), ("stepsize", c_double), ("beta1", c_double),
+                ("beta2", c_double), ("eps", c_double), ("it", c_int64), ("flags", c_int32)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -117,6 +126,7 @@ _SIGS = {
     "pg_arena_get_scalar": [_P, _L, POINTER(c_double)],
     "pg_arena_set_scalar": [_P, _L, _D],
     "pg_vec_expr": [_P, _I, _P, POINTER(_P), _I, POINTER(c_int32), _I, POINTER(c_double), _I, _L, _I, POINTER(c_int64)],
+    "pg_mlp_step": [_P, _P],
     "pg_plan_create": [_P, _P, _I, _I, _I, POINTER(_P)],
     "pg_plan_destroy": [_P],
     "pg_plan_node_flags": [_P, _I, POINTER(c_int)],

@@ -352,7 +352,7 @@ int pg_colsum_launch(pg_ctx* ctx, int in_dtype, const void* X, void* out, int64_
   int S = (int)(want < maxs ? want : maxs);
   if (S < 1) S = 1;
   if (S > 1024) S = 1024;
-  if (N <= 64 && S > 32) S = 32;   // tiny outputs: keep the final reduce short
+  if (N <= 1024 && S > 32) S = 32;   // the final reduce is one thread per column walking S partials (128 partials of a 120-wide layer: 10 us)
   int64_t rps = pg_cdiv(M, S);
   S = (int)pg_cdiv(M, rps);
   if (M <= 0) { S = 1; rps = 1; }

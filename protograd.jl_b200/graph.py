@@ -143,3 +143,108 @@ class GraphStep:
             capi.lib.pg_graph_destroy(self.ctx.h, self._graph)
         except Exception:
             pass
+
+
+class MegaStep:
+    """One training step of a small Float32 MLP in a SINGLE cooperative launch (csrc/mlp_step.cu, pg_mlp_step).
+
+    The reference's own example (examples/01_mnist_mlp.jl: 784-100-10, minibatch 128) is 41 MFLOP per step: as
+    eval_with_pullback -> pb() -> step! it is 13 dependent launches and launch latency is all there is.  `MegaStep(f, m,
+    state)` traces `f(m)` once, checks that it is Linear -> relu -> ... -> Linear -> softmax -> cross_entropy over FIXED
+    Float32 device buffers (write every new minibatch into them, as with GraphStep) and then runs forward, loss,
+    backward and the optimizer update (GradientDescent or Adam, same arithmetic as `step`) in one kernel per call.
+    Gradients land in `gradient_container(m)` and stay readable; the return value is the step's Loss handle.
+    Envelope: 2-4 Linear layers, widths and batch <= 1536, no dropout; anything else raises (use GraphStep)."""
+
+    def __init__(self, f, model, state):
+        from . import trace as T
+        from .gradient import gradient_container
+        if state.variable is not model:
+            raise ValueError("the optimizer state must have been created for this model (init(optimizer, model))")
+        ctx, _, _, leaves = model.arena()
+        self.ctx, self.model, self.state = ctx, model, state
+        tr = T.Trace(ctx, leaves, "fp32")
+        prev = T.set_current(tr)
+        try:
+            out = f(model)
+        finally:
+            T.set_current(prev)
+
+        def need(cond, what):
+            if not cond:
+                raise NotImplementedError("MegaStep covers Linear -> relu -> ... -> Linear -> softmax -> cross_entropy on Float32 device "
+                                          f"buffers: {what}")
+        need(isinstance(out, T.Tensor) and out.op == "cross_entropy", "the objective must end in cross_entropy")
+        probs, label = out.inputs
+        need(probs.op == "softmax", "cross_entropy must take softmax probabilities")
+        need(label.op == "input" and isinstance(label.attrs["src"], DeviceArray) and label.dtype == np.float32, "labels must be a Float32 DeviceArray")
+        cur, layers = probs.inputs[0], []
+        while True:
+            need(cur.op == "linear", f"unexpected op {cur.op}")
+            x, Wn, bn = cur.inputs
+            need(Wn.attrs["grad_index"] is not None and bn.attrs["grad_index"] is not None, "every Linear must be trainable")
+            layers.append((Wn.attrs["leaf"], bn.attrs["leaf"]))
+            if x.op == "relu":
+                cur = x.inputs[0]
+            else:
+                need(x.op == "input" and isinstance(x.attrs["src"], DeviceArray) and x.dtype == np.float32 and len(x.shape) == 2,
+                     "the input must be a 2-D Float32 DeviceArray")
+                xin = x
+                break
+        layers.reverse()
+        flat = [p for Wb in layers for p in Wb]
+        need(2 <= len(layers) <= 4, "2 to 4 Linear layers")
+        need(len(flat) == len(leaves) and all(a is b for a, b in zip(flat, leaves)), "the Linear layers must be exactly the model's leaves, in order")
+        need(all(p.dtype == np.float32 for p in flat), "Float32 parameters")
+        B = xin.shape[0]
+        dims = [layers[0][0].shape[0]] + [W.shape[1] for W, _ in layers]
+        need(xin.shape[1] == dims[0] and label.shape == (B, dims[-1]), "shape mismatch")
+        need(max(dims + [B]) <= 1536, "widths and batch <= 1536")
+        self._x, self._y = xin.attrs["src"], label.attrs["src"]          # keep the buffers alive
+        self._grad = gradient_container(model)
+        gl = self._grad.allparams()
+        d = capi.MlpDesc()
+        d.n_layers, d.batch = len(layers), B
+        for i, v in enumerate(dims):
+            d.dims[i] = v
+        d.x, d.labels = self._x.ptr, self._y.ptr
+        for l, (W, b) in enumerate(layers):
+            d.W[l], d.b[l], d.gW[l], d.gb[l] = W.ptr, b.ptr, gl[2 * l].ptr, gl[2 * l + 1].ptr
+        gb = out.attrs.get("global_batch")
+        d.loss_scale = 1.0 / float(gb if gb else B)
+        st = state
+        _, code, p, pg_, n = st._arena(self._grad)
+        d.arena_p, d.arena_g, d.arena_n = p, pg_, n
+        d.stepsize = float(st.stepsize)
+        if isinstance(st, AdamState):
+            o = st.optimizer
+            d.opt = 2
+            d.arena_m, d.arena_v = st._ptr(st.m), st._ptr(st.v)
+            d.arena_m_hat = st._ptr(st._m_hat) if st._m_hat is not None else None
+            d.arena_v_hat = st._ptr(st._v_hat) if st._v_hat is not None else None
+            d.beta1, d.beta2, d.eps = float(o.beta1), float(o.beta2), float(o.epsilon)
+            d.flags = _f64(st.stepsize) | (capi.MATH_FAST if o.fast else 0)
+        elif isinstance(st, GradientDescentState):
+            d.opt, d.flags = 1, _f64(st.stepsize)
+        else:
+            raise NotImplementedError(f"MegaStep updates with GradientDescent or Adam, not {type(st).__name__}")
+        self._desc = d
+        self._loss = DeviceArray.empty(ctx, (64,), np.float32)
+        self.steps = 0
+
+    def __call__(self):
+        from .trace import _Borrowed
+        d, st = self._desc, self.state
+        k = self.steps % 64
+        d.loss_out = self._loss.ptr + 4 * k
+        if d.opt == 2:
+            d.it = st.it
+        call("pg_mlp_step", self.ctx.h, ctypes.byref(d))
+        if d.opt == 2:
+            st.it += 1
+        self.steps += 1
+        self.model._mutated()
+        self._grad._mutated()
+        n = self.steps
+        slot = DeviceArray(_Borrowed(self.ctx, d.loss_out), 0, (1,), np.float32)
+        return Loss(slot, lambda: self.steps - n < 64)

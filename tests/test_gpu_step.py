@@ -276,6 +276,59 @@ def test_graph_replay_matches_eager_steps(pg, opt):
         assert st_g.it == st_e.it == 7
 
 
+@pytest.mark.parametrize("opt", ["gd", "adam", "adam_fast", "adam_f32"])
+@pytest.mark.parametrize("case", ["c1_b128", "ragged3"])
+def test_mega_step_matches_oracle_and_eager(pg, opt, case):
+    """MegaStep (csrc/mlp_step.cu: forward, softmax + cross-entropy, backward and the optimizer update in ONE cooperative
+    launch) against the float64 oracle (loss and gradients of the first step <= 1e-5) and against the eager
+    eval_with_pullback / pb() / step sequence over four steps (parameters <= 1e-6: same arithmetic, other summation order)."""
+    if case == "c1_b128":      # the reference's example model at its own minibatch (examples/01_mnist_mlp.jl:20,34)
+        spec, B = MG.C1_SPEC, 128
+    else:                      # three Linear layers, nothing a multiple of the 16 x 8 tile
+        spec, B = [("linear", 21, 33), ("relu",), ("linear", 33, 17), ("relu",), ("linear", 17, 10), ("softmax",)], 37
+    x, lab = MG.class_data(spec, B, np.float32, 77)
+    p0 = MG.biased_params(spec, np.float32, 77)
+    ctx = pg.Context.get()
+    xd, ld = pg.DeviceArray.from_numpy(ctx, x), pg.DeviceArray.from_numpy(ctx, lab)
+    mk = lambda: {"gd": pg.GradientDescent(0.1), "adam": pg.Adam(1e-3), "adam_fast": pg.Adam(1e-3, fast=True),
+                  "adam_f32": pg.Adam(np.float32(1e-3), np.float32(0.9), np.float32(0.999), np.float32(1e-8))}[opt]
+    f = lambda mm: pg.cross_entropy(mm(xd), ld)
+    m_e = build_model(pg, spec, p0); st_e = pg.init(mk(), m_e)
+    m_m = build_model(pg, spec, p0); st_m = pg.init(mk(), m_m)
+    ms = pg.MegaStep(f, m_m, st_m)
+    loss0 = float(ms())
+    v, gr = O.net_loss_and_grad(spec, [p.astype(np.float64) for p in p0], x.astype(np.float64), lab.astype(np.float64))
+    assert abs(loss0 - v) <= TOL * abs(v)
+    for a, r in zip(leaves_numpy(pg.gradient_container(m_m)), gr):
+        assert rel_err(a, r) <= TOL
+    losses_m = [loss0] + [float(ms()) for _ in range(3)]
+    losses_e = []
+    for _ in range(4):
+        out, pb = pg.eval_with_pullback(f, m_e)
+        pg.step(st_e, pb())
+        losses_e.append(float(out))
+    assert np.allclose(losses_m, losses_e, rtol=2e-6)
+    assert rel_err(m_m.vec(), m_e.vec()) <= 1e-6
+    if opt.startswith("adam"):
+        assert st_m.it == st_e.it == 5
+    # deterministic: a second run from the same start is bit-identical
+    m_2 = build_model(pg, spec, p0); st_2 = pg.init(mk(), m_2)
+    ms2 = pg.MegaStep(f, m_2, st_2)
+    for _ in range(4):
+        ms2()
+    assert np.array_equal(m_2.vec(), m_m.vec())
+
+
+def test_mega_step_rejects_other_graphs(pg):
+    spec = MG.C3_SPEC
+    x, lab = MG.class_data(spec, 8, np.float32, 5)
+    ctx = pg.Context.get()
+    xd, ld = pg.DeviceArray.from_numpy(ctx, x), pg.DeviceArray.from_numpy(ctx, lab)
+    m = build_model(pg, spec, MG.biased_params(spec, np.float32, 5))
+    with pytest.raises(NotImplementedError):
+        pg.MegaStep(lambda mm: pg.cross_entropy(mm(xd), ld), m, pg.init(pg.GradientDescent(0.1), m))
+
+
 def test_loss_fetch_async_and_prefetcher(pg):
     """Loss.fetch_async (pinned D2H behind the step) and Prefetcher (double-buffered H2D) give the same numbers as the plain path."""
     spec = MG.C1_SPEC
