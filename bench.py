@@ -387,9 +387,13 @@ def main():
     #      loss is read back to the host (D2H + sync) ----
     pf = pg.Prefetcher(ctx, e2e_specs, depth=2)
 
-    def e2e_loop(n):
+    def e2e_loop(n, lag=2):
+        # the host reads EVERY step's loss (D2H copy queued right behind the step), `lag` steps after enqueueing it: with
+        # lag = 1 the host can never be more than one step ahead of the GPU, and at 8 ranks — coupled by the exchange of every
+        # step — any rank's enqueue jitter stalled all of them
+        from collections import deque
         pf.submit(x_p, lab_p)
-        last, prev = None, None
+        pending, last = deque(), None
         for i in range(n):
             xd, ld = pf.next()
             if i + 1 < n:
@@ -397,10 +401,12 @@ def main():
             out = train_step(xd, ld)
             pf.release()
             out.fetch_async()              # D2H of this step's loss, queued right behind the step
-            if prev is not None:
-                last = float(prev)         # read step i-1's loss while step i runs
-            prev = out
-        return float(prev)
+            pending.append(out)
+            if len(pending) > lag:
+                last = float(pending.popleft())
+        while pending:
+            last = float(pending.popleft())
+        return last
     e2e_loop(3)
     e2e_steps = max(5, args.steps // 2)
     ms_e2e = timed(lambda: e2e_loop(e2e_steps), 1)

@@ -54,11 +54,11 @@ __device__ long long g_mlp_trace[16];
 
 // Shared-memory budget of a CTA (floats) and the panel geometry of a macro tile of mi x ni sub-tiles (16 x 8 outputs each):
 // A panel [16 mi][KP] row-major (KP = K rounded up to 8 mod 32: the four rows a warp reads land in different banks, rows stay
-// 16-byte aligned), B panel [K4][8 ni + 1], 128 floats for the K-half exchange.
+// 16-byte aligned), B panel [K4][8 ni + 4] (rows 16-byte aligned), 8 x 128 floats for the exchange of the K-slice partials.
 constexpr int SMEM_FLOATS = 50 * 1024;            // 200 KB
 __host__ __device__ __forceinline__ int kp_of(int K) { return ((K + 3) & ~3) + ((40 - (((K + 3) & ~3) & 31)) & 31); }
 __host__ __device__ __forceinline__ int k4_of(int K) { return (K + 3) & ~3; }
-__host__ __device__ __forceinline__ bool fits(int K, int mi, int ni) { return (long long)TM * mi * kp_of(K) + (long long)k4_of(K) * (TN * ni + 1) + 128 <= SMEM_FLOATS; }
+__host__ __device__ __forceinline__ bool fits(int K, int mi, int ni) { return (long long)TM * mi * kp_of(K) + 4ll * k4_of(K) + (long long)k4_of(K) * (TN * ni + 4) + 1024 <= SMEM_FLOATS; }
 // grow the macro tile until the GEMM is at most `budget` work items (one round of the grid) or shared memory is full
 __device__ __forceinline__ void pick_macro(int M, int N, int K, int budget, int& mi, int& ni) {
   mi = 1; ni = 1;
@@ -84,15 +84,19 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool pr
 }
 
 // one macro tile of C = A B:  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]; panels staged once (coalesced, no
-// divisions in the loops), then the 16 x 8 sub-tiles one after the other: two threads per output (K halves), float4 along k
+// divisions in the loops), then the 16 x 8 sub-tiles one after the other.  The inner product is shared-memory-bound (one
+// wavefront per LDS instruction, broadcast or not), so a thread owns 2 x 2 outputs (two float4 of A along k and four float2 of
+// B feed 16 FMAs: one wavefront per FMA instruction instead of two) and the eight warps split K; the partials are summed in a
+// fixed order through shared memory.
 template <int EPI>
 __device__ void macro_gemm(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ Bm, long long sbk, long long sbn,
                            int M, int N, int K, int m0, int n0, int mi, int ni, float* __restrict__ C, int ldc, const float* __restrict__ aux, float* smem,
                            [[maybe_unused]] int trace_slot = -1) {
-  const int KP = kp_of(K), K4 = k4_of(K), rows = TM * mi, cols = TN * ni, BPn = cols + 1;
-  float* As = smem;                             // [rows][KP]
-  float* Bs = smem + (size_t)rows * KP;         // [K4][BPn]
-  float* red = Bs + (size_t)K4 * BPn;           // [128]
+  const int KP = kp_of(K), K4 = k4_of(K), rows = TM * mi, cols = TN * ni, BPn = cols + 4, RP = rows + 4;
+  const bool a_kmajor = sak != 1;               // transposed operand: panel stored [K4][RP] instead of [rows][KP]
+  float* As = smem;                             // [rows][KP] or [K4][RP]
+  float* Bs = smem + (a_kmajor ? (size_t)K4 * RP : (size_t)rows * KP);         // [K4][BPn]
+  float* red = Bs + (size_t)K4 * BPn;           // [8][128]
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   // cp.async: every copy of the panels is in flight at once (a load -> store loop ran one latency per element: 9 us for 75 KB)
   if (sak == 1) {                               // rows of A are contiguous in k: warp per row
@@ -107,20 +111,32 @@ __device__ void macro_gemm(const float* __restrict__ A, long long sam, long long
         for (int k = lane; k < K4; k += 32) cp_async4(dst + k, src + (k < K ? k : 0), live && k < K);
       }
     }
-  } else {                                      // A is contiguous in m (a transposed operand): lanes along m
-    for (int k = warp; k < K4; k += THREADS / 32)
-      for (int m = lane; m < rows; m += 32) {
-        const bool ok = m0 + m < M && k < K;
-        cp_async4(As + (size_t)m * KP + k, A + (ok ? (long long)(m0 + m) * sam + (long long)k * sak : 0), ok);
-      }
+  } else {                                      // A is contiguous in m (a transposed operand): k-major panel [K4][rows + 4], 16-byte copies along m
+    if ((sak & 3) == 0 && m0 + rows <= M && ((uintptr_t)A & 15) == 0 && sam == 1) {
+      const int groups = rows >> 2, per = THREADS / groups, kk = t / groups, g = t - kk * groups;
+      if (kk < per)
+        for (int k = kk; k < K4; k += per) cp_async16(As + (size_t)k * RP + 4 * g, A + (k < K ? (long long)k * sak + m0 + 4 * g : 0), k < K);
+    } else {
+      for (int k = warp; k < K4; k += THREADS / 32)
+        for (int m = lane; m < rows; m += 32) {
+          const bool ok = m0 + m < M && k < K;
+          cp_async4(As + (size_t)k * RP + m, A + (ok ? (long long)(m0 + m) * sam + (long long)k * sak : 0), ok);
+        }
+    }
   }
   if (sbn == 1) {                               // rows of B are contiguous in n
-    const int per = THREADS / cols, kk = t / cols, n = t - kk * cols;
-    if (kk < per)
-      for (int k = kk; k < K4; k += per) {
-        const bool ok = n0 + n < N && k < K;
-        cp_async4(Bs + (size_t)k * BPn + n, Bm + (ok ? (long long)k * sbk + (n0 + n) : 0), ok);
-      }
+    if ((sbk & 3) == 0 && (n0 & 3) == 0 && n0 + cols <= N && ((uintptr_t)Bm & 15) == 0) {
+      const int groups = cols >> 2, per = THREADS / groups, kk = t / groups, g = t - kk * groups;
+      if (kk < per)
+        for (int k = kk; k < K4; k += per) cp_async16(Bs + (size_t)k * BPn + 4 * g, Bm + (k < K ? (long long)k * sbk + n0 + 4 * g : 0), k < K);
+    } else {
+      const int per = THREADS / cols, kk = t / cols, n = t - kk * cols;
+      if (kk < per)
+        for (int k = kk; k < K4; k += per) {
+          const bool ok = n0 + n < N && k < K;
+          cp_async4(Bs + (size_t)k * BPn + n, Bm + (ok ? (long long)k * sbk + (n0 + n) : 0), ok);
+        }
+    }
   } else {                                      // B is contiguous in k
     for (int n = 0; n < cols; ++n)
       for (int k = t; k < K4; k += THREADS) {
@@ -131,30 +147,49 @@ __device__ void macro_gemm(const float* __restrict__ A, long long sam, long long
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   if (trace_slot >= 0) MLP_TRACE(trace_slot);
-  const int o = t & 127, kh = t >> 7, r = o >> 3, c = o & 7;
-  const int khalf = (((K4 >> 1) + 3) & ~3);
-  const int k0 = kh * khalf, k1 = min(K4, k0 + khalf);
+  const int rp = lane >> 2, cp = lane & 3;                       // rows rp, rp + 8; columns 2 cp, 2 cp + 1 of the sub-tile
+  const int ks = (((K4 + 7) >> 3) + 3) & ~3;                     // K slice of this warp
+  const int k0 = warp * ks, k1 = min(K4, k0 + ks);
   for (int si = 0; si < mi; ++si) {
     if (m0 + si * TM >= M) break;
     for (int sj = 0; sj < ni; ++sj) {
       if (n0 + sj * TN >= N) break;
-      const float* ar = As + (size_t)(si * TM + r) * KP;
-      const float* bc = Bs + sj * TN + c;
-      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+      const float* bc = Bs + sj * TN + 2 * cp;
+      float c00 = 0.0f, c01 = 0.0f, c10 = 0.0f, c11 = 0.0f;
+      if (a_kmajor) {
+        const float* ac = As + si * TM + rp;
 #pragma unroll 4
-      for (int k = k0; k < k1; k += 4) {
-        const float4 av = *reinterpret_cast<const float4*>(ar + k);
-        a0 = fmaf(av.x, bc[(size_t)k * BPn], a0);
-        a1 = fmaf(av.y, bc[(size_t)(k + 1) * BPn], a1);
-        a2 = fmaf(av.z, bc[(size_t)(k + 2) * BPn], a2);
-        a3 = fmaf(av.w, bc[(size_t)(k + 3) * BPn], a3);
+        for (int k = k0; k < k1; ++k) {
+          const float lo = ac[(size_t)k * RP], hi = ac[(size_t)k * RP + 8];
+          const float2 b0 = *reinterpret_cast<const float2*>(bc + (size_t)k * BPn);
+          c00 = fmaf(lo, b0.x, c00); c01 = fmaf(lo, b0.y, c01); c10 = fmaf(hi, b0.x, c10); c11 = fmaf(hi, b0.y, c11);
+        }
+      } else {
+        const float* a_lo = As + (size_t)(si * TM + rp) * KP;
+        const float* a_hi = a_lo + (size_t)8 * KP;
+#pragma unroll 2
+        for (int k = k0; k < k1; k += 4) {
+          const float4 lo = *reinterpret_cast<const float4*>(a_lo + k);
+          const float4 hi = *reinterpret_cast<const float4*>(a_hi + k);
+          const float2 b0 = *reinterpret_cast<const float2*>(bc + (size_t)k * BPn);
+          const float2 b1 = *reinterpret_cast<const float2*>(bc + (size_t)(k + 1) * BPn);
+          const float2 b2 = *reinterpret_cast<const float2*>(bc + (size_t)(k + 2) * BPn);
+          const float2 b3 = *reinterpret_cast<const float2*>(bc + (size_t)(k + 3) * BPn);
+          c00 = fmaf(lo.x, b0.x, c00); c01 = fmaf(lo.x, b0.y, c01); c10 = fmaf(hi.x, b0.x, c10); c11 = fmaf(hi.x, b0.y, c11);
+          c00 = fmaf(lo.y, b1.x, c00); c01 = fmaf(lo.y, b1.y, c01); c10 = fmaf(hi.y, b1.x, c10); c11 = fmaf(hi.y, b1.y, c11);
+          c00 = fmaf(lo.z, b2.x, c00); c01 = fmaf(lo.z, b2.y, c01); c10 = fmaf(hi.z, b2.x, c10); c11 = fmaf(hi.z, b2.y, c11);
+          c00 = fmaf(lo.w, b3.x, c00); c01 = fmaf(lo.w, b3.y, c01); c10 = fmaf(hi.w, b3.x, c10); c11 = fmaf(hi.w, b3.y, c11);
+        }
       }
-      float acc = (a0 + a1) + (a2 + a3);
-      if (kh == 1) red[o] = acc;
+      float* rw = red + warp * 128;
+      rw[rp * 8 + 2 * cp] = c00; rw[rp * 8 + 2 * cp + 1] = c01;
+      rw[(rp + 8) * 8 + 2 * cp] = c10; rw[(rp + 8) * 8 + 2 * cp + 1] = c11;
       __syncthreads();
-      if (kh == 0) {
-        acc += red[o];
-        const int gm = m0 + si * TM + r, gn = n0 + sj * TN + c;
+      if (t < 128) {
+        float acc = red[t];
+#pragma unroll
+        for (int w = 1; w < THREADS / 32; ++w) acc += red[w * 128 + t];
+        const int gm = m0 + si * TM + (t >> 3), gn = n0 + sj * TN + (t & 7);
         if (gm < M && gn < N) {
           if (EPI == EPI_BIAS_RELU) { acc += aux[gn]; acc = acc < 0.0f ? 0.0f : acc; }
           else if (EPI == EPI_BIAS) acc += aux[gn];
