@@ -53,6 +53,17 @@ static inline bool pg_deferred_overlaps(const pg_ctx* ctx, const void* p, size_t
 
 void pg_set_error(const char* fmt, ...);
 
+// cudaFuncSetAttribute is a per-device setting: a function-static PgOnce remembers it per (call site, device)
+struct PgOnce {
+  bool done[32] = {};
+  bool need(int dev) {
+    if (dev < 0 || dev >= 32) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 #define PG_CHECK_CUDA(expr)                                                                   \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \

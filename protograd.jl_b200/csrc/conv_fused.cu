@@ -434,8 +434,8 @@ template <typename G>
 int run_fwd(pg_ctx* ctx, const float* x, const float* w, const float* b, float* y, uint8_t* amax, int64_t N) {
   using C = FwdCfg<G>;
   const int smem = C::SMEM_FLOATS * 4;
-  static bool attr = false;
-  if (!attr) { PG_CHECK_CUDA(cudaFuncSetAttribute(conv_relu_pool_fwd_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+  static PgOnce attr;
+  if (attr.need(ctx->device)) PG_CHECK_CUDA(cudaFuncSetAttribute(conv_relu_pool_fwd_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int64_t blocks = pg_cdiv(N, C::SPB);
   const int64_t cap = (int64_t)ctx->num_sms * 4;
   if (blocks > cap) blocks = cap;
@@ -449,8 +449,8 @@ int run_bwd(pg_ctx* ctx, const float* x, const float* w, const float* y, const u
   if (dw != nullptr || db != nullptr) {
     using C = WgCfg<G>;
     const int smem = C::SMEM_FLOATS * 4;
-    static bool attr = false;
-    if (!attr) { PG_CHECK_CUDA(cudaFuncSetAttribute(conv_relu_pool_wgrad_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    static PgOnce attr;
+    if (attr.need(ctx->device)) PG_CHECK_CUDA(cudaFuncSetAttribute(conv_relu_pool_wgrad_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int64_t blocks = pg_cdiv(N, C::SLOTS);
     const int64_t cap = (int64_t)ctx->num_sms * 2;
     if (blocks > cap) blocks = cap;
@@ -465,8 +465,8 @@ int run_bwd(pg_ctx* ctx, const float* x, const float* w, const float* y, const u
   if (dx != nullptr) {
     using C = DgCfg<G>;
     const int smem = C::SMEM_FLOATS * 4;
-    static bool attr = false;
-    if (!attr) { PG_CHECK_CUDA(cudaFuncSetAttribute(conv_relu_pool_dgrad_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    static PgOnce attr;
+    if (attr.need(ctx->device)) PG_CHECK_CUDA(cudaFuncSetAttribute(conv_relu_pool_dgrad_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int64_t blocks = pg_cdiv(N, C::SLOTS);
     const int64_t cap = (int64_t)ctx->num_sms * 4;
     if (blocks > cap) blocks = cap;

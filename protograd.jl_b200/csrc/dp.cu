@@ -391,10 +391,11 @@ int launch_p2p_tma_t(int world, int grid, cudaStream_t st, const P2PArgs& a, con
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   const int smem = stages * stage_bytes + out_bytes + 8 * stages + 64;
-  static bool attr_set = false;                      // (per instantiation)
-  if (!attr_set) {
+  static PgOnce attr_set;                      // (per instantiation)
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  if (attr_set.need(dev_)) {
     PG_CHECK_CUDA(cudaFuncSetAttribute(p2p_update_tma_kernel<F, STATE, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    attr_set = true;
   }
   p2p_update_tma_kernel<F, STATE, TILE><<<grid, 512, smem, st>>>(a, f, stages);
   return PG_OK;

@@ -403,10 +403,9 @@ int pg_mlp_step(pg_ctx* ctx, const pg_mlp_desc* d) {
   }
   (void)kmax;
   const size_t smem = (size_t)SMEM_FLOATS * sizeof(float);
-  static bool smem_set = false;
-  if (!smem_set) {
+  static PgOnce smem_set;
+  if (smem_set.need(ctx->device)) {
     PG_CHECK_CUDA(cudaFuncSetAttribute(mlp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = true;
   }
   void* args[] = {(void*)&a};
   PG_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)mlp_step_kernel, dim3((unsigned)ctx->num_sms), dim3(THREADS), args, smem, ctx->stream));

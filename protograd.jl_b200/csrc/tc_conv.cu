@@ -538,7 +538,8 @@ bool plan_launch(ConvArgs& a, int dy_floats_per_sample, int* bytes_out) {
 template <int MODE, int NKB, bool SMALL>
 int launch_geo(pg_ctx* ctx, const ConvArgs& a, int bytes) {
   using G_ = Geo<SMALL>;
-  static int attr_bytes = 0;
+  static int attr_bytes_dev[32] = {};
+  int& attr_bytes = attr_bytes_dev[ctx->device & 31];
   if (bytes > attr_bytes) {
     PG_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<MODE, NKB, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     attr_bytes = bytes;

@@ -1009,10 +1009,9 @@ int launch_tc(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, int
   rc = B_MN ? make_map(ctx, &mb, B, K, N, ldb, 64, BLOCK_K) : make_map(ctx, &mb, B, N, K, ldb, BLOCK_K, BN);
   if (rc != PG_OK) return rc;
   auto kern = tc_gemm_kernel<A_MN, B_MN, BN, DBW>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PgOnce attr_set;
+  if (attr_set.need(ctx->device)) {
     PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
-    attr_set = true;
   }
   int64_t tiles = pg_cdiv(M, BLOCK_M) * pg_cdiv(N, BN) * epi.splits;
   int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
@@ -1053,10 +1052,9 @@ int launch_tc2_impl(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t 
   }
   PG_REQUIRE(epi.tail == 0 || (epi.out_f32 && epi.mask == nullptr && epi.bias == nullptr && !epi.relu), "tail split: plain fp32 outputs only");
   auto kern = tc_gemm2_kernel<A_MN, B_MN, DBW, STAGED>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PgOnce attr_set;
+  if (attr_set.need(ctx->device)) {
     PG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-    attr_set = true;
   }
   int64_t tiles = pg_cdiv(M, 256) * pg_cdiv(N, 256) + epi.tail;
   int clusters = (int)(tiles < ctx->num_sms / 2 ? tiles : ctx->num_sms / 2);
@@ -1334,12 +1332,11 @@ int launch_narrow_dgrad(pg_ctx* ctx, const void* dZ, const void* W, const void* 
   PG_REQUIRE(gy <= 65535, "narrow data gradient: batch too large");
   const bool has_mask = mask != nullptr;
   const size_t smem = (has_mask ? (size_t)ND_STAGES * ND_ROWS * ND_SEG : 0) + 64 + (size_t)rows_per_block * N * sizeof(unsigned long long);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PgOnce attr_set;
+  if (attr_set.need(ctx->device)) {
     const int max_smem = ND_STAGES * ND_ROWS * ND_SEG + 64 + 256 * N * (int)sizeof(unsigned long long);
     PG_CHECK_CUDA(cudaFuncSetAttribute(narrow_dgrad_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PG_CHECK_CUDA(cudaFuncSetAttribute(narrow_dgrad_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr_set = true;
   }
   const dim3 grid((unsigned)gx, (unsigned)gy);
   if (has_mask)
