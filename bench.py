@@ -236,6 +236,17 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = None
+    if world > 1 and os.environ.get("PG_BENCH_NO_AFFINITY") is None:
+        # one process per GPU: run on the cores next to this rank's GPU, so that the pinned input buffers (first-touch) live in
+        # the NUMA node its PCIe root hangs off — with eight ranks uploading at once, remote-socket reads were the e2e bound
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            numa = sorted(os.sched_getaffinity(0))
+        except Exception as e:          # no NVML / restricted container: keep the default placement
+            numa = "unavailable: " + repr(e)[:80]
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -498,7 +509,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(x_p.nbytes + lab_p.nbytes), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / e2e_steps,
                     "inputs": "bf16 pixels + int32 class indices from pinned host memory, double-buffered on a copy stream" if args.math == "bf16" else "fp32 pixels + fp32 one-hot labels from pinned host memory"},
-            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms, "clocks": clk, "loss_after_warmup": first_loss,
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms, "cpu_affinity_rank0": numa, "clocks": clk, "loss_after_warmup": first_loss,
             "tflops_per_gpu": FLOP_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12, "parity": parity,
         }
         if roofline:

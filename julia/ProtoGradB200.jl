@@ -484,6 +484,66 @@ function forward(dm::DeviceModel{M,T}, x; math::Symbol = :fp32) where {M,T}
     return res
 end
 
+# ---- the whole step of a small MLP in one cooperative launch (csrc/mlp_step.cu) -------------------------------------------
+# struct pg_mlp_desc of the header (320 bytes); NTuples are inline storage, i.e. C arrays
+struct PgMlpDesc
+    n_layers::Int32
+    opt::Int32
+    batch::Int64
+    dims::NTuple{5,Int64}
+    x::Ptr{Cvoid}
+    labels::Ptr{Cvoid}
+    W::NTuple{4,Ptr{Cvoid}}
+    b::NTuple{4,Ptr{Cvoid}}
+    gW::NTuple{4,Ptr{Cvoid}}
+    gb::NTuple{4,Ptr{Cvoid}}
+    loss_out::Ptr{Cvoid}
+    loss_scale::Float64
+    arena_p::Ptr{Cvoid}
+    arena_g::Ptr{Cvoid}
+    arena_m::Ptr{Cvoid}
+    arena_v::Ptr{Cvoid}
+    arena_m_hat::Ptr{Cvoid}
+    arena_v_hat::Ptr{Cvoid}
+    arena_n::Int64
+    stepsize::Float64
+    beta1::Float64
+    beta2::Float64
+    eps::Float64
+    it::Int64
+    flags::Int32
+end
+pad4(v, fill) = ntuple(i -> i <= length(v) ? v[i] : fill, 4)
+
+"""
+    mega_step!(state, grad, x, label, loss) -> state
+
+One iteration of the loop of examples/01_mnist_mlp.jl:44-55 — `eval_with_pullback(m -> cross_entropy(m(x), label), m)`,
+`pb()`, `step!(state, grad)` — for a model that is Linear -> relu -> ... -> Linear -> softmax (2 to 4 Linear layers,
+Float32, widths and batch <= 1536) as ONE launch.  `x` (in x batch), `label` (classes x batch) are device arrays of fixed
+address, `grad` receives the gradient (same type as the model, test/test_models.jl:147-148), `loss` is a 1-element device
+array; `state` is a GradientDescentState or an AdamState whose `variable` is the DeviceModel.
+"""
+function mega_step!(state, grad::DeviceModel{M,Float32}, x::Ptr{Cvoid}, label::Ptr{Cvoid}, loss::Ptr{Cvoid}, batch::Integer;
+                    global_batch::Integer = batch) where {M}
+    dm = state.variable
+    ls, gs = allparams(inner(dm)), allparams(inner(grad))               # W1, b1, W2, b2, ... in vec(m) order
+    L = length(ls) ÷ 2
+    dims = Int64[size(ls[1], 2); [size(ls[2l - 1], 1) for l in 1:L]]    # Julia W[out, in]
+    adam = state isa ProtoGrad.AdamState
+    o = state.optimizer
+    d = PgMlpDesc(L, adam ? 2 : 1, batch, ntuple(i -> i <= L + 1 ? dims[i] : 0, 5), x, label,
+                  pad4([ptr(ls[2l - 1]) for l in 1:L], C_NULL), pad4([ptr(ls[2l]) for l in 1:L], C_NULL),
+                  pad4([ptr(gs[2l - 1]) for l in 1:L], C_NULL), pad4([ptr(gs[2l]) for l in 1:L], C_NULL),
+                  loss, 1.0 / global_batch, bp(dm), bp(grad), adam ? bp(state.m) : C_NULL, adam ? bp(state.v) : C_NULL,
+                  adam ? bp(state.m_hat) : C_NULL, adam ? bp(state.v_hat) : C_NULL, np(grad), Float64(state.stepsize),
+                  adam ? Float64(o.beta1) : 0.0, adam ? Float64(o.beta2) : 0.0, adam ? Float64(o.epsilon) : 0.0,
+                  adam ? state.it : 1, isf64(state.stepsize))
+    check(ccall((:pg_mlp_step, LIB), Cint, (Ptr{Cvoid}, Ref{PgMlpDesc}), ctx().h, Ref(d)))
+    adam && (state.it += 1)                                             # adam.jl:40
+    return state
+end
+
 # ---- data parallelism: one Julia process per GPU (MPI.jl or any launcher distributes the 128-byte id) ----------------
 mutable struct DataParallel
     h::Ptr{Cvoid}

@@ -1077,7 +1077,7 @@ int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, in
 // parallel backward pass) that becomes resident FIRST lands on arbitrary SMs and breaks pairs; the pairs
 // that cannot be placed only become resident — and let the GEMM launch complete — once the collective
 // has finished.  dp.GradientBuckets therefore reserves whole TPCs (pg_set_sm_limit) and starts the
-// collective a few microseconds after the GEMM (pg_delay_on), so the collective fills the free TPCs.
+// collective on its own stream, so the collective fills the free TPCs.
 bool use_2cta(const pg_ctx* ctx, int64_t M, int64_t N) {
   static int mode = -1;                        // PG_TC_1CTA=1 forces the single-CTA kernel
   if (mode < 0) { const char* e = getenv("PG_TC_1CTA"); mode = (e && e[0] == '1') ? 0 : 1; }

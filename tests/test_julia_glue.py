@@ -84,3 +84,21 @@ def test_julia_pg_op_struct_matches_the_header_layout():
         off = (off + size[t] - 1) // size[t] * size[t]
         off += size[t]
     assert off == 80 and [t for _, t in fields] == ["Int32"] * 6 + ["Int64"] * 4 + ["Int32"] * 2 + ["Float64"] * 2
+
+
+def test_julia_mlp_desc_struct_matches_the_header_layout():
+    """PgMlpDesc (julia/ProtoGradB200.jl) has the field order, types and size of pg_mlp_desc (= capi.MlpDesc)."""
+    from protograd_b200.capi import MlpDesc
+    src = open(JULIA[0]).read()
+    body = src[src.index("struct PgMlpDesc"):src.index("\nend", src.index("struct PgMlpDesc"))]
+    fields = re.findall(r"^\s+(\w+)::(NTuple\{(\d),(Int64|Ptr\{Cvoid\})\}|Int32|Int64|Float64|Ptr\{Cvoid\})", body, re.M)
+    size = {"Int32": 4, "Int64": 8, "Float64": 8, "Ptr{Cvoid}": 8}
+    off, names = 0, []
+    for name, t, cnt, elt in fields:
+        n, e = (int(cnt), elt) if cnt else (1, t)
+        off = (off + size[e] - 1) // size[e] * size[e]
+        assert getattr(MlpDesc, name).offset == off, (name, off, getattr(MlpDesc, name).offset)
+        off += n * size[e]
+        names.append(name)
+    assert names == [f[0] for f in MlpDesc._fields_]
+    assert (off + 7) // 8 * 8 == ctypes.sizeof(MlpDesc)
