@@ -548,7 +548,7 @@ __host__ __device__ constexpr uint32_t make_idesc2(bool a_mn, bool b_mn) {   // 
 
 // DBW (weight-gradient launches): one extra reducer warp per CTA sums the CTA's half of the staged dY
 // tiles (see the 1-CTA kernel).  The peer CTA cannot wait on the leader's full barrier, so the leader's
-// MMA thread forwards every "stage landed" to the peer's ready[] barrier with a remote arrive.
+// reducer warp forwards every "stage landed" to the peer's ready[] barrier with a remote arrive.
 //
 // STAGED epilogue (default).  The mainloop keeps the SM's shared-memory pipe saturated (64 B/clk of tensor-core operand reads +
 // 64 B/clk of TMA writes = its 128 B/clk): a direct epilogue — every lane storing 16 B of its own output row, 32 lines per
@@ -686,6 +686,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ===== MMA issuer: one thread of the leader CTA drives the tensor cores of both SMs =====
     if (rank == 0 && lane == 0) {
       constexpr uint32_t idesc = make_idesc2(A_MN, B_MN);
+      constexpr int A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4, B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      const uint64_t a_desc0 = A_MN ? make_desc(smem_base, BLOCK_K * 128, 1024) : make_desc(smem_base, 16, 1024);
+      const uint64_t b_desc0 = B_MN ? make_desc(smem_base + A_STAGE_BYTES, BLOCK_K * 128, 1024) : make_desc(smem_base + A_STAGE_BYTES, 16, 1024);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       TileFeed feed(ring_base, false);
@@ -701,19 +704,20 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);             // both CTAs' bytes have landed
           if (kb == kb0) TC_TRACE(1, tn, 2);
-          if (DBW) mbar_arrive_cluster(map_to_rank(ready_bar(stage), 1));   // tell the peer's reducer warp
           tcgen05_fence_after();
-          const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
+          // descriptors: the start-address field (bits 0-13, address >> 4) is the only part that moves, and it never
+          // carries out of its 14 bits (shared memory < 256 KB): one 64-bit add per operand and k-step instead of
+          // rebuilding the descriptor — the issuer thread's instruction stream is on the critical path (a few more
+          // instructions per MMA measured 8 % slower on the 4096-deep launches)
+          const uint64_t a_st = a_desc0 + (uint64_t)((uint32_t)stage * (STAGE2_BYTES >> 4));
+          const uint64_t b_st = b_desc0 + (uint64_t)((uint32_t)stage * (STAGE2_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t ad = A_MN ? make_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t bd = B_MN ? make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16_2sm(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16_2sm(d_tmem, a_st + (uint64_t)(k * A_KSTEP), b_st + (uint64_t)(k * B_KSTEP), idesc, ((kb - kb0) | k) != 0);
           tcgen05_commit_2sm(empty_bar(stage));          // frees the slot in both CTAs
-          if (kb == kb1 - 1) tcgen05_commit_2sm(tfull_bar(acc));
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
+        tcgen05_commit_2sm(tfull_bar(acc));              // tracks every MMA issued so far: the accumulator is complete
         TC_TRACE(1, tn, 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -735,6 +739,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int m_blk = m0 / 256;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(rank == 0 ? full_bar(stage) : ready_bar(stage), phase);
+        // the peer CTA cannot wait on the leader's full barrier: the leader's reducer forwards "stage landed" (it used to be the
+        // MMA issuer's job, whose instruction stream is the pair's critical path)
+        if (rank == 0 && lane == 0) mbar_arrive_cluster(map_to_rank(ready_bar(stage), 1));
         if (kb % num_m == m_blk) {
           const uint8_t* sb = smem_aligned + stage * STAGE2_BYTES + A_STAGE_BYTES + box_off;
 #pragma unroll 8
