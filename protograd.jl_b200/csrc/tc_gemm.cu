@@ -489,6 +489,8 @@ constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;      // 32 KB per C
 constexpr int OUT_BOX_BYTES = 128 * 128;                           // staged epilogue: one 128-row x 128-byte TMA box per column half
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 2 * OUT_BOX_BYTES + 1024 + 256 + 256 + TRACE_BYTES;
 constexpr int GROUP_M2 = 8;                                        // rasterisation group, in 256-row blocks
+constexpr int DBW_WARPS2 = 4;                                      // bias-gradient reducer warps per CTA (weight-gradient launches)
+constexpr int DBW_SLOTS2 = 5;                                      // warp slots they occupy: the slot on the MMA issuer's scheduler (warp id % 4 == 1) stays idle
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -558,7 +560,7 @@ __host__ __device__ constexpr uint32_t make_idesc2(bool a_mn, bool b_mn) {   // 
 // the TMA store unit: whole-line writes, 1/4 of the wavefronts.  The data gradient's ReLU' mask tile arrives the same way (a
 // TMA load into the staging box it will be overwritten in).
 template <bool A_MN, bool B_MN, bool DBW, bool STAGED>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS + (DBW ? 32 : 0), 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS + (DBW ? 32 * DBW_SLOTS2 : 0), 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_c,
                 const __grid_constant__ CUtensorMap map_mask, void* __restrict__ C, int M, int N, int K, Epi epi, unsigned int* __restrict__ sched) {
   constexpr int BN = 256;
@@ -606,7 +608,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (threadIdx.x < 3 * TRACE_TILES * 4) reinterpret_cast<volatile long long*>(smem_aligned + BAR_OFF + 512)[threadIdx.x] = 0;
 #endif
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), DBW ? 2 : 1); mbar_init(ready_bar(s), 1); }
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), DBW ? 1 + DBW_WARPS2 : 1); mbar_init(ready_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); mbar_init(mask_bar(a), 1); }
     for (int i = 0; i < RING; ++i) mbar_init(ring_base + 8u * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -722,12 +724,19 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (DBW && warp == 2 + EPI_WARPS + 3) {
+    // idle slot: this warp id would share the MMA issuer's scheduler (its instruction stream is the pair's critical path)
   } else if (DBW && warp >= 2 + EPI_WARPS) {
-    // ===== bias-gradient reducer warp (one per CTA): this CTA's 128 columns of the dY tile =====
+    // ===== bias-gradient reducer warps (DBW_WARPS2 per CTA): this CTA's 128 columns of the dY tile, 16 k-rows of a stage each.
+    //       One warp took 1.6k cycles per summed stage — three k-blocks of MMA time during which it could not release the
+    //       following stages either, and the 6-stage ring ran dry (first layer: every 4th stage is summed).  Every warp
+    //       writes its own partial row; the rows are summed in a fixed order by the reduce kernel. =====
     static_assert(!DBW || B_MN, "reducer warps read MN-major B tiles");
+    const int rw = warp - (2 + EPI_WARPS) - (warp > 2 + EPI_WARPS + 3 ? 1 : 0);      // warps 10, 11, 12, 14
     const int col0 = lane * 4;                           // 4 consecutive columns of the CTA's half
     const uint32_t box_off = (uint32_t)(col0 >> 6) * (BLOCK_K * 128) + (uint32_t)(col0 & 7) * 2;
     const int chunk = (col0 & 63) >> 3;
+    constexpr int ROWS_PER_WARP = BLOCK_K / DBW_WARPS2;
     float acc4[4] = {0.f, 0.f, 0.f, 0.f};
     int stage = 0; uint32_t phase = 0;
     TileFeed feed(ring_base, false);
@@ -739,13 +748,13 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int m_blk = m0 / 256;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(rank == 0 ? full_bar(stage) : ready_bar(stage), phase);
-        // the peer CTA cannot wait on the leader's full barrier: the leader's reducer forwards "stage landed" (it used to be the
-        // MMA issuer's job, whose instruction stream is the pair's critical path)
-        if (rank == 0 && lane == 0) mbar_arrive_cluster(map_to_rank(ready_bar(stage), 1));
+        // the peer CTA cannot wait on the leader's full barrier: the leader's first reducer warp forwards "stage landed" (it
+        // used to be the MMA issuer's job, whose instruction stream is the pair's critical path)
+        if (rank == 0 && rw == 0 && lane == 0) mbar_arrive_cluster(map_to_rank(ready_bar(stage), 1));
         if (kb % num_m == m_blk) {
           const uint8_t* sb = smem_aligned + stage * STAGE2_BYTES + A_STAGE_BYTES + box_off;
 #pragma unroll 8
-          for (int r = 0; r < BLOCK_K; ++r) {
+          for (int r = rw * ROWS_PER_WARP; r < (rw + 1) * ROWS_PER_WARP; ++r) {
             const uint2 v = *reinterpret_cast<const uint2*>(sb + r * 128 + ((chunk ^ (r & 7)) << 4));
             const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
             const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
@@ -761,8 +770,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (cbase + j < N) {
-          epi.db[(size_t)(m_blk * db_rows + (part == 1 ? 1 : 0)) * N + cbase + j] = acc4[j];
-          if (db_rows == 2 && part < 0) epi.db[(size_t)(m_blk * 2 + 1) * N + cbase + j] = 0.0f;
+          epi.db[(size_t)((m_blk * db_rows + (part == 1 ? 1 : 0)) * DBW_WARPS2 + rw) * N + cbase + j] = acc4[j];
+          if (db_rows == 2 && part < 0) epi.db[(size_t)((m_blk * 2 + 1) * DBW_WARPS2 + rw) * N + cbase + j] = 0.0f;
         }
         acc4[j] = 0.f;
       }
@@ -1065,7 +1074,7 @@ int launch_tc2_impl(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t 
   }
   int64_t tiles = pg_cdiv(M, 256) * pg_cdiv(N, 256) + epi.tail;
   int clusters = (int)(tiles < ctx->num_sms / 2 ? tiles : ctx->num_sms / 2);
-  kern<<<2 * clusters, NUM_THREADS + (DBW ? 32 : 0), SMEM2_BYTES, ctx->stream>>>(ma, mb, mc, mm, C, (int)M, (int)N, (int)K, epi, ctx->counters + SCHED_SLOT);
+  kern<<<2 * clusters, NUM_THREADS + (DBW ? 32 * DBW_SLOTS2 : 0), SMEM2_BYTES, ctx->stream>>>(ma, mb, mc, mm, C, (int)M, (int)N, (int)K, epi, ctx->counters + SCHED_SLOT);
   PG_LAUNCHED(ctx);
   return PG_OK;
 }
@@ -1157,6 +1166,25 @@ __global__ void __launch_bounds__(256) reduce_f32_kernel(const float* __restrict
   float s = 0.0f;
   for (int z = 0; z < splits; ++z) s += part[(int64_t)z * n + i];
   out[i] = s;
+}
+
+// out[n] = sum over `rows` partial rows of part[r][n], fixed order: block (32 columns, 8 row lanes), each lane walks rows
+// ty, ty + 8, ... (coalesced 128-byte reads), the 8 lanes are added in order.  For the fused bias gradient's partials
+// (up to 128 rows: a one-thread-per-column walk over them took ~12 us).
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int rows) {
+  __shared__ float sm[8][33];
+  const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  float s = 0.0f;
+  if (c < n)
+    for (int r = threadIdx.y; r < rows; r += 8) s += part[(int64_t)r * n + c];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < n) {
+    float t = sm[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += sm[i][threadIdx.x];
+    out[c] = t;
+  }
 }
 
 int aux_ensure(pg_ctx* ctx, size_t bytes) {
@@ -1535,7 +1563,7 @@ static int tc_linear_bwd_impl(pg_ctx* ctx, const void* X, const void* W, const v
     // the partial last wave of the pair kernel is split in two K halves (Epi::tail); scratch: [db partials][tail partial tiles]
     static const bool direct_epi = getenv("PG_TC_DIRECT_EPI") != nullptr;
     const int tail = (two && !direct_epi) ? tail_split_tiles(ctx, K, N, M) : 0;
-    const int db_rows = tail > 0 ? 2 : 1;
+    const int db_rows = (tail > 0 ? 2 : 1) * (two ? DBW_WARPS2 : 1);     // partial rows per m-block (pair kernel: one per reducer warp)
     const size_t db_bytes = fuse_db ? (((size_t)m_blocks * db_rows * N * sizeof(float) + 1023) & ~(size_t)1023) : 0;
     float* db_part = nullptr;
     float* tail_ws = nullptr;
@@ -1571,7 +1599,7 @@ static int tc_linear_bwd_impl(pg_ctx* ctx, const void* X, const void* W, const v
       PG_LAUNCHED(ctx);
     }
     if (fuse_db) {
-      reduce_f32_kernel<<<(unsigned)pg_cdiv(N, 256), 256, 0, ctx->stream>>>(db_part, (float*)db, N, (int)m_blocks * db_rows);
+      reduce_rows_kernel<<<(unsigned)pg_cdiv(N, 32), dim3(32, 8), 0, ctx->stream>>>(db_part, (float*)db, N, (int)m_blocks * db_rows);
       PG_LAUNCHED(ctx);
       db = nullptr;
     }
