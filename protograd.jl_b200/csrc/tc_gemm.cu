@@ -347,6 +347,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== MMA issuer (single thread) =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BLOCK_N);
+      constexpr int A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4, B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      const uint64_t a_desc0 = A_MN ? make_desc(smem_base, BLOCK_K * 128, 1024) : make_desc(smem_base, 16, 1024);
+      const uint64_t b_desc0 = B_MN ? make_desc(smem_base + A_STAGE_BYTES, BLOCK_K * 128, 1024) : make_desc(smem_base + A_STAGE_BYTES, 16, 1024);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       TileFeed feed(ring_base, false);
@@ -359,19 +362,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);             // TMA bytes have landed
           tcgen05_fence_after();
-          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          // K-major: a k-step advances 16 elements = 32 B inside the 128 B swizzled row; MN-major: 16 k-rows = 2 swizzle
+          // atoms = 2048 B.  Only the descriptor's start-address field (address >> 4, 14 bits, never carries) moves: one
+          // 64-bit add per operand and k-step (the issuer's instruction stream is on the critical path, see the pair kernel)
+          const uint64_t a_st = a_desc0 + (uint64_t)((uint32_t)stage * (STAGE_BYTES >> 4));
+          const uint64_t b_st = b_desc0 + (uint64_t)((uint32_t)stage * (STAGE_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // K-major: advance 16 elements = 32 B inside the 128 B swizzled row.
-            // MN-major: advance 16 k-rows = 2 swizzle atoms = 2048 B.
-            const uint64_t ad = A_MN ? make_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t bd = B_MN ? make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024) : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(d_tmem, a_st + (uint64_t)(k * A_KSTEP), b_st + (uint64_t)(k * B_KSTEP), idesc, ((kb - kb0) | k) != 0);
           tcgen05_commit(empty_bar(stage));              // frees the smem slot once these MMAs retire
-          if (kb == kb1 - 1) tcgen05_commit(tfull_bar(acc));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        tcgen05_commit(tfull_bar(acc));                  // tracks every MMA issued so far: the accumulator is complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
