@@ -48,12 +48,15 @@ C5_SPEC = [("conv", 1, 6, 5, False), ("relu",), ("maxpool", 2), ("conv", 6, 16, 
 FLOPS_OTHER = {"C1": 319_600, "C3": 1_517_040, "C5": 490_240}
 
 
-def synth(B, seed):
+def synth(B, seed, with_u8=False):
+    """MNIST-shaped synthetic batch: uniform 8-bit pixels scaled to Float32 in [0, 1] exactly like the reference's loader
+    (MLDatasets yields Float32(pixel / 255), examples/01_mnist_mlp.jl:9-12) and random one-hot labels"""
     rng = np.random.default_rng(seed)
-    x = rng.random((B, D_IN), dtype=np.float32)
+    u8 = rng.integers(0, 256, (B, D_IN), dtype=np.uint8)
+    x = u8.astype(np.float32) / np.float32(255)
     lab = np.zeros((B, D_OUT), dtype=np.float32)
     lab[np.arange(B), rng.integers(0, D_OUT, B)] = 1.0
-    return x, lab
+    return (x, lab, u8) if with_u8 else (x, lab)
 
 
 def init_params(seed=0):
@@ -70,6 +73,7 @@ def workload_config(B, world, math, dp_mode, exact_adam):
     return {"workload": "wide MLP 784-4096-4096-10 (BASELINE configs[3]), softmax+cross-entropy, Adam(1e-3), %d samples/GPU" % B,
             "global_batch": B * world, "parallelism": "dp%d" % world, "dp_mode": dp_mode if world > 1 else None, "math": math,
             "adam": "float64-promoted (bit-exact)" if exact_adam else "fused float32 (normwise 1e-7 of the reference form)",
+            "inputs": "synthetic: uniform 8-bit pixels / 255 as Float32 (MNIST's own value grid), random one-hot labels",
             "l2": "working set per step (>600 MB of activations, weights, gradients, optimizer state) exceeds the 126 MB L2"}
 
 
@@ -267,17 +271,20 @@ def main():
     state = pg.init(pg.Adam(stepsize=1e-3, fast=not args.exact_adam), model)
     if world > 1:
         dp.broadcast_parameters(model, dp=dp.init(ctx))
-    x_h, lab_h = synth(B, 1000 + rank)
+    x_h, lab_h, u8_h = synth(B, 1000 + rank, with_u8=True)
     x_d, lab_d = pg.DeviceArray.from_numpy(ctx, x_h), pg.DeviceArray.from_numpy(ctx, lab_h)
-    # pinned host copies for the end-to-end leg: the minibatch as the host holds it for this path — bf16 pixels (the first
-    # GEMM rounds its input to bf16 anyway, so results are identical to uploading fp32 and casting on the device) and int32
-    # class indices instead of a dense one-hot matrix (pg_softmax_ce_idx_fwd_bwd): 12.9 MB instead of 26 MB per step
+    # pinned host copies for the end-to-end leg: the minibatch as the host holds it for this path — the 8-bit pixels the
+    # dataset is stored in (converted on the device by pg_vec_cast_u8_bf16 to exactly the bf16 values the first GEMM would
+    # round the reference's Float32(pixel / 255) array to) and int32 class indices instead of a dense one-hot matrix
+    # (pg_softmax_ce_idx_fwd_bwd): 6.5 MB per step instead of 26 MB — at 8 ranks the uploads share the host's PCIe uplinks
+    # and 12.9 MB of bf16 pixels per rank and step made the end-to-end leg upload-bound (1.04 vs 0.86 ms)
     if args.math == "bf16":
-        xb_h, cls_h = f32_to_bf16(x_h), np.argmax(lab_h, axis=1).astype(np.int32)
-        pin_x, pin_l = pg.PinnedBuffer(xb_h.nbytes), pg.PinnedBuffer(cls_h.nbytes)
-        x_p, lab_p = pin_x.as_numpy(np.uint16, xb_h.shape), pin_l.as_numpy(np.int32, cls_h.shape)
-        x_p[...] = xb_h; lab_p[...] = cls_h
-        e2e_specs = [(x_h.shape, pg.BF16), (cls_h.shape, np.int32)]
+        cls_h = np.argmax(lab_h, axis=1).astype(np.int32)
+        pin_x, pin_l = pg.PinnedBuffer(u8_h.nbytes), pg.PinnedBuffer(cls_h.nbytes)
+        x_p, lab_p = pin_x.as_numpy(np.uint8, u8_h.shape), pin_l.as_numpy(np.int32, cls_h.shape)
+        x_p[...] = u8_h; lab_p[...] = cls_h
+        e2e_specs = [(u8_h.shape, np.uint8), (cls_h.shape, np.int32)]
+        xb_dev = pg.DeviceArray.empty(ctx, x_h.shape, pg.BF16)
     else:
         pin_x, pin_l = pg.PinnedBuffer(x_h.nbytes), pg.PinnedBuffer(lab_h.nbytes)
         x_p, lab_p = pin_x.as_numpy(np.float32, x_h.shape), pin_l.as_numpy(np.float32, lab_h.shape)
@@ -409,8 +416,13 @@ def main():
             xd, ld = pf.next()
             if i + 1 < n:
                 pf.submit(x_p, lab_p)
-            out = train_step(xd, ld)
-            pf.release()
+            if args.math == "bf16":        # 8-bit pixels -> bf16(pixel / 255) on the device; the upload slot is free again after it
+                call("pg_vec_cast_u8_bf16", ctx.h, xb_dev.ptr, xd.ptr, xd.size, 255.0)
+                pf.release()
+                out = train_step(xb_dev, ld)
+            else:
+                out = train_step(xd, ld)
+                pf.release()
             out.fetch_async()              # D2H of this step's loss, queued right behind the step
             pending.append(out)
             if len(pending) > lag:
@@ -508,7 +520,7 @@ def main():
             "config": workload_config(B, world, args.math, args.dp_mode, args.exact_adam),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(x_p.nbytes + lab_p.nbytes), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / e2e_steps,
-                    "inputs": "bf16 pixels + int32 class indices from pinned host memory, double-buffered on a copy stream" if args.math == "bf16" else "fp32 pixels + fp32 one-hot labels from pinned host memory"},
+                    "inputs": "uint8 pixels (converted to bf16(pixel / 255) on the device) + int32 class indices from pinned host memory, double-buffered on a copy stream" if args.math == "bf16" else "fp32 pixels + fp32 one-hot labels from pinned host memory"},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms, "cpu_affinity_rank0": numa, "clocks": clk, "loss_after_warmup": first_loss,
             "tflops_per_gpu": FLOP_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12, "parity": parity,
         }

@@ -97,6 +97,10 @@ int pg_vec_fill(pg_ctx* ctx, int dtype, void* out, double c, int64_t n);        
 int pg_vec_dot(pg_ctx* ctx, int dtype, const void* x, const void* y, int64_t n, double* result);
 /* f32 -> bf16 shadow of an arena (operands of the tensor-core path) */
 int pg_vec_cast_bf16(pg_ctx* ctx, void* out_bf16, const void* x_f32, int64_t n);
+/* out = bf16(Float32(x_u8) / divisor): 8-bit pixels as the dataset stores them (the reference's examples read MNIST through
+ * MLDatasets, /root/reference/examples/01_mnist_mlp.jl:9-12, which yields Float32(pixel / 255)); bit-identical to
+ * pg_vec_cast_bf16 of that Float32 array, at a quarter of the upload bytes */
+int pg_vec_cast_u8_bf16(pg_ctx* ctx, void* out_bf16, const void* x_u8, int64_t n, double divisor);
 
 /* ---- Optimizers: one fused pass over the arena (src/optimizers/*.jl) ---------------------- */
 /* `shadow_bf16` (nullable): also write bf16(p_new) at the same index (tensor-core operand copy). */

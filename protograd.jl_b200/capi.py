@@ -75,6 +75,7 @@ _SIGS = {
     "pg_vec_fill": [_P, _I, _P, _D, _L],
     "pg_vec_dot": [_P, _I, _P, _P, _L, POINTER(c_double)],
     "pg_vec_cast_bf16": [_P, _P, _P, _L],
+    "pg_vec_cast_u8_bf16": [_P, _P, _P, _L, _D],
     "pg_opt_gd": [_P, _I, _P, _P, _L, _D, _I, _P],
     "pg_opt_heavyball": [_P, _I, _P, _P, _P, _L, _D, _D, _I, _P],
     "pg_opt_nesterov": [_P, _I, _P, _P, _P, _L, _D, _D, _I, _P],

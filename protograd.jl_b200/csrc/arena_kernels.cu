@@ -306,6 +306,44 @@ int pg_vec_dot(pg_ctx* ctx, int dtype, const void* x, const void* y, int64_t n, 
   return PG_OK;
 }
 
+// 8-bit pixels -> bf16(float(u8) / divisor): the device half of an input pipeline that keeps images as the bytes they are
+// stored in (MNIST's IDX files, examples/01_mnist_mlp.jl:9-12 via MLDatasets) — bit-identical to casting the Float32 array
+// the reference builds on the host, at a quarter of its upload bytes
+__global__ void __launch_bounds__(256) cast_u8_bf16_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n, float divisor) {
+  const int64_t n16 = n >> 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat162 o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[2 * j] = __floats2bfloat162_rn(__fdiv_rn((float)(w[j] & 0xffu), divisor), __fdiv_rn((float)((w[j] >> 8) & 0xffu), divisor));
+      o[2 * j + 1] = __floats2bfloat162_rn(__fdiv_rn((float)((w[j] >> 16) & 0xffu), divisor), __fdiv_rn((float)(w[j] >> 24), divisor));
+    }
+    uint4* op = reinterpret_cast<uint4*>(out) + 2 * i;
+    op[0] = *reinterpret_cast<const uint4*>(&o[0]);
+    op[1] = *reinterpret_cast<const uint4*>(&o[4]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 15)) {
+    const int64_t i = (n16 << 4) + threadIdx.x;
+    out[i] = __float2bfloat16_rn(__fdiv_rn((float)x[i], divisor));
+  }
+}
+
+int pg_vec_cast_u8_bf16(pg_ctx* ctx, void* out, const void* x, int64_t n, double divisor) {
+  PG_CHECK_CTX(ctx);
+  PG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0, "pointers must be 16-byte aligned");
+  PG_REQUIRE(divisor != 0.0, "zero divisor");
+  if (n <= 0) return PG_OK;
+  int64_t blocks = pg_cdiv(pg_cdiv(n, 16), 256);
+  int64_t cap = (int64_t)ctx->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cast_u8_bf16_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint8_t*)x, (__nv_bfloat16*)out, n, (float)divisor);
+  PG_LAUNCHED(ctx);
+  return PG_OK;
+}
+
 int pg_vec_cast_bf16(pg_ctx* ctx, void* out, const void* x, int64_t n) {
   PG_CHECK_CTX(ctx);
   PG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0, "pointers must be 16-byte aligned");

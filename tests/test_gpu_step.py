@@ -388,3 +388,19 @@ def test_device_dataset_and_checkpoint(pg, tmp_path):
         out, pb = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(xb), yb), mm_)
         pg.step(s_, pb())
     assert np.array_equal(m.vec(), m2.vec())
+
+
+def test_u8_pixels_cast_matches_the_float32_pipeline(pg):
+    """pg_vec_cast_u8_bf16 (8-bit pixels -> bf16(pixel / 255) on the device) == the bf16 rounding of the Float32(pixel / 255)
+    array the reference's loader builds on the host, bit for bit (incl. a length that is not a multiple of 16)."""
+    from protograd_b200.capi import call
+    from protograd_b200.device import f32_to_bf16
+    ctx = pg.Context.get()
+    rng = np.random.default_rng(3)
+    for n in (784 * 37, 16 * 1000 + 5):
+        u8 = rng.integers(0, 256, n, dtype=np.uint8)
+        ref = f32_to_bf16(u8.astype(np.float32) / np.float32(255))
+        src = pg.DeviceArray.from_numpy(ctx, u8)
+        dst = pg.DeviceArray.empty(ctx, (n,), pg.BF16)
+        call("pg_vec_cast_u8_bf16", ctx.h, dst.ptr, src.ptr, n, 255.0)
+        assert np.array_equal(dst.numpy(), ref)
