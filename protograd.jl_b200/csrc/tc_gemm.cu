@@ -2,13 +2,21 @@
 // hand-written tcgen05.mma GEMMs with TMEM accumulators and TMA-fed shared-memory pipelines, warp-specialised
 // (1 TMA producer warp, 1 MMA-issuer warp, 8 epilogue warps, optional bias-gradient reducer warps) and
 // persistent, with double-buffered accumulators (2 x 256 TMEM columns) so the epilogue of tile i overlaps the
-// MMAs of tile i+1.  Two kernels share the epilogue code:
+// MMAs of tile i+1.  Two kernels:
 //   tc_gemm2_kernel  wide layers: a cluster of two CTAs (one SM pair) owns a 256x256 tile (cta_group::2),
-//                    6 stages of 32 KB per CTA;
-//   tc_gemm_kernel   128 x 256 (or 128 x 32) tiles on one CTA: narrow layers, small shapes, split-K.
+//                    6 stages of 32 KB per CTA; staged epilogue (TMEM -> registers -> swizzled shared-memory
+//                    box -> TMA store; the ReLU' mask tile and the K-split partial arrive by TMA load into the
+//                    same box); K-split of the partial last wave for fp32 outputs;
+//   tc_gemm_kernel   128 x 256 (or 128 x 32) tiles on one CTA: narrow layers, small shapes, split-K;
+//                    direct epilogue (epilogue_chunk).
 // Tiles are handed out by a dynamic scheduler (atomic work counter + shared-memory id ring, see below).
 // fp32 accumulation; epilogues fuse bias+ReLU (forward), the ReLU' mask (data gradient) or write fp32 straight
 // into the gradient arena (weight gradient, with the bias gradient summed from the staged dY tiles).
+// What the round-2 timelines (tools/tc_trace.py, -DPG_TC_TRACE) showed, in order of cost: the shared-memory pipe is
+// saturated by the mainloop, so an epilogue that spends L1 wavefronts slows the MMAs; a release-fenced DSMEM store
+// in the producer stalls it for a MEMBAR.ALL.GPU per tile; the MMA issuer thread's instruction stream is on the
+// critical path (16 -> 8 instructions per MMA: -5 % time); a bias-gradient reducer that holds a stage for 1.6k
+// cycles starves the 6-stage ring.
 //
 // No physical transposes: the three products use K-major or MN-major shared-memory operand
 // descriptors directly on the row-major tensors:
