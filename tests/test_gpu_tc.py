@@ -35,7 +35,9 @@ def _dev_bf16(pg, a):
 
 
 @pytest.mark.parametrize("layout", [0, 1, 2])
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (384, 768, 320), (136, 264, 72), (8, 8, 8), (1024, 784, 4096), (784, 4096, 1024)])
+# (520, 776, 264) and (1288, 520, 72): pair kernel on ragged tiles in both directions (8 valid rows / columns in the last box)
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (384, 768, 320), (136, 264, 72), (8, 8, 8), (1024, 784, 4096), (784, 4096, 1024),
+                                   (520, 776, 264), (1288, 520, 72)])
 def test_tc_gemm_layouts(pg, layout, M, N, K):
     from protograd_b200.capi import call
     rng = np.random.default_rng(M + N + K + layout)
@@ -52,6 +54,26 @@ def test_tc_gemm_layouts(pg, layout, M, N, K):
 
 # (1000, 776, 520): pair kernel with the staged TMA-store epilogue on ragged tiles — partial row blocks, a last column box of 8
 # valid columns, the ReLU' mask box clipped the same way
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K", [(520, 776, 264), (1024, 4096, 136)])
+def test_tc_gemm_bf16_output(pg, layout, M, N, K):
+    """pg_tc_gemm with a bf16 result (the pair kernel's staged epilogue without bias / mask): the fp32 accumulator rounded once."""
+    from protograd_b200.capi import call
+    from protograd_b200.device import bf16_to_f32
+    rng = np.random.default_rng(M + N + K + layout)
+    A = _bf(pg, rng.standard_normal((M, K))); B = _bf(pg, rng.standard_normal((K, N)))
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    a_st = np.ascontiguousarray(A.T) if layout == 2 else A
+    b_st = np.ascontiguousarray(B.T) if layout == 1 else B
+    ctx = pg.Context.get()
+    ad, bd = _dev_bf16(pg, a_st), _dev_bf16(pg, b_st)
+    cd = pg.DeviceArray.empty(ctx, (M, N), pg.BF16)
+    call("pg_tc_gemm", ctx.h, layout, ad.ptr, bd.ptr, cd.ptr, 2, M, N, K)
+    got = bf16_to_f32(cd.numpy())
+    assert rel_err(got, ref) <= 4e-3                                   # bf16 output rounding 2^-9
+    assert np.all(np.abs(got - ref) <= np.abs(ref) * 2.0 ** -8 + 1e-4)   # elementwise: that rounding + fp32 accumulation noise on near-zero sums
+
+
 @pytest.mark.parametrize("M,K,N,act", [(256, 784, 512, 1), (1024, 512, 4096, 1), (200, 264, 72, 0), (512, 4096, 10, 0), (64, 128, 32, 0), (1000, 776, 520, 1)])
 def test_tc_linear_fwd_bwd(pg, M, K, N, act):
     """pg_tc_linear_fwd/bwd (wide: tcgen05; N <= 32: skinny) vs float64 on bf16-rounded operands."""
