@@ -132,7 +132,13 @@ __global__ void __launch_bounds__(FwdCfg<G>::THREADS) conv_relu_pool_fwd_kernel(
 // ---------------------------------------------------------------------------------------------------------------
 template <typename G>
 struct WgCfg {
-  static constexpr int TPS = G::CIN * G::K * G::HO;            // threads per sample slot
+  static constexpr int TPS0 = G::CIN * G::K * G::HO;           // (ci, u, i) row-threads of one sample
+  // output channels are split over CS thread groups when that keeps a sample within 512 threads: K x COUTP accumulators
+  // plus the input row pushed the kernel to 255 registers with spills and one 8-warp CTA per SM (ncu: 12.5 % warps
+  // active, FMA pipe 23-32 % active); half the channels per thread fit 128 registers: twice the warps per SM
+  static constexpr int CS = (2 * TPS0 <= 512 && G::COUTP % 8 == 0) ? 2 : 1;
+  static constexpr int CT = G::COUTP / CS;                     // output channels per thread
+  static constexpr int TPS = CS * TPS0;                        // threads per sample slot
   static constexpr int SLOTS = (256 / TPS) > 0 ? (256 / TPS) : 1;
   static constexpr int THREADS = ((SLOTS * TPS + 31) / 32) * 32;
   static constexpr int NW = G::COUT * G::CIN * G::K * G::K;    // filter elements
@@ -141,10 +147,10 @@ struct WgCfg {
   static constexpr int XV = (G::XS / 4 + TPS - 1) / TPS;       // float4 of the input tile per thread
   static constexpr int SV = (G::YS + TPS - 1) / TPS;           // pooled elements per thread
   static constexpr int BUF = G::XS + DY;                       // one sample's tiles (floats)
-  static constexpr int RED = SLOTS * TPS * G::K * G::COUTP;    // final cross-thread reduction buffer (floats)
+  static constexpr int RED = SLOTS * TPS * G::K * CT;          // final cross-thread reduction buffer (floats)
   static constexpr int STAGE = SLOTS * 2 * BUF;
   static constexpr int SMEM_FLOATS = STAGE > RED ? STAGE : RED;
-  static constexpr int MINB = PG_WGRAD_MINB;                   // CTAs per SM the register budget is sized for
+  static constexpr int MINB = (CS == 2 && THREADS <= 256) ? 2 : PG_WGRAD_MINB;   // CTAs per SM the register budget is sized for
 };
 
 template <typename G>
@@ -152,20 +158,21 @@ __global__ void __launch_bounds__(WgCfg<G>::THREADS, WgCfg<G>::MINB) conv_relu_p
                                                                                  const uint8_t* __restrict__ amax, const float* __restrict__ gy,
                                                                                  float* __restrict__ partial, int64_t N) {
   using C = WgCfg<G>;
-  constexpr int K = G::K, CIN = G::CIN, COUT = G::COUT, COUTP = G::COUTP, HO = G::HO, WO = G::WO;
+  constexpr int K = G::K, CIN = G::CIN, COUT = G::COUT, COUTP = G::COUTP, HO = G::HO, WO = G::WO, CT = C::CT;
   extern __shared__ __align__(16) float smem[];
   const int slot = threadIdx.x / C::TPS, t = threadIdx.x % C::TPS;
   const bool worker = threadIdx.x < C::SLOTS * C::TPS;
-  const int i = t % HO, u = (t / HO) % K, ci = t / (HO * K);
+  const int i = t % HO, u = (t / HO) % K, ci = C::CS > 1 ? (t / (HO * K)) % CIN : t / (HO * K);
+  const int cs = C::CS > 1 ? t / (HO * K * CIN) : 0;           // which group of CT channels
   float* base = smem + slot * 2 * C::BUF;
-  float acc[K][COUTP];
-  float dbacc[COUTP];
+  float acc[K][CT];
+  float dbacc[CT];
 #pragma unroll
   for (int v = 0; v < K; ++v)
 #pragma unroll
-    for (int c = 0; c < COUTP; ++c) acc[v][c] = 0.0f;
+    for (int c = 0; c < CT; ++c) acc[v][c] = 0.0f;
 #pragma unroll
-  for (int c = 0; c < COUTP; ++c) dbacc[c] = 0.0f;
+  for (int c = 0; c < CT; ++c) dbacc[c] = 0.0f;
   // ---- register prefetch of one sample ----
   float4 xr[C::XV];
   float gr[C::SV];
@@ -223,11 +230,11 @@ __global__ void __launch_bounds__(WgCfg<G>::THREADS, WgCfg<G>::MINB) conv_relu_p
     float row[G::W];
 #pragma unroll
     for (int c = 0; c < G::W; ++c) row[c] = buf[(ci * G::H + i + u) * G::W + c];
-    const float4* dv = reinterpret_cast<const float4*>(buf + G::XS + i * C::DROW);
+    const float4* dv = reinterpret_cast<const float4*>(buf + G::XS + i * C::DROW) + cs * (CT / 4);
 #pragma unroll
     for (int j = 0; j < WO; ++j) {
 #pragma unroll
-      for (int c4 = 0; c4 < COUTP / 4; ++c4) {
+      for (int c4 = 0; c4 < CT / 4; ++c4) {
         const float4 d = dv[j * (COUTP / 4) + c4];
 #pragma unroll
         for (int v = 0; v < K; ++v) {
@@ -239,11 +246,11 @@ __global__ void __launch_bounds__(WgCfg<G>::THREADS, WgCfg<G>::MINB) conv_relu_p
       }
       asm volatile("" ::: "memory");     // keep the (fully unrolled) tile loads next to their FMAs: hoisting all of them costs > 128 registers
     }
-    if (ci == 0 && u == 0) {            // bias gradient: row i of the tile, by the HO threads of (ci = 0, u = 0) only
+    if (ci == 0 && u == 0) {            // bias gradient: row i of the tile, by the HO threads of (ci = 0, u = 0) of each channel group
 #pragma unroll
       for (int j = 0; j < WO; ++j)
 #pragma unroll
-        for (int c4 = 0; c4 < COUTP / 4; ++c4) {
+        for (int c4 = 0; c4 < CT / 4; ++c4) {
           const float4 d = dv[j * (COUTP / 4) + c4];
           dbacc[4 * c4] += d.x; dbacc[4 * c4 + 1] += d.y; dbacc[4 * c4 + 2] += d.z; dbacc[4 * c4 + 3] += d.w;
         }
@@ -251,12 +258,12 @@ __global__ void __launch_bounds__(WgCfg<G>::THREADS, WgCfg<G>::MINB) conv_relu_p
   }
   // ---- reduce over the HO row-threads and the sample slots (fixed order), one partial per CTA ----
   __syncthreads();
-  float* red = smem;                                             // [SLOTS*TPS][K*COUTP]
+  float* red = smem;                                             // [SLOTS*TPS][K*CT]
   if (worker) {
 #pragma unroll
     for (int v = 0; v < K; ++v)
 #pragma unroll
-      for (int c = 0; c < COUTP; ++c) red[threadIdx.x * (K * COUTP) + v * COUTP + c] = acc[v][c];
+      for (int c = 0; c < CT; ++c) red[threadIdx.x * (K * CT) + v * CT + c] = acc[v][c];
   }
   __syncthreads();
   float* out = partial + (int64_t)blockIdx.x * (C::NW + COUT);
@@ -264,21 +271,23 @@ __global__ void __launch_bounds__(WgCfg<G>::THREADS, WgCfg<G>::MINB) conv_relu_p
     // e = ((co*CIN + ci)*K + a)*K + bq with a, bq the UNFLIPPED filter indices: correlation tap (u, v) = (K-1-a, K-1-bq)
     const int bq = e % K, a = (e / K) % K, ci2 = (e / (K * K)) % CIN, co = e / (K * K * CIN);
     const int u2 = K - 1 - a, v2 = K - 1 - bq;
+    const int cs2 = co / CT, cl = co % CT;
     float s = 0.0f;
     for (int sl = 0; sl < C::SLOTS; ++sl)
-      for (int r = 0; r < HO; ++r) s += red[(sl * C::TPS + (ci2 * K + u2) * HO + r) * (K * COUTP) + v2 * COUTP + co];
+      for (int r = 0; r < HO; ++r) s += red[(sl * C::TPS + ((cs2 * CIN + ci2) * K + u2) * HO + r) * (K * CT) + v2 * CT + cl];
     out[e] = s;
   }
   __syncthreads();
   if (worker && ci == 0 && u == 0) {
 #pragma unroll
-    for (int c = 0; c < COUTP; ++c) red[threadIdx.x * COUTP + c] = dbacc[c];
+    for (int c = 0; c < CT; ++c) red[threadIdx.x * CT + c] = dbacc[c];
   }
   __syncthreads();
   for (int co = threadIdx.x; co < COUT; co += blockDim.x) {
+    const int cs2 = co / CT, cl = co % CT;
     float s = 0.0f;
     for (int sl = 0; sl < C::SLOTS; ++sl)
-      for (int r = 0; r < HO; ++r) s += red[(sl * C::TPS + r) * COUTP + co];     // threads (ci = 0, u = 0, i = r)
+      for (int r = 0; r < HO; ++r) s += red[(sl * C::TPS + cs2 * (CIN * K * HO) + r) * CT + cl];     // threads (cs2, ci = 0, u = 0, i = r)
     out[C::NW + co] = s;
   }
 }
