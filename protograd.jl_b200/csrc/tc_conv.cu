@@ -36,8 +36,9 @@ constexpr int MAX_STAGES = 8, MAX_SLOTS = 4;
 
 // Warp roles of a CTA: warp 0 issues the MMAs, then EPI_WARPS epilogue warps (groups of four, one warp per TMEM
 // lane quarter, the groups taking alternate tiles), one bulk-copy loader warp, PROD_WARPS producer warps
-// (8 chunk lanes x HALVES row halves).  The regular geometry runs one CTA per SM; SMALL (PG_TCCONV_SMALL=1,
-// experimental) halves everything so that two CTAs — two independent pipelines and MMA issuers — share an SM.
+// (8 chunk lanes x HALVES row halves).  The regular geometry runs one CTA per SM and is the only one instantiated; SMALL
+// halves everything so that two CTAs — two independent pipelines and MMA issuers — share an SM (measured in round 2:
+// no net gain, profiles/r2_tc_conv_small.md; the template parameter is kept, the instantiations are gone).
 template <bool SMALL>
 struct Geo {
   static constexpr int PROD_WARPS = SMALL ? 8 : 16;
