@@ -35,10 +35,20 @@ class GraphStep:
             self._sync_scalars_to_device()
         # warm-up steps allocate plan buffers / scratch (not allowed during capture); they are real
         # steps, so snapshot and restore the parameters and optimizer state around them
+        # bf16 mode on a Float32 arena: the captured optimizer pass also writes the bf16 operand copy of the new parameters, so
+        # the captured forward contains no cast pass (as `step(..., shadow=True)` does for eager steps)
+        self._shadow = False
+        if math == "bf16" and isinstance(state, (AdamState, NesterovState, GradientDescentState, HeavyBallMethodState)):
+            leaves = model.arena()[3]
+            self._shadow = len(leaves) > 0 and leaves[0].dtype == np.float32 and leaves[0].offset == 0
         snap = self._snapshot()
         for _ in range(max(1, warmup)):
             self._one_step()
         self._restore(snap)
+        if self._shadow:
+            # the restore invalidated the shadow: one forward (no state change) re-casts it, so that the capture below sees a
+            # valid copy and records no cast
+            eval_with_pullback(self.f, self.model, math=self.math)
         self.ctx.sync()
         # no Python garbage collection while capturing: a finalizer freeing device memory (cudaFree)
         # in the middle of a stream capture would invalidate it
@@ -108,28 +118,48 @@ class GraphStep:
         g = pb()
         st = self.state
         ctx, code, p, pg_, n = st._arena(g)
+        shadow = None
+        if self._shadow:
+            from .trace import shadow_target
+            shadow = shadow_target(self.model)
         if isinstance(st, AdamState):
             o = st.optimizer
             fl = _f64(st.stepsize) | (capi.MATH_FAST if o.fast else 0)
             call("pg_opt_adam_dev", ctx.h, code, p, st._ptr(st.m), st._ptr(st.v),
                  st._ptr(st._m_hat) if st._m_hat is not None else None, st._ptr(st._v_hat) if st._v_hat is not None else None,
-                 pg_, n, float(st.stepsize), float(o.beta1), float(o.beta2), float(o.epsilon), self._scalars.ptr, fl, None)
+                 pg_, n, float(st.stepsize), float(o.beta1), float(o.beta2), float(o.epsilon), self._scalars.ptr, fl, shadow)
         elif isinstance(st, NesterovState):
-            call("pg_opt_nesterov_dev", ctx.h, code, p, st._ptr(st.variable_prev), pg_, n, float(st.stepsize), self._scalars.ptr, _f64(st.stepsize), None)
+            call("pg_opt_nesterov_dev", ctx.h, code, p, st._ptr(st.variable_prev), pg_, n, float(st.stepsize), self._scalars.ptr, _f64(st.stepsize), shadow)
         elif isinstance(st, (GradientDescentState, HeavyBallMethodState)):
-            st.step(g)
+            st.step(g, shadow)
         else:
             raise TypeError(f"unsupported optimizer state {type(st).__name__}")
         self._loss_buf = out._buf
-        self.model._mutated()
+        self._params_updated()
         return out
+
+    def _params_updated(self):
+        """the parameters changed (version bump); a step that also wrote the bf16 shadow stamps it for the new version"""
+        self.model._mutated()
+        if self._shadow:
+            from .trace import shadow_written
+            shadow_written(self.model)
 
     # ---- replay --------------------------------------------------------------------------------
     def __call__(self):
         """run one training step (graph replay); returns the step's Loss handle"""
+        if self._shadow:
+            # the captured forward contains no cast: if the parameters were changed behind the graph's back (checkpoint load,
+            # assign, indexing) the bf16 copy is stale — refresh it before the replay
+            from .trace import _shadow_entry
+            leaves = self.model.arena()[3]
+            ent = _shadow_entry(self.ctx, leaves[0].buf)
+            if ent.version != leaves[0].buf.version:
+                call("pg_vec_cast_bf16", self.ctx.h, ent.ptr, leaves[0].buf.ptr, leaves[0].buf.nbytes // 4)
+                ent.version = leaves[0].buf.version
         call("pg_graph_launch", self.ctx.h, self._graph)
         self.steps += 1
-        self.model._mutated()
+        self._params_updated()
         if isinstance(self.state, AdamState):
             self.state.it += 1
         elif isinstance(self.state, NesterovState):

@@ -239,3 +239,37 @@ def _gemm_case(pg, layout, M, N, K):
     # blockwise (keeps host memory bounded) and exact-ish: every 128-row block must match
     for r0 in range(0, M, 8192):
         assert rel_err(got[r0:r0 + 8192], ref[r0:r0 + 8192]) <= 1e-5, r0
+
+
+def test_graph_replay_bf16_with_optimizer_written_shadow(pg):
+    """GraphStep in bf16 mode: the captured Adam pass writes the bf16 operand copy and the captured forward has no cast pass;
+    replays must equal eager steps (`step(..., shadow=True)`) bit for bit, also after the parameters are changed behind the
+    graph's back (the stale copy is refreshed before the replay)."""
+    spec = [("linear", 256, 512), ("relu",), ("linear", 512, 512), ("relu",), ("linear", 512, 10), ("softmax",)]
+    p0 = O.init_params(spec, np.float32, seed=5)
+    rng = np.random.default_rng(9)
+    B = 512
+    x = rng.random((B, 256)).astype(np.float32)
+    lab = np.eye(10, dtype=np.float32)[rng.integers(0, 10, B)]
+    ctx = pg.Context.get()
+    xd, ld = pg.DeviceArray.from_numpy(ctx, x), pg.DeviceArray.from_numpy(ctx, lab)
+    f = lambda mm: pg.cross_entropy(mm(xd), ld)
+    mk = lambda: pg.Compose(pg.Linear(W=p0[0], b=p0[1]), pg.relu, pg.Linear(W=p0[2], b=p0[3]), pg.relu, pg.Linear(W=p0[4], b=p0[5]), pg.softmax)
+    m_e = mk(); st_e = pg.init(pg.Adam(1e-3, fast=True), m_e)
+    m_g = mk(); st_g = pg.init(pg.Adam(1e-3, fast=True), m_g)
+    gs = pg.GraphStep(f, m_g, st_g, math="bf16")
+    assert gs._shadow
+
+    def eager():
+        out, pb = pg.eval_with_pullback(f, m_e, math="bf16")
+        pg.step(st_e, pb(), shadow=True)
+        return float(out)
+    le = [eager() for _ in range(3)]
+    lg = [float(gs()) for _ in range(3)]
+    assert le == lg
+    assert np.array_equal(m_e.vec(), m_g.vec())
+    # change the parameters outside the graph: both models get the same new vector
+    v = m_e.vec() * np.float32(0.5)
+    m_e.set_vec(v); m_g.set_vec(v)
+    assert eager() == float(gs())
+    assert np.array_equal(m_e.vec(), m_g.vec())
