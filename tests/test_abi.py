@@ -68,3 +68,29 @@ def test_tensor_core_conv_envelope_is_a_host_query():
     assert sup(16, 12, 12, 16, 5, 5) == 0       # im2col width 16*25 + 1 > 256 (weight-gradient UMMA N)
     assert sup(3, 224, 224, 8, 3, 3) == 0       # one sample does not fit a shared-memory slot
     assert sup(1, 4, 4, 1, 5, 5) == 0           # filter larger than the image
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """pg_op and pg_mlp_desc as gcc lays them out from include/protograd_b200.h == the ctypes mirrors the host side fills."""
+    import subprocess
+    import ctypes
+    from protograd_b200.capi import MlpDesc
+    from protograd_b200.trace import PgOp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cname = {"inp": "in"}                                 # `in` is a Python keyword: the ctypes mirror calls it `inp`
+    fields = {"pg_op": [f[0] for f in PgOp._fields_], "pg_mlp_desc": [f[0] for f in MlpDesc._fields_]}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "protograd_b200.h"', 'int main(void) {']
+    for st, names in fields.items():
+        src.append(f'  printf("{st} %zu\\n", sizeof({st}));')
+        for n in names:
+            src.append(f'  printf("{st}.{n} %zu\\n", offsetof({st}, {cname.get(n, n)}));')
+    src += ['  return 0;', '}']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(c), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for st, cls in (("pg_op", PgOp), ("pg_mlp_desc", MlpDesc)):
+        assert int(out[st]) == ctypes.sizeof(cls), st
+        for n in fields[st]:
+            assert int(out[f"{st}.{n}"]) == getattr(cls, n).offset, (st, n)
