@@ -102,7 +102,7 @@ int pg_vec_cast_bf16(pg_ctx* ctx, void* out_bf16, const void* x_f32, int64_t n);
  * pg_vec_cast_bf16 of that Float32 array, at a quarter of the upload bytes */
 int pg_vec_cast_u8_bf16(pg_ctx* ctx, void* out_bf16, const void* x_u8, int64_t n, double divisor);
 
-/* ---- Optimizers: one fused pass over the arena (src/optimizers/*.jl) ---------------------- */
+/* ---- Optimizers: one fused pass over the arena (src/optimizers/ *.jl) ---------------------- */
 /* `shadow_bf16` (nullable): also write bf16(p_new) at the same index (tensor-core operand copy). */
 /* gradient_descent.jl:15-17   p -= s*g */
 int pg_opt_gd(pg_ctx* ctx, int dtype, void* p, const void* g, int64_t n, double stepsize, int flags, void* shadow_bf16);
@@ -139,7 +139,9 @@ int pg_tc_linear_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, v
 int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
                      const void* relu_mask, int64_t M, int64_t K, int64_t N);
 /* same, plus dx_colsum (nullable, f32 [K]): column sums of the masked dX, i.e. the bias gradient of the
- * layer that produced X — accumulated in the data-gradient epilogue instead of a separate pass over dX. */
+ * layer that produced X — accumulated in the data-gradient epilogue instead of a separate pass over dX (fp32 atomics: the
+ * one result of this ABI that is not bit-stable from run to run; the planner takes bias gradients from the weight-gradient
+ * launches instead and never passes it). */
 int pg_tc_linear_bwd_ex(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
                         const void* relu_mask, void* dx_colsum, int64_t M, int64_t K, int64_t N);
 /* raw GEMM entry for unit tests: C[M][N] (f32 or bf16) = A op B, bf16 operands, fp32 accumulate.
@@ -156,7 +158,7 @@ int pg_conv2d_bwd(pg_ctx* ctx, int dtype, const void* x, const void* w, const vo
  * Float32 NCHW; operands are rounded to bf16 on the way into shared memory, products accumulate in fp32.
  * Envelope (pg_tc_conv2d_supported returns 1): Cin, Cout <= 16, Cin*kH*kW < 256, Cout*kH*kW <= 448 and one
  * sample (plus its output gradient / zero-padded copy) fits a shared-memory slot; other shapes use pg_conv2d_*.
- * The weight-gradient launch adds per-CTA partial sums with fp32 atomics (dw / db are zeroed first). */
+ * The weight-gradient launch writes one partial dw / db per CTA; a small kernel sums them in CTA order (deterministic). */
 int pg_tc_conv2d_supported(int Cin, int H, int W, int Cout, int kH, int kW);
 int pg_tc_conv2d_fwd(pg_ctx* ctx, const void* x, const void* w, const void* b, void* y,
                      int64_t N, int Cin, int H, int W, int Cout, int kH, int kW, int act);

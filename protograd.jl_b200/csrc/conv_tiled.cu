@@ -169,7 +169,7 @@ conv_wgrad_tiled_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __
   const int nitem = Cout * Cin * KS;            // (co, ci, a)
   T* xs = reinterpret_cast<T*>(smem_raw);       // [SB][chw]   SB staged samples per iteration
   T* dys = xs + SB * chw;                       // [SB][ych]
-  T* red = dys + SB * ych;                     // [nitem][KS + 1]  (block result, accumulated with atomics in smem)
+  T* red = dys + SB * ych;                     // [nitem][KS + 1]  (block result: the contributing threads add in a fixed order)
   for (int i = threadIdx.x; i < nitem * (KS + 1); i += blockDim.x) red[i] = T(0);
   // thread -> (slot, item, row-group).  nitem <= 256: one item per thread, RG row-groups, SPB sample slots.
   // nitem > 256: RG = SPB = 1 and each thread owns up to NI = ceil(nitem / 256) items (it, it + 256, ...).
@@ -231,19 +231,25 @@ conv_wgrad_tiled_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __
     }
   }
   __syncthreads();
-  if (live) {
+  // an item has SPB * RG contributing threads (one per sample slot and row-group): they add in turn, in a fixed order, so the
+  // block result does not depend on scheduling (no floating-point atomics; with several items per thread every item has one owner)
+  const int ncontrib = (NI > 1) ? 1 : SPB * RG;
+  const int mine = (NI > 1) ? 0 : slot * RG + rg;
+  for (int c = 0; c < ncontrib; ++c) {
+    if (live && mine == c) {
 #pragma unroll
-    for (int p = 0; p < NIMAX; ++p) {
-      const int it = it0 + p * 256;
-      if (p < NI && it < nitem) {
-        const int ci = (it / KS) % Cin, a = it % KS;
+      for (int p = 0; p < NIMAX; ++p) {
+        const int it = it0 + p * 256;
+        if (p < NI && it < nitem) {
+          const int ci = (it / KS) % Cin, a = it % KS;
 #pragma unroll
-        for (int k = 0; k < KS; ++k) atomicAdd(&red[it * (KS + 1) + k], acc[p][k]);
-        if (ci == 0 && a == 0) atomicAdd(&red[it * (KS + 1) + KS], dbacc[p]);
+          for (int k = 0; k < KS; ++k) red[it * (KS + 1) + k] += acc[p][k];
+          if (ci == 0 && a == 0) red[it * (KS + 1) + KS] += dbacc[p];
+        }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
   // block partials: dw_part[block][co][ci][a][b], db_part[block][co]
   for (int i = threadIdx.x; i < nitem * KS; i += blockDim.x) dw_part[(size_t)blockIdx.x * nitem * KS + i] = red[(i / KS) * (KS + 1) + (i % KS)];
   if (db_part != nullptr)

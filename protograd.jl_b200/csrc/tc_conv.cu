@@ -14,7 +14,8 @@
 // matrix lives in shared memory for the whole kernel; an 8-deep ring of TMEM accumulators lets the epilogue
 // warps (bias + ReLU, coalesced NCHW stores) run several tiles behind the MMA issuer.  Weight gradient: M = 128
 // rows of dY^T (only Cout <= 16 are non-zero), N = the im2col width (<= 256), K = 64 positions per block; every
-// CTA accumulates its share of the positions in TMEM and adds its partial dW / db with fp32 atomics at the end.
+// CTA accumulates its share of the positions in TMEM and writes its partial dW / db to the workspace; a small kernel
+// sums the partials over the CTAs in a fixed order (deterministic: no floating-point atomics).
 // Tensors stay fp32 in HBM (26 KB of activations per sample at the LeNet shapes: these layers are not
 // bandwidth-bound), products are bf16 x bf16 with fp32 accumulation.  Measured behaviour and what bounds it:
 // profiles/r1_tc_conv_ablation.md (the stage round trip producer -> MMA -> commit -> producer, not the gathers).
@@ -59,8 +60,9 @@ struct ConvArgs {
   const float* bias;       // forward only (nullable)
   const float* dy;         // weight gradient: [n][Cout][Hp][Wp]
   float* out;              // forward: y [n][Cout][Hp][Wp]; data gradient: dx [n][Cin][Hp][Wp]
-  float* dw;               // weight gradient (pre-zeroed)
-  float* db;               // weight gradient (pre-zeroed, nullable)
+  float* dw;               // weight gradient
+  float* db;               // weight gradient (nullable)
+  float* part;             // weight gradient: per-CTA partials [grid][Ktot + 1][Cout] (column Ktot = the ones column, i.e. db)
   long long nsamples;
   int G;                   // samples per group: one bulk copy of G whole samples feeds G*Hp*Wp positions
   int Cs, Hs, Ws;          // source channels / height / width
@@ -466,17 +468,11 @@ __global__ void __launch_bounds__(Geo<SMALL>::THREADS, Geo<SMALL>::CTAS_PER_SM) 
           tmem_ld32(tmem_base + c0, r);
           tmem_ld_wait();
           if (lane < a.Cout) {
+            float* part = a.part + (size_t)blockIdx.x * (a.Ktot + 1) * a.Cout + lane;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int k = c0 + j;
-              const float v = __uint_as_float(r[j]);
-              if (k < a.Ktot) {
-                const int2 t = tab[k];
-                const int ci = k / kk, i = t.y >> 16, jj = t.y & 0xffff;
-                atomicAdd(a.dw + ((lane * a.Cin + ci) * a.kH + (a.kH - 1 - i)) * a.kW + (a.kW - 1 - jj), v);
-              } else if (k == a.Ktot && a.db != nullptr) {
-                atomicAdd(a.db + lane, v);
-              }
+              if (k <= a.Ktot) part[(size_t)k * a.Cout] = __uint_as_float(r[j]);
             }
           }
         }
@@ -491,6 +487,23 @@ __global__ void __launch_bounds__(Geo<SMALL>::THREADS, Geo<SMALL>::CTAS_PER_SM) 
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
+}
+
+// Sums the weight-gradient partials of all CTAs in CTA order (deterministic) and scatters them into dw (flipped taps: the
+// product's column k = (ci, i, j) pairs dY with x[.., oy + i, ox + j], which is the gradient of w[co][ci][kH-1-i][kW-1-j]) and db.
+__global__ void tc_conv_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ db, int nparts,
+                                            int Ktot, int Cin, int Cout, int kH, int kW) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;       // e = k * Cout + co
+  if (e >= (Ktot + 1) * Cout) return;
+  const int k = e / Cout, co = e - k * Cout;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * (Ktot + 1) * Cout + e];
+  if (k == Ktot) {
+    if (db != nullptr) db[co] = s;
+    return;
+  }
+  const int kk = kH * kW, ci = k / kk, t = k - ci * kk, i = t / kW, j = t - i * kW;
+  dw[((co * Cin + ci) * kH + (kH - 1 - i)) * kW + (kW - 1 - j)] = s;
 }
 
 // samples per group: whole samples, 16-byte aligned group starts, bounded bytes per slot, <= max_pos
@@ -537,7 +550,7 @@ bool plan_launch(ConvArgs& a, int dy_floats_per_sample, int* bytes_out) {
 }
 
 template <int MODE, int NKB, bool SMALL>
-int launch_geo(pg_ctx* ctx, const ConvArgs& a, int bytes) {
+int launch_geo(pg_ctx* ctx, const ConvArgs& a, int bytes, int* grid_out) {
   using G_ = Geo<SMALL>;
   static int attr_bytes_dev[32] = {};
   int& attr_bytes = attr_bytes_dev[ctx->device & 31];
@@ -550,33 +563,34 @@ int launch_geo(pg_ctx* ctx, const ConvArgs& a, int bytes) {
   const int grid = (int)(groups < ctas ? groups : ctas);
   tc_conv_kernel<MODE, NKB, SMALL><<<grid, G_::THREADS, bytes, ctx->stream>>>(a);
   PG_LAUNCHED(ctx);
+  if (grid_out != nullptr) *grid_out = grid;
   return PG_OK;
 }
 
 template <int MODE, int NKB>
-int launch_nkb(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
+int launch_nkb(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample, int* grid_out) {
   // (the half-size two-CTAs-per-SM geometry of round 1 was measured in round 2 — conv1 forward 138 -> 113 us, conv2
   //  backward 346 -> 435 us at C3 B = 8192, profiles/r2_tc_conv_small.md — and is no longer instantiated)
   int bytes = 0;
   const bool ok = plan_launch<MODE, NKB, false>(a, dy_floats_per_sample, &bytes);
   PG_REQUIRE(a.G > 0, "tensor-core conv: a sample (with its output gradient) does not fit a shared-memory slot");
   PG_REQUIRE(ok, "tensor-core conv: shared-memory budget exceeded");
-  return launch_geo<MODE, NKB, false>(ctx, a, bytes);
+  return launch_geo<MODE, NKB, false>(ctx, a, bytes, grid_out);
 }
 
 template <int MODE>
-int launch(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample) {
+int launch(pg_ctx* ctx, ConvArgs& a, int dy_floats_per_sample, int* grid_out = nullptr) {
   switch (a.nkb) {
-    case 1: return launch_nkb<MODE, 1>(ctx, a, dy_floats_per_sample);
-    case 2: return launch_nkb<MODE, 2>(ctx, a, dy_floats_per_sample);
-    case 3: return launch_nkb<MODE, 3>(ctx, a, dy_floats_per_sample);
-    case 4: return launch_nkb<MODE, 4>(ctx, a, dy_floats_per_sample);
+    case 1: return launch_nkb<MODE, 1>(ctx, a, dy_floats_per_sample, grid_out);
+    case 2: return launch_nkb<MODE, 2>(ctx, a, dy_floats_per_sample, grid_out);
+    case 3: return launch_nkb<MODE, 3>(ctx, a, dy_floats_per_sample, grid_out);
+    case 4: return launch_nkb<MODE, 4>(ctx, a, dy_floats_per_sample, grid_out);
   }
   if (MODE == 0) {
     switch (a.nkb) {
-      case 5: return launch_nkb<0, 5>(ctx, a, dy_floats_per_sample);
-      case 6: return launch_nkb<0, 6>(ctx, a, dy_floats_per_sample);
-      case 7: return launch_nkb<0, 7>(ctx, a, dy_floats_per_sample);
+      case 5: return launch_nkb<0, 5>(ctx, a, dy_floats_per_sample, grid_out);
+      case 6: return launch_nkb<0, 6>(ctx, a, dy_floats_per_sample, grid_out);
+      case 7: return launch_nkb<0, 7>(ctx, a, dy_floats_per_sample, grid_out);
     }
   }
   pg_set_error("tensor-core conv: %d k-blocks not instantiated", a.nkb);
@@ -625,16 +639,22 @@ int pg_tc_conv2d_bwd(pg_ctx* ctx, const void* x, const void* w, const void* dy, 
   const int Ho = H - kH + 1, Wo = W - kW + 1;
   if (dw != nullptr || db != nullptr) {
     PG_REQUIRE(dw != nullptr, "pg_tc_conv2d_bwd: db without dw is not supported on the tensor-core path");
-    PG_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * kH * kW * sizeof(float), ctx->stream));
-    if (db != nullptr) PG_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), ctx->stream));
     ConvArgs a{};
     a.src = (const float*)x; a.dy = (const float*)dy; a.dw = (float*)dw; a.db = (float*)db;
     a.Cs = Cin; a.Hs = H; a.Ws = W; a.Hp = Ho; a.Wp = Wo;
     a.kH = kH; a.kW = kW; a.Cin = Cin; a.Cout = Cout;
     a.Ktot = Cin * kH * kW; a.nkb = (int)pg_cdiv(a.Ktot + 1, 64);
     a.nsamples = N;
-    int rc = launch<1>(ctx, a, Cout * Ho * Wo);
+    // one partial [Ktot + 1][Cout] per CTA (one CTA per SM at most), summed in CTA order afterwards
+    const size_t part_floats = (size_t)(a.Ktot + 1) * Cout;
+    int rc = pg_ws_ensure(ctx, (size_t)ctx->real_sms * part_floats * sizeof(float));
     if (rc != PG_OK) return rc;
+    a.part = (float*)ctx->ws;
+    int grid = 0;
+    rc = launch<1>(ctx, a, Cout * Ho * Wo, &grid);
+    if (rc != PG_OK) return rc;
+    tc_conv_wgrad_reduce_kernel<<<(unsigned)pg_cdiv((int64_t)part_floats, 128), 128, 0, ctx->stream>>>(a.part, a.dw, a.db, grid, a.Ktot, Cin, Cout, kH, kW);
+    PG_LAUNCHED(ctx);
   }
   if (dx != nullptr) {
     ConvArgs a{};

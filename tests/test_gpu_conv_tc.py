@@ -1,7 +1,8 @@
 """GPU parity: BF16 tensor-core conv (tcgen05 implicit GEMM, csrc/tc_conv.cu) through the C ABI.
 The kernels round x, w and dy to bf16 on the way into shared memory and accumulate in fp32, so they are
 compared against the float64 oracle (src/layers.jl:59 semantics) evaluated on the bf16-ROUNDED operands:
-normwise relative error <= 2e-5 (fp32 accumulation; the weight gradient adds per-CTA partials atomically)."""
+normwise relative error <= 2e-5 (fp32 accumulation; the weight gradient sums per-CTA partials in a fixed order, so two
+runs are bit-identical)."""
 import numpy as np
 import pytest
 
@@ -60,6 +61,13 @@ def test_tc_conv_fwd_bwd(pg, geom):
     assert rel_err(dw_.numpy(), dw) <= TOL
     assert rel_err(db_.numpy(), db) <= TOL
     assert rel_err(dx_.numpy(), dx) <= TOL
+    # deterministic: per-CTA partials summed in CTA order (no floating-point atomics) — a second run into buffers holding
+    # garbage (every element is overwritten, nothing accumulates into the old contents) gives the same bits
+    dw1, db1 = dw_.numpy().copy(), db_.numpy().copy()
+    dw_.upload(np.full_like(w, 7.0)); db_.upload(np.full_like(b, -3.0))
+    call("pg_tc_conv2d_bwd", ctx.h, xd.ptr, wd.ptr, dyd.ptr, dw_.ptr, db_.ptr, dx_.ptr, N, Cin, H, W, Cout, k, k)
+    assert np.array_equal(dw_.numpy().view(np.uint32), dw1.view(np.uint32))
+    assert np.array_equal(db_.numpy().view(np.uint32), db1.view(np.uint32))
     # frozen trunk: data gradient only / weight gradient only
     dx_.upload(np.zeros_like(x)); dw_.upload(np.zeros_like(w))
     call("pg_tc_conv2d_bwd", ctx.h, xd.ptr, wd.ptr, dyd.ptr, None, None, dx_.ptr, N, Cin, H, W, Cout, k, k)

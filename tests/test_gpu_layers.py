@@ -95,6 +95,11 @@ def test_conv_fwd_bwd(pg, T, geom):
     tol = TOL[T]
     assert rel_err(y_.numpy(), y) <= tol and rel_err(dw_.numpy(), dw) <= tol
     assert rel_err(db_.numpy(), db) <= tol and rel_err(dx_.numpy(), dx) <= tol
+    # weight / bias gradients are summed in a fixed order (no floating-point atomics): a second run gives the same bits
+    dw1, db1 = dw_.numpy().copy(), db_.numpy().copy()
+    dw_.upload(np.full_like(w, 5)); db_.upload(np.full_like(b, -2))
+    call("pg_conv2d_bwd", ctx.h, code, xd.ptr, wd.ptr, dyd.ptr, dw_.ptr, db_.ptr, dx_.ptr, N, Cin, H, W, Cout, k, k)
+    assert dw_.numpy().tobytes() == dw1.tobytes() and db_.numpy().tobytes() == db1.tobytes()
     call("pg_conv2d_fwd", ctx.h, code, xd.ptr, wd.ptr, bd.ptr, y_.ptr, N, Cin, H, W, Cout, k, k, 1)
     assert rel_err(y_.numpy(), np.maximum(y, 0)) <= tol
 
