@@ -194,7 +194,6 @@ class GradientBuckets:
         self.param_arena = h
         weakref.finalize(self, capi.lib.pg_arena_destroy, h)
         ent = _shadow_entry(ctx, leaves[0].buf, halves=2)
-        assert ent.half_bytes == total * 2 or ent.half_bytes >= total * 2
         self._shadow = ent
         try:
             # the double buffer's halves must be `total` bf16 elements apart (csrc/dp.cu indexes [2][n_padded])
@@ -280,6 +279,8 @@ class GradientBuckets:
             call("pg_dp_p2p_shadow_half", self.dp.h, ctypes.byref(half))
             ent.half = half.value
             ent.version = ent.buf.version
+            if self.comm_sms:
+                self.ctx.set_sm_limit(0)
             if hasattr(state, "it"):
                 state.it += 1
                 return state.it
