@@ -60,23 +60,30 @@ int pg_init(int device, pg_ctx** out) {
   pg_ctx* c = new pg_ctx();
   c->device = device;
   c->num_sms = c->real_sms = prop.multiProcessorCount;
-  PG_CHECK_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-  c->stream = c->own_stream;
-  PG_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  PG_CHECK_CUDA(cudaMalloc((void**)&c->counters, 256 * sizeof(unsigned int)));
-  PG_CHECK_CUDA(cudaMemset(c->counters, 0, 256 * sizeof(unsigned int)));
-  PG_CHECK_CUDA(cudaMalloc((void**)&c->result_slot, 16 * sizeof(double)));
-  PG_CHECK_CUDA(cudaMallocHost((void**)&c->result_host, 16 * sizeof(double)));
+  // a failure half-way leaves no handle behind: everything created so far is released again
+  auto setup = [&]() -> int {
+    PG_CHECK_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    PG_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    PG_CHECK_CUDA(cudaMalloc((void**)&c->counters, 256 * sizeof(unsigned int)));
+    PG_CHECK_CUDA(cudaMemset(c->counters, 0, 256 * sizeof(unsigned int)));
+    PG_CHECK_CUDA(cudaMalloc((void**)&c->result_slot, 16 * sizeof(double)));
+    PG_CHECK_CUDA(cudaMallocHost((void**)&c->result_host, 16 * sizeof(double)));
+    return pg_ws_ensure(c, (size_t)32 << 20);
+  };
+  const int rc = setup();
+  if (rc != PG_OK) {
+    pg_destroy(c);          // (keeps the error message: pg_destroy sets none)
+    return rc;
+  }
   *out = c;
-  int rc = pg_ws_ensure(c, (size_t)32 << 20);
-  if (rc != PG_OK) return rc;
   return PG_OK;
 }
 
 int pg_destroy(pg_ctx* ctx) {
   if (!ctx) return PG_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->switch_event) cudaEventDestroy(ctx->switch_event);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->aux) cudaFree(ctx->aux);
@@ -109,6 +116,7 @@ int pg_set_stream(pg_ctx* ctx, void* s) {
 }
 int pg_get_stream(pg_ctx* ctx, void** s) {
   PG_CHECK_CTX_NF(ctx);
+  PG_REQUIRE(s != nullptr, "null out pointer");
   *s = (void*)ctx->stream;
   return PG_OK;
 }
@@ -119,6 +127,7 @@ int pg_sync(pg_ctx* ctx) {
 }
 int pg_launch_count(pg_ctx* ctx, int64_t* n) {
   PG_CHECK_CTX_NF(ctx);
+  PG_REQUIRE(n != nullptr, "null out pointer");
   *n = ctx->launches;
   return PG_OK;
 }
@@ -232,6 +241,7 @@ int pg_graph_begin(pg_ctx* ctx) {
 int pg_graph_end(pg_ctx* ctx, void** graph_exec) {
   PG_CHECK_CTX(ctx);
   PG_REQUIRE(ctx->capturing, "not capturing");
+  PG_REQUIRE(graph_exec != nullptr, "null out pointer");
   ctx->capturing = false;
   cudaGraph_t g = nullptr;
   PG_CHECK_CUDA(cudaStreamEndCapture(ctx->stream, &g));
@@ -256,10 +266,35 @@ int pg_loss_read(pg_ctx* ctx, int dtype, const void* loss_dev, double* result) {
   PG_CHECK_CTX_NF(ctx);
   if (pg_deferred_overlaps(ctx, loss_dev, 8)) pg_flush_deferred(ctx);
   PG_REQUIRE(result != nullptr && loss_dev != nullptr, "null pointer");
-  size_t sz = dtype == PG_F64 ? 8 : 4;
+  PG_REQUIRE(dtype == PG_F32 || dtype == PG_F64 || dtype == PG_F16 || dtype == PG_BF16, "pg_loss_read: dtype must be a floating-point type");
+  const size_t sz = dtype == PG_F64 ? 8 : (dtype == PG_F32 ? 4 : 2);
   PG_CHECK_CUDA(cudaMemcpyAsync(ctx->result_host, loss_dev, sz, cudaMemcpyDeviceToHost, ctx->stream));
   PG_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-  *result = dtype == PG_F64 ? *(double*)ctx->result_host : (double)*(float*)ctx->result_host;
+  if (dtype == PG_F64) {
+    *result = *(double*)ctx->result_host;
+  } else if (dtype == PG_F32) {
+    *result = (double)*(float*)ctx->result_host;
+  } else {
+    const uint16_t h = *(uint16_t*)ctx->result_host;
+    uint32_t bits;
+    if (dtype == PG_BF16) {
+      bits = (uint32_t)h << 16;
+    } else {                                  // IEEE binary16 -> binary32 (exact)
+      const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+      if (e == 0) {
+        if (m == 0) bits = sign;
+        else {                                // subnormal: renormalise
+          int sh = 0; uint32_t mm = m;
+          while (!(mm & 0x400u)) { mm <<= 1; ++sh; }
+          bits = sign | ((uint32_t)(113 - sh) << 23) | ((mm & 0x3ffu) << 13);
+        }
+      } else if (e == 31) bits = sign | 0x7f800000u | (m << 13);
+      else bits = sign | ((e + 112) << 23) | (m << 13);
+    }
+    float f;
+    memcpy(&f, &bits, 4);
+    *result = (double)f;
+  }
   return PG_OK;
 }
 

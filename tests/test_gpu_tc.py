@@ -187,6 +187,39 @@ def test_tc_training_step_c4_bench_batch(pg):
     assert rel_err(m.vec(), state.x) <= 1e-6
 
 
+def test_c4_full_global_batch_is_the_sum_of_its_shards(pg):
+    """BASELINE configs[3] at its FULL size (global batch 65,536) on one GPU, through the size-independent property the
+    data-parallel design rests on: with the loss scaled by 1 / B_global, loss and gradient of the whole
+    batch equal the SUM over the eight 8,192-sample shards (what the eight ranks exchange).  Rows are independent in every
+    kernel, so the two sides differ only in the fp32 summation order over the batch: <= 1e-4 normwise (a dropped or doubled
+    shard is an error of 1e-1)."""
+    spec = [("linear", 784, 4096), ("relu",), ("linear", 4096, 4096), ("relu",), ("linear", 4096, 10), ("softmax",)]
+    rng = np.random.default_rng(65536)
+    p0 = O.init_params(spec, np.float32, seed=8)
+    GB, S = 65536, 8
+    x = rng.random((GB, 784), dtype=np.float32)
+    lab_i = rng.integers(0, 10, GB).astype(np.int32)
+    m = pg.Compose(pg.Linear(W=p0[0], b=p0[1]), pg.relu, pg.Linear(W=p0[2], b=p0[3]), pg.relu, pg.Linear(W=p0[4], b=p0[5]), pg.softmax)
+    ctx = pg.Context.get()
+    xd, ld = pg.DeviceArray.from_numpy(ctx, x), pg.DeviceArray.from_numpy(ctx, lab_i)
+    out, pb = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(xd), ld), m, math="bf16")
+    full_loss = float(out)
+    full = [p.numpy().astype(np.float64) for p in pb().allparams()]
+    per = GB // S
+    acc, loss_sum = [np.zeros_like(a) for a in full], 0.0
+    for r in range(S):
+        xs = pg.DeviceArray.from_numpy(ctx, x[r * per:(r + 1) * per]); ls = pg.DeviceArray.from_numpy(ctx, lab_i[r * per:(r + 1) * per])
+        o, pbs = pg.eval_with_pullback(lambda mm: pg.cross_entropy(mm(xs), ls, global_batch=GB), m, math="bf16")
+        loss_sum += float(o)
+        for a, p in zip(acc, pbs().allparams()):
+            a += p.numpy()
+    assert abs(loss_sum - full_loss) <= 1e-5 * abs(full_loss), (loss_sum, full_loss)
+    errs = [rel_err(a, f) for a, f in zip(acc, full)]
+    assert max(errs) <= 1e-4, errs
+    # and the value itself: a random-label 10-class problem at xavier initialisation sits near ln(10)
+    assert 2.0 < full_loss < 2.8, full_loss
+
+
 def test_tc_wgrad_tail_k_split(pg):
     """Weight gradient with 9 x 9 = 81 pair tiles on 74 SM pairs: the 7 tiles of the partial last wave are split into two K
     halves (17 k-blocks: 8 + 9, the last one ragged), the second half's partial travels through the scratch tile + flag and
