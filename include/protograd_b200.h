@@ -139,9 +139,8 @@ int pg_tc_linear_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, v
 int pg_tc_linear_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
                      const void* relu_mask, int64_t M, int64_t K, int64_t N);
 /* same, plus dx_colsum (nullable, f32 [K]): column sums of the masked dX, i.e. the bias gradient of the
- * layer that produced X — accumulated in the data-gradient epilogue instead of a separate pass over dX (fp32 atomics: the
- * one result of this ABI that is not bit-stable from run to run; the planner takes bias gradients from the weight-gradient
- * launches instead and never passes it). */
+ * layer that produced X (a deterministic pass over the stored dX; the planner takes bias gradients from the weight-gradient
+ * launches instead). */
 int pg_tc_linear_bwd_ex(pg_ctx* ctx, const void* X, const void* W, const void* dY, int dy_dtype, void* dW, void* db, void* dX,
                         const void* relu_mask, void* dx_colsum, int64_t M, int64_t K, int64_t N);
 /* raw GEMM entry for unit tests: C[M][N] (f32 or bf16) = A op B, bf16 operands, fp32 accumulate.

@@ -119,6 +119,74 @@ int analyse(pg_plan& P) {
     for (int k = 0; k < 3; ++k)
       if (ops[i].in[k] >= i) return P.fail(PG_ERR_ARG, "nodes must be in topological order");
   }
+  // ---- shape / arity validation: a malformed node list from any host is an error here, never an out-of-bounds kernel ----
+  auto bad = [&](int i, const char* what) {
+    pg_set_error("plan: node %d (kind %d): %s", i, ops[i].kind, what);
+    return PG_ERR_ARG;
+  };
+  for (int i = 0; i < n; ++i) {
+    const pg_op& o = ops[i];
+    if (o.kind < PG_OP_INPUT || o.kind > PG_OP_LOSS_MSE) return bad(i, "unknown op kind");
+    for (int d = 0; d < o.ndim; ++d)
+      if (o.shape[d] < 0) return bad(i, "negative extent");
+    static const int arity[] = {0, 0, 3, 3, 1, 1, 1, 1, 1, 1, 2, 2};
+    for (int k = 0; k < 3; ++k) {
+      if (k < arity[o.kind] ? o.in[k] < 0 : o.in[k] >= 0) return bad(i, "wrong number of inputs for this op");
+    }
+    const pg_op* a = arity[o.kind] > 0 ? &ops[o.in[0]] : nullptr;
+    const int64_t sa = a ? P.size[o.in[0]] : 0;
+    switch (o.kind) {
+      case PG_OP_LINEAR: {
+        const pg_op& w = ops[o.in[1]];
+        if (w.ndim != 2 || a->ndim < 1 || o.ndim < 1) return bad(i, "Linear needs x [..., in], W [in][out]");
+        const int64_t K = w.shape[0], N = w.shape[1];
+        if (K <= 0 || N <= 0 || a->shape[a->ndim - 1] != K) return bad(i, "DimensionMismatch: Linear input width != rows of W");
+        if (P.size[o.in[2]] != N) return bad(i, "DimensionMismatch: Linear bias length != columns of W");
+        if (o.shape[o.ndim - 1] != N || P.size[i] != sa / K * N) return bad(i, "Linear output shape must be [..., out]");
+        break;
+      }
+      case PG_OP_CONV2D: {
+        const pg_op& w = ops[o.in[1]];
+        if (a->ndim != 4 || w.ndim != 4 || o.ndim != 4) return bad(i, "Conv needs x [N][Cin][H][W], w [Cout][Cin][kH][kW]");
+        if (a->shape[1] != w.shape[1]) return bad(i, "DimensionMismatch: Conv input channels != filter channels");
+        if (w.shape[2] < 1 || w.shape[3] < 1 || a->shape[2] < w.shape[2] || a->shape[3] < w.shape[3]) return bad(i, "Conv filter larger than the image");
+        if (P.size[o.in[2]] != w.shape[0]) return bad(i, "DimensionMismatch: Conv bias length != output channels");
+        if (o.shape[0] != a->shape[0] || o.shape[1] != w.shape[0] || o.shape[2] != a->shape[2] - w.shape[2] + 1 ||
+            o.shape[3] != a->shape[3] - w.shape[3] + 1)
+          return bad(i, "Conv output shape must be [N][Cout][H-kH+1][W-kW+1]");
+        break;
+      }
+      case PG_OP_MAXPOOL: case PG_OP_MEANPOOL: {
+        if (a->ndim != 4 || o.ndim != 4 || o.k < 1) return bad(i, "pooling needs x [N][C][H][W] and a window k >= 1");
+        if (a->shape[2] < o.k || a->shape[3] < o.k) return bad(i, "pooling window larger than the image");
+        if (o.shape[0] != a->shape[0] || o.shape[1] != a->shape[1] || o.shape[2] != (a->shape[2] - o.k) / o.k + 1 ||
+            o.shape[3] != (a->shape[3] - o.k) / o.k + 1)
+          return bad(i, "pooling output shape must be [N][C][(H-k)/k+1][(W-k)/k+1]");
+        break;
+      }
+      case PG_OP_RELU: case PG_OP_RESHAPE: case PG_OP_SOFTMAX: case PG_OP_DROPOUT:
+        if (P.size[i] != sa) return bad(i, "DimensionMismatch: elementwise / reshape output must have the input's number of elements");
+        if (o.kind == PG_OP_SOFTMAX && (o.ndim < 1 || a->ndim < 1 || o.shape[o.ndim - 1] != a->shape[a->ndim - 1]))
+          return bad(i, "softmax keeps the class axis");
+        if (o.kind == PG_OP_DROPOUT && !(o.p >= 0.0 && o.p < 1.0)) return bad(i, "dropout probability must be in [0, 1)");
+        break;
+      case PG_OP_LOSS_CE: {
+        const pg_op& y = ops[o.in[1]];
+        if (a->ndim < 1 || sa <= 0) return bad(i, "cross_entropy of an empty tensor");
+        const int64_t C = a->shape[a->ndim - 1];
+        const bool idx = y.dtype == PG_I32;
+        if (idx ? P.size[o.in[1]] != sa / C : P.size[o.in[1]] != sa)
+          return bad(i, "DimensionMismatch: labels must match probs (dense) or hold one Int32 class per sample");
+        if (o.ndim != 0) return bad(i, "a loss is a scalar (ndim 0)");
+        break;
+      }
+      case PG_OP_LOSS_MSE:
+        if (P.size[o.in[1]] != sa || sa <= 0) return bad(i, "DimensionMismatch: mse output and label sizes differ");
+        if (o.ndim != 0) return bad(i, "a loss is a scalar (ndim 0)");
+        break;
+      default: break;
+    }
+  }
   P.need.assign(n, 0);
   P.need[P.root] = 1;
   for (int i = n - 1; i >= 0; --i)
@@ -708,6 +776,11 @@ int pg_plan_forward(pg_plan* P, const void* const* leaf_ptrs, const void* const*
                     int64_t sample_offset, void** loss_dev, int64_t* generation) {
   PG_REQUIRE(P != nullptr && leaf_ptrs != nullptr, "null plan / leaf pointers");
   PG_CHECK_CTX(P->ctx);
+  for (int i = 0; i < P->n; ++i)
+    if (P->need[i] && (P->is(i, PG_OP_INPUT) || P->is(i, PG_OP_PARAM)) && leaf_ptrs[i] == nullptr) {
+      pg_set_error("pg_plan_forward: no device pointer bound for %s node %d", P->is(i, PG_OP_INPUT) ? "INPUT" : "PARAM", i);
+      return PG_ERR_ARG;
+    }
   int rc = allocate(*P);
   if (rc != PG_OK) return rc;
   P->leaf.assign(leaf_ptrs, leaf_ptrs + P->n);

@@ -56,8 +56,6 @@ struct Epi {
   int relu;
   int out_f32;                  // 1: float output, 0: bf16 output
   int narrow;                   // 1: N not a multiple of 8 -> scalar guarded loads/stores (f32 out only)
-  float* colsum;                // data-gradient launches: also accumulate column sums of the (masked, bf16-rounded) output
-                                // = the bias gradient of the layer that produced the masking activation (nullable, pre-zeroed)
   float* db;                    // weight-gradient launches: fused bias gradient, as partials db[m_blk][n] = sum over this m-block's share of the k-blocks of B[k][n] (nullable)
   int splits;                   // split-K: work item = (tile, split); split s writes its fp32 partial to C + s*M*N
   int kb_per_split;
@@ -159,33 +157,6 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) 
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Epi& epi, void* __restrict__ C, int M, int N,
                                                int row, int col, int split, const uint4* mk4, float bias_lane = 0.0f, int has_bias_lane = 0) {
 
-  if (epi.colsum != nullptr) {
-    // column sums of this warp's 32 x 32 block (rows = lanes): butterfly transpose-reduce, 31 shuffles;
-    // afterwards lane l holds the sum of column l.  Values are masked and bf16-rounded exactly like the
-    // stored output, rows beyond M contribute zero.  All 32 lanes take part (no early exit above).
-    float t[32];
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = __uint_as_float(r[j]);
-      if (epi.mask != nullptr) {
-        const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&mk4[j / 8]);
-        x = (__bfloat162float(me[j & 7]) > 0.0f) ? x : 0.0f;
-      }
-      t[j] = (row < M) ? __bfloat162float(__float2bfloat16_rn(x)) : 0.0f;
-    }
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-      const bool up = (lane & s) != 0;
-#pragma unroll
-      for (int i = 0; i < s; ++i) {
-        const float send = up ? t[i] : t[i + s];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, s);
-        t[i] = (up ? t[i + s] : t[i]) + recv;
-      }
-    }
-    if (col + lane < N) atomicAdd(epi.colsum + col + lane, t[0]);
-  }
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -251,8 +222,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
 // already staged in shared memory and accumulate their column sums, so the bias gradient costs no extra
 // pass over dY.  The num_m tiles that share an n-block split the k-blocks between them (tile m_blk sums
 // the stages with kb % num_m == m_blk, ~1.6k cycles each, hidden behind num_m x 512 cycles of MMAs) and
-// add their partial sums to db with one atomicAdd per column; for every stage the reducer warps wait on
-// the full barrier and arrive on the empty barrier like the MMA warp does.  db must be zeroed first.
+// write one partial row per m-block (summed in a fixed order by reduce_rows_kernel afterwards: deterministic); for
+// every stage the reducer warps wait on the full barrier and arrive on the empty barrier like the MMA warp does.
 template <bool A_MN, bool B_MN, int BLOCK_N, bool DBW>
 __global__ void __launch_bounds__(NUM_THREADS + (DBW ? 64 : 0), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ C,
@@ -1094,7 +1065,7 @@ int launch_tc2(pg_ctx* ctx, const void* A, const void* B, void* C, int64_t M, in
   // the staged (TMA-store) epilogue covers bf16 outputs with bias / ReLU / ReLU' mask and plain fp32 outputs; the rest (fused
   // column sums, fp32 outputs with an elementwise epilogue) keeps the direct one.  PG_TC_DIRECT_EPI=1: A/B switch.
   static const bool direct = getenv("PG_TC_DIRECT_EPI") != nullptr;
-  const bool staged = !direct && epi.colsum == nullptr && !(epi.out_f32 && (epi.bias != nullptr || epi.relu || epi.mask != nullptr));
+  const bool staged = !direct && !(epi.out_f32 && (epi.bias != nullptr || epi.relu || epi.mask != nullptr));
   return staged ? launch_tc2_impl<A_MN, B_MN, DBW, true>(ctx, A, B, C, M, N, K, lda, ldb, epi)
                 : launch_tc2_impl<A_MN, B_MN, DBW, false>(ctx, A, B, C, M, N, K, lda, ldb, epi);
 }
@@ -1238,7 +1209,7 @@ int narrow_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, void* Z
     if (rc != PG_OK) return rc;
     target = ctx->ws;
   }
-  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, 1, 1, nullptr, nullptr, splits, kb_per};
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, 1, 1, nullptr, splits, kb_per};
   rc = launch_tc<false, false, NARROW_N>(ctx, X, Wt, target, M, N, K, K, K, epi);
   if (rc != PG_OK) return rc;
   if (splits > 1) {
@@ -1477,7 +1448,7 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
     if (splits > 8) splits = 8;
     int kb_per = (int)pg_cdiv(num_kb, splits);
     splits = (int)pg_cdiv(num_kb, kb_per);
-    Epi epi{nullptr, nullptr, 0, 1, 1, nullptr, nullptr, splits, kb_per};
+    Epi epi{nullptr, nullptr, 0, 1, 1, nullptr, splits, kb_per};
     void* target = dW;
     if (splits > 1) {
       rc = pg_ws_ensure(ctx, (size_t)splits * K * N * sizeof(float));
@@ -1511,9 +1482,12 @@ int narrow_bwd(pg_ctx* ctx, const void* X, const void* W, const void* dZ, void* 
     int64_t total = K * NARROW_K;
     pad_copy_kernel<__nv_bfloat16><<<(unsigned)pg_cdiv(total, 256), 256, 0, ctx->stream>>>((const __nv_bfloat16*)W, Wp, nullptr, K, (int)N, NARROW_K, 0);
     PG_LAUNCHED(ctx);
-    if (dx_colsum) PG_CHECK_CUDA(cudaMemsetAsync(dx_colsum, 0, (size_t)K * sizeof(float), ctx->stream));
-    Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, dx_f32, 0, (float*)dx_colsum, nullptr, 1, 1 << 30};
+    Epi epi{nullptr, (const __nv_bfloat16*)mask, 0, dx_f32, 0, nullptr, 1, 1 << 30};
     rc = tc_dispatch(ctx, 1, dZp, Wp, dX, M, K, NARROW_K, epi);      // pair kernel + staged epilogue when the output is wide enough
+    if (rc != PG_OK) return rc;
+  }
+  if (dx_colsum) {   // column sums of the stored (masked, rounded) dX: a separate deterministic pass (round 1: fp32 atomics in the epilogue)
+    rc = pg_colsum_launch(ctx, dx_f32 ? PG_F32 : PG_BF16, dX, dx_colsum, M, K);
     if (rc != PG_OK) return rc;
   }
   return PG_OK;
@@ -1533,7 +1507,7 @@ int pg_tc_gemm(pg_ctx* ctx, int layout, const void* A, const void* B, void* C, i
   PG_CHECK_CTX(ctx);
   PG_REQUIRE(A && B && C, "null pointer");
   PG_REQUIRE(c_dtype == PG_F32 || c_dtype == PG_BF16, "C must be f32 or bf16");
-  Epi epi{nullptr, nullptr, 0, c_dtype == PG_F32, 0, nullptr, nullptr, 1, 1 << 30};
+  Epi epi{nullptr, nullptr, 0, c_dtype == PG_F32, 0, nullptr, 1, 1 << 30};
   return tc_dispatch(ctx, layout, A, B, C, M, N, K, epi);
 }
 
@@ -1545,7 +1519,7 @@ int pg_tc_linear_fwd(pg_ctx* ctx, const void* X, const void* W, const void* b, v
     return narrow_fwd(ctx, X, W, b, Y, M, K, N, act);
   }
   PG_REQUIRE(y_dtype == PG_BF16 || y_dtype == PG_F32, "Y must be bf16 or f32");
-  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, y_dtype == PG_F32, 0, nullptr, nullptr, 1, 1 << 30};
+  Epi epi{(const float*)b, nullptr, act == PG_ACT_RELU, y_dtype == PG_F32, 0, nullptr, 1, 1 << 30};
   return tc_dispatch(ctx, 0, X, W, Y, M, N, K, epi);
 }
 
@@ -1601,7 +1575,7 @@ static int tc_linear_bwd_impl(pg_ctx* ctx, const void* X, const void* W, const v
       if (rc != PG_OK) return rc;
       target = ctx->ws;
     }
-    Epi epi{nullptr, nullptr, 0, 1, 0, nullptr, db_part, splits, kb_per, tail, tail_ws, ctx->counters + TAIL_FLAG_SLOT};
+    Epi epi{nullptr, nullptr, 0, 1, 0, db_part, splits, kb_per, tail, tail_ws, ctx->counters + TAIL_FLAG_SLOT};
     rc = tc_dispatch(ctx, 2, X, dY, target, K, N, M, epi);
     if (rc != PG_OK) return rc;
     if (splits > 1) {
@@ -1619,10 +1593,13 @@ static int tc_linear_bwd_impl(pg_ctx* ctx, const void* X, const void* W, const v
     if (rc != PG_OK) return rc;
   }
   if (dX) {  // dX[M][K] = dY W^T: GEMM (M'=M, N'=K, K'=N), A = dY [M][N] K-major, B = W [K][N] K-major
-    if (dx_colsum) PG_CHECK_CUDA(cudaMemsetAsync(dx_colsum, 0, (size_t)K * sizeof(float), ctx->stream));
-    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, dx_dtype == PG_F32, 0, (float*)dx_colsum, nullptr, 1, 1 << 30};
+    Epi epi{nullptr, (const __nv_bfloat16*)relu_mask, 0, dx_dtype == PG_F32, 0, nullptr, 1, 1 << 30};
     rc = tc_dispatch(ctx, 1, dY, W, dX, M, K, N, epi);
     if (rc != PG_OK) return rc;
+    if (dx_colsum) {   // column sums of the stored (masked, rounded) dX: a separate deterministic pass (round 1: fp32 atomics in the epilogue)
+      rc = pg_colsum_launch(ctx, dx_dtype == PG_F32 ? PG_F32 : PG_BF16, dX, dx_colsum, M, K);
+      if (rc != PG_OK) return rc;
+    }
   }
   return PG_OK;
 }

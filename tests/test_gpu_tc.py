@@ -107,6 +107,15 @@ def test_tc_linear_fwd_bwd(pg, M, K, N, act):
     assert rel_err(dWd.numpy(), dW) <= 1e-5
     assert rel_err(dbd.numpy(), db) <= 1e-5
     assert rel_err(bf16_to_f32(dXd.numpy()), dX) <= 4e-3
+    # pg_tc_linear_bwd_ex: the same call plus the column sums of the stored (masked, bf16-rounded) dX — the bias gradient of the
+    # layer below; a deterministic pass (no floating-point atomics): equal to the sums of the dX it returns, bit-identical run to run
+    sums = []
+    for _ in range(2):
+        csd = pg.DeviceArray.from_numpy(ctx, np.full(K, 9.0, dtype=np.float32))
+        call("pg_tc_linear_bwd_ex", ctx.h, Xd.ptr, Wd.ptr, dYd.ptr, 0 if skinny else 2, dWd.ptr, dbd.ptr, dXd.ptr, Xd.ptr, csd.ptr, M, K, N)
+        sums.append(csd.numpy())
+    assert rel_err(sums[0], bf16_to_f32(dXd.numpy()).astype(np.float64).sum(0)) <= 1e-5
+    assert sums[0].tobytes() == sums[1].tobytes()
 
 
 def test_tc_training_step_c4_shape_small_batch(pg):

@@ -134,3 +134,91 @@ def test_graph_rules_are_enforced_by_the_library():
     root = T.mse(T.linear(h, W, b), np.zeros((4, 8), dtype=np.float32))       # the same trainable leaf used twice
     with pytest.raises(PGError, match="weight sharing"):
         T.Plan(tr, root)
+
+
+# ---- malformed node lists from a (non-Python) host: every one is an error message from pg_plan_create, none reaches a kernel ----
+
+def _raw_plan(nodes, root=None, math=0):
+    """nodes: list of dicts (kind, shape, ins, dtype, k, p) straight into pg_op[] — bypasses the Python tracer's own checks"""
+    import ctypes
+    from protograd_b200.capi import call
+    ops = (T.PgOp * len(nodes))()
+    for i, nd in enumerate(nodes):
+        o = ops[i]
+        o.kind, o.dtype, o.ndim = nd["kind"], nd.get("dtype", 0), len(nd["shape"])
+        o.grad_leaf, o.k, o.p, o.denom = nd.get("grad_leaf", -1), nd.get("k", 0), nd.get("p", 0.0), 0.0
+        ins = list(nd.get("ins", ())) + [-1, -1, -1]
+        o.inp[0], o.inp[1], o.inp[2] = ins[:3]
+        for d, s in enumerate(nd["shape"]):
+            o.shape[d] = s
+    plan = ctypes.c_void_p()
+    call("pg_plan_create", None, ops, len(nodes), len(nodes) - 1 if root is None else root, math, ctypes.byref(plan))
+    call("pg_plan_destroy", plan)
+
+
+INPUT, PARAM, LINEAR, CONV2D, RELU, MAXPOOL, MEANPOOL, RESHAPE, DROPOUT, SOFTMAX, LOSS_CE, LOSS_MSE = range(12)
+
+
+def _mlp_nodes(B=8, K=16, N=4):
+    return [dict(kind=INPUT, shape=(B, K)), dict(kind=INPUT, shape=(B, N)), dict(kind=PARAM, shape=(K, N), grad_leaf=0),
+            dict(kind=PARAM, shape=(N,), grad_leaf=1), dict(kind=LINEAR, shape=(B, N), ins=(0, 2, 3)), dict(kind=SOFTMAX, shape=(B, N), ins=(4,)),
+            dict(kind=LOSS_CE, shape=(), ins=(5, 1))]
+
+
+def test_well_formed_raw_node_lists_are_accepted():
+    _raw_plan(_mlp_nodes())
+    nodes = _mlp_nodes()
+    nodes[1] = dict(kind=INPUT, shape=(8,), dtype=4)                  # Int32 class indices instead of the one-hot matrix
+    _raw_plan(nodes)
+    # conv (bias stored as Julia's b[1,1,Cout] = C order [Cout][1][1]) -> relu -> maxpool -> flatten -> mse
+    _raw_plan([dict(kind=INPUT, shape=(2, 1, 12, 12)), dict(kind=INPUT, shape=(2, 96)), dict(kind=PARAM, shape=(6, 1, 5, 5), grad_leaf=0),
+               dict(kind=PARAM, shape=(6, 1, 1), grad_leaf=1), dict(kind=CONV2D, shape=(2, 6, 8, 8), ins=(0, 2, 3)), dict(kind=RELU, shape=(2, 6, 8, 8), ins=(4,)),
+               dict(kind=MAXPOOL, shape=(2, 6, 4, 4), ins=(5,), k=2), dict(kind=RESHAPE, shape=(2, 96), ins=(6,)), dict(kind=LOSS_MSE, shape=(), ins=(7, 1))])
+
+
+def test_malformed_raw_node_lists_are_rejected_with_a_message():
+    import pytest
+    from protograd_b200.capi import PGError
+
+    def broken(edit, match):
+        nodes = _mlp_nodes()
+        edit(nodes)
+        with pytest.raises(PGError, match=match):
+            _raw_plan(nodes)
+
+    broken(lambda n: n[4].update(ins=(0, 2)), "wrong number of inputs")                       # Linear without its bias
+    broken(lambda n: n[4].update(ins=(0, 2, 9)), "topological")                                # forward reference
+    broken(lambda n: n[5].update(ins=(4, 1)), "wrong number of inputs")                        # softmax with two inputs
+    broken(lambda n: n[2].update(shape=(15, 4)), "input width != rows of W")                   # x [8][16] times W [15][4]
+    broken(lambda n: n[3].update(shape=(5,)), "bias length")
+    broken(lambda n: n[4].update(shape=(8, 5)), r"output shape must be \[\.\.\., out\]")
+    broken(lambda n: n[2].update(shape=(16, 4, 1)), "Linear needs")                            # W is not a matrix
+    broken(lambda n: n[5].update(shape=(8, 5)), "number of elements")                          # softmax changes the size
+    broken(lambda n: n[1].update(shape=(8, 5)), "labels must match")                           # one-hot labels of the wrong width
+    broken(lambda n: n[1].update(shape=(7,), dtype=4), "labels must match")                    # 7 class indices for 8 samples
+    broken(lambda n: n[6].update(shape=(1,)), "scalar")
+    broken(lambda n: n[5].update(kind=17), "unknown op kind")
+    broken(lambda n: n[0].update(shape=(8, -16)), "negative extent")
+    broken(lambda n: n[5].update(kind=DROPOUT, p=1.0), "dropout probability")
+
+    def conv_nodes():
+        return [dict(kind=INPUT, shape=(2, 3, 12, 12)), dict(kind=INPUT, shape=(2, 6, 4, 4)), dict(kind=PARAM, shape=(6, 3, 5, 5), grad_leaf=0),
+                dict(kind=PARAM, shape=(6,), grad_leaf=1), dict(kind=CONV2D, shape=(2, 6, 8, 8), ins=(0, 2, 3)), dict(kind=MAXPOOL, shape=(2, 6, 4, 4), ins=(4,), k=2),
+                dict(kind=LOSS_MSE, shape=(), ins=(5, 1))]
+
+    def broken_conv(edit, match):
+        nodes = conv_nodes()
+        edit(nodes)
+        with pytest.raises(PGError, match=match):
+            _raw_plan(nodes)
+
+    _raw_plan(conv_nodes())
+    broken_conv(lambda n: n[2].update(shape=(6, 2, 5, 5)), "input channels != filter channels")
+    broken_conv(lambda n: n[2].update(shape=(6, 3, 13, 5)), "filter larger than the image")
+    broken_conv(lambda n: n[3].update(shape=(5,)), "bias length != output channels")
+    broken_conv(lambda n: n[4].update(shape=(2, 6, 9, 8)), "Conv output shape")
+    broken_conv(lambda n: n[5].update(k=0), "window k >= 1")
+    broken_conv(lambda n: n[5].update(k=16), "window larger than the image")
+    broken_conv(lambda n: n[5].update(shape=(2, 6, 5, 4)), "pooling output shape")
+    broken_conv(lambda n: n[1].update(shape=(2, 6, 4, 5)), "mse output and label sizes differ")
+    broken_conv(lambda n: n[0].update(shape=(2, 3, 144)), "Conv needs")
