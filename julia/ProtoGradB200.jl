@@ -2,7 +2,7 @@
 #
 # SOURCE ONLY: there is no Julia toolchain in the build image, so this file has never been executed.  What IS checked
 # here (tests/test_julia_glue.py): every `ccall` names a symbol that include/protograd_b200.h declares, with the same
-# number of arguments.  The Python host mirror (protograd.jl_b200/) drives exactly the same C ABI and is what the GPU
+# number of arguments; PgOp / PgMlpDesc have the header's struct layouts; blocks and brackets balance.  The Python host mirror (protograd.jl_b200/) drives exactly the same C ABI and is what the GPU
 # tests run; tests/abi_driver.py drives a whole step through pg_arena_* / pg_plan_* / pg_opt_* only, i.e. through the
 # calls this file makes.
 #
@@ -133,20 +133,36 @@ function to_device(m::M) where {M<:Model}
     GC.@preserve flat check(ccall((:pg_arena_upload, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), a.h, -1, pointer(flat)))
     return DeviceModel(rebuild(m, a), a)
 end
-"same struct types, leaves replaced by views into `a` (map_recursively of src/model.jl:42-47 with a running leaf index)"
+# The structural map of src/model.jl:42-47 (`map_recursively`) rebuilds a struct as `T(fields...)` with T the CONCRETE
+# parametric type of the source — `Linear{Matrix{Float32},Vector{Float32}}(leaf, leaf)` would `convert` the new leaves
+# back to host Arrays — and maps a Tuple with `fun.(t)` (no recursion into the layers of a Compose).  Both are fine for
+# similar / copy / zero, which keep the array types; changing the leaf type needs the type WRAPPER's constructor
+# (`Linear(W, b)` infers the parameters) and its own recursion.  Field-less models (ReLU, SoftMax{D}, MaxPool{S},
+# Dropout{P,D}) carry their configuration in type parameters only and are shared as they are.
+remap(fun, f::Function) = f
+remap(fun, a::AbstractArray) = fun(a)
+remap(fun, t::Tuple) = map(x -> remap(fun, x), t)
+function remap(fun, m::T) where {T<:Model}
+    names = fieldnames(T)
+    isempty(names) && return m
+    return Base.typename(T).wrapper((remap(fun, getfield(m, k)) for k in names)...)
+end
+"same struct (wrapper) types, leaves replaced by views into `a`, numbered in allparams / vec(m) order (src/model.jl:9-24)"
 function rebuild(m::Model, a::Arena{T}) where {T}
     k = Ref(-1)
-    move(x::AbstractArray) = (k[] += 1; DeviceLeaf{T,ndims(x)}(a, k[], size(x)))
-    return ProtoGrad.map_recursively(move, m)
+    return remap(x -> (k[] += 1; DeviceLeaf{T,ndims(x)}(a, k[], size(x))), m)
 end
-function to_host(d::DeviceModel{M,T}) where {M,T}
+"vec(m) of the device model: the whole arena in leaf order, padding skipped (src/model.jl:33)"
+function Base.vec(d::DeviceModel{M,T}) where {M,T}
     flat = Vector{T}(undef, length(d))
     GC.@preserve flat check(ccall((:pg_arena_download, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), arena(d).h, -1, pointer(flat)))
-    off = Ref(0)
-    take(x::DeviceLeaf) = (n = length(x); r = reshape(flat[off[]+1:off[]+n], size(x)); off[] += n; r)
-    return ProtoGrad.map_recursively(take, inner(d))
+    return flat
 end
-Base.vec(d::DeviceModel) = vec(to_host(d))
+function to_host(d::DeviceModel{M,T}) where {M,T}
+    flat = vec(d)
+    off = Ref(0)
+    return remap(x -> (n = length(x); r = reshape(flat[off[]+1:off[]+n], size(x)); off[] += n; r), inner(d))
+end
 Base.collect(d::DeviceModel) = vec(d)
 Base.iterate(d::DeviceModel, st = (vec(d), 1)) = st[2] > length(st[1]) ? nothing : (st[1][st[2]], (st[1], st[2] + 1))
 
@@ -297,7 +313,10 @@ struct Tracer{T,N} <: AbstractArray{T,N}
     id::Int
     dims::NTuple{N,Int}
     pending::Symbol             # :none, or :matmul / :conv waiting for its `.+ b` (layers.jl:31,59)
+    px::Int                     # pending product: node ids of its input and of its weight leaf
+    pw::Int
 end
+Tracer{T,N}(tr, id, dims, pending) where {T,N} = Tracer{T,N}(tr, id, dims, pending, -1, -1)
 Base.size(t::Tracer) = t.dims
 Base.getindex(::Tracer, I...) = error("a traced value has no elements on the host")
 function push_node!(tr::Trace{T}, kind, ins, dims; dtype = code(T), grad_leaf = -1, k = 0, p = 0.0, denom = 0.0, data = nothing, pending = :none) where {T}
@@ -313,40 +332,48 @@ end
 function lift(tr::Trace{T}, x::AbstractArray) where {T}
     haskey(tr.seen, x) && return tr.seen[x]
     dt = eltype(x) === Int32 ? PG_I32 : code(T)
-    t = push_node!(tr, OP_INPUT, (), size(x); dtype = dt, data = x)
+    # the bytes handed to pg_upload must be a dense Array of T (or Int32 class indices): views, Bool one-hot matrices
+    # (Flux.onehotbatch, examples/01_mnist_mlp.jl:17) and other eltypes are materialised once per step
+    host = (x isa Array && (eltype(x) === T || eltype(x) === Int32)) ? x : Array{T}(x)
+    t = push_node!(tr, OP_INPUT, (), size(x); dtype = dt, data = host)
     return tr.seen[x] = t.id
 end
 lift(::Trace, x::Tracer) = x.id
-trace_of(x::Tracer, _...) = x.trace
-trace_of(_, y::Tracer) = y.trace
-trace_of(_, _) = ACTIVE[]::Trace
+trace_of(a, b) = b isa Tracer ? b.trace : (a isa Tracer ? a.trace : ACTIVE[])        # `nothing` outside a trace
 
-Base.reshape(x::Tracer, dims::Union{Int,Colon}...) = begin
+function traced_reshape(x::Tracer, dims::Tuple)
+    x.pending === :none || error("protograd_b200: `W*x` / `conv(x, w)` must be followed by `.+ b` (layers.jl:31,59)")
     n = prod(x.dims)
     known = prod(d for d in dims if d isa Int; init = 1)
     nd = map(d -> d isa Colon ? n ÷ known : d, dims)
+    prod(nd) == n || throw(DimensionMismatch("new dimensions $(nd) must be consistent with array size $n"))
     push_node!(x.trace, OP_RESHAPE, (x.id,), nd)
 end
-Base.reshape(x::Tracer, dims::Tuple) = reshape(x, dims...)
+# one method per Base.reshape signature an AbstractArray would otherwise reach, so that none of them is ambiguous with
+# Base's (`reshape(::AbstractArray, ::Int...)`, `(::AbstractArray, ::Dims)`, `(::AbstractArray, ::Union{Int,Colon}...)`,
+# `(::AbstractArray, ::Tuple{Vararg{Union{Int,Colon}}})`): layers.jl:30,32 use the Colon forms, Reshape{S} the tuple form
+Base.reshape(x::Tracer, dims::Int...) = traced_reshape(x, dims)
+Base.reshape(x::Tracer, dims::Union{Int,Colon}...) = traced_reshape(x, dims)
+Base.reshape(x::Tracer, dims::Dims) = traced_reshape(x, dims)
+Base.reshape(x::Tracer, dims::Tuple{Vararg{Union{Int,Colon}}}) = traced_reshape(x, dims)
 # l.W * x_reshaped  (layers.jl:31): recorded when the bias arrives
 function Base.:*(W::DeviceLeaf{T,2}, x::AbstractMatrix{T}) where {T}
     tr = trace_of(W, x)
     tr === nothing && error("protograd_b200: a device model can only be called inside eval_with_pullback(f, m, :B200) or forward(m, x)")
     size(W, 2) == size(x, 1) || throw(DimensionMismatch("Linear expects $(size(W, 2)) features, got $(size(x, 1))"))
-    Tracer{T,2}(tr, -1, (size(W, 1), size(x, 2)), :matmul) |> t -> (PENDING[t] = (lift(tr, x), lift(tr, W)); t)
+    return Tracer{T,2}(tr, -1, (size(W, 1), size(x, 2)), :matmul, lift(tr, x), lift(tr, W))
 end
-const PENDING = IdDict{Any,Tuple{Int,Int}}()
 function NNlib.conv(x::AbstractArray{T,4}, w::DeviceLeaf{T,4}) where {T}
     tr = trace_of(w, x)
+    tr === nothing && error("protograd_b200: a device model can only be called inside eval_with_pullback(f, m, :B200) or forward(m, x)")
     size(x, 3) == size(w, 3) || throw(DimensionMismatch("Conv expects $(size(w, 3)) channels, got $(size(x, 3))"))
     dims = (size(x, 1) - size(w, 1) + 1, size(x, 2) - size(w, 2) + 1, size(w, 4), size(x, 4))
-    Tracer{T,4}(tr, -1, dims, :conv) |> t -> (PENDING[t] = (lift(tr, x), lift(tr, w)); t)
+    return Tracer{T,4}(tr, -1, dims, :conv, lift(tr, x), lift(tr, w))
 end
 # `.+ b` completes Linear / Conv
 function broadcasted(::typeof(+), y::Tracer{T,N}, b::DeviceLeaf{T}) where {T,N}
     y.pending === :none && error("protograd_b200: only `W*x .+ b` / `conv(x, w) .+ b` add a parameter to a traced value")
-    xi, wi = pop!(PENDING, y)
-    push_node!(y.trace, y.pending === :matmul ? OP_LINEAR : OP_CONV2D, (xi, wi, lift(y.trace, b)), y.dims)
+    push_node!(y.trace, y.pending === :matmul ? OP_LINEAR : OP_CONV2D, (y.px, y.pw, lift(y.trace, b)), y.dims)
 end
 broadcasted(::typeof(NNlib.relu), x::Tracer) = push_node!(x.trace, OP_RELU, (x.id,), x.dims)
 NNlib.softmax(x::Tracer; dims = 1) = (dims == 1 || error("softmax over the class axis only"); push_node!(x.trace, OP_SOFTMAX, (x.id,), x.dims))
@@ -464,6 +491,9 @@ function ProtoGrad.eval_with_pullback(f, dm::DeviceModel{M,T}, ::Val{:B200}; mat
     return T(val[]), pullback
 end
 
+# the reference's Symbol entry point (src/gradient.jl:2) forwards no keyword arguments: this one does, for device models only
+ProtoGrad.eval_with_pullback(f, dm::DeviceModel, backend::Symbol; kw...) = ProtoGrad.eval_with_pullback(f, dm, Val(backend); kw...)
+
 "inference: `forward(dm, x)` == `m(x)` of the reference, host result"
 function forward(dm::DeviceModel{M,T}, x; math::Symbol = :fp32) where {M,T}
     tr = Trace{T}(Node[], IdDict{Any,Int}(), C_NULL)
@@ -479,6 +509,7 @@ function forward(dm::DeviceModel{M,T}, x; math::Symbol = :fp32) where {M,T}
                 plan.h, ptrs, C_NULL, 0, 0, 0, C_NULL, C_NULL))
     p, dt, pitch = Ref{Ptr{Cvoid}}(C_NULL), Ref{Cint}(0), Ref{Int64}(0)
     check(ccall((:pg_plan_value, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}, Ref{Cint}, Ref{Int64}), plan.h, out.id, p, dt, pitch))
+    (dt[] == code(T) && pitch[] == out.dims[1]) || error("protograd_b200: forward() returns dense $(T) values only (the root of this trace is stored as dtype $(dt[]), pitch $(pitch[]))")
     res = Array{T}(undef, out.dims)
     GC.@preserve res check(ccall((:pg_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), ctx().h, pointer(res), p[], sizeof(res)))
     return res

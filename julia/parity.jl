@@ -27,10 +27,14 @@ function build(case, d)
     if case == "c1_mlp"
         return Compose(Linear(leaf(0), leaf(1)), x -> relu.(x), Linear(leaf(2), leaf(3)), softmax)
     elseif case == "c3_conv" || case == "c5_finetune"
+        # c3 head (tests/golden/make_golden.py C3_SPEC, examples/02_mnist_conv.jl:36-42): 256 -> 120 -> relu -> 84 -> relu -> 10;
+        # c5 head (C5_SPEC): one trainable Linear 256 -> 10 — layer 8 of the Compose in both cases
+        head = case == "c3_conv" ?
+            (Linear(leaf(4), leaf(5)), x -> relu.(x), Linear(leaf(6), leaf(7)), x -> relu.(x), Linear(leaf(8), leaf(9))) :
+            (Linear(leaf(4), leaf(5)),)
         return Compose(Conv(leaf(0), reshape(leaf(1), 1, 1, :)), x -> relu.(x), x -> maxpool(x, (2, 2)),
                        Conv(leaf(2), reshape(leaf(3), 1, 1, :)), x -> relu.(x), x -> maxpool(x, (2, 2)),
-                       x -> reshape(x, :, size(x, 4)),
-                       (Linear(leaf(i), leaf(i + 1)) for i in 4:2:(haskey(d, "p0_8") ? 8 : 4))..., softmax)
+                       x -> reshape(x, :, size(x, 4)), head..., softmax)
     end
     error("unknown case $case")
 end

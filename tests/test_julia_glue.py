@@ -102,3 +102,94 @@ def test_julia_mlp_desc_struct_matches_the_header_layout():
         names.append(name)
     assert names == [f[0] for f in MlpDesc._fields_]
     assert (off + 7) // 8 * 8 == ctypes.sizeof(MlpDesc)
+
+
+def _julia_tokens(src):
+    """(token, bracket_depth) for identifiers / keywords of a Julia source, with comments, strings, chars and symbols removed;
+    bracket_depth counts enclosing (), [] and {} (an `end` inside [] is an index, a `for` / `if` inside brackets a generator)"""
+    out, i, n, depth = [], 0, len(src), 0
+    while i < n:
+        c = src[i]
+        if c == "#":
+            if src.startswith("#=", i):
+                i = src.index("=#", i) + 2
+            else:
+                while i < n and src[i] != "\n":
+                    i += 1
+        elif src.startswith('"""', i):
+            i = src.index('"""', i + 3) + 3
+        elif c == '"':
+            i += 1
+            while src[i] != '"':
+                if src[i] == "\\":
+                    i += 1
+                elif src.startswith("$(", i):          # interpolation: skip to its closing parenthesis (may hold strings)
+                    d, i = 1, i + 2
+                    while d:
+                        if src[i] == '"':              # a nested string literal inside the interpolation
+                            i += 1
+                            while src[i] != '"':
+                                i += 2 if src[i] == "\\" else 1
+                        d += {"(": 1, ")": -1}.get(src[i], 0)
+                        i += 1
+                    continue
+                i += 1
+            i += 1
+        elif c == "'" and i + 2 < n and (src[i + 2] == "'" or (src[i + 1] == "\\" and src[i + 3] == "'")):
+            i += 3 if src[i + 2] == "'" else 4          # character literal (a lone ' is the adjoint operator)
+        elif c in "([{":
+            depth += 1; i += 1
+        elif c in ")]}":
+            depth -= 1; i += 1
+            assert depth >= 0, "unbalanced closing bracket near line %d" % (src.count("\n", 0, i) + 1)
+        elif c == ":" and i + 1 < n and (src[i + 1].isalpha() or src[i + 1] == "_") and (i == 0 or not (src[i - 1].isalnum() or src[i - 1] in "_)]}")):
+            i += 1                                       # a Symbol literal such as :none, :end — not a keyword
+            while i < n and (src[i].isalnum() or src[i] in "_!"):
+                i += 1
+        elif c.isalpha() or c == "_" or c == "@":
+            j = i + 1
+            while j < n and (src[j].isalnum() or src[j] in "_!"):
+                j += 1
+            prev_dot = i > 0 and src[i - 1] == "."       # field access such as x.end never happens, but x.begin could
+            if not prev_dot:
+                out.append((src[i:j], depth, src.count("\n", 0, i) + 1))
+            i = j
+        else:
+            i += 1
+    assert depth == 0, "unbalanced brackets at end of file"
+    return out
+
+
+def _check_julia_blocks(src, name):
+    openers = {"module", "baremodule", "function", "struct", "if", "for", "while", "try", "let", "do", "begin", "quote", "macro"}
+    block_exprs = {"begin", "function", "let", "quote", "try", "do"}      # may also open inside a call's parentheses
+    stack = []
+    for t, depth, line in _julia_tokens(src):
+        if t in openers and (depth == 0 or t in block_exprs):
+            stack.append((t, line, depth))
+        elif t == "end":
+            if stack and stack[-1][2] == depth:
+                stack.pop()
+            else:
+                assert depth > 0, f"{name}:{line}: `end` without an opener"      # inside brackets: the `end` of an index, a[2:end]
+    assert not stack, f"{name}: unclosed `{stack[-1][0]}` opened at line {stack[-1][1]}"
+
+
+def test_julia_sources_have_balanced_blocks_and_brackets():
+    """No Julia here to parse the glue: a tokenizer (comments, strings, interpolations, symbols stripped) checks that every (), [], {}
+    closes and that the block openers (module, function, struct, if, for, while, try, let, do, begin, quote, macro; generators and
+    ternaries inside brackets excluded) are matched one to one by `end` at the same bracket depth — the class of slip a hand edit
+    of a never-executed file makes.  The checker is itself checked on broken copies."""
+    import pytest
+    for path in JULIA:
+        src = open(path).read()
+        _check_julia_blocks(src, os.path.basename(path))
+    src = open(JULIA[0]).read()
+    k = src.index("function check(rc::Cint)")
+    cut = src.index("\nend\n", k)
+    with pytest.raises(AssertionError, match="unclosed"):
+        _check_julia_blocks(src[:cut] + src[cut + 4:], "one `end` removed")
+    with pytest.raises(AssertionError, match="without an opener|unclosed"):
+        _check_julia_blocks(src[:cut] + "\nend" + src[cut:], "one `end` too many")
+    with pytest.raises(AssertionError, match="unbalanced"):
+        _check_julia_blocks(src.replace("ccall((:pg_sync, LIB), Cint, (Ptr{Cvoid},), ctx().h))", "ccall((:pg_sync, LIB), Cint, (Ptr{Cvoid},), ctx().h)", 1), "a parenthesis removed")
