@@ -19,7 +19,10 @@ Pinning status
   these the restatement follows NNlib's published semantics (true convolution with flipped
   kernel, first-argmax pooling, max-shifted softmax) anchored on the reference call sites, and
   is cross-checked against torch-CPU float64 autograd and central finite differences in
-  tests/test_oracle.py.  Julia itself is not installed here, so no reference output could be
+  tests/test_oracle.py; conv / maxpool / meanpool forward values are additionally checked on the
+  known-answer vectors of NNlib's own test-suite (x = reshape(1:20, 5, 4, 1, 1), w = reshape(1:4, 2, 2, 1, 1);
+  quoted from the published package, which cannot be fetched here, and hand-derivable from the
+  definitions) — test_nnlib_published_known_answers_conv_and_pooling.  Julia itself is not installed here, so no reference output could be
   generated; `julia/parity.jl` closes the loop on any machine with Julia.
 
 Layout convention: everything is in row-major/C terms, i.e. exactly the bytes Julia holds:

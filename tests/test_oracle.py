@@ -237,6 +237,31 @@ def test_conv_is_true_convolution_against_direct_loops():
     assert np.allclose(y, ref, rtol=1e-13, atol=1e-13)
 
 
+def test_nnlib_published_known_answers_conv_and_pooling():
+    """The arithmetic of conv / maxpool / meanpool lives in NNlib (compat "0.9", /root/reference/Project.toml:21; call sites
+    /root/reference/src/layers.jl:59,93,99), which is not under /root/reference.  NNlib's own test-suite pins these ops on
+    x = reshape(1:20, 5, 4, 1, 1), w = reshape(1:4, 2, 2, 1, 1) (test/conv.jl, test/pooling.jl of NNlib 0.9 — quoted from the
+    published package, which cannot be fetched here; each value is also what the definition gives by hand:
+    y[1,1] = 1*7 + 2*6 + 3*2 + 4*1 = 29 only for a FLIPPED kernel, cross-correlation would give 1*1 + 2*2 + 3*6 + 4*7 = 51):
+        conv(x, w)         == [29 79 129; 39 89 139; 49 99 149; 59 109 159]
+        maxpool(x, (2,2))  == [7 17; 9 19]          (the fifth row is dropped: floor((5 - 2) / 2) + 1 = 2)
+        meanpool(x, (2,2)) == [4 14; 6 16]
+    Julia x[W,H,C,N] column-major is the same memory as C x[N][C][H][W]: the printed Julia matrices are [W'][H'] = the transpose
+    of the oracle's [H'][W'] planes."""
+    x = np.arange(1.0, 21.0).reshape(1, 1, 4, 5)            # H = 4, W = 5  ==  Julia reshape(1:20, 5, 4, 1, 1)
+    w = np.arange(1.0, 5.0).reshape(1, 1, 2, 2)
+    y = O.conv2d_fwd(x, w, np.zeros(1))
+    assert np.array_equal(y[0, 0].T, np.array([[29, 79, 129], [39, 89, 139], [49, 99, 149], [59, 109, 159.0]]))
+    assert np.array_equal(O.maxpool2d_fwd(x, (2, 2))[0, 0].T, np.array([[7, 17], [9, 19.0]]))
+    assert np.array_equal(O.meanpool2d_fwd(x, (2, 2))[0, 0].T, np.array([[4, 14], [6, 16.0]]))
+    # their pullbacks are then pinned by the adjoint identity <conv(x, w), dy> == <x, dx> == <w, dw> (exact in integers here)
+    dy = np.arange(1.0, 13.0).reshape(1, 1, 3, 4)
+    dw, db, dx = O.conv2d_bwd(x, w, dy)
+    assert (y * dy).sum() == (x * dx).sum() == (w * dw).sum() and db[0] == dy.sum()
+    dyp = np.array([[[[1.0, 2.0], [3.0, 4.0]]]])
+    assert (O.maxpool2d_fwd(x, (2, 2)) * dyp).sum() == (x * O.maxpool2d_bwd(x, dyp, (2, 2))).sum()
+
+
 def test_ce_gradient_finite_difference_keeps_eps():
     """the eps inside log() must be part of the gradient."""
     rng = np.random.default_rng(0)
