@@ -262,6 +262,18 @@ def test_nnlib_published_known_answers_conv_and_pooling():
     assert (O.maxpool2d_fwd(x, (2, 2)) * dyp).sum() == (x * O.maxpool2d_bwd(x, dyp, (2, 2))).sum()
 
 
+def test_nnlib_softmax_known_answers():
+    """NNlib's softmax tests (test/softmax.jl of NNlib 0.9, quoted from the published package): the max-shifted form does not
+    overflow — softmax([-100_000, -100_000]) == [0.5, 0.5], softmax(Float32[1, 2, 3000]) == [0, 0, 1] — every column sums to 1,
+    and the pullback of an all-ones cotangent is zero (d/dz of sum_c p_c = 1).  Class axis = Julia dims 1 = the LAST C axis here."""
+    assert np.array_equal(O.softmax_fwd(np.array([[-100000.0, -100000.0]])), np.array([[0.5, 0.5]]))
+    assert np.array_equal(O.softmax_fwd(np.array([[1.0, 2.0, 3000.0]], dtype=np.float32)), np.array([[0.0, 0.0, 1.0]], dtype=np.float32))
+    rng = np.random.default_rng(0)
+    p = O.softmax_fwd(rng.standard_normal((5, 5)))
+    assert np.allclose(p.sum(axis=1), 1.0, rtol=0, atol=1e-15)
+    assert np.abs(O.softmax_bwd(p, np.ones_like(p))).max() <= 1e-15          # p * (1 - sum p): rounding of the row sum only
+
+
 def test_ce_gradient_finite_difference_keeps_eps():
     """the eps inside log() must be part of the gradient."""
     rng = np.random.default_rng(0)
