@@ -125,3 +125,25 @@ def test_c_host_trains_c1_through_the_abi(tmp_path):
     dot over the arena, then 30 Adam steps that must reduce the loss"""
     r = _build_c_host(tmp_path)
     assert r.returncode == 0 and "abi_smoke ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_no_floating_point_atomics_and_blackwell_instructions_in_the_sass():
+    """Determinism and "B200-native" as properties of the shipped binary (cuobjdump works without a GPU): the library holds no
+    floating-point ATOM / ATOMG / ATOMS / RED instruction — every gradient sum is a fixed-order reduction of partials, the only
+    atomics are integer tickets, tile counters and timing — and its GEMM / conv kernels are tcgen05 + TMA code (UTCHMMA incl. the
+    cta_group::2 form, LDTM, UTMALDG / UTMASTG, UBLKCP), not mma.sync recompiles (no HMMA)."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    ops = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\w+\s+)?([A-Za-z0-9_.]+)", sass, flags=re.M)
+    atomics = {o for o in ops if o.split(".")[0] in ("ATOM", "ATOMG", "ATOMS", "RED")}
+    assert atomics, "no atomics at all: the mnemonic filter is broken"
+    fp = {o for o in atomics if re.search(r"\.(F16|F32|F64|BF16)", o)}
+    assert not fp, fp
+    have = {o.split(".")[0] for o in ops}
+    for must in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR"):
+        assert must in have, must
+    assert any(o.startswith("UTCHMMA.2CTA") for o in ops) and any(o.startswith("UTMALDG.2D.2CTA") for o in ops)
+    assert "HMMA" not in have
